@@ -1,0 +1,179 @@
+// Optimal-ate pairing on BLS12-381, split the B200 way:
+//
+//   (1) g2_prepare_*   one thread per G2 point: walks T <- 2T / T+Q over the 63+5 steps of
+//                      |x| = 0xd201000000010000 and emits the 68 line-coefficient triples
+//                      (3 x Fp2 = 288 B each, 19,584 B per point) into HBM.  Small state
+//                      (T = 72 words), shared by every ComT entry that uses the point.
+//   (2) miller_*       one thread per GT accumulator: f <- f^2 * prod_k line_k(P_k); the only
+//                      wide state is f itself; line triples are streamed from HBM.
+//   (3) final_exp      easy part + the arkworks hard part (x-1)^2 (x+p)(x^2+p^2-1) + 3.
+//
+// Replaces: ark-ec `Bls12::multi_miller_loop` + `final_exponentiation` as reached from
+// ComT::pairing / ComT::pairing_sum (src/data_structures.rs:484-502) and generator.rs:116.
+// Any Miller function that differs by proper-subfield factors gives identical final bits;
+// the final exponent is arkworks' (3x the textbook one), see SURVEY.md §8c.
+#pragma once
+#include "curve.cuh"
+
+namespace gs {
+
+constexpr int GS_NUM_LINES = 68;  // 63 doublings + 5 additions
+constexpr uint64_t GS_X_ABS = 0xd201000000010000ull;
+
+struct line_coeffs {  // ell = c0 + (c1 * xP) v + (c2 * yP) v w      (M-twist => mul_by_014)
+  fp2 c0, c1, c2;
+};
+
+struct g2_proj {  // homogeneous projective
+  fp2 x, y, z;
+};
+
+GS_HD GS_INL void fp2_mul_b_twist(fp2& r, const fp2& a) {
+  // * 4(1+u):  4 * (a0 - a1, a0 + a1)
+  fp2 t;
+  fp2::mul_xi(t, a);
+  fp2::dbl(t, t);
+  fp2::dbl(r, t);
+}
+GS_HD GS_INL void fp_half(fp& r, const fp& a) {
+  fp h;
+#pragma unroll
+  for (int i = 0; i < 12; i++) h.l[i] = FP_TWO_INV(i);
+  fp::mul(r, a, h);
+}
+GS_HD GS_INL void fp2_half(fp2& r, const fp2& a) {
+  fp_half(r.c0, a.c0);
+  fp_half(r.c1, a.c1);
+}
+
+// Costello-Lange-Naehrig doubling step in homogeneous projective coordinates.
+GS_HD GS_NOINL void g2_double_step(g2_proj& t, line_coeffs& l) {
+  fp2 a, b, c, e, f, g, h, i, j, e2, s;
+  fp2::mul(a, t.x, t.y);
+  fp2_half(a, a);
+  fp2::sqr(b, t.y);
+  fp2::sqr(c, t.z);
+  fp2::dbl(s, c);
+  fp2::add(s, s, c);
+  fp2_mul_b_twist(e, s);  // e = b' * 3c
+  fp2::dbl(f, e);
+  fp2::add(f, f, e);  // f = 3e
+  fp2::add(g, b, f);
+  fp2_half(g, g);
+  fp2::add(h, t.y, t.z);
+  fp2::sqr(h, h);
+  fp2::add(s, b, c);
+  fp2::sub(h, h, s);  // h = 2yz
+  fp2::sub(i, e, b);
+  fp2::sqr(j, t.x);
+  fp2::sqr(e2, e);
+  fp2::sub(s, b, f);
+  fp2::mul(t.x, a, s);
+  fp2::sqr(g, g);
+  fp2::dbl(s, e2);
+  fp2::add(s, s, e2);
+  fp2::sub(t.y, g, s);
+  fp2::mul(t.z, b, h);
+  l.c0 = i;
+  fp2::dbl(s, j);
+  fp2::add(l.c1, s, j);
+  fp2::neg(l.c2, h);
+}
+
+GS_HD GS_NOINL void g2_add_step(g2_proj& t, const g2_aff& q, line_coeffs& l) {
+  fp2 theta, lambda, c, d, e, f, g, h, s, j;
+  fp2::mul(s, q.y, t.z);
+  fp2::sub(theta, t.y, s);
+  fp2::mul(s, q.x, t.z);
+  fp2::sub(lambda, t.x, s);
+  fp2::sqr(c, theta);
+  fp2::sqr(d, lambda);
+  fp2::mul(e, lambda, d);
+  fp2::mul(f, t.z, c);
+  fp2::mul(g, t.x, d);
+  fp2::add(h, e, f);
+  fp2::sub(h, h, g);
+  fp2::sub(h, h, g);
+  fp2::mul(t.x, lambda, h);
+  fp2::sub(s, g, h);
+  fp2::mul(s, theta, s);
+  fp2::mul(j, e, t.y);
+  fp2::sub(t.y, s, j);
+  fp2::mul(t.z, t.z, e);
+  fp2::mul(j, theta, q.x);
+  fp2::mul(s, lambda, q.y);
+  fp2::sub(l.c0, j, s);
+  fp2::neg(l.c1, theta);
+  l.c2 = lambda;
+}
+
+// Writes the 68 line triples of Q to out[step * stride]  (stride in units of line_coeffs).
+// Q must not be the identity (callers drop identity pairs, as ark-ec does).
+GS_HD GS_INL void g2_prepare(line_coeffs* out, size_t stride, const g2_aff& q) {
+  g2_proj t;
+  t.x = q.x;
+  t.y = q.y;
+  t.z.set_one();
+  int idx = 0;
+  for (int b = 62; b >= 0; b--) {
+    line_coeffs l;
+    g2_double_step(t, l);
+    out[(size_t)idx * stride] = l;
+    idx++;
+    if ((GS_X_ABS >> b) & 1) {
+      g2_add_step(t, q, l);
+      out[(size_t)idx * stride] = l;
+      idx++;
+    }
+  }
+}
+
+// f *= line evaluated at the affine G1 point (px, py)
+GS_HD GS_INL void miller_apply_line(fp12& f, const line_coeffs& l, const fp& px, const fp& py) {
+  fp2 c1, c2;
+  fp2::mul_fp(c1, l.c1, px);
+  fp2::mul_fp(c2, l.c2, py);
+  fp12::mul_by_014(f, f, l.c0, c1, c2);
+}
+
+// ------------------------------------------------------------------ final exponentiation
+// f^|x| for f in the cyclotomic subgroup, then conjugate (x < 0)
+GS_HD GS_NOINL void cyclotomic_exp_x(fp12& r, const fp12& a) {
+  fp12 acc = a;
+  for (int b = 62; b >= 0; b--) {
+    fp12::cyclotomic_sqr(acc, acc);
+    if ((GS_X_ABS >> b) & 1) fp12::mul(acc, acc, a);
+  }
+  fp12::conj(r, acc);
+}
+
+GS_HD GS_NOINL void final_exponentiation(fp12& out, const fp12& f) {
+  fp12 r, t, a, b, c;
+  // easy part: r = f^((p^6-1)(p^2+1))
+  fp12::inv(t, f);
+  fp12::conj(r, f);
+  fp12::mul(r, r, t);
+  fp12::frobenius<2>(t, r);
+  fp12::mul(r, r, t);
+  // hard part: r^((x-1)^2 (x+p)(x^2+p^2-1)) * r^3
+  cyclotomic_exp_x(a, r);
+  fp12::conj(t, r);
+  fp12::mul(a, a, t);  // a = r^(x-1)
+  cyclotomic_exp_x(b, a);
+  fp12::conj(t, a);
+  fp12::mul(b, b, t);  // b = a^(x-1)
+  cyclotomic_exp_x(c, b);
+  fp12::frobenius<1>(t, b);
+  fp12::mul(c, c, t);  // c = b^(x+p)
+  cyclotomic_exp_x(a, c);
+  cyclotomic_exp_x(a, a);  // c^(x^2)
+  fp12::frobenius<2>(t, c);
+  fp12::mul(a, a, t);
+  fp12::conj(t, c);
+  fp12::mul(a, a, t);  // a = c^(x^2+p^2-1)
+  fp12::cyclotomic_sqr(t, r);
+  fp12::mul(t, t, r);  // r^3
+  fp12::mul(out, a, t);
+}
+
+}  // namespace gs

@@ -1,0 +1,69 @@
+// Host instantiation of the DEVICE math headers (tests only; never linked into the product).
+// Lets the CPU-only CI check the exact limb algorithms / tower / curve / pairing formulas
+// that the CUDA kernels execute, against oracle/ (a separately written big-int restatement).
+#include <cstring>
+#include <vector>
+#include "../../groth-sahai-rs_b200/csrc/pairing.cuh"
+using namespace gs;
+
+#define LD(T, v, p) T v; memcpy(&v, p, sizeof(T))
+#define ST(p, v) memcpy(p, &v, sizeof(v))
+extern "C" {
+void hs_fp_mul(void* r, const void* a, const void* b) { LD(fp, x, a); LD(fp, y, b); fp z; fp::mul(z, x, y); ST(r, z); }
+void hs_fp_add(void* r, const void* a, const void* b) { LD(fp, x, a); LD(fp, y, b); fp z; fp::add(z, x, y); ST(r, z); }
+void hs_fp_sub(void* r, const void* a, const void* b) { LD(fp, x, a); LD(fp, y, b); fp z; fp::sub(z, x, y); ST(r, z); }
+void hs_fp_neg(void* r, const void* a) { LD(fp, x, a); fp z; fp::neg(z, x); ST(r, z); }
+void hs_fp_inv(void* r, const void* a) { LD(fp, x, a); fp z; fp_inv(z, x); ST(r, z); }
+void hs_fr_mul(void* r, const void* a, const void* b) { LD(fr, x, a); LD(fr, y, b); fr z; fr::mul(z, x, y); ST(r, z); }
+void hs_fr_add(void* r, const void* a, const void* b) { LD(fr, x, a); LD(fr, y, b); fr z; fr::add(z, x, y); ST(r, z); }
+void hs_fr_sub(void* r, const void* a, const void* b) { LD(fr, x, a); LD(fr, y, b); fr z; fr::sub(z, x, y); ST(r, z); }
+void hs_fr_from_mont(void* r, const void* a) { LD(fr, x, a); uint32_t o[8]; fr_from_mont(o, x); memcpy(r, o, 32); }
+void hs_fp2_mul(void* r, const void* a, const void* b) { LD(fp2, x, a); LD(fp2, y, b); fp2::mul(x, x, y); ST(r, x); }
+void hs_fp2_sqr(void* r, const void* a) { LD(fp2, x, a); fp2::sqr(x, x); ST(r, x); }
+void hs_fp2_inv(void* r, const void* a) { LD(fp2, x, a); fp2::inv(x, x); ST(r, x); }
+void hs_fp6_mul(void* r, const void* a, const void* b) { LD(fp6, x, a); LD(fp6, y, b); fp6::mul(x, x, y); ST(r, x); }
+void hs_fp6_inv(void* r, const void* a) { LD(fp6, x, a); fp6::inv(x, x); ST(r, x); }
+void hs_fp12_mul(void* r, const void* a, const void* b) { LD(fp12, x, a); LD(fp12, y, b); fp12::mul(x, x, y); ST(r, x); }
+void hs_fp12_sqr(void* r, const void* a) { LD(fp12, x, a); fp12::sqr(x, x); ST(r, x); }
+void hs_fp12_inv(void* r, const void* a) { LD(fp12, x, a); fp12::inv(x, x); ST(r, x); }
+void hs_fp12_frob1(void* r, const void* a) { LD(fp12, x, a); fp12::frobenius<1>(x, x); ST(r, x); }
+void hs_fp12_frob2(void* r, const void* a) { LD(fp12, x, a); fp12::frobenius<2>(x, x); ST(r, x); }
+void hs_fp12_cyclo_sqr(void* r, const void* a) { LD(fp12, x, a); fp12::cyclotomic_sqr(x, x); ST(r, x); }
+void hs_fp12_mul_by_014(void* r, const void* a, const void* c0, const void* c1, const void* c4) {
+  LD(fp12, x, a); LD(fp2, p, c0); LD(fp2, q, c1); LD(fp2, s, c4); fp12::mul_by_014(x, x, p, q, s); ST(r, x); }
+
+// group ops: affine in / affine out (identity = all-zero)
+void hs_g1_add(void* r, const void* a, const void* b) {
+  LD(g1_aff, p, a); LD(g1_aff, q, b); g1_jac j; j.from_affine(p); g1_jac::add_mixed(j, j, q); g1_aff o; g1_jac::to_affine(o, j); ST(r, o); }
+void hs_g1_add_full(void* r, const void* a, const void* b) {
+  LD(g1_aff, p, a); LD(g1_aff, q, b); g1_jac j, k; j.from_affine(p); k.from_affine(q);
+  g1_jac::dbl(j, j); g1_jac::dbl(k, k); g1_jac::add(j, j, k); g1_aff o; g1_jac::to_affine(o, j); ST(r, o); }  // 2a + 2b
+void hs_g1_mul(void* r, const void* a, const void* k_mont) {
+  LD(g1_aff, p, a); LD(fr, k, k_mont); uint32_t kk[8]; fr_from_mont(kk, k); g1_jac j; scalar_mul<FpOps>(j, p, kk); g1_aff o; g1_jac::to_affine(o, j); ST(r, o); }
+void hs_g2_add(void* r, const void* a, const void* b) {
+  LD(g2_aff, p, a); LD(g2_aff, q, b); g2_jac j; j.from_affine(p); g2_jac::add_mixed(j, j, q); g2_aff o; g2_jac::to_affine(o, j); ST(r, o); }
+void hs_g2_add_full(void* r, const void* a, const void* b) {
+  LD(g2_aff, p, a); LD(g2_aff, q, b); g2_jac j, k; j.from_affine(p); k.from_affine(q);
+  g2_jac::dbl(j, j); g2_jac::dbl(k, k); g2_jac::add(j, j, k); g2_aff o; g2_jac::to_affine(o, j); ST(r, o); }
+void hs_g2_mul(void* r, const void* a, const void* k_mont) {
+  LD(g2_aff, p, a); LD(fr, k, k_mont); uint32_t kk[8]; fr_from_mont(kk, k); g2_jac j; scalar_mul<Fp2Ops>(j, p, kk); g2_aff o; g2_jac::to_affine(o, j); ST(r, o); }
+
+// Miller product over n (G1,G2) affine pairs (identity pairs dropped), NO final exponentiation
+void hs_miller(void* r, int n, const void* g1s, const void* g2s) {
+  const g1_aff* P = (const g1_aff*)g1s; const g2_aff* Q = (const g2_aff*)g2s;
+  std::vector<std::vector<line_coeffs>> lines; std::vector<g1_aff> ps;
+  for (int i = 0; i < n; i++) {
+    if (P[i].is_inf() || Q[i].is_inf()) continue;
+    lines.emplace_back(GS_NUM_LINES); g2_prepare(lines.back().data(), 1, Q[i]); ps.push_back(P[i]);
+  }
+  fp12 f; f.set_one(); int idx = 0;
+  for (int b = 62; b >= 0; b--) {
+    fp12::sqr(f, f);
+    for (size_t k = 0; k < ps.size(); k++) miller_apply_line(f, lines[k][idx], ps[k].x, ps[k].y);
+    idx++;
+    if ((GS_X_ABS >> b) & 1) { for (size_t k = 0; k < ps.size(); k++) miller_apply_line(f, lines[k][idx], ps[k].x, ps[k].y); idx++; }
+  }
+  fp12::conj(f, f); ST(r, f);
+}
+void hs_final_exp(void* r, const void* a) { LD(fp12, x, a); fp12 o; final_exponentiation(o, x); ST(r, o); }
+}
