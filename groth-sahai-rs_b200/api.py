@@ -1,0 +1,314 @@
+"""Host-side mirror of the reference's Rust API for the hot path (same names, argument
+meaning and error behaviour), over the C ABI.  Every arithmetic step runs on the GPU.
+
+Reference surface mirrored (paths relative to /root/reference):
+  generator.rs:25-42     AbstractCrs::generate_crs, CRS{u, v, g1_gen, g2_gen, gt_gen}
+  prover/commit.rs       Commit1/Commit2 (+append), commit_G1, batch_commit_G1, commit_scalar_to_B1,
+                         batch_commit_scalar_to_B1 and the four G2/B2 mirrors
+  prover/prove.rs        Provable::{commit_and_prove, prove}, EquProof, CProof
+  statement.rs           EquType, PPE, MSMEG1, MSMEG2, QuadEqu
+  verifier.rs            Verifiable::verify
+  data_structures.rs     ComT::{pairing, pairing_sum, linear_map_*}, Mat::{left_mul, right_mul, ...}
+
+Elements are `bytes` in the C-ABI encoding (arkworks Montgomery limbs; see include/gs_b200.h):
+Fr 32 B, G1 96 B, G2 192 B, GT 576 B; Com1 = (G1, G1) and Com2 = (G2, G2) are 192 / 384 B
+strings; a Matrix<Fr> is a list of rows of Fr.  `rng` is any object with a method
+``fr() -> bytes`` (and ``g1()``, ``g2()`` for generate_crs); draws happen on the host in the
+reference's order, which makes every output reproducible bit-for-bit.
+The reference signals misuse by assert!/panic; here those are AssertionError / GsError.
+"""
+from dataclasses import dataclass, field
+from typing import List
+
+from . import ffi
+from .ffi import Engine, GsError
+
+FR, G1, G2, GT = ffi.FR, ffi.G1, ffi.G2, ffi.GT
+G1_ZERO, G2_ZERO = bytes(G1), bytes(G2)
+
+
+class EquType:  # statement.rs:42-50, serialised as one byte :68-73
+    PairingProduct, MultiScalarG1, MultiScalarG2, Quadratic = 0, 1, 2, 3
+
+
+_default_engine = None
+
+
+def default_engine() -> Engine:
+    global _default_engine
+    if _default_engine is None:
+        _default_engine = Engine(0)
+    return _default_engine
+
+
+def _split(b, size):
+    return [b[i:i + size] for i in range(0, len(b), size)]
+
+
+def _flat(m):
+    return b"".join(x for row in m for x in row)
+
+
+# ---------------------------------------------------------------- CRS  (generator.rs)
+@dataclass
+class CRS:
+    u: List[bytes]       # 2 x Com1
+    v: List[bytes]       # 2 x Com2
+    g1_gen: bytes
+    g2_gen: bytes
+    gt_gen: bytes
+    engine: Engine = field(default=None, repr=False, compare=False)
+
+    @staticmethod
+    def generate_crs(rng, engine: Engine = None) -> "CRS":
+        """generator.rs:81-118; RNG order p1 <- G1, p2 <- G2, a1, a2, t1, t2 <- Fr (:86-93)."""
+        eng = engine or default_engine()
+        p1, p2 = rng.g1(), rng.g2()
+        a1, a2, t1, t2 = rng.fr(), rng.fr(), rng.fr(), rng.fr()
+        return CRS.from_bytes(eng.crs_generate(p1, p2, a1, a2, t1, t2), eng, loaded=True)
+
+    def to_bytes(self) -> bytes:
+        return b"".join(self.u) + b"".join(self.v) + self.g1_gen + self.g2_gen + self.gt_gen
+
+    @staticmethod
+    def from_bytes(b: bytes, engine: Engine = None, loaded=False) -> "CRS":
+        eng = engine or default_engine()
+        o = 0
+        u = [b[0:192], b[192:384]]
+        v = [b[384:768], b[768:1152]]
+        o = 1152
+        crs = CRS(u, v, b[o:o + G1], b[o + G1:o + G1 + G2], b[o + G1 + G2:o + G1 + G2 + GT], eng)
+        if not loaded:
+            eng.crs_load(b)
+        eng._loaded_crs = b
+        return crs
+
+    def _use(self) -> Engine:
+        """Make this key the engine's current one (any `&CRS` argument of the reference)."""
+        b = self.to_bytes()
+        if getattr(self.engine, "_loaded_crs", None) != b:
+            self.engine.crs_load(b)
+            self.engine._loaded_crs = b
+        return self.engine
+
+
+# ---------------------------------------------------------------- commitments  (prover/commit.rs)
+@dataclass
+class _Commit:
+    coms: List[bytes]
+    rand: List[List[bytes]]   # Matrix<Fr>
+
+    def append(self, other):   # Commit::append :42-51
+        self.coms.extend(other.coms)
+        self.rand.extend(other.rand)
+
+
+class Commit1(_Commit):
+    pass
+
+
+class Commit2(_Commit):
+    pass
+
+
+def batch_commit_G1(xvars, key: CRS, rng) -> Commit1:            # :78-100
+    rand = [[rng.fr(), rng.fr()] for _ in xvars]                 # row-major draws :85-88
+    out = key._use().batch_commit_g1(b"".join(xvars), _flat(rand))
+    return Commit1(_split(out, 192), rand)
+
+
+def batch_commit_G2(yvars, key: CRS, rng) -> Commit2:            # :178-200
+    rand = [[rng.fr(), rng.fr()] for _ in yvars]
+    out = key._use().batch_commit_g2(b"".join(yvars), _flat(rand))
+    return Commit2(_split(out, 384), rand)
+
+
+def batch_commit_scalar_to_B1(scalar_xvars, key: CRS, rng) -> Commit1:   # :125-156
+    rand = [[rng.fr()] for _ in scalar_xvars]
+    out = key._use().batch_commit_scalar_b1(b"".join(scalar_xvars), _flat(rand))
+    return Commit1(_split(out, 192), rand)
+
+
+def batch_commit_scalar_to_B2(scalar_yvars, key: CRS, rng) -> Commit2:   # :225-256
+    rand = [[rng.fr()] for _ in scalar_yvars]
+    out = key._use().batch_commit_scalar_b2(b"".join(scalar_yvars), _flat(rand))
+    return Commit2(_split(out, 384), rand)
+
+
+def commit_G1(xvar, key, rng): return batch_commit_G1([xvar], key, rng)                       # :59-75
+def commit_G2(yvar, key, rng): return batch_commit_G2([yvar], key, rng)                       # :159-175
+def commit_scalar_to_B1(x, key, rng): return batch_commit_scalar_to_B1([x], key, rng)         # :103-122
+def commit_scalar_to_B2(y, key, rng): return batch_commit_scalar_to_B2([y], key, rng)         # :203-222
+
+
+# ---------------------------------------------------------------- proofs  (prover/prove.rs)
+@dataclass
+class EquProof:               # :55-61
+    pi: List[bytes]
+    theta: List[bytes]
+    equ_type: int
+    rand: List[List[bytes]]
+
+
+@dataclass
+class CProof:                 # :64-69
+    xcoms: Commit1
+    ycoms: Commit2
+    equ_proofs: List[EquProof]
+
+
+@dataclass
+class _Equation:
+    a_consts: List[bytes]
+    b_consts: List[bytes]
+    gamma: List[List[bytes]]
+    target: bytes
+    equ_type = None
+
+    def get_type(self): return self.equ_type
+
+    def _cx(self): return 2 if self.equ_type in (0, 1) else 1
+    def _cy(self): return 2 if self.equ_type in (0, 2) else 1
+
+    def prove(self, xvars, yvars, xcoms, ycoms, crs: CRS, rng) -> EquProof:
+        # the reference's dimension asserts (prove.rs:106-114 and mirrors)
+        assert len(xvars) == len(xcoms.rand) and len(self.gamma) == len(xcoms.rand)
+        assert len(xcoms.rand[0]) == self._cx()
+        assert len(yvars) == len(ycoms.rand) and len(self.gamma[0]) == len(ycoms.rand)
+        assert len(ycoms.rand[0]) == self._cy()
+        m, n = len(xvars), len(yvars)
+        cx, cy = self._cx(), self._cy()
+        pf_rand = [[rng.fr() for _ in range(cx)] for _ in range(cy)]    # T, row-major (:123-126 etc.)
+        pi, theta = crs._use().prove(self.equ_type, m, n, b"".join(self.a_consts), b"".join(self.b_consts),
+                                     _flat(self.gamma), b"".join(xvars), b"".join(yvars),
+                                     _flat(xcoms.rand), _flat(ycoms.rand), _flat(pf_rand))
+        return EquProof(_split(pi, 384), _split(theta, 192), self.equ_type, pf_rand)
+
+    def commit_and_prove(self, xvars, yvars, crs: CRS, rng) -> CProof:
+        # RNG order: x commitments, y commitments, then T (prove.rs:82-88)
+        xc = (batch_commit_G1 if self.equ_type in (0, 1) else batch_commit_scalar_to_B1)(xvars, crs, rng)
+        yc = (batch_commit_G2 if self.equ_type in (0, 2) else batch_commit_scalar_to_B2)(yvars, crs, rng)
+        return CProof(xc, yc, [self.prove(xvars, yvars, xc, yc, crs, rng)])
+
+    def verify(self, com_proof: CProof, crs: CRS) -> bool:              # verifier.rs:23-157
+        assert len(com_proof.equ_proofs) == 1
+        ep = com_proof.equ_proofs[0]
+        assert self.get_type() == ep.equ_type
+        m, n = len(com_proof.xcoms.coms), len(com_proof.ycoms.coms)
+        # pairing_sum's assert_eq!(x_vec.len(), y_vec.len()) (data_structures.rs:495) and left_mul's (:705)
+        assert len(self.a_consts) == n and len(self.b_consts) == m
+        assert len(self.gamma) == m and all(len(r) == n for r in self.gamma)
+        return crs._use().verify(self.equ_type, m, n, b"".join(self.a_consts), b"".join(self.b_consts),
+                                 _flat(self.gamma), self.target, b"".join(com_proof.xcoms.coms),
+                                 b"".join(com_proof.ycoms.coms), b"".join(ep.pi), b"".join(ep.theta))
+
+
+class PPE(_Equation):
+    equ_type = EquType.PairingProduct
+
+
+class MSMEG1(_Equation):
+    equ_type = EquType.MultiScalarG1
+
+
+class MSMEG2(_Equation):
+    equ_type = EquType.MultiScalarG2
+
+
+class QuadEqu(_Equation):
+    equ_type = EquType.Quadratic
+
+
+def verify_batch(equations, proofs, crs: CRS) -> List[bool]:
+    """Many independent (equation, CProof) pairs of one type and shape in one GPU pass."""
+    assert len(equations) == len(proofs) and equations
+    ty = equations[0].equ_type
+    m, n = len(proofs[0].xcoms.coms), len(proofs[0].ycoms.coms)
+    cat = lambda f: b"".join(f(e, p) for e, p in zip(equations, proofs))
+    ok = crs._use().verify_batch(
+        ty, len(equations), m, n, cat(lambda e, p: b"".join(e.a_consts)), cat(lambda e, p: b"".join(e.b_consts)),
+        cat(lambda e, p: _flat(e.gamma)), cat(lambda e, p: e.target), cat(lambda e, p: b"".join(p.xcoms.coms)),
+        cat(lambda e, p: b"".join(p.ycoms.coms)), cat(lambda e, p: b"".join(p.equ_proofs[0].pi)),
+        cat(lambda e, p: b"".join(p.equ_proofs[0].theta)))
+    return [b == 1 for b in ok]
+
+
+# ---------------------------------------------------------------- Com1 / Com2 / ComT  (data_structures.rs)
+class Com1:
+    @staticmethod
+    def linear_map(x): return G1_ZERO + x                                   # :310-312
+    @staticmethod
+    def batch_linear_map(xs): return [G1_ZERO + x for x in xs]
+    @staticmethod
+    def scalar_linear_map(x, key: CRS):                                     # :323-326  x * (u2 + (O, g1))
+        return batch_commit_scalar_b1_norand(key, [x])[0]
+    @staticmethod
+    def scalar_mul(c, s, engine=None):                                      # :336-342
+        return (engine or default_engine()).com1_matmul(1, 1, 1, s, c)
+
+
+class Com2:
+    @staticmethod
+    def linear_map(y): return G2_ZERO + y                                   # :355-357
+    @staticmethod
+    def batch_linear_map(ys): return [G2_ZERO + y for y in ys]
+    @staticmethod
+    def scalar_mul(c, s, engine=None):                                      # :381-387
+        return (engine or default_engine()).com2_matmul(1, 1, 1, s, c)
+
+
+def batch_commit_scalar_b1_norand(key: CRS, xs):
+    """iota_1'(x) = x W1: a scalar commitment with zero randomness."""
+    out = key._use().batch_commit_scalar_b1(b"".join(xs), bytes(FR * len(xs)))
+    return _split(out, 192)
+
+
+class ComT:
+    @staticmethod
+    def pairing(x, y, engine=None):                                         # :484-491
+        return (engine or default_engine()).comt_pairing(x, y)
+    @staticmethod
+    def pairing_sum(xs, ys, engine=None):                                   # :494-502
+        if len(xs) != len(ys):
+            raise AssertionError("pairing_sum: x_vec.len() != y_vec.len()")
+        return (engine or default_engine()).comt_pairing_sum(b"".join(xs), b"".join(ys))
+    @staticmethod
+    def linear_map_PPE(z, key: CRS): return key._use().comt_linear_map(0, z)       # :509-516
+    @staticmethod
+    def linear_map_MSMEG1(z, key: CRS): return key._use().comt_linear_map(1, z)    # :519-524
+    @staticmethod
+    def linear_map_MSMEG2(z, key: CRS): return key._use().comt_linear_map(2, z)    # :527-532
+    @staticmethod
+    def linear_map_quad(z, key: CRS): return key._use().comt_linear_map(3, z)      # :535-540
+
+
+# ---------------------------------------------------------------- Mat  (data_structures.rs:545-913)
+def _dims(mat): return len(mat), (len(mat[0]) if mat else 0)
+
+
+def fr_right_mul(a, rhs, engine=None):
+    """Matrix<Fr>::right_mul :824-868 (self * rhs)."""
+    (r, k), (k2, c) = _dims(a), _dims(rhs)
+    if r == 0 or k == 0 or k2 == 0 or c == 0:
+        return []
+    assert k == k2
+    out = (engine or default_engine()).fr_matmul(r, k, c, _flat(a), _flat(rhs))
+    return [_split(out[i * c * FR:(i + 1) * c * FR], FR) for i in range(r)]
+
+
+def fr_left_mul(a, lhs, engine=None):
+    """Matrix<Fr>::left_mul :870-912 (lhs * self)."""
+    return fr_right_mul(lhs, a, engine)
+
+
+def com_left_mul(mat, lhs, which, engine=None):
+    """Matrix<Com1|Com2>::left_mul :696-742: out[i][j] = sum_k lhs[i][k] * mat[k][j]."""
+    (r, k), (k2, c) = _dims(lhs), _dims(mat)
+    if r == 0 or k == 0 or k2 == 0 or c == 0:
+        return []
+    assert k == k2
+    eng = engine or default_engine()
+    size = 192 if which == 1 else 384
+    fn = eng.com1_matmul if which == 1 else eng.com2_matmul
+    out = fn(r, k, c, _flat(lhs), _flat(mat))
+    return [_split(out[i * c * size:(i + 1) * c * size], size) for i in range(r)]

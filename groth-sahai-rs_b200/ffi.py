@@ -1,0 +1,240 @@
+"""ctypes binding of libgs_b200.so (include/gs_b200.h).  Bytes in, bytes out.
+
+Element encodings are the C ABI's (= arkworks' in-memory Montgomery limbs, see the header):
+Fr 32 B, G1 96 B, G2 192 B, Com1 192 B, Com2 384 B, GT 576 B, ComT 2304 B; the identity
+point is all-zero bytes.  There is no CPU fallback: a missing library or GPU raises GsError.
+"""
+import ctypes
+import os
+
+FR, G1, G2, COM1, COM2, GT, COMT = 32, 96, 192, 192, 384, 576, 2304
+CRS_BYTES = 2 * COM1 + 2 * COM2 + G1 + G2 + GT
+PPE, MSMEG1, MSMEG2, QUAD = 0, 1, 2, 3
+
+EXPORTED_SYMBOLS = [
+    "gs_ctx_create", "gs_ctx_destroy", "gs_last_error", "gs_launch_count", "gs_stream",
+    "gs_crs_generate", "gs_crs_load",
+    "gs_batch_commit_g1", "gs_batch_commit_g2", "gs_batch_commit_scalar_b1", "gs_batch_commit_scalar_b2",
+    "gs_prove", "gs_verify_batch", "gs_verify_batch_dev",
+    "gs_comt_pairing", "gs_comt_pairing_sum", "gs_comt_linear_map", "gs_pairing",
+    "gs_com1_matmul", "gs_com2_matmul", "gs_fr_matmul",
+]
+
+
+class GsError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"gs_b200 error {code}: {msg}")
+        self.code = code
+
+
+def lib_path():
+    return os.path.join(os.path.dirname(os.path.abspath(__file__)), "libgs_b200.so")
+
+
+_lib = None
+
+
+def load_library():
+    """dlopen the in-tree library; fails loudly when it has not been built."""
+    global _lib
+    if _lib is None:
+        path = lib_path()
+        if not os.path.exists(path):
+            raise GsError(-1, f"{path} not built -- run `python groth-sahai-rs_b200/build.py` (no CPU fallback exists)")
+        lib = ctypes.CDLL(path)
+        vp, sz, ci = ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int
+        lib.gs_ctx_create.argtypes = [ci, ctypes.POINTER(vp)]
+        lib.gs_ctx_destroy.argtypes = [vp]
+        lib.gs_ctx_destroy.restype = None
+        lib.gs_last_error.argtypes = [vp]
+        lib.gs_last_error.restype = ctypes.c_char_p
+        lib.gs_launch_count.argtypes = [vp]
+        lib.gs_launch_count.restype = ctypes.c_uint64
+        lib.gs_stream.argtypes = [vp]
+        lib.gs_stream.restype = vp
+        lib.gs_crs_generate.argtypes = [vp] * 8
+        lib.gs_crs_load.argtypes = [vp, vp]
+        for f in ("gs_batch_commit_g1", "gs_batch_commit_g2", "gs_batch_commit_scalar_b1", "gs_batch_commit_scalar_b2"):
+            getattr(lib, f).argtypes = [vp, sz, vp, vp, vp]
+        lib.gs_prove.argtypes = [vp, ci, sz, sz] + [vp] * 10
+        lib.gs_verify_batch.argtypes = [vp, ci, sz, sz, sz] + [vp] * 9
+        lib.gs_verify_batch_dev.argtypes = [vp, ci, sz, sz, sz] + [vp] * 9
+        lib.gs_comt_pairing.argtypes = [vp, sz, vp, vp, vp]
+        lib.gs_comt_pairing_sum.argtypes = [vp, sz, vp, vp, vp]
+        lib.gs_comt_linear_map.argtypes = [vp, ci, vp, vp]
+        lib.gs_pairing.argtypes = [vp, sz, vp, vp, vp]
+        for f in ("gs_com1_matmul", "gs_com2_matmul", "gs_fr_matmul"):
+            getattr(lib, f).argtypes = [vp, sz, sz, sz, vp, vp, vp]
+        _lib = lib
+    return _lib
+
+
+def _buf(b):
+    """bytes-like -> (keepalive, void*)"""
+    if isinstance(b, (bytes, bytearray, memoryview)):
+        arr = (ctypes.c_char * len(b)).from_buffer_copy(bytes(b)) if len(b) else (ctypes.c_char * 1)()
+        return arr, ctypes.cast(arr, ctypes.c_void_p)
+    if hasattr(b, "ctypes"):  # numpy array (must be C-contiguous)
+        return b, ctypes.c_void_p(b.ctypes.data)
+    raise TypeError(f"unsupported buffer type {type(b)}")
+
+
+def _a_size(ty): return G1 if ty in (PPE, MSMEG1) else FR
+def _b_size(ty): return G2 if ty in (PPE, MSMEG2) else FR
+def _t_size(ty): return {PPE: GT, MSMEG1: G1, MSMEG2: G2, QUAD: FR}[ty]
+def _cx(ty): return 2 if ty in (PPE, MSMEG1) else 1
+def _cy(ty): return 2 if ty in (PPE, MSMEG2) else 1
+
+
+class Engine:
+    """One GPU context (stream + device CRS + fixed-base tables + scratch)."""
+
+    def __init__(self, device=0):
+        self.lib = load_library()
+        h = ctypes.c_void_p()
+        rc = self.lib.gs_ctx_create(int(device), ctypes.byref(h))
+        if rc != 0 or not h.value:
+            raise GsError(rc, f"gs_ctx_create(device={device}) failed -- a CUDA device is required (no CPU fallback)")
+        self.h = h
+        self.device = device
+
+    def close(self):
+        if getattr(self, "h", None) is not None and self.h.value:
+            self.lib.gs_ctx_destroy(self.h)
+            self.h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _chk(self, rc):
+        if rc != 0:
+            raise GsError(rc, self.lib.gs_last_error(self.h).decode())
+
+    @property
+    def launch_count(self):
+        return int(self.lib.gs_launch_count(self.h))
+
+    @property
+    def stream(self):
+        return int(self.lib.gs_stream(self.h) or 0)
+
+    # ---- CRS
+    def crs_generate(self, p1, p2, a1, a2, t1, t2) -> bytes:
+        out = ctypes.create_string_buffer(CRS_BYTES)
+        ks = [_buf(x) for x in (p1, p2, a1, a2, t1, t2)]
+        self._chk(self.lib.gs_crs_generate(self.h, *[k[1] for k in ks], ctypes.cast(out, ctypes.c_void_p)))
+        return out.raw
+
+    def crs_load(self, crs: bytes):
+        assert len(crs) == CRS_BYTES
+        k = _buf(crs)
+        self._chk(self.lib.gs_crs_load(self.h, k[1]))
+
+    # ---- commitments
+    def _commit(self, fn, n, a, b, out_size):
+        out = ctypes.create_string_buffer(max(1, n * out_size))
+        ka, kb = _buf(a), _buf(b)
+        self._chk(fn(self.h, n, ka[1], kb[1], ctypes.cast(out, ctypes.c_void_p)))
+        return out.raw[: n * out_size]
+
+    def batch_commit_g1(self, xvars: bytes, rand: bytes) -> bytes:
+        n = len(xvars) // G1
+        assert len(xvars) == n * G1 and len(rand) == 2 * n * FR
+        return self._commit(self.lib.gs_batch_commit_g1, n, xvars, rand, COM1)
+
+    def batch_commit_g2(self, yvars: bytes, rand: bytes) -> bytes:
+        n = len(yvars) // G2
+        assert len(yvars) == n * G2 and len(rand) == 2 * n * FR
+        return self._commit(self.lib.gs_batch_commit_g2, n, yvars, rand, COM2)
+
+    def batch_commit_scalar_b1(self, xs: bytes, rand: bytes) -> bytes:
+        n = len(xs) // FR
+        assert len(xs) == n * FR and len(rand) == n * FR
+        return self._commit(self.lib.gs_batch_commit_scalar_b1, n, xs, rand, COM1)
+
+    def batch_commit_scalar_b2(self, ys: bytes, rand: bytes) -> bytes:
+        n = len(ys) // FR
+        assert len(ys) == n * FR and len(rand) == n * FR
+        return self._commit(self.lib.gs_batch_commit_scalar_b2, n, ys, rand, COM2)
+
+    # ---- prove / verify
+    def prove(self, ty, m, n, a_consts, b_consts, gamma, xvars, yvars, x_rand, y_rand, pf_rand):
+        cx, cy = _cx(ty), _cy(ty)
+        if m and n:
+            assert len(a_consts) == n * _a_size(ty) and len(b_consts) == m * _b_size(ty)
+            assert len(gamma) == m * n * FR and len(xvars) == m * _a_size(ty) and len(yvars) == n * _b_size(ty)
+            assert len(x_rand) == m * cx * FR and len(y_rand) == n * cy * FR and len(pf_rand) == cx * cy * FR
+        pi = ctypes.create_string_buffer(cx * COM2)
+        th = ctypes.create_string_buffer(cy * COM1)
+        ks = [_buf(x) for x in (a_consts, b_consts, gamma, xvars, yvars, x_rand, y_rand, pf_rand)]
+        self._chk(self.lib.gs_prove(self.h, ty, m, n, *[k[1] for k in ks], ctypes.cast(pi, ctypes.c_void_p),
+                                    ctypes.cast(th, ctypes.c_void_p)))
+        return pi.raw, th.raw
+
+    def verify_batch(self, ty, count, m, n, a_consts, b_consts, gamma, target, xcoms, ycoms, pi, theta) -> bytes:
+        cx, cy = _cx(ty), _cy(ty)
+        if count and m and n:
+            assert len(a_consts) == count * n * _a_size(ty) and len(b_consts) == count * m * _b_size(ty)
+            assert len(gamma) == count * m * n * FR and len(target) == count * _t_size(ty)
+            assert len(xcoms) == count * m * COM1 and len(ycoms) == count * n * COM2
+            assert len(pi) == count * cx * COM2 and len(theta) == count * cy * COM1
+        ok = ctypes.create_string_buffer(max(1, count))
+        ks = [_buf(x) for x in (a_consts, b_consts, gamma, target, xcoms, ycoms, pi, theta)]
+        self._chk(self.lib.gs_verify_batch(self.h, ty, count, m, n, *[k[1] for k in ks], ctypes.cast(ok, ctypes.c_void_p)))
+        return ok.raw[:count]
+
+    def verify_batch_dev(self, ty, count, m, n, ptrs, out_ok_ptr):
+        """All-device variant: `ptrs` = 8 device addresses (ints) in C-ABI order; asynchronous on self.stream."""
+        self._chk(self.lib.gs_verify_batch_dev(self.h, ty, count, m, n, *[ctypes.c_void_p(int(p)) for p in ptrs],
+                                               ctypes.c_void_p(int(out_ok_ptr))))
+
+    def verify(self, ty, m, n, a_consts, b_consts, gamma, target, xcoms, ycoms, pi, theta) -> bool:
+        return self.verify_batch(ty, 1, m, n, a_consts, b_consts, gamma, target, xcoms, ycoms, pi, theta) == b"\x01"
+
+    # ---- ComT
+    def comt_pairing(self, xs: bytes, ys: bytes) -> bytes:
+        n = len(xs) // COM1
+        assert len(xs) == n * COM1 and len(ys) == n * COM2
+        out = ctypes.create_string_buffer(max(1, n * COMT))
+        kx, ky = _buf(xs), _buf(ys)
+        self._chk(self.lib.gs_comt_pairing(self.h, n, kx[1], ky[1], ctypes.cast(out, ctypes.c_void_p)))
+        return out.raw[: n * COMT]
+
+    def comt_pairing_sum(self, xs: bytes, ys: bytes) -> bytes:
+        k = len(xs) // COM1
+        if len(xs) != k * COM1 or len(ys) != k * COM2:
+            raise GsError(1, "pairing_sum: length mismatch")  # reference: assert_eq!(x_vec.len(), y_vec.len())
+        out = ctypes.create_string_buffer(COMT)
+        kx, ky = _buf(xs), _buf(ys)
+        self._chk(self.lib.gs_comt_pairing_sum(self.h, k, kx[1], ky[1], ctypes.cast(out, ctypes.c_void_p)))
+        return out.raw
+
+    def comt_linear_map(self, ty, target: bytes) -> bytes:
+        assert len(target) == _t_size(ty)
+        out = ctypes.create_string_buffer(COMT)
+        kt = _buf(target)
+        self._chk(self.lib.gs_comt_linear_map(self.h, ty, kt[1], ctypes.cast(out, ctypes.c_void_p)))
+        return out.raw
+
+    def pairing(self, ps: bytes, qs: bytes) -> bytes:
+        n = len(ps) // G1
+        assert len(ps) == n * G1 and len(qs) == n * G2
+        out = ctypes.create_string_buffer(max(1, n * GT))
+        kp, kq = _buf(ps), _buf(qs)
+        self._chk(self.lib.gs_pairing(self.h, n, kp[1], kq[1], ctypes.cast(out, ctypes.c_void_p)))
+        return out.raw[: n * GT]
+
+    # ---- Mat
+    def _matmul(self, fn, r, k, c, lhs, mat, esize_l, esize_m, esize_o):
+        assert len(lhs) == r * k * esize_l and len(mat) == k * c * esize_m
+        out = ctypes.create_string_buffer(max(1, r * c * esize_o))
+        kl, km = _buf(lhs), _buf(mat)
+        self._chk(fn(self.h, r, k, c, kl[1], km[1], ctypes.cast(out, ctypes.c_void_p)))
+        return out.raw[: r * c * esize_o]
+
+    def com1_matmul(self, r, k, c, lhs, mat): return self._matmul(self.lib.gs_com1_matmul, r, k, c, lhs, mat, FR, COM1, COM1)
+    def com2_matmul(self, r, k, c, lhs, mat): return self._matmul(self.lib.gs_com2_matmul, r, k, c, lhs, mat, FR, COM2, COM2)
+    def fr_matmul(self, r, k, c, a, b): return self._matmul(self.lib.gs_fr_matmul, r, k, c, a, b, FR, FR, FR)

@@ -1,0 +1,146 @@
+/* gs_b200.h -- C ABI of the B200-native Groth-Sahai engine (libgs_b200.so).
+ *
+ * The reference (jdwhite48/groth-sahai-rs) has no FFI layer: its boundary is its public
+ * Rust API.  These entry points are what a thin Rust shim for the hot path
+ * binds (see INTEGRATION.md for the `extern "C"` block and the shim); each one names the
+ * reference function it replaces (paths relative to /root/reference).
+ *
+ * Data layout (identical to arkworks' in-memory representation, so the shim passes slices
+ * without conversion):
+ *   Fr   : 4 x u64 little-endian limbs, Montgomery form, R = 2^256            (32 B)
+ *   Fp   : 6 x u64 little-endian limbs, Montgomery form, R = 2^384            (48 B)
+ *   G1   : affine x || y                                                      (96 B)
+ *   G2   : affine x.c0 || x.c1 || y.c0 || y.c1                                (192 B)
+ *          the point at infinity is encoded as all-zero bytes (not on either curve)
+ *   Com1 : two G1 (192 B)      Com2 : two G2 (384 B)
+ *   GT   : Fp12 = 12 Fp in tower order c0.c0.c0, c0.c0.c1, c0.c1.c0, ...      (576 B)
+ *   ComT : four GT, row-major [e(x0,y0), e(x0,y1), e(x1,y0), e(x1,y1)]        (2304 B)
+ *   Matrix<Fr> : dense row-major.
+ *
+ * All pointers are HOST pointers unless the function name ends in `_dev`.  Randomness is
+ * always supplied by the caller, drawn in the reference's order (commit.rs:85-88,
+ * prove.rs:123-126), which is what makes results bit-reproducible.
+ *
+ * Every function returns GS_OK or an error code; gs_last_error() gives the message.  The
+ * reference signals the same conditions by assert!/panic; the shim re-panics on GS_EDIM.
+ * There is no CPU fallback: without a CUDA device gs_ctx_create fails with GS_ECUDA.
+ */
+#ifndef GS_B200_H
+#define GS_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GS_OK 0
+#define GS_EDIM 1   /* dimension / argument error (reference: assert_eq! panic) */
+#define GS_ECUDA 2  /* CUDA runtime error */
+#define GS_EARG 3   /* null pointer / bad enum */
+
+/* EquType byte, src/statement.rs:68-73 */
+#define GS_PPE 0
+#define GS_MSMEG1 1
+#define GS_MSMEG2 2
+#define GS_QUAD 3
+
+typedef struct gs_ctx gs_ctx;
+
+typedef struct { uint64_t l[4]; } gs_fr;
+typedef struct { uint64_t x[6], y[6]; } gs_g1;
+typedef struct { uint64_t x[12], y[12]; } gs_g2;
+typedef struct { gs_g1 p[2]; } gs_com1;
+typedef struct { gs_g2 p[2]; } gs_com2;
+typedef struct { uint64_t c[72]; } gs_gt;
+typedef struct { gs_gt e[4]; } gs_comt;
+
+/* CRS<E>, src/generator.rs:36-42 (u, v, g1_gen, g2_gen, gt_gen) */
+typedef struct {
+  gs_com1 u[2];
+  gs_com2 v[2];
+  gs_g1 g1_gen;
+  gs_g2 g2_gen;
+  gs_gt gt_gen;
+} gs_crs;
+
+/* ---- context ------------------------------------------------------------------------- */
+/* One context per host thread and per GPU (owns a stream, the device copy of the CRS, the
+ * fixed-base tables and scratch).  `device` is the CUDA ordinal. */
+int gs_ctx_create(int device, gs_ctx** out);
+void gs_ctx_destroy(gs_ctx* ctx);
+const char* gs_last_error(const gs_ctx* ctx);
+/* number of CUDA kernels this context has launched so far (bench.py's gpu_launches) */
+uint64_t gs_launch_count(const gs_ctx* ctx);
+/* the cudaStream_t the context launches on (as an opaque pointer, for event timing) */
+void* gs_stream(const gs_ctx* ctx);
+
+/* ---- CRS ------------------------------------------------------------------------------ */
+/* CRS::generate_crs, src/generator.rs:81-118.  The six values are the reference's RNG draws
+ * in its order (p1 <- G1, p2 <- G2, a1, a2, t1, t2 <- Fr, :86-93).  Also loads the result. */
+int gs_crs_generate(gs_ctx* ctx, const gs_g1* p1, const gs_g2* p2, const gs_fr* a1, const gs_fr* a2,
+                    const gs_fr* t1, const gs_fr* t2, gs_crs* out);
+/* Makes `crs` the context's key (any `&CRS<E>` argument of the reference): uploads it and
+ * builds the fixed-base window tables for u1, u2, W1 = u2 + (O, g1) and v1, v2, W2. */
+int gs_crs_load(gs_ctx* ctx, const gs_crs* crs);
+
+/* ---- commitments (src/prover/commit.rs) ----------------------------------------------- */
+/* batch_commit_G1 :78-100 -- c_i = iota_1(X_i) + R[i][0] u1 + R[i][1] u2;  rand is n x 2 */
+int gs_batch_commit_g1(gs_ctx* ctx, size_t n, const gs_g1* xvars, const gs_fr* rand, gs_com1* out);
+/* batch_commit_G2 :178-200 */
+int gs_batch_commit_g2(gs_ctx* ctx, size_t n, const gs_g2* yvars, const gs_fr* rand, gs_com2* out);
+/* batch_commit_scalar_to_B1 :125-156 -- c_i = x_i W1 + r_i u1;  rand is n x 1 */
+int gs_batch_commit_scalar_b1(gs_ctx* ctx, size_t n, const gs_fr* xs, const gs_fr* rand, gs_com1* out);
+/* batch_commit_scalar_to_B2 :225-256 */
+int gs_batch_commit_scalar_b2(gs_ctx* ctx, size_t n, const gs_fr* ys, const gs_fr* rand, gs_com2* out);
+
+/* ---- proofs (src/prover/prove.rs) ------------------------------------------------------ */
+/* Provable::prove for the four equation types (:92-171, :195-274, :298-379, :409-488).
+ * m x-variables, n y-variables, gamma is m x n.  Variables / constants are G1 / G2 points or
+ * Fr scalars depending on `type`:
+ *   a_consts : n elements (G1 for PPE, MSMEG1; Fr otherwise)     b_consts : m (G2 for PPE, MSMEG2)
+ *   xvars    : m elements (G1 for PPE, MSMEG1; Fr otherwise)     yvars    : n (G2 for PPE, MSMEG2)
+ *   x_rand   : m x cx  (cx = 2 for G1 variables, 1 for scalars)   y_rand : n x cy
+ *   pf_rand  : T, cy x cx row-major (the reference's draw order)
+ *   out_pi   : cx Com2      out_theta : cy Com1 */
+int gs_prove(gs_ctx* ctx, int type, size_t m, size_t n, const void* a_consts, const void* b_consts,
+             const gs_fr* gamma, const void* xvars, const void* yvars, const gs_fr* x_rand,
+             const gs_fr* y_rand, const gs_fr* pf_rand, gs_com2* out_pi, gs_com1* out_theta);
+
+/* ---- verification (src/verifier.rs) ----------------------------------------------------- */
+/* Verifiable::verify :23-157 for `count` independent (equation, proof) instances of the same
+ * type and shape, each laid out contiguously with the given element counts:
+ *   a_consts[count][n], b_consts[count][m], gamma[count][m][n], target[count],
+ *   xcoms[count][m], ycoms[count][n], pi[count][cx], theta[count][cy].
+ * target is GT (PPE), G1 (MSMEG1), G2 (MSMEG2) or Fr (Quad).  out_ok[i] = 1 iff lhs == rhs. */
+int gs_verify_batch(gs_ctx* ctx, int type, size_t count, size_t m, size_t n, const void* a_consts,
+                    const void* b_consts, const gs_fr* gamma, const void* target, const gs_com1* xcoms,
+                    const gs_com2* ycoms, const gs_com2* pi, const gs_com1* theta, uint8_t* out_ok);
+/* Same with DEVICE pointers (inputs already resident in HBM), asynchronous on gs_stream();
+ * out_ok_dev is a device buffer of `count` bytes. */
+int gs_verify_batch_dev(gs_ctx* ctx, int type, size_t count, size_t m, size_t n, const void* a_consts,
+                        const void* b_consts, const gs_fr* gamma, const void* target,
+                        const gs_com1* xcoms, const gs_com2* ycoms, const gs_com2* pi,
+                        const gs_com1* theta, uint8_t* out_ok_dev);
+
+/* ---- ComT (src/data_structures.rs) ------------------------------------------------------- */
+/* ComT::pairing :484-491, batched: out[i] = F(xs[i], ys[i]) (4 full pairings each) */
+int gs_comt_pairing(gs_ctx* ctx, size_t count, const gs_com1* xs, const gs_com2* ys, gs_comt* out);
+/* ComT::pairing_sum :494-502: out = sum_i F(xs[i], ys[i]) (one final exponentiation per entry) */
+int gs_comt_pairing_sum(gs_ctx* ctx, size_t k, const gs_com1* xs, const gs_com2* ys, gs_comt* out);
+/* The four iota_T maps :509-540 (type selects linear_map_PPE / _MSMEG1 / _MSMEG2 / _quad) */
+int gs_comt_linear_map(gs_ctx* ctx, int type, const void* target, gs_comt* out);
+/* E::pairing batched: out[i] = e(ps[i], qs[i]) */
+int gs_pairing(gs_ctx* ctx, size_t count, const gs_g1* ps, const gs_g2* qs, gs_gt* out);
+
+/* ---- Mat (src/data_structures.rs:645-742, 768-913) ---------------------------------------- */
+/* out (r x c) = lhs (r x k, Fr) * mat (k x c, Com1) -- Matrix<Com1>::left_mul */
+int gs_com1_matmul(gs_ctx* ctx, size_t r, size_t k, size_t c, const gs_fr* lhs, const gs_com1* mat, gs_com1* out);
+int gs_com2_matmul(gs_ctx* ctx, size_t r, size_t k, size_t c, const gs_fr* lhs, const gs_com2* mat, gs_com2* out);
+/* out (r x c) = a (r x k) * b (k x c) over Fr -- Matrix<Fr>::right_mul */
+int gs_fr_matmul(gs_ctx* ctx, size_t r, size_t k, size_t c, const gs_fr* a, const gs_fr* b, gs_fr* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GS_B200_H */

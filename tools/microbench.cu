@@ -1,0 +1,89 @@
+// Register-only microbenchmarks that calibrate the integer-multiply roofline on the box:
+//   (1) raw IMAD.WIDE.U32 issue rate (independent chains)
+//   (2) Fp Montgomery products per second (fp::mul chains), for several occupancies
+// build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o tools/microbench tools/microbench.cu
+#include <cstdio>
+#include <cuda_runtime.h>
+#include "../groth-sahai-rs_b200/csrc/fp.cuh"
+using namespace gs;
+
+__global__ void k_imad_wide(unsigned long long* out, unsigned a, unsigned b, int iters) {
+  unsigned long long x0 = threadIdx.x, x1 = a, x2 = b, x3 = a + b, x4 = 5, x5 = 6, x6 = 7, x7 = 8;
+  unsigned m = a | 1;
+  for (int i = 0; i < iters; i++) {
+#pragma unroll
+    for (int j = 0; j < 16; j++) {
+      asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(x0) : "r"(m), "r"((unsigned)x1));
+      asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(x1) : "r"(m), "r"((unsigned)x2));
+      asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(x2) : "r"(m), "r"((unsigned)x3));
+      asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(x3) : "r"(m), "r"((unsigned)x4));
+      asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(x4) : "r"(m), "r"((unsigned)x5));
+      asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(x5) : "r"(m), "r"((unsigned)x6));
+      asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(x6) : "r"(m), "r"((unsigned)x7));
+      asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(x7) : "r"(m), "r"((unsigned)x0));
+    }
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = x0 ^ x1 ^ x2 ^ x3 ^ x4 ^ x5 ^ x6 ^ x7;
+}
+__global__ void k_imad_lo(unsigned* out, unsigned a, unsigned b, int iters) {
+  unsigned x0 = threadIdx.x, x1 = a, x2 = b, x3 = a + b, x4 = 5, x5 = 6, x6 = 7, x7 = 8;
+  unsigned m = a | 1;
+  for (int i = 0; i < iters; i++) {
+#pragma unroll
+    for (int j = 0; j < 16; j++) {
+      asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(x0) : "r"(m), "r"(x1));
+      asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(x1) : "r"(m), "r"(x2));
+      asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(x2) : "r"(m), "r"(x3));
+      asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(x3) : "r"(m), "r"(x4));
+      asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(x4) : "r"(m), "r"(x5));
+      asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(x5) : "r"(m), "r"(x6));
+      asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(x6) : "r"(m), "r"(x7));
+      asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(x7) : "r"(m), "r"(x0));
+    }
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = x0 ^ x1 ^ x2 ^ x3 ^ x4 ^ x5 ^ x6 ^ x7;
+}
+template <int ILP>
+__global__ void k_fpmul(fp* out, const fp* in, int iters) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  fp x[ILP], y = in[t];
+  for (int j = 0; j < ILP; j++) x[j] = in[t + j + 1];
+  for (int i = 0; i < iters; i++) {
+#pragma unroll
+    for (int j = 0; j < ILP; j++) fp::mul(x[j], x[j], y);
+  }
+  fp r = x[0];
+  for (int j = 1; j < ILP; j++) fp::add(r, r, x[j]);
+  out[t] = r;
+}
+template <class K, class... A>
+float timeit(K k, dim3 g, dim3 b, A... args) {
+  cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+  k<<<g, b>>>(args...); cudaDeviceSynchronize();
+  cudaEventRecord(e0); k<<<g, b>>>(args...); cudaEventRecord(e1); cudaEventSynchronize(e1);
+  float ms; cudaEventElapsedTime(&ms, e0, e1); return ms;
+}
+int main() {
+  cudaDeviceProp p; cudaGetDeviceProperties(&p, 0);
+  int sms = p.multiProcessorCount;
+  printf("device %s, %d SMs, clock %d kHz\n", p.name, sms, p.clockRate);
+  void* buf; cudaMalloc(&buf, 1 << 28); cudaMemset(buf, 1, 1 << 28);
+  for (int wps : {4, 8, 16, 32}) {  // warps per SM
+    int iters = 4096;
+    dim3 g(sms), b(wps * 32);
+    float ms = timeit(k_imad_wide, g, b, (unsigned long long*)buf, 3u, 5u, iters);
+    double ops = (double)sms * wps * 32 * iters * 128;
+    float ms2 = timeit(k_imad_lo, g, b, (unsigned*)buf, 3u, 5u, iters);
+    printf("warps/SM %2d: IMAD.WIDE %.3e/s (%.1f /clk/SM @1.9GHz)   IMAD.lo %.3e/s (%.1f /clk/SM)\n", wps, ops / ms * 1e3,
+           ops / ms * 1e3 / sms / 1.9e9, ops / ms2 * 1e3, ops / ms2 * 1e3 / sms / 1.9e9);
+  }
+  for (int wps : {4, 8, 12, 16, 24, 32}) {
+    int iters = 2000;
+    dim3 g(sms), b(wps * 32);
+    float m1 = timeit(k_fpmul<1>, g, b, (fp*)buf + (1 << 20), (const fp*)buf, iters);
+    float m2 = timeit(k_fpmul<2>, g, b, (fp*)buf + (1 << 20), (const fp*)buf, iters);
+    double n1 = (double)sms * wps * 32 * iters, n2 = n1 * 2;
+    printf("warps/SM %2d: fp::mul ILP1 %.3e M/s   ILP2 %.3e M/s\n", wps, n1 / m1 * 1e3, n2 / m2 * 1e3);
+  }
+  return 0;
+}
