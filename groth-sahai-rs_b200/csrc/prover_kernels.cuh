@@ -70,11 +70,6 @@ __global__ void k_crs_generate(const crs_gen_in* in, crs_gen_out* out) {
   if (t == 1 || t == 4) s = (t == 1) ? in->t1 : in->t2;
   if (t == 2) fr::mul(s, in->a1, in->t1);
   if (t == 5) fr::mul(s, in->a2, in->t2);
-  if (t == 2 || t == 5) {  // product of two Montgomery values: one more R to restore the form
-    fr r2;
-    for (int i = 0; i < 8; i++) r2.l[i] = FR_R2(i);
-    fr::mul(s, s, r2);
-  }
   uint32_t k[8];
   fr_from_mont(k, s);
   if (t < 3) {
