@@ -29,6 +29,12 @@ struct gs_ctx {
   bool crs_loaded = false;
   fixed_tables tabs;       // device fixed-base tables (prover_kernels.cuh)
   uint64_t launches = 0;
+  bool profile = false;
+  struct prof_rec {
+    const char* name;
+    cudaEvent_t e0, e1;
+  };
+  std::vector<prof_rec> prof;
   size_t verify_batch_max = 16384;  // problems per pass (bounds the line-coefficient scratch)
   std::string err;
 };
@@ -51,7 +57,17 @@ struct gs_ctx {
     size_t nt_ = (nthreads);                                                            \
     if (nt_ > 0) {                                                                      \
       unsigned grid_ = (unsigned)((nt_ + 127) / 128);                                   \
+      gs_ctx::prof_rec pr_{#kern, nullptr, nullptr};                                    \
+      if (ctx->profile) {                                                               \
+        cudaEventCreate(&pr_.e0);                                                       \
+        cudaEventCreate(&pr_.e1);                                                       \
+        cudaEventRecord(pr_.e0, ctx->stream);                                           \
+      }                                                                                 \
       kern<<<grid_, 128, 0, ctx->stream>>>(__VA_ARGS__);                                \
+      if (ctx->profile) {                                                               \
+        cudaEventRecord(pr_.e1, ctx->stream);                                           \
+        ctx->prof.push_back(pr_);                                                       \
+      }                                                                                 \
       ctx->launches++;                                                                  \
       CUDA_TRY(cudaGetLastError());                                                     \
     }                                                                                   \
@@ -123,7 +139,89 @@ const char* gs_last_error(const gs_ctx* ctx) { return ctx ? ctx->err.c_str() : "
 uint64_t gs_launch_count(const gs_ctx* ctx) { return ctx ? ctx->launches : 0; }
 void* gs_stream(const gs_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
 
+
+int gs_profile_enable(gs_ctx* ctx, int on) {
+  if (!ctx) return GS_EARG;
+  ctx->profile = on != 0;
+  return GS_OK;
+}
+
+int gs_profile_read(gs_ctx* ctx, char* buf, size_t cap) {
+  if (!ctx || !buf || cap == 0) return -GS_EARG;
+  cudaSetDevice(ctx->device);
+  if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) return -GS_ECUDA;
+  std::vector<std::string> names;
+  std::vector<double> ms;
+  std::vector<int> cnt;
+  for (auto& r : ctx->prof) {
+    float t = 0;
+    cudaEventElapsedTime(&t, r.e0, r.e1);
+    cudaEventDestroy(r.e0);
+    cudaEventDestroy(r.e1);
+    size_t i = 0;
+    for (; i < names.size(); i++)
+      if (names[i] == r.name) break;
+    if (i == names.size()) {
+      names.push_back(r.name);
+      ms.push_back(0);
+      cnt.push_back(0);
+    }
+    ms[i] += t;
+    cnt[i]++;
+  }
+  ctx->prof.clear();
+  std::string out;
+  for (size_t i = 0; i < names.size(); i++) {
+    char line[256];
+    snprintf(line, sizeof line, "%s %d %.6f\n", names[i].c_str(), cnt[i], ms[i]);
+    out += line;
+  }
+  size_t n = out.size() < cap - 1 ? out.size() : cap - 1;
+  memcpy(buf, out.data(), n);
+  buf[n] = 0;
+  return (int)n;
+}
+
 }  // extern "C"
+
+// register-only Fp product chain (the measured integer-multiply roofline)
+__global__ void __launch_bounds__(256) k_diag_fpmul(fp* out, const fp* in, int iters) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  fp x = in[t], y = in[t + 1];
+  for (int i = 0; i < iters; i++) fp::mul(x, x, y);
+  out[t] = x;
+}
+
+extern "C" int gs_diag_fpmul_rate(gs_ctx* ctx, double* fpmul_per_sec) {
+  if (!ctx || !fpmul_per_sec) return GS_EARG;
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  cudaDeviceProp prop;
+  CUDA_TRY(cudaGetDeviceProperties(&prop, ctx->device));
+  const int blocks = prop.multiProcessorCount * 2, threads = 256, iters = 4000;
+  Scratch sc(ctx);
+  fp *in, *out;
+  CUDA_TRY(sc.alloc(&in, (size_t)blocks * threads + 1));
+  CUDA_TRY(sc.alloc(&out, (size_t)blocks * threads));
+  CUDA_TRY(cudaMemsetAsync(in, 1, ((size_t)blocks * threads + 1) * sizeof(fp), ctx->stream));
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  double best = 0;
+  for (int rep = 0; rep < 4; rep++) {
+    cudaEventRecord(e0, ctx->stream);
+    k_diag_fpmul<<<blocks, threads, 0, ctx->stream>>>(out, in, iters);
+    cudaEventRecord(e1, ctx->stream);
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    double rate = (double)blocks * threads * iters / (ms * 1e-3);
+    if (rep > 0 && rate > best) best = rate;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  *fpmul_per_sec = best;
+  return GS_OK;
+}
 
 // ------------------------------------------------------------------ pairing-product pipeline
 // X, Y: device slot arrays [2][K][nprob].  Produces either ComT values (out_comt, AoS [p][4]) or

@@ -13,6 +13,7 @@ PPE, MSMEG1, MSMEG2, QUAD = 0, 1, 2, 3
 
 EXPORTED_SYMBOLS = [
     "gs_ctx_create", "gs_ctx_destroy", "gs_last_error", "gs_launch_count", "gs_stream",
+    "gs_profile_enable", "gs_profile_read", "gs_diag_fpmul_rate",
     "gs_crs_generate", "gs_crs_load",
     "gs_batch_commit_g1", "gs_batch_commit_g2", "gs_batch_commit_scalar_b1", "gs_batch_commit_scalar_b2",
     "gs_prove", "gs_verify_batch", "gs_verify_batch_dev",
@@ -52,6 +53,9 @@ def load_library():
         lib.gs_launch_count.restype = ctypes.c_uint64
         lib.gs_stream.argtypes = [vp]
         lib.gs_stream.restype = vp
+        lib.gs_profile_enable.argtypes = [vp, ci]
+        lib.gs_profile_read.argtypes = [vp, vp, sz]
+        lib.gs_diag_fpmul_rate.argtypes = [vp, ctypes.POINTER(ctypes.c_double)]
         lib.gs_crs_generate.argtypes = [vp] * 8
         lib.gs_crs_load.argtypes = [vp, vp]
         for f in ("gs_batch_commit_g1", "gs_batch_commit_g2", "gs_batch_commit_scalar_b1", "gs_batch_commit_scalar_b2"):
@@ -120,6 +124,27 @@ class Engine:
     @property
     def stream(self):
         return int(self.lib.gs_stream(self.h) or 0)
+
+    # ---- measurement hooks
+    def profile_enable(self, on=True):
+        self._chk(self.lib.gs_profile_enable(self.h, 1 if on else 0))
+
+    def profile_read(self):
+        """{kernel name: (launches, total_ms)} since the last read (CUDA events on the engine's stream)."""
+        buf = ctypes.create_string_buffer(1 << 16)
+        n = self.lib.gs_profile_read(self.h, ctypes.cast(buf, ctypes.c_void_p), len(buf))
+        if n < 0:
+            raise GsError(-n, "gs_profile_read failed")
+        out = {}
+        for line in buf.value.decode().splitlines():
+            name, cnt, ms = line.rsplit(" ", 2)
+            out[name.strip("()")] = (int(cnt), float(ms))
+        return out
+
+    def fpmul_rate(self) -> float:
+        r = ctypes.c_double()
+        self._chk(self.lib.gs_diag_fpmul_rate(self.h, ctypes.byref(r)))
+        return r.value
 
     # ---- CRS
     def crs_generate(self, p1, p2, a1, a2, t1, t2) -> bytes:

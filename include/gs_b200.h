@@ -75,6 +75,16 @@ uint64_t gs_launch_count(const gs_ctx* ctx);
 /* the cudaStream_t the context launches on (as an opaque pointer, for event timing) */
 void* gs_stream(const gs_ctx* ctx);
 
+/* ---- measurement hooks (bench.py) -------------------------------------------------------- */
+/* When enabled, every kernel launch is bracketed by CUDA events on gs_stream(). */
+int gs_profile_enable(gs_ctx* ctx, int on);
+/* Synchronises, then writes one line per kernel: "<name> <launches> <total_ms>\n" (and clears the log).
+ * Returns the number of bytes written (truncated to cap-1) or a negative error code. */
+int gs_profile_read(gs_ctx* ctx, char* buf, size_t cap);
+/* Register-only Fp Montgomery-product chain on every SM: the measured integer-multiply roofline,
+ * in Fp products per second (1 product = 600 IMAD-equivalents in SURVEY.md §8d's accounting). */
+int gs_diag_fpmul_rate(gs_ctx* ctx, double* fpmul_per_sec);
+
 /* ---- CRS ------------------------------------------------------------------------------ */
 /* CRS::generate_crs, src/generator.rs:81-118.  The six values are the reference's RNG draws
  * in its order (p1 <- G1, p2 <- G2, a1, a2, t1, t2 <- Fr, :86-93).  Also loads the result. */
