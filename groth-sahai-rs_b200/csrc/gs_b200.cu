@@ -121,6 +121,10 @@ int gs_ctx_create(int device, gs_ctx** out) {
   }
   // deep call chains (Fp12 -> Fp6 -> Fp2) with big local frames
   cudaDeviceSetLimit(cudaLimitStackSize, 32 * 1024);
+  if (cudaFuncSetAttribute(k_miller, cudaFuncAttributeMaxDynamicSharedMemorySize, GS_MV2_SMEM) != cudaSuccess) {
+    delete ctx;
+    return GS_ECUDA;
+  }
   *out = ctx;
   return GS_OK;
 }
@@ -229,10 +233,10 @@ extern "C" int gs_diag_fpmul_rate(gs_ctx* ctx, double* fpmul_per_sec) {
 static int run_pairing_product(gs_ctx* ctx, Scratch& sc, const g1_aff* X, const g2_aff* Y, size_t nprob, int K,
                                fp12* out_comt, uint8_t* ok4, const fp12* target) {
   size_t npoints = 2 * (size_t)K * nprob;
-  line_coeffs* L;
+  uint32_t* L;
   uint8_t* yinf;
   fp12* F;
-  CUDA_TRY(sc.alloc(&L, npoints * GS_NUM_LINES));
+  CUDA_TRY(sc.alloc(&L, npoints * GS_NUM_LINES * GS_LINE_WORDS));
   CUDA_TRY(sc.alloc(&yinf, npoints));
   // split the slots over threads when there are few problems (one big statement)
   int S = K, nchunk = 1;
@@ -246,7 +250,23 @@ static int run_pairing_product(gs_ctx* ctx, Scratch& sc, const g1_aff* X, const 
   }
   CUDA_TRY(sc.alloc(&F, (size_t)nchunk * 4 * nprob));
   LAUNCH(k_g2_prepare, npoints, Y, L, yinf, npoints, nprob);
-  LAUNCH(k_miller, nprob * 4 * (size_t)nchunk, X, yinf, L, F, nprob, K, S, nchunk);
+  {
+    size_t nt_ = nprob * 4 * (size_t)nchunk;
+    gs_ctx::prof_rec pr_{"k_miller", nullptr, nullptr};
+    if (ctx->profile) {
+      cudaEventCreate(&pr_.e0);
+      cudaEventCreate(&pr_.e1);
+      cudaEventRecord(pr_.e0, ctx->stream);
+    }
+    k_miller<<<(unsigned)((nt_ + GS_MV2_NT - 1) / GS_MV2_NT), GS_MV2_NT, GS_MV2_SMEM, ctx->stream>>>(X, yinf, L, F, nprob, K, S,
+                                                                                                      nchunk);
+    if (ctx->profile) {
+      cudaEventRecord(pr_.e1, ctx->stream);
+      ctx->prof.push_back(pr_);
+    }
+    ctx->launches++;
+    CUDA_TRY(cudaGetLastError());
+  }
   LAUNCH(k_final_exp, nprob * 4, F, nprob, nchunk, out_comt, ok4, target);
   return GS_OK;
 }
@@ -446,7 +466,10 @@ int gs_verify_batch_dev(gs_ctx* ctx, int type, size_t count, size_t m, size_t n,
     CUDA_TRY(sc.alloc(&part, (size_t)s.nchunk * s.n_out * 2 * nprob));
     CUDA_TRY(sc.alloc(&ok4, 4 * nprob));
     LAUNCH(k_verify_assemble, nprob * (size_t)s.K, s, v, ctx->crs, X, Y, nprob);
-    LAUNCH(k_vmsm_partial, nprob * (size_t)s.n_out * 2 * s.nchunk, s, v, ctx->crs, part, nprob);
+    g1_aff* vtab;
+    CUDA_TRY(sc.alloc(&vtab, (size_t)s.nbases * 2 * GS_VTAB * nprob));
+    LAUNCH(k_vmsm_tables, nprob * (size_t)s.nbases * 2, s, v, ctx->crs, vtab, nprob);
+    LAUNCH(k_vmsm_partial, nprob * (size_t)s.n_out * 2 * s.nchunk, s, v, vtab, part, nprob);
     LAUNCH(k_vmsm_reduce, nprob * (size_t)s.n_out * 2, s, v, part, X, nprob);
     int rc = run_pairing_product(ctx, sc, X, Y, nprob, s.K, nullptr, ok4, type == GS_PPE ? (const fp12*)v.target : nullptr);
     if (rc) return rc;

@@ -6,9 +6,9 @@
 // Points are stored SoA over problems so that a warp (32 consecutive problems, same slot,
 // same coordinate) reads contiguous memory:
 //     X[(a*K + k) * nprob + p]   g1_aff        Y[(b*K + k) * nprob + p]   g2_aff
-//     L[((b*K + k) * 68 + step) * nprob + p]   line_coeffs  (output of k_g2_prepare)
+//     L[(((b*K + k) * 68 + step) * 72 + w) * nprob + p]   32-bit word w of a line triple (k_g2_prepare)
 #pragma once
-#include "pairing.cuh"
+#include "miller_v2.cuh"
 
 namespace gs {
 
@@ -57,7 +57,7 @@ inline verify_shape make_verify_shape(int type, int m, int n) {
 
 // ------------------------------------------------------------------ G2 preparation
 // one thread per G2 point q = (b*K + k) * nprob + p
-__global__ void __launch_bounds__(128) k_g2_prepare(const g2_aff* __restrict__ Y, line_coeffs* __restrict__ L,
+__global__ void __launch_bounds__(128) k_g2_prepare(const g2_aff* __restrict__ Y, uint32_t* __restrict__ L,
                                                     uint8_t* __restrict__ yinf, size_t npoints, size_t nprob) {
   size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (q >= npoints) return;
@@ -66,14 +66,21 @@ __global__ void __launch_bounds__(128) k_g2_prepare(const g2_aff* __restrict__ Y
   yinf[q] = inf ? 1 : 0;
   if (inf) return;
   size_t bk = q / nprob, p = q % nprob;
-  g2_prepare(L + (bk * GS_NUM_LINES) * nprob + p, nprob, pt);
+  g2_prepare(L + (bk * GS_NUM_LINES * GS_LINE_WORDS) * nprob + p, nprob, pt);
 }
 
-// ------------------------------------------------------------------ Miller accumulation
-// thread -> (p, e = 2a+b, chunk);  F[(chunk*4 + e) * nprob + p] = conj( prod over its slots )
-__global__ void __launch_bounds__(128) k_miller(const g1_aff* __restrict__ X, const uint8_t* __restrict__ yinf,
-                                                const line_coeffs* __restrict__ L, fp12* __restrict__ F,
-                                                size_t nprob, int K, int S, int nchunk) {
+// ------------------------------------------------------------------ Miller accumulation (v2)
+// thread -> (p, e = 2a+b, chunk);  F[(chunk*4 + e) * nprob + p] = conj( prod over its slots ).
+// The accumulator and the current line triple live in shared memory (miller_v2.cuh): 864 B / thread,
+// 2 blocks of 128 threads per SM, no local-memory temporaries.
+constexpr int GS_MV2_NT = 128;
+constexpr int GS_MV2_SMEM = (144 + 72) * GS_MV2_NT * 4;
+__global__ void __launch_bounds__(GS_MV2_NT, 2) k_miller(const g1_aff* __restrict__ X, const uint8_t* __restrict__ yinf,
+                                                        const uint32_t* __restrict__ L, fp12* __restrict__ F, size_t nprob,
+                                                        int K, int S, int nchunk) {
+  extern __shared__ uint32_t sm[];
+  uint32_t* f = sm + threadIdx.x;
+  uint32_t* lc = sm + 144 * GS_MV2_NT + threadIdx.x;
   size_t id = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (id >= nprob * 4 * (size_t)nchunk) return;
   size_t p = id % nprob;
@@ -81,19 +88,20 @@ __global__ void __launch_bounds__(128) k_miller(const g1_aff* __restrict__ X, co
   int ch = (int)(id / (nprob * 4));
   int a = e >> 1, b = e & 1;
   int k0 = ch * S, k1 = min(K, k0 + S);
-  fp12 f;
-  f.set_one();
-  // anything to do at all?
   bool any = false;
   for (int k = k0; k < k1; k++) {
     if (yinf[((size_t)b * K + k) * nprob + p]) continue;
     if (X[((size_t)a * K + k) * nprob + p].is_inf()) continue;
     any = true;
   }
-  if (any) {
+  fp12 out;
+  if (!any) {
+    out.set_one();
+  } else {
+    f12w_set_one(f, GS_MV2_NT);
     int idx = 0;
     for (int bit = 62; bit >= 0; bit--) {
-      fp12::sqr(f, f);
+      if (bit != 62) f12w_sqr(f, lc, GS_MV2_NT);  // f = 1 on the first pass
       int nl = ((GS_X_ABS >> bit) & 1) ? 2 : 1;
       for (int t = 0; t < nl; t++, idx++) {
         for (int k = k0; k < k1; k++) {
@@ -102,14 +110,33 @@ __global__ void __launch_bounds__(128) k_miller(const g1_aff* __restrict__ X, co
           const g1_aff* P = &X[((size_t)a * K + k) * nprob + p];
           fp px = P->x, py = P->y;
           if (px.is_zero() && py.is_zero()) continue;
-          line_coeffs l = L[(bk * GS_NUM_LINES + idx) * nprob + p];
-          miller_apply_line(f, l, px, py);
+          const uint32_t* lp = L + ((bk * GS_NUM_LINES + idx) * GS_LINE_WORDS) * nprob + p;
+          // c0 straight to shared memory; c1 * xP and c2 * yP on the way
+#pragma unroll
+          for (int w = 0; w < 24; w++) lc[w * GS_MV2_NT] = lp[(size_t)w * nprob];
+          fp t0, t1;
+#pragma unroll
+          for (int h = 0; h < 2; h++) {
+#pragma unroll
+            for (int w = 0; w < 12; w++) {
+              t0.l[w] = lp[(size_t)(24 + h * 12 + w) * nprob];
+              t1.l[w] = lp[(size_t)(48 + h * 12 + w) * nprob];
+            }
+            fp::mul(t0, t0, px);
+            fp::mul(t1, t1, py);
+#pragma unroll
+            for (int w = 0; w < 12; w++) {
+              lc[(24 + h * 12 + w) * GS_MV2_NT] = t0.l[w];
+              lc[(48 + h * 12 + w) * GS_MV2_NT] = t1.l[w];
+            }
+          }
+          f12w_mul_line(f, lc, GS_MV2_NT);
         }
       }
     }
-    fp12::conj(f, f);
+    f12w_store_conj(out, f, GS_MV2_NT);
   }
-  F[((size_t)ch * 4 + e) * nprob + p] = f;
+  F[((size_t)ch * 4 + e) * nprob + p] = out;
 }
 
 // ------------------------------------------------------------------ final exponentiation (+ compare)
@@ -249,10 +276,106 @@ __global__ void k_verify_assemble(verify_shape s, verify_args v, const crs_dev* 
   Y[((size_t)1 * K + k) * nprob + p] = y1;
 }
 
-// ------------------------------------------------------------------ verify: G1-side statement MSM
+// ------------------------------------------------------------------ block-level batch inversion
+// Montgomery's trick as a product tree in shared memory with CONTIGUOUS active threads
+// (3 products per element + one Fermat inversion per block).  All `NT` threads must call.
+// z == 0 is passed through as 0.   sm: 2*NT fp.
+template <int NT>
+__device__ void block_batch_inv(fp& z, fp* sm) {
+  int t = threadIdx.x;
+  bool zero = z.is_zero();
+  fp v = z;
+  if (zero) fp_one(v);
+  sm[NT + t] = v;
+  __syncthreads();
+  for (int half = NT / 2; half >= 1; half >>= 1) {
+    if (t < half) {
+      fp a = sm[2 * (half + t)], b = sm[2 * (half + t) + 1];
+      fp::mul(a, a, b);
+      sm[half + t] = a;
+    }
+    __syncthreads();
+  }
+  if (t == 0) {
+    fp r = sm[1];
+    fp_inv(r, r);
+    sm[1] = r;
+  }
+  __syncthreads();
+  for (int half = 1; half <= NT / 2; half <<= 1) {
+    if (t < half) {
+      int i = half + t;
+      fp inv_i = sm[i], l = sm[2 * i], r = sm[2 * i + 1], nl, nr;
+      fp::mul(nl, inv_i, r);
+      fp::mul(nr, inv_i, l);
+      sm[2 * i] = nl;
+      sm[2 * i + 1] = nr;
+    }
+    __syncthreads();
+  }
+  z = sm[NT + t];
+  if (zero) z.set_zero();
+}
+
+// Jacobian -> affine for a whole block at once (one field inversion per block).
+template <int NT>
+__device__ void block_to_affine(g1_aff& out, const g1_jac& p, fp* sm) {
+  fp zi = p.Z;
+  block_batch_inv<NT>(zi, sm);
+  g1_jac::to_affine_with_zinv(out, p, zi);
+}
+template <int NT>
+__device__ void block_to_affine(g2_aff& out, const g2_jac& p, fp* sm) {
+  // 1/z = conj(z) / (z0^2 + z1^2): batch the Fp norm inversion
+  fp n, t;
+  fp::sqr(n, p.Z.c0);
+  fp::sqr(t, p.Z.c1);
+  fp::add(n, n, t);
+  block_batch_inv<NT>(n, sm);
+  fp2 zi;
+  fp::mul(zi.c0, p.Z.c0, n);
+  fp::mul(t, p.Z.c1, n);
+  fp::neg(zi.c1, t);
+  g2_jac::to_affine_with_zinv(out, p, zi);
+}
+
+// ------------------------------------------------------------------ verify: G1-side statement MSM (v2)
 // P_j = iota(A_j) + sum_i Gamma_ij c_i      (re-association of verifier.rs:39-42, SURVEY.md §8a ‡)
-// thread -> (p, jj, a, chunk): Straus (shared doublings) over <= GS_MSM_CHUNK bases
-__global__ void __launch_bounds__(128) k_vmsm_partial(verify_shape s, verify_args v, const crs_dev* __restrict__ crs,
+// Signed 4-bit windows (Straus: the 4 doublings per window are shared by all bases of the chunk).
+// The odd/even multiples 1B..8B of every base are built ONCE per problem by k_vmsm_tables and shared by
+// all n outputs; v1's binary double-and-add left half the lanes of every addition idle.
+constexpr int GS_VTAB = 8;
+// base index i of problem p, coordinate a:  i < m -> xcoms[p][i].a ;  i == m (scalar A) -> W1.a
+__device__ GS_INL g1_aff vmsm_base(const verify_shape& s, const verify_args& v, const crs_dev* crs, size_t p, int i, int a) {
+  if (i < s.m) return v.xcoms[(p * s.m + i) * 2 + a];
+  return crs->w1[a];
+}
+// thread -> (p, i, a): tab[((i*2 + a)*8 + d) * nprob + p] = (d+1) * base
+__global__ void __launch_bounds__(128) k_vmsm_tables(verify_shape s, verify_args v, const crs_dev* __restrict__ crs,
+                                                     g1_aff* __restrict__ tab, size_t nprob) {
+  __shared__ fp sm[2 * 128];
+  size_t id = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  bool active = id < nprob * (size_t)s.nbases * 2;
+  size_t p = active ? id % nprob : 0;
+  size_t r = active ? id / nprob : 0;
+  int a = (int)(r & 1), i = (int)(r >> 1);
+  g1_aff B;
+  B.set_inf();
+  if (active) B = vmsm_base(s, v, crs, p, i, a);
+  g1_jac acc;
+  acc.from_affine(B);
+  g1_aff* out = tab + ((size_t)(i * 2 + a) * GS_VTAB) * nprob + p;
+  for (int d = 0; d < GS_VTAB; d++) {
+    if (d == 1) g1_jac::dbl(acc, acc);
+    if (d > 1) g1_jac::add_mixed(acc, acc, B);
+    g1_aff e;
+    block_to_affine<128>(e, acc, sm);
+    if (active) out[(size_t)d * nprob] = e;
+  }
+}
+
+// thread -> (p, jj, a, chunk)
+__global__ void __launch_bounds__(128) k_vmsm_partial(verify_shape s, verify_args v, const g1_aff* __restrict__ tab,
                                                       g1_jac* __restrict__ part, size_t nprob) {
   size_t id = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   size_t total = nprob * (size_t)s.n_out * 2 * s.nchunk;
@@ -264,56 +387,65 @@ __global__ void __launch_bounds__(128) k_vmsm_partial(verify_shape s, verify_arg
   int jj = (int)(r % s.n_out);
   int ch = (int)(r / s.n_out);
 
-  uint32_t sc[GS_MSM_CHUNK][8];
-  g1_aff base[GS_MSM_CHUNK];
+  // biased scalars k' = k + 0x88..8 (64 nibbles): digit_w = nibble_w(k') - 8 in [-8, 7], no carries
+  uint32_t sc[GS_MSM_CHUNK][9];
+  int bidx[GS_MSM_CHUNK];
   int cnt = 0;
   int i0 = ch * GS_MSM_CHUNK, i1 = min(s.nbases, i0 + GS_MSM_CHUNK);
   for (int i = i0; i < i1; i++) {
     fr sv;
     bool have = false;
-    g1_aff bp;
     if (jj < s.n) {
       if (i < s.m) {
         sv = v.gamma[(p * s.m + i) * s.n + jj];
-        bp = v.xcoms[(p * s.m + i) * 2 + a];
         have = true;
       } else {  // scalar A: extra base W1 with scalar a_j
         sv = ((const fr*)v.a_consts)[p * s.n + jj];
-        bp = crs->w1[a];
         have = true;
       }
     } else if (jj == s.n && !s.groupB) {  // C_B = sum_i b_i c_i
       if (i < s.m) {
         sv = ((const fr*)v.b_consts)[p * s.m + i];
-        bp = v.xcoms[(p * s.m + i) * 2 + a];
         have = true;
       }
-    } else {  // Quad target: t * W1
-      if (i == 0) {
+    } else {  // Quad target: t * W1  (W1 is base index m)
+      if (i == s.m) {
         sv = ((const fr*)v.target)[p];
-        bp = crs->w1[a];
         have = true;
       }
     }
-    if (!have || bp.is_inf() || sv.is_zero()) continue;
-    fr_from_mont(sc[cnt], sv);
-    base[cnt] = bp;
+    if (!have || sv.is_zero()) continue;
+    uint32_t k[8];
+    fr_from_mont(k, sv);
+    uint32_t carry = 0;
+#pragma unroll
+    for (int w = 0; w < 8; w++) {
+      uint64_t t = (uint64_t)k[w] + 0x88888888u + carry;
+      sc[cnt][w] = (uint32_t)t;
+      carry = (uint32_t)(t >> 32);
+    }
+    sc[cnt][8] = carry;
+    bidx[cnt] = i;
     cnt++;
   }
   g1_jac acc;
   acc.set_inf();
   if (cnt > 0) {
-    // highest set bit over the chunk
-    int top = -1;
-    for (int w = 7; w >= 0 && top < 0; w--) {
-      uint32_t o = 0;
-      for (int i = 0; i < cnt; i++) o |= sc[i][w];
-      if (o) top = w * 32 + 31 - __clz(o);
-    }
-    for (int bit = top; bit >= 0; bit--) {
-      g1_jac::dbl(acc, acc);
-      for (int i = 0; i < cnt; i++)
-        if ((sc[i][bit >> 5] >> (bit & 31)) & 1) g1_jac::add_mixed(acc, acc, base[i]);
+    for (int w = 64; w >= 0; w--) {
+      if (w != 64) {
+        g1_jac::dbl(acc, acc);
+        g1_jac::dbl(acc, acc);
+        g1_jac::dbl(acc, acc);
+        g1_jac::dbl(acc, acc);
+      }
+      for (int i = 0; i < cnt; i++) {
+        int d = (int)((sc[i][w >> 3] >> ((w & 7) * 4)) & 15u) - (w == 64 ? 0 : 8);
+        if (d == 0) continue;
+        int mag = d < 0 ? -d : d;
+        g1_aff e = tab[((size_t)(bidx[i] * 2 + a) * GS_VTAB + (mag - 1)) * nprob + p];
+        if (d < 0) fp::neg(e.y, e.y);
+        g1_jac::add_mixed(acc, acc, e);
+      }
     }
   }
   part[(((size_t)ch * s.n_out + jj) * 2 + a) * nprob + p] = acc;
@@ -322,33 +454,38 @@ __global__ void __launch_bounds__(128) k_vmsm_partial(verify_shape s, verify_arg
 // thread -> (p, jj, a): sum the chunk partials, add iota_1(A_j), negate the Quad target, normalise, write slot
 __global__ void __launch_bounds__(128) k_vmsm_reduce(verify_shape s, verify_args v, const g1_jac* __restrict__ part,
                                                      g1_aff* __restrict__ X, size_t nprob) {
+  __shared__ fp sm[2 * 128];
   size_t id = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (id >= nprob * (size_t)s.n_out * 2) return;
-  size_t p = id % nprob;
-  size_t r = id / nprob;
+  bool active = id < nprob * (size_t)s.n_out * 2;
+  size_t p = active ? id % nprob : 0;
+  size_t r = active ? id / nprob : 0;
   int a = (int)(r & 1);
   int jj = (int)(r >> 1);
-  g1_jac acc = part[((size_t)jj * 2 + a) * nprob + p];
-  for (int ch = 1; ch < s.nchunk; ch++) {
-    g1_jac t = part[(((size_t)ch * s.n_out + jj) * 2 + a) * nprob + p];
-    g1_jac::add(acc, acc, t);
-  }
-  int slot;
-  if (jj < s.n) {
-    slot = jj;
-    if (s.groupA && a == 1) {
-      g1_aff A = ((const g1_aff*)v.a_consts)[p * s.n + jj];
-      g1_jac::add_mixed(acc, acc, A);
+  g1_jac acc;
+  acc.set_inf();
+  int slot = 0;
+  if (active) {
+    acc = part[((size_t)jj * 2 + a) * nprob + p];
+    for (int ch = 1; ch < s.nchunk; ch++) {
+      g1_jac t = part[(((size_t)ch * s.n_out + jj) * 2 + a) * nprob + p];
+      g1_jac::add(acc, acc, t);
     }
-  } else if (jj == s.n && !s.groupB) {
-    slot = s.sB;
-  } else {
-    slot = s.sT;
-    g1_jac::neg(acc, acc);
+    if (jj < s.n) {
+      slot = jj;
+      if (s.groupA && a == 1) {
+        g1_aff A = ((const g1_aff*)v.a_consts)[p * s.n + jj];
+        g1_jac::add_mixed(acc, acc, A);
+      }
+    } else if (jj == s.n && !s.groupB) {
+      slot = s.sB;
+    } else {
+      slot = s.sT;
+      g1_jac::neg(acc, acc);
+    }
   }
   g1_aff out;
-  g1_jac::to_affine(out, acc);
-  X[((size_t)a * s.K + slot) * nprob + p] = out;
+  block_to_affine<128>(out, acc, sm);
+  if (active) X[((size_t)a * s.K + slot) * nprob + p] = out;
 }
 
 }  // namespace gs

@@ -107,9 +107,24 @@ GS_HD GS_NOINL void g2_add_step(g2_proj& t, const g2_aff& q, line_coeffs& l) {
   l.c2 = lambda;
 }
 
-// Writes the 68 line triples of Q to out[step * stride]  (stride in units of line_coeffs).
-// Q must not be the identity (callers drop identity pairs, as ark-ec does).
-GS_HD GS_INL void g2_prepare(line_coeffs* out, size_t stride, const g2_aff& q) {
+// Line storage: word-interleaved so that both the writer (one thread per G2 point) and the reader
+// (one thread per accumulator) are perfectly coalesced over consecutive problems:
+//     word w (0..71) of line `idx` of a point lives at  base[(idx*72 + w) * stride]
+constexpr int GS_LINE_WORDS = 72;
+GS_HD GS_INL void st_line(uint32_t* base, size_t stride, int idx, const line_coeffs& l) {
+  const uint32_t* w = (const uint32_t*)&l;
+  uint32_t* o = base + (size_t)idx * GS_LINE_WORDS * stride;
+  for (int i = 0; i < GS_LINE_WORDS; i++) o[(size_t)i * stride] = w[i];
+}
+GS_HD GS_INL void ld_line(line_coeffs& l, const uint32_t* base, size_t stride, int idx) {
+  uint32_t* w = (uint32_t*)&l;
+  const uint32_t* o = base + (size_t)idx * GS_LINE_WORDS * stride;
+  for (int i = 0; i < GS_LINE_WORDS; i++) w[i] = o[(size_t)i * stride];
+}
+
+// Writes the 68 line triples of Q (layout above).  Q must not be the identity (callers drop
+// identity pairs, as ark-ec does).
+GS_HD GS_INL void g2_prepare(uint32_t* out, size_t stride, const g2_aff& q) {
   g2_proj t;
   t.x = q.x;
   t.y = q.y;
@@ -118,11 +133,11 @@ GS_HD GS_INL void g2_prepare(line_coeffs* out, size_t stride, const g2_aff& q) {
   for (int b = 62; b >= 0; b--) {
     line_coeffs l;
     g2_double_step(t, l);
-    out[(size_t)idx * stride] = l;
+    st_line(out, stride, idx, l);
     idx++;
     if ((GS_X_ABS >> b) & 1) {
       g2_add_step(t, q, l);
-      out[(size_t)idx * stride] = l;
+      st_line(out, stride, idx, l);
       idx++;
     }
   }

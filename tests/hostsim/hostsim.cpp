@@ -54,7 +54,7 @@ void hs_miller(void* r, int n, const void* g1s, const void* g2s) {
   std::vector<std::vector<line_coeffs>> lines; std::vector<g1_aff> ps;
   for (int i = 0; i < n; i++) {
     if (P[i].is_inf() || Q[i].is_inf()) continue;
-    lines.emplace_back(GS_NUM_LINES); g2_prepare(lines.back().data(), 1, Q[i]); ps.push_back(P[i]);
+    lines.emplace_back(GS_NUM_LINES); g2_prepare((uint32_t*)lines.back().data(), 1, Q[i]); ps.push_back(P[i]);
   }
   fp12 f; f.set_one(); int idx = 0;
   for (int b = 62; b >= 0; b--) {
@@ -66,4 +66,33 @@ void hs_miller(void* r, int n, const void* g1s, const void* g2s) {
   fp12::conj(f, f); ST(r, f);
 }
 void hs_final_exp(void* r, const void* a) { LD(fp12, x, a); fp12 o; final_exponentiation(o, x); ST(r, o); }
+}
+
+// ---- v2 Miller accumulator (w-basis, strided): same inputs/outputs as hs_miller
+#include "../../groth-sahai-rs_b200/csrc/miller_v2.cuh"
+extern "C" void hs_miller_v2(void* r, int n, const void* g1s, const void* g2s, int stride) {
+  const g1_aff* P = (const g1_aff*)g1s; const g2_aff* Q = (const g2_aff*)g2s;
+  std::vector<std::vector<line_coeffs>> lines; std::vector<g1_aff> ps;
+  for (int i = 0; i < n; i++) {
+    if (P[i].is_inf() || Q[i].is_inf()) continue;
+    lines.emplace_back(GS_NUM_LINES); g2_prepare((uint32_t*)lines.back().data(), 1, Q[i]); ps.push_back(P[i]);
+  }
+  std::vector<uint32_t> f(144 * stride, 0xdeadbeef), lc(72 * stride, 0xdeadbeef);
+  f12w_set_one(f.data(), stride);
+  int idx = 0;
+  for (int b = 62; b >= 0; b--) {
+    f12w_sqr(f.data(), lc.data(), stride);
+    int nl = ((GS_X_ABS >> b) & 1) ? 2 : 1;
+    for (int t = 0; t < nl; t++, idx++)
+      for (size_t k = 0; k < ps.size(); k++) {
+        fp2 c1, c2;
+        fp2::mul_fp(c1, lines[k][idx].c1, ps[k].x);
+        fp2::mul_fp(c2, lines[k][idx].c2, ps[k].y);
+        st_fp2(GS_COEF(lc.data(), 0, stride), stride, lines[k][idx].c0);
+        st_fp2(GS_COEF(lc.data(), 1, stride), stride, c1);
+        st_fp2(GS_COEF(lc.data(), 2, stride), stride, c2);
+        f12w_mul_line(f.data(), lc.data(), stride);
+      }
+  }
+  fp12 out; f12w_store_conj(out, f.data(), stride); ST(r, out);
 }

@@ -120,3 +120,15 @@ def test_pairing(L):
     # all-identity input -> one
     ml = call(L.hs_miller, 576, 1, g1_b(None), g2_b(G2_GEN_FP2))
     assert fp12_i(call(L.hs_final_exp, 576, ml)) == FP12_ONE
+
+
+def test_miller_v2_matches_v1(L):
+    """The shared-memory (w-basis, in-place) Miller accumulator must equal the tower one bit for bit."""
+    ps = [g1_mul(G1_GEN, rng.randrange(R)) for _ in range(3)]
+    qs = [g2_mul(G2_GEN_FP2, rng.randrange(R)) for _ in range(3)]
+    g1s = b"".join(g1_b(p) for p in ps)
+    g2s = b"".join(g2_b(q) for q in qs)
+    v1 = call(L.hs_miller, 576, 3, g1s, g2s)
+    for stride in (1, 5):
+        assert call(L.hs_miller_v2, 576, 3, g1s, g2s, stride) == v1
+    assert fp12_i(v1) == multi_miller_loop(list(zip(ps, qs)))
