@@ -1,0 +1,154 @@
+// Host-side context shared by the translation units of libgs_b200.so (one .cu per kernel family so
+// that cicc/ptxas run in parallel; every kernel lives in exactly one TU, device helpers are header
+// inline).  Nothing here is part of the C ABI: include/gs_b200.h is.
+#pragma once
+#include "../../include/gs_b200.h"
+
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "shapes.cuh"
+
+// fixed-base window tables of one group (prover_impl.cuh builds them):
+//   t[((base*2 + a) * W + w) * H + (d-1)] = d * 2^(c w) * Base.a,  bases u1 u2 W1 (G1) / v1 v2 W2 (G2)
+template <class F>
+struct gs_fixed_table {
+  int c = 0, W = 0;
+  size_t H = 0;
+  gs::Aff<F>* t = nullptr;
+};
+
+struct gs_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  gs::crs_dev* crs = nullptr;  // device
+  bool crs_loaded = false;
+  gs_fixed_table<gs::FpOps> tab1;
+  gs_fixed_table<gs::Fp2Ops> tab2;
+  uint32_t* crs_lines = nullptr;  // prepared line triples of the fixed G2 points v1.0 v1.1 v2.0 v2.1 W2.0 W2.1 (pairing.cu)
+  uint64_t launches = 0;
+  bool profile = false;
+  struct prof_rec {
+    const char* name;
+    cudaEvent_t e0, e1;
+  };
+  std::vector<prof_rec> prof;
+  size_t verify_batch_max = 16384;  // problems per pass (bounds the line-coefficient scratch)
+  std::string err;
+};
+
+#define CUDA_TRY(x)                                               \
+  do {                                                            \
+    cudaError_t e_ = (x);                                         \
+    if (e_ != cudaSuccess) {                                      \
+      ctx->err = std::string(#x) + ": " + cudaGetErrorString(e_); \
+      return GS_ECUDA;                                            \
+    }                                                             \
+  } while (0)
+#define FAIL(code, msg) \
+  do {                  \
+    ctx->err = (msg);   \
+    return (code);      \
+  } while (0)
+// launch `kern` with `nthreads` logical threads in blocks of `bs` and `smem` dynamic shared bytes
+#define LAUNCH_CFG(kern, nthreads, bs, smem, ...)                         \
+  do {                                                                    \
+    size_t nt_ = (nthreads);                                              \
+    if (nt_ > 0) {                                                        \
+      unsigned grid_ = (unsigned)((nt_ + (bs)-1) / (bs));                 \
+      gs_ctx::prof_rec pr_{#kern, nullptr, nullptr};                      \
+      if (ctx->profile) {                                                 \
+        cudaEventCreate(&pr_.e0);                                         \
+        cudaEventCreate(&pr_.e1);                                         \
+        cudaEventRecord(pr_.e0, ctx->stream);                             \
+      }                                                                   \
+      kern<<<grid_, (bs), (smem), ctx->stream>>>(__VA_ARGS__);            \
+      if (ctx->profile) {                                                 \
+        cudaEventRecord(pr_.e1, ctx->stream);                             \
+        ctx->prof.push_back(pr_);                                         \
+      }                                                                   \
+      ctx->launches++;                                                    \
+      CUDA_TRY(cudaGetLastError());                                       \
+    }                                                                     \
+  } while (0)
+#define LAUNCH(kern, nthreads, ...) LAUNCH_CFG(kern, nthreads, 128, 0, __VA_ARGS__)
+
+// stream-ordered scratch with RAII release
+struct Scratch {
+  gs_ctx* ctx;
+  std::vector<void*> ptrs;
+  explicit Scratch(gs_ctx* c) : ctx(c) {}
+  template <class T>
+  cudaError_t alloc(T** p, size_t count) {
+    void* q = nullptr;
+    cudaError_t e = cudaMallocAsync(&q, count * sizeof(T) + 16, ctx->stream);
+    if (e == cudaSuccess) ptrs.push_back(q);
+    *p = (T*)q;
+    return e;
+  }
+  ~Scratch() {
+    for (void* q : ptrs) cudaFreeAsync(q, ctx->stream);
+  }
+};
+
+template <class T>
+static inline cudaError_t upload(gs_ctx* ctx, Scratch& s, T** dst, const void* src, size_t count) {
+  cudaError_t e = s.alloc(dst, count);
+  if (e != cudaSuccess) return e;
+  if (count == 0) return cudaSuccess;
+  return cudaMemcpyAsync(*dst, src, count * sizeof(T), cudaMemcpyHostToDevice, ctx->stream);
+}
+
+static inline size_t elem_size_A(int type) { return (type == 0 || type == 1) ? sizeof(gs::g1_aff) : sizeof(gs::fr); }
+static inline size_t elem_size_B(int type) { return (type == 0 || type == 2) ? sizeof(gs::g2_aff) : sizeof(gs::fr); }
+static inline size_t elem_size_T(int type) {
+  return type == 0 ? sizeof(gs::fp12) : type == 1 ? sizeof(gs::g1_aff) : type == 2 ? sizeof(gs::g2_aff) : sizeof(gs::fr);
+}
+
+// ---- functions that cross translation units (namespace gsi = "internal") ----
+namespace gsi {
+using namespace gs;
+
+// pairing.cu
+int pairing_init(gs_ctx* ctx);  // per-context kernel attributes
+// X, Y: device slot arrays [2][K][nprob]  ->  ComT values (out_comt, AoS [p][4]) or per-entry verdict
+// bytes ok4[4][nprob] (compared with 1 / target).
+int run_pairing_product(gs_ctx* ctx, Scratch& sc, const g1_aff* X, const g2_aff* Y, size_t nprob, int K, fp12* out_comt,
+                        uint8_t* ok4, const fp12* target);
+
+// finalexp.cu: f = prod_chunks F[(ch*4 + e)*nprob + p]; g = FE(f); writes out_comt[p*4+e] and/or ok4[e*nprob + p]
+int launch_final_exp(gs_ctx* ctx, const fp12* F, size_t nprob, int nchunk, fp12* out_comt, uint8_t* ok4, const fp12* target);
+
+// prover.cu
+int crs_generate_points(gs_ctx* ctx, const gs_g1* p1, const gs_g2* p2, const gs_fr* a1, const gs_fr* a2, const gs_fr* t1,
+                        const gs_fr* t2, gs_crs* out);
+int crs_derive(gs_ctx* ctx);
+
+// prover_g1.cu / prover_g2.cu (explicit instantiations of prover_impl.cuh)
+template <class F>
+gs_fixed_table<F>& table_of(gs_ctx* ctx);
+template <>
+inline gs_fixed_table<FpOps>& table_of<FpOps>(gs_ctx* ctx) { return ctx->tab1; }
+template <>
+inline gs_fixed_table<Fp2Ops>& table_of<Fp2Ops>(gs_ctx* ctx) { return ctx->tab2; }
+
+template <class F>
+int fixed_table_rebuild(gs_ctx* ctx, int c);
+template <class F>
+void fixed_table_release(gs_ctx* ctx);
+template <class F>
+int batch_commit_impl(gs_ctx* ctx, size_t n, int base0, int base1, const gs_fr* s0, size_t s0_stride, const gs_fr* s1,
+                      size_t s1_stride, size_t nscal, const void* addend, void* out);
+// one proof element vector (pi: F = G2, theta: F = G1); `e` = collapsed scalar for scalar-typed sides (else null)
+template <class F>
+int proof_element(gs_ctx* ctx, Scratch& sc, int rows, bool group_typed, const fr* sv, const void* dconst, size_t nconst,
+                  const void* dvars, size_t nvars, int ncoef, const fr* coef, size_t coef_rs, const Aff<F>* key,
+                  const Aff<F>* W, const fr* e, Aff<F>* dout);
+template <class F>
+int com_matmul_impl(gs_ctx* ctx, size_t r, size_t k, size_t c, const gs_fr* lhs, const void* mat, void* out);
+
+}  // namespace gsi

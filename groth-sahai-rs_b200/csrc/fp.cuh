@@ -240,6 +240,64 @@ struct Mont {
     final_sub(r, t);
   }
   GS_HD static GS_INL void sqr(Mont& r, const Mont& a) { mul(r, a, a); }
+
+  // ---- sum of products with ONE interleaved Montgomery reduction ("lazy reduction"):
+  //     r = (a[0] b[0] + ... + a[NT-1] b[NT-1]) / R  mod p
+  // Every CIOS row adds the NT partial-product rows first and then a single m*p row, i.e.
+  // NT*N*N + N*N + N multiply-adds instead of NT*(2*N*N + N).  `units` = sum over the terms of
+  // (bound of a[t] / p) * (bound of b[t] / p) (1 for canonical inputs; operands that are plain sums
+  // of two canonical values count 2).  Requires (units + 1) * p < 2^(32N): the running value stays
+  // below that, and the final value is < (units * p / R + 1) * p < 2p, so one conditional
+  // subtraction canonicalises it.  For BLS12-381 Fp (R/p = 9.84): units <= 8.
+  template <int NT>
+  GS_HD static GS_INL void mulsum(Mont& r, const Mont (&a)[NT], const Mont (&b)[NT]) {
+    uint32_t E[N], O[N];
+#pragma unroll
+    for (int i = 0; i < N; i += 2) {
+      rowsum<NT>(E, O, a, b, i, i == 0);
+      rowsum<NT>(O, E, a, b, i + 1, false);
+    }
+    uint32_t t[N];
+    t[0] = add_cc(O[1], E[0]);
+#pragma unroll
+    for (int i = 1; i < N - 1; i++) t[i] = addc_cc(O[i + 1], E[i]);
+    t[N - 1] = addc(0u, E[N - 1]);
+    final_sub(r, t);
+  }
+  template <int NT>
+  GS_HD static GS_INL void rowsum(uint32_t* E, uint32_t* O, const Mont (&a)[NT], const Mont (&b)[NT], int i, bool first) {
+    if (first) {
+#pragma unroll
+      for (int j = 0; j < N; j += 2) {
+        E[j] = mul_lo(a[0].l[j], b[0].l[i]);
+        E[j + 1] = mul_hi(a[0].l[j], b[0].l[i]);
+        O[j] = mul_lo(a[0].l[j + 1], b[0].l[i]);
+        O[j + 1] = mul_hi(a[0].l[j + 1], b[0].l[i]);
+      }
+    } else {
+      E[0] = add_cc(E[0], O[1]);
+      madc_row_rshift(O, a[0].l + 1, b[0].l[i]);
+      cmad_row(E, a[0].l, b[0].l[i]);
+      O[N - 1] = addc(O[N - 1], 0u);
+    }
+#pragma unroll
+    for (int t = 1; t < NT; t++) {
+      cmad_row(O, a[t].l + 1, b[t].l[i]);  // no carry out of the window: the value is < 2^(32(N+1))
+      cmad_row(E, a[t].l, b[t].l[i]);
+      O[N - 1] = addc(O[N - 1], 0u);
+    }
+    uint32_t m = mul_lo(E[0], PR::M0);
+    cmad_row_mod<1>(O, m);
+    cmad_row_mod<0>(E, m);
+    O[N - 1] = addc(O[N - 1], 0u);
+  }
+  // plain limb-wise sum without reduction (inputs < p, result < 2p): an operand for mulsum that counts 2 units
+  GS_HD static GS_INL void add_noreduce(Mont& r, const Mont& a, const Mont& b) {
+    r.l[0] = add_cc(a.l[0], b.l[0]);
+#pragma unroll
+    for (int i = 1; i < N - 1; i++) r.l[i] = addc_cc(a.l[i], b.l[i]);
+    r.l[N - 1] = addc(a.l[N - 1], b.l[N - 1]);
+  }
 };
 
 typedef Mont<FpParams> fp;

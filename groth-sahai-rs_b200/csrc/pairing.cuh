@@ -47,7 +47,7 @@ GS_HD GS_INL void fp2_half(fp2& r, const fp2& a) {
 }
 
 // Costello-Lange-Naehrig doubling step in homogeneous projective coordinates.
-GS_HD GS_NOINL void g2_double_step(g2_proj& t, line_coeffs& l) {
+inline GS_HD GS_NOINL void g2_double_step(g2_proj& t, line_coeffs& l) {
   fp2 a, b, c, e, f, g, h, i, j, e2, s;
   fp2::mul(a, t.x, t.y);
   fp2_half(a, a);
@@ -80,7 +80,7 @@ GS_HD GS_NOINL void g2_double_step(g2_proj& t, line_coeffs& l) {
   fp2::neg(l.c2, h);
 }
 
-GS_HD GS_NOINL void g2_add_step(g2_proj& t, const g2_aff& q, line_coeffs& l) {
+inline GS_HD GS_NOINL void g2_add_step(g2_proj& t, const g2_aff& q, line_coeffs& l) {
   fp2 theta, lambda, c, d, e, f, g, h, s, j;
   fp2::mul(s, q.y, t.z);
   fp2::sub(theta, t.y, s);
@@ -153,7 +153,7 @@ GS_HD GS_INL void miller_apply_line(fp12& f, const line_coeffs& l, const fp& px,
 
 // ------------------------------------------------------------------ final exponentiation
 // f^|x| for f in the cyclotomic subgroup, then conjugate (x < 0)
-GS_HD GS_NOINL void cyclotomic_exp_x(fp12& r, const fp12& a) {
+inline GS_HD GS_NOINL void cyclotomic_exp_x(fp12& r, const fp12& a) {
   fp12 acc = a;
   for (int b = 62; b >= 0; b--) {
     fp12::cyclotomic_sqr(acc, acc);
@@ -162,7 +162,7 @@ GS_HD GS_NOINL void cyclotomic_exp_x(fp12& r, const fp12& a) {
   fp12::conj(r, acc);
 }
 
-GS_HD GS_NOINL void final_exponentiation(fp12& out, const fp12& f) {
+inline GS_HD GS_NOINL void final_exponentiation(fp12& out, const fp12& f) {
   fp12 r, t, a, b, c;
   // easy part: r = f^((p^6-1)(p^2+1))
   fp12::inv(t, f);

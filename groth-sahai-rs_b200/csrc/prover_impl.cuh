@@ -1,0 +1,342 @@
+// Prover-side kernels templated over the group (F = FpOps: G1, F = Fp2Ops: G2) and their host drivers.
+// Instantiated once per group in prover_g1.cu / prover_g2.cu so the two halves compile in parallel.
+// Reference: src/prover/commit.rs:78-256, src/prover/prove.rs:92-488, src/data_structures.rs:645-742.
+#pragma once
+#include "batchinv.cuh"
+#include "ctx.h"
+
+namespace gs {
+
+// ------------------------------------------------------------------ fixed-base window tables
+// For base point B (one coordinate of u1, u2, W1 / v1, v2, W2) and window w:
+//     T[w][d-1] = d * 2^(c w) * B,   d = 1 .. 2^(c-1)     (signed digits => half tables)
+// layout: tab[((base*2 + a) * W + w) * H + (d-1)]
+constexpr int GS_TAB_NT = 128;
+
+template <class F>
+__global__ void k_table_window_bases(const Aff<F>* __restrict__ bases, Aff<F>* __restrict__ tab, int c, int W, size_t H) {
+  // one thread per base point: writes d = 1 entries (2^(cw) B) for every window
+  int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= 6) return;
+  Jac<F> j;
+  j.from_affine(bases[b]);
+  for (int w = 0; w < W; w++) {
+    Aff<F> a;
+    Jac<F>::to_affine(a, j);
+    tab[((size_t)b * W + w) * H] = a;
+    for (int i = 0; i < c; i++) Jac<F>::dbl(j, j);
+  }
+}
+
+// thread -> (base b, window w, run r): entries d = r*RUN+1 .. r*RUN+RUN of T[b][w] by a chain of
+// mixed additions from a small scalar-mul start, normalised with a block-wide batch inversion per step.
+template <class F, int RUN>
+__global__ void __launch_bounds__(GS_TAB_NT) k_table_fill(Aff<F>* __restrict__ tab, int W, size_t H) {
+  __shared__ fp sm[2 * GS_TAB_NT];
+  size_t id = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t runs_per_row = (H + RUN - 1) / RUN;
+  size_t total = (size_t)6 * W * runs_per_row;
+  bool active = id < total;
+  size_t row = active ? id / runs_per_row : 0, r = active ? id % runs_per_row : 0;
+  Aff<F>* T = tab + row * H;
+  Aff<F> B = T[0];
+  Jac<F> acc;
+  uint32_t k[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  k[0] = (uint32_t)(r * RUN);  // start = (r*RUN) * B
+  scalar_mul<F>(acc, B, k);
+  for (int i = 0; i < RUN; i++) {
+    Jac<F>::add_mixed(acc, acc, B);
+    Aff<F> a;
+    block_to_affine<GS_TAB_NT>(a, acc, sm);
+    size_t d1 = r * RUN + i;  // d - 1
+    if (active && d1 < H && d1 > 0) T[d1] = a;
+  }
+}
+
+// ------------------------------------------------------------------ batch commitments
+// out[i].p[a] = s0_i * Base0.a + s1_i * Base1.a  (+ addend_i when a == 1)
+//   batch_commit_G1 (commit.rs:78-100):            s0,s1 = R[i][0], R[i][1]; bases u1,u2; addend X_i
+//   batch_commit_scalar_to_B1 (commit.rs:125-156): s0 = x_i, s1 = r_i;     bases W1,u1; no addend
+// thread -> (i, a); signed c-bit windows; one table lookup + one mixed addition per window.
+// c bits of the 256-bit integer k starting at `bit` (zero beyond bit 255); c <= 16
+GS_HD GS_INL uint32_t get_bits(const uint32_t k[8], int bit, int c) {
+  int w = bit >> 5, s = bit & 31;
+  if (w >= 8) return 0;
+  uint64_t v = k[w];
+  if (w + 1 < 8) v |= (uint64_t)k[w + 1] << 32;
+  return (uint32_t)(v >> s) & ((1u << c) - 1u);
+}
+
+template <class F>
+GS_HD GS_INL void fixed_base_accumulate(Jac<F>& acc, const Aff<F>* __restrict__ T /* [W][H] */, const uint32_t k[8], int c,
+                                        int W, size_t H) {
+  uint32_t carry = 0;
+  const uint32_t half = 1u << (c - 1);
+  for (int w = 0; w < W; w++) {
+    uint32_t d = get_bits(k, w * c, c) + carry;   // digits recoded into (-2^(c-1), 2^(c-1)]
+    bool negd = d > half;
+    carry = negd ? 1u : 0u;
+    uint32_t mag = negd ? (1u << c) - d : d;
+    if (mag == 0) continue;
+    Aff<F> e = T[(size_t)w * H + (mag - 1)];
+    if (negd) F::neg(e.y, e.y);
+    Jac<F>::add_mixed(acc, acc, e);
+  }
+}
+
+template <class F>
+__global__ void __launch_bounds__(GS_TAB_NT) k_fixed_commit(const Aff<F>* __restrict__ tab, int c, int W, size_t H, int base0,
+                                                            int base1, const fr* __restrict__ s0, size_t s0_stride,
+                                                            const fr* __restrict__ s1, size_t s1_stride,
+                                                            const Aff<F>* __restrict__ addend, Aff<F>* __restrict__ out, size_t n) {
+  __shared__ fp sm[2 * GS_TAB_NT];
+  size_t id = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  bool active = id < 2 * n;
+  size_t i = active ? id >> 1 : 0;
+  int a = (int)(id & 1);
+  Jac<F> acc;
+  acc.set_inf();
+  if (active) {
+    uint32_t k[8];
+    fr_from_mont(k, s0[i * s0_stride]);
+    fixed_base_accumulate<F>(acc, tab + ((size_t)(base0 * 2 + a) * W) * H, k, c, W, H);
+    fr_from_mont(k, s1[i * s1_stride]);
+    fixed_base_accumulate<F>(acc, tab + ((size_t)(base1 * 2 + a) * W) * H, k, c, W, H);
+    if (addend != nullptr && a == 1) Jac<F>::add_mixed(acc, acc, addend[i]);
+  }
+  Aff<F> r;
+  block_to_affine<GS_TAB_NT>(r, acc, sm);
+  if (active) out[i * 2 + a] = r;
+}
+
+// ------------------------------------------------------------------ variable-base MSM (proof elements)
+// terms[row][t] = sv[row][t] * base[t]   (4-bit signed windows per term), bases = two concatenated segments
+template <class F>
+__global__ void __launch_bounds__(128) k_msm_terms(Jac<F>* __restrict__ terms, const fr* __restrict__ sv, const Aff<F>* __restrict__ b0,
+                                                   size_t n0, const Aff<F>* __restrict__ b1, size_t n1, int rows) {
+  size_t id = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t nt = n0 + n1;
+  if (id >= nt * rows) return;
+  size_t t = id % nt;
+  Aff<F> B = t < n0 ? b0[t] : b1[t - n0];
+  uint32_t k[8];
+  fr_from_mont(k, sv[id]);
+  Jac<F> j;
+  scalar_mul<F>(j, B, k);
+  terms[id] = j;
+}
+
+// in-place pairwise tree reduction: terms[row][t] += terms[row][t + half] for t < half (one launch per level)
+template <class F>
+__global__ void __launch_bounds__(128) k_jac_reduce_step(Jac<F>* __restrict__ terms, size_t row_stride, size_t cur, size_t half, int rows) {
+  size_t id = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (id >= half * rows) return;
+  size_t row = id / half, t = id % half;
+  if (t + half >= cur) return;
+  Jac<F>* base = terms + row * row_stride;
+  Jac<F> a = base[t], b = base[t + half];
+  Jac<F>::add(a, a, b);
+  base[t] = a;
+}
+
+// final assembly of a proof element (prove.rs:146, 162):
+//   out[i].p[0] =                  sum_l coef[i][l] key_l.0  (+ e_i W.0)
+//   out[i].p[1] = varsum[i]      + sum_l coef[i][l] key_l.1  (+ e_i W.1)
+// thread -> (i, a).  `varsum` = reduced MSM rows (group-typed) or null; `e` = collapsed scalar (scalar-typed) or null.
+template <class F>
+__global__ void k_proof_finish(Aff<F>* __restrict__ out, int rows, int ncoef, const fr* __restrict__ coef, size_t coef_rs,
+                               size_t coef_cs, const Aff<F>* __restrict__ key /* [2][2] */, const Jac<F>* __restrict__ varsum,
+                               size_t var_stride, const fr* __restrict__ e, const Aff<F>* __restrict__ W /* [2] */) {
+  int id = blockIdx.x * blockDim.x + threadIdx.x;
+  if (id >= rows * 2) return;
+  int i = id >> 1, a = id & 1;
+  Jac<F> acc;
+  acc.set_inf();
+  if (varsum != nullptr && a == 1) acc = varsum[(size_t)i * var_stride];
+  uint32_t k[8];
+  for (int l = 0; l < ncoef; l++) {
+    fr_from_mont(k, coef[i * coef_rs + l * coef_cs]);
+    Jac<F> t;
+    scalar_mul<F>(t, key[l * 2 + a], k);
+    Jac<F>::add(acc, acc, t);
+  }
+  if (e != nullptr) {
+    fr_from_mont(k, e[i]);
+    Jac<F> t;
+    scalar_mul<F>(t, W[a], k);
+    Jac<F>::add(acc, acc, t);
+  }
+  Aff<F> r;
+  Jac<F>::to_affine(r, acc);
+  out[i * 2 + a] = r;
+}
+
+// ------------------------------------------------------------------ Mat::left_mul on Com matrices
+// terms[(i*c + j)*2 + a][t] = lhs[i][t] * mat[t][j].a      (data_structures.rs:696-742)
+template <class F>
+__global__ void __launch_bounds__(128) k_com_matmul_terms(Jac<F>* __restrict__ terms, const fr* __restrict__ lhs,
+                                                          const Aff<F>* __restrict__ mat, size_t r, size_t k, size_t c) {
+  size_t id = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (id >= r * c * 2 * k) return;
+  size_t t = id % k;
+  size_t o = id / k;
+  int a = (int)(o & 1);
+  size_t ij = o >> 1;
+  size_t i = ij / c, j = ij % c;
+  uint32_t kk[8];
+  fr_from_mont(kk, lhs[i * k + t]);
+  Jac<F> acc;
+  scalar_mul<F>(acc, mat[(t * c + j) * 2 + a], kk);
+  terms[id] = acc;
+}
+template <class F>
+__global__ void k_jac_rows_to_affine(Aff<F>* __restrict__ out, const Jac<F>* __restrict__ terms, size_t row_stride, size_t rows) {
+  size_t id = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (id >= rows) return;
+  Aff<F> r;
+  Jac<F>::to_affine(r, terms[id * row_stride]);
+  out[id] = r;
+}
+
+}  // namespace gs
+
+namespace gsi {
+
+template <class F>
+struct crs_side;
+template <>
+struct crs_side<FpOps> {
+  static const g1_aff* key(const crs_dev* c) { return &c->u[0][0]; }
+  static const g1_aff* w(const crs_dev* c) { return &c->w1[0]; }
+};
+template <>
+struct crs_side<Fp2Ops> {
+  static const g2_aff* key(const crs_dev* c) { return &c->v[0][0]; }
+  static const g2_aff* w(const crs_dev* c) { return &c->w2[0]; }
+};
+
+template <class F>
+void fixed_table_release(gs_ctx* ctx) {
+  gs_fixed_table<F>& T = table_of<F>(ctx);
+  if (T.t) cudaFree(T.t);
+  T.t = nullptr;
+  T.c = 0;
+}
+
+// T[w][d-1] = d * 2^(c w) * B for the six base coordinates (u1 u2 W1 / v1 v2 W2); c = 8 at CRS load
+// (L2-resident), c = 16 lazily for big batches.
+template <class F>
+int fixed_table_rebuild(gs_ctx* ctx, int c) {
+  gs_fixed_table<F>& T = table_of<F>(ctx);
+  fixed_table_release<F>(ctx);
+  T.c = c;
+  T.W = (256 + c - 1) / c;
+  T.H = (size_t)1 << (c - 1);
+  size_t n = (size_t)6 * T.W * T.H;
+  CUDA_TRY(cudaMalloc(&T.t, n * sizeof(Aff<F>)));
+  // the six base points: u[2][2] then w1[2]  (v[2][2] then w2[2])
+  Scratch sc(ctx);
+  Aff<F>* b;
+  CUDA_TRY(sc.alloc(&b, 6));
+  const Aff<F>* key = crs_side<F>::key(ctx->crs);
+  const Aff<F>* W = crs_side<F>::w(ctx->crs);
+  CUDA_TRY(cudaMemcpyAsync(b, key, 4 * sizeof(Aff<F>), cudaMemcpyDeviceToDevice, ctx->stream));
+  CUDA_TRY(cudaMemcpyAsync(b + 4, W, 2 * sizeof(Aff<F>), cudaMemcpyDeviceToDevice, ctx->stream));
+  LAUNCH_CFG((k_table_window_bases<F>), 6, 32, 0, b, T.t, T.c, T.W, T.H);
+  constexpr int RUN = 16;
+  size_t threads = (size_t)6 * T.W * ((T.H + RUN - 1) / RUN);
+  LAUNCH_CFG((k_table_fill<F, RUN>), threads, GS_TAB_NT, 0, T.t, T.W, T.H);
+  return GS_OK;
+}
+
+// out[i] = s0[i] Base0 + s1[i] Base1 (+ iota(addend[i]))    -- all four batch_commit_* variants
+template <class F>
+int batch_commit_impl(gs_ctx* ctx, size_t n, int base0, int base1, const gs_fr* s0, size_t s0_stride, const gs_fr* s1,
+                      size_t s1_stride, size_t nscal, const void* addend, void* out) {
+  if (!ctx || !s0 || !out) return GS_EARG;
+  if (!ctx->crs_loaded) FAIL(GS_EARG, "commit: no CRS loaded");
+  if (n == 0) return GS_OK;  // reference: empty input -> empty Commit (left_mul returns vec![])
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  // big batches amortise bigger windows: 16 windows of 16 bits instead of 32 of 8
+  gs_fixed_table<F>& T = table_of<F>(ctx);
+  int want_c = n >= 8192 ? 16 : 8;
+  if (T.c != want_c) {
+    int rc = fixed_table_rebuild<F>(ctx, want_c);
+    if (rc) return rc;
+  }
+  Scratch sc(ctx);
+  fr* ds;
+  Aff<F>* dadd = nullptr;
+  Aff<F>* dout;
+  CUDA_TRY(upload(ctx, sc, &ds, s0, nscal));
+  if (addend) CUDA_TRY(upload(ctx, sc, &dadd, addend, n));
+  CUDA_TRY(sc.alloc(&dout, 2 * n));
+  const fr* d0 = ds;
+  const fr* d1 = ds + ((const fr*)s1 - (const fr*)s0);
+  LAUNCH((k_fixed_commit<F>), 2 * n, T.t, T.c, T.W, T.H, base0, base1, d0, s0_stride,
+         d1, s1_stride, dadd, dout, n);
+  CUDA_TRY(cudaMemcpyAsync(out, dout, 2 * n * sizeof(Aff<F>), cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  return GS_OK;
+}
+
+// reduce rows of Jacobian terms in place (row i occupies terms[i*stride .. i*stride+cnt))
+template <class F>
+int reduce_rows(gs_ctx* ctx, Jac<F>* terms, size_t stride, size_t cnt, int rows) {
+  size_t cur = cnt;
+  while (cur > 1) {
+    size_t half = (cur + 1) / 2;
+    LAUNCH((k_jac_reduce_step<F>), half * rows, terms, stride, cur, half, rows);
+    cur = half;
+  }
+  return GS_OK;
+}
+
+// one proof element vector (pi: F = G2, theta: F = G1), see k_proof_finish
+template <class F>
+int proof_element(gs_ctx* ctx, Scratch& sc, int rows, bool group_typed, const fr* sv, const void* dconst, size_t nconst,
+                  const void* dvars, size_t nvars, int ncoef, const fr* coef, size_t coef_rs, const Aff<F>* key,
+                  const Aff<F>* W, const fr* e, Aff<F>* dout) {
+  size_t nt = nconst + nvars;
+  if (group_typed) {
+    Jac<F>* terms;
+    CUDA_TRY(sc.alloc(&terms, nt * rows));
+    LAUNCH((k_msm_terms<F>), nt * rows, terms, sv, (const Aff<F>*)dconst, nconst, (const Aff<F>*)dvars, nvars, rows);
+    int rc = reduce_rows<F>(ctx, terms, nt, nt, rows);
+    if (rc) return rc;
+    LAUNCH((k_proof_finish<F>), (size_t)rows * 2, dout, rows, ncoef, coef, coef_rs, (size_t)1, key, terms, nt, (const fr*)nullptr,
+           (const Aff<F>*)nullptr);
+  } else {
+    // scalar-typed side: the caller collapsed the terms into e_i = <sv_i, (consts | vars)> (k_fr_dot, prover.cu)
+    LAUNCH((k_proof_finish<F>), (size_t)rows * 2, dout, rows, ncoef, coef, coef_rs, (size_t)1, key, (const Jac<F>*)nullptr,
+           (size_t)0, e, W);
+  }
+  return GS_OK;
+}
+
+template <class F>
+int com_matmul_impl(gs_ctx* ctx, size_t r, size_t k, size_t c, const gs_fr* lhs, const void* mat, void* out) {
+  if (!ctx || !lhs || !mat || !out) return GS_EARG;
+  // reference: empty operands give an empty matrix (data_structures.rs:697-702)
+  if (r == 0 || k == 0 || c == 0) return GS_OK;
+  if (r * c * k > ((size_t)1 << 26)) FAIL(GS_EDIM, "matmul: too large");
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  Scratch sc(ctx);
+  fr* dl;
+  Aff<F>*dm, *dout;
+  Jac<F>* terms;
+  CUDA_TRY(upload(ctx, sc, &dl, lhs, r * k));
+  CUDA_TRY(upload(ctx, sc, &dm, mat, k * c * 2));
+  CUDA_TRY(sc.alloc(&dout, r * c * 2));
+  CUDA_TRY(sc.alloc(&terms, r * c * 2 * k));
+  LAUNCH((k_com_matmul_terms<F>), r * c * 2 * k, terms, dl, dm, r, k, c);
+  int rc = reduce_rows<F>(ctx, terms, k, k, (int)(r * c * 2));
+  if (rc) return rc;
+  LAUNCH((k_jac_rows_to_affine<F>), r * c * 2, dout, terms, k, r * c * 2);
+  CUDA_TRY(cudaMemcpyAsync(out, dout, r * c * 2 * sizeof(Aff<F>), cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  return GS_OK;
+}
+
+
+}  // namespace gsi

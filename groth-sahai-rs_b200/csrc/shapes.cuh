@@ -1,0 +1,63 @@
+// Host/device shared plain-data descriptions: device copy of the CRS, verify slot bookkeeping.
+#pragma once
+#include "curve.cuh"
+
+namespace gs {
+
+struct crs_dev {  // device copy of the key + derived constants  (generator.rs:36-42)
+  g1_aff u[2][2];      // u[k][a]
+  g2_aff v[2][2];      // v[k][b]
+  g1_aff w1[2];        // W1 = u2 + (O, g1)       data_structures.rs:325
+  g2_aff w2[2];        // W2 = v2 + (O, g2)       data_structures.rs:370
+  g1_aff neg_u[2][2];  // -u[k][a]
+  g1_aff neg_w1[2];
+  g1_aff g1;
+  g2_aff g2;
+};
+
+struct verify_shape {  // slot bookkeeping shared by host and device
+  int type, m, n;
+  int groupA, groupB;  // 1: constants are group elements (iota), 0: scalars (iota')
+  int cx, cy;
+  int sB, nB, sPi, sTh, sT, K;
+  int n_out;    // MSM outputs per problem: n (+1 scalar-B) (+1 Quad target)
+  int nbases;   // m (+1 when A is scalar: W1 is an extra base)
+  int nchunk;   // MSM base chunks
+};
+constexpr int GS_MSM_CHUNK = 16;
+
+inline verify_shape make_verify_shape(int type, int m, int n) {
+  verify_shape s;
+  s.type = type;
+  s.m = m;
+  s.n = n;
+  s.groupA = (type == 0 || type == 1);
+  s.groupB = (type == 0 || type == 2);
+  s.cx = s.groupA ? 2 : 1;  // x-variables (and A) are G1 for PPE / MSMEG1  => R is m x 2, |pi| = 2
+  s.cy = s.groupB ? 2 : 1;  // y-variables (and B) are G2 for PPE / MSMEG2  => S is n x 2, |theta| = 2
+  s.sB = n;
+  s.nB = s.groupB ? m : 1;
+  s.sPi = s.sB + s.nB;
+  s.sTh = s.sPi + s.cx;
+  s.sT = s.sTh + s.cy;
+  s.K = s.sT + (type == 0 ? 0 : 1);
+  s.n_out = n + (s.groupB ? 0 : 1) + (type == 3 ? 1 : 0);
+  s.nbases = m + (s.groupA ? 0 : 1);
+  s.nchunk = (s.nbases + GS_MSM_CHUNK - 1) / GS_MSM_CHUNK;
+  return s;
+}
+
+struct verify_args {
+  const void* a_consts;  // [p][n]  g1_aff | fr
+  const void* b_consts;  // [p][m]  g2_aff | fr
+  const fr* gamma;       // [p][m][n]
+  const void* target;    // [p]     fp12 | g1_aff | g2_aff | fr
+  const g1_aff* xcoms;   // [p][m][2]
+  const g2_aff* ycoms;   // [p][n][2]
+  const g2_aff* pi;      // [p][cx][2]
+  const g1_aff* theta;   // [p][cy][2]
+};
+
+constexpr int GS_VTAB = 8;  // multiples 1B..8B per base in the verify-side Straus tables
+
+}  // namespace gs

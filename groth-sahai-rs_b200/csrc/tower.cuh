@@ -27,7 +27,7 @@ GS_HD GS_INL void fp_one(fp& r) {
 }
 
 // a^(p-2) by 4-bit fixed windows (380 squarings + ~110 products); a = 0 -> 0.
-GS_HD GS_NOINL void fp_inv(fp& r, const fp& a) {
+inline GS_HD GS_NOINL void fp_inv(fp& r, const fp& a) {
   fp tab[16];
   fp_one(tab[0]);
   tab[1] = a;

@@ -1,0 +1,315 @@
+// Verifiable::verify for the four equation types (src/verifier.rs:23-157): slot assembly, the G1-side
+// statement MSM (re-association of verifier.rs:39-42), then the pairing-product pipeline.
+#include "batchinv.cuh"
+#include "ctx.h"
+
+using namespace gs;
+
+namespace gs {
+
+// ------------------------------------------------------------------ verify: slot assembly
+// thread -> (p, k): fills every slot that is a plain copy / negation.  X slots [0,n), the scalar-B
+// slot and the Quad target slot are written later by k_vmsm_reduce.
+__global__ void k_verify_assemble(verify_shape s, verify_args v, const crs_dev* __restrict__ crs, g1_aff* __restrict__ X,
+                                  g2_aff* __restrict__ Y, size_t nprob) {
+  size_t id = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (id >= nprob * (size_t)s.K) return;
+  size_t p = id % nprob;
+  int k = (int)(id / nprob);
+  const int K = s.K;
+  g1_aff x0, x1;
+  g2_aff y0, y1;
+  bool writeX = true;
+  if (k < s.n) {  // (P_j, d_j)
+    writeX = false;
+    y0 = v.ycoms[(p * s.n + k) * 2 + 0];
+    y1 = v.ycoms[(p * s.n + k) * 2 + 1];
+  } else if (k < s.sPi) {
+    if (s.groupB) {  // (c_i, (O, B_i))
+      int i = k - s.sB;
+      x0 = v.xcoms[(p * s.m + i) * 2 + 0];
+      x1 = v.xcoms[(p * s.m + i) * 2 + 1];
+      y0.set_inf();
+      y1 = ((const g2_aff*)v.b_consts)[p * s.m + i];
+    } else {  // (sum_i b_i c_i, W2)
+      writeX = false;
+      y0 = crs->w2[0];
+      y1 = crs->w2[1];
+    }
+  } else if (k < s.sTh) {  // (-u_k, pi_k)
+    int j = k - s.sPi;
+    x0 = crs->neg_u[j][0];
+    x1 = crs->neg_u[j][1];
+    y0 = v.pi[(p * s.cx + j) * 2 + 0];
+    y1 = v.pi[(p * s.cx + j) * 2 + 1];
+  } else if (k < s.sT) {  // (-theta_k, v_k)
+    int j = k - s.sTh;
+    x0 = v.theta[(p * s.cy + j) * 2 + 0];
+    x1 = v.theta[(p * s.cy + j) * 2 + 1];
+    fp::neg(x0.y, x0.y);
+    fp::neg(x1.y, x1.y);
+    y0 = crs->v[j][0];
+    y1 = crs->v[j][1];
+  } else {  // target slot
+    if (s.type == 1) {  // (-(O, t), W2)
+      x0.set_inf();
+      x1 = ((const g1_aff*)v.target)[p];
+      fp::neg(x1.y, x1.y);
+      y0 = crs->w2[0];
+      y1 = crs->w2[1];
+    } else if (s.type == 2) {  // (-W1, (O, t))
+      x0 = crs->neg_w1[0];
+      x1 = crs->neg_w1[1];
+      y0.set_inf();
+      y1 = ((const g2_aff*)v.target)[p];
+    } else {  // Quad: (-(t W1), W2)
+      writeX = false;
+      y0 = crs->w2[0];
+      y1 = crs->w2[1];
+    }
+  }
+  if (writeX) {
+    X[((size_t)0 * K + k) * nprob + p] = x0;
+    X[((size_t)1 * K + k) * nprob + p] = x1;
+  }
+  Y[((size_t)0 * K + k) * nprob + p] = y0;
+  Y[((size_t)1 * K + k) * nprob + p] = y1;
+}
+
+// ------------------------------------------------------------------ verify: G1-side statement MSM (v2)
+// P_j = iota(A_j) + sum_i Gamma_ij c_i      (re-association of verifier.rs:39-42, SURVEY.md §8a ‡)
+// Signed 4-bit windows (Straus: the 4 doublings per window are shared by all bases of the chunk).
+// The odd/even multiples 1B..8B of every base are built ONCE per problem by k_vmsm_tables and shared by
+// all n outputs; v1's binary double-and-add left half the lanes of every addition idle.
+// base index i of problem p, coordinate a:  i < m -> xcoms[p][i].a ;  i == m (scalar A) -> W1.a
+__device__ GS_INL g1_aff vmsm_base(const verify_shape& s, const verify_args& v, const crs_dev* crs, size_t p, int i, int a) {
+  if (i < s.m) return v.xcoms[(p * s.m + i) * 2 + a];
+  return crs->w1[a];
+}
+// thread -> (p, i, a): tab[((i*2 + a)*8 + d) * nprob + p] = (d+1) * base
+__global__ void __launch_bounds__(128) k_vmsm_tables(verify_shape s, verify_args v, const crs_dev* __restrict__ crs,
+                                                     g1_aff* __restrict__ tab, size_t nprob) {
+  __shared__ fp sm[2 * 128];
+  size_t id = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  bool active = id < nprob * (size_t)s.nbases * 2;
+  size_t p = active ? id % nprob : 0;
+  size_t r = active ? id / nprob : 0;
+  int a = (int)(r & 1), i = (int)(r >> 1);
+  g1_aff B;
+  B.set_inf();
+  if (active) B = vmsm_base(s, v, crs, p, i, a);
+  g1_jac acc;
+  acc.from_affine(B);
+  g1_aff* out = tab + ((size_t)(i * 2 + a) * GS_VTAB) * nprob + p;
+  for (int d = 0; d < GS_VTAB; d++) {
+    if (d == 1) g1_jac::dbl(acc, acc);
+    if (d > 1) g1_jac::add_mixed(acc, acc, B);
+    g1_aff e;
+    block_to_affine<128>(e, acc, sm);
+    if (active) out[(size_t)d * nprob] = e;
+  }
+}
+
+// thread -> (p, jj, a, chunk)
+__global__ void __launch_bounds__(128) k_vmsm_partial(verify_shape s, verify_args v, const g1_aff* __restrict__ tab,
+                                                      g1_jac* __restrict__ part, size_t nprob) {
+  size_t id = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t total = nprob * (size_t)s.n_out * 2 * s.nchunk;
+  if (id >= total) return;
+  size_t p = id % nprob;
+  size_t r = id / nprob;
+  int a = (int)(r & 1);
+  r >>= 1;
+  int jj = (int)(r % s.n_out);
+  int ch = (int)(r / s.n_out);
+
+  // biased scalars k' = k + 0x88..8 (64 nibbles): digit_w = nibble_w(k') - 8 in [-8, 7], no carries
+  uint32_t sc[GS_MSM_CHUNK][9];
+  int bidx[GS_MSM_CHUNK];
+  int cnt = 0;
+  int i0 = ch * GS_MSM_CHUNK, i1 = min(s.nbases, i0 + GS_MSM_CHUNK);
+  for (int i = i0; i < i1; i++) {
+    fr sv;
+    bool have = false;
+    if (jj < s.n) {
+      if (i < s.m) {
+        sv = v.gamma[(p * s.m + i) * s.n + jj];
+        have = true;
+      } else {  // scalar A: extra base W1 with scalar a_j
+        sv = ((const fr*)v.a_consts)[p * s.n + jj];
+        have = true;
+      }
+    } else if (jj == s.n && !s.groupB) {  // C_B = sum_i b_i c_i
+      if (i < s.m) {
+        sv = ((const fr*)v.b_consts)[p * s.m + i];
+        have = true;
+      }
+    } else {  // Quad target: t * W1  (W1 is base index m)
+      if (i == s.m) {
+        sv = ((const fr*)v.target)[p];
+        have = true;
+      }
+    }
+    if (!have || sv.is_zero()) continue;
+    uint32_t k[8];
+    fr_from_mont(k, sv);
+    uint32_t carry = 0;
+#pragma unroll
+    for (int w = 0; w < 8; w++) {
+      uint64_t t = (uint64_t)k[w] + 0x88888888u + carry;
+      sc[cnt][w] = (uint32_t)t;
+      carry = (uint32_t)(t >> 32);
+    }
+    sc[cnt][8] = carry;
+    bidx[cnt] = i;
+    cnt++;
+  }
+  g1_jac acc;
+  acc.set_inf();
+  if (cnt > 0) {
+    for (int w = 64; w >= 0; w--) {
+      if (w != 64) {
+        g1_jac::dbl(acc, acc);
+        g1_jac::dbl(acc, acc);
+        g1_jac::dbl(acc, acc);
+        g1_jac::dbl(acc, acc);
+      }
+      for (int i = 0; i < cnt; i++) {
+        int d = (int)((sc[i][w >> 3] >> ((w & 7) * 4)) & 15u) - (w == 64 ? 0 : 8);
+        if (d == 0) continue;
+        int mag = d < 0 ? -d : d;
+        g1_aff e = tab[((size_t)(bidx[i] * 2 + a) * GS_VTAB + (mag - 1)) * nprob + p];
+        if (d < 0) fp::neg(e.y, e.y);
+        g1_jac::add_mixed(acc, acc, e);
+      }
+    }
+  }
+  part[(((size_t)ch * s.n_out + jj) * 2 + a) * nprob + p] = acc;
+}
+
+// thread -> (p, jj, a): sum the chunk partials, add iota_1(A_j), negate the Quad target, normalise, write slot
+__global__ void __launch_bounds__(128) k_vmsm_reduce(verify_shape s, verify_args v, const g1_jac* __restrict__ part,
+                                                     g1_aff* __restrict__ X, size_t nprob) {
+  __shared__ fp sm[2 * 128];
+  size_t id = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  bool active = id < nprob * (size_t)s.n_out * 2;
+  size_t p = active ? id % nprob : 0;
+  size_t r = active ? id / nprob : 0;
+  int a = (int)(r & 1);
+  int jj = (int)(r >> 1);
+  g1_jac acc;
+  acc.set_inf();
+  int slot = 0;
+  if (active) {
+    acc = part[((size_t)jj * 2 + a) * nprob + p];
+    for (int ch = 1; ch < s.nchunk; ch++) {
+      g1_jac t = part[(((size_t)ch * s.n_out + jj) * 2 + a) * nprob + p];
+      g1_jac::add(acc, acc, t);
+    }
+    if (jj < s.n) {
+      slot = jj;
+      if (s.groupA && a == 1) {
+        g1_aff A = ((const g1_aff*)v.a_consts)[p * s.n + jj];
+        g1_jac::add_mixed(acc, acc, A);
+      }
+    } else if (jj == s.n && !s.groupB) {
+      slot = s.sB;
+    } else {
+      slot = s.sT;
+      g1_jac::neg(acc, acc);
+    }
+  }
+  g1_aff out;
+  block_to_affine<128>(out, acc, sm);
+  if (active) X[((size_t)a * s.K + slot) * nprob + p] = out;
+}
+
+__global__ void k_and4(const uint8_t* __restrict__ ok4, uint8_t* __restrict__ out, size_t nprob) {
+  size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= nprob) return;
+  out[p] = ok4[p] & ok4[nprob + p] & ok4[2 * nprob + p] & ok4[3 * nprob + p];
+}
+
+}  // namespace gs
+
+extern "C" {
+
+int gs_verify_batch_dev(gs_ctx* ctx, int type, size_t count, size_t m, size_t n, const void* a_consts,
+                        const void* b_consts, const gs_fr* gamma, const void* target, const gs_com1* xcoms,
+                        const gs_com2* ycoms, const gs_com2* pi, const gs_com1* theta, uint8_t* out_ok_dev) {
+  if (!ctx) return GS_EARG;
+  if (type < 0 || type > 3) FAIL(GS_EARG, "verify: bad equation type");
+  if (!ctx->crs_loaded) FAIL(GS_EARG, "verify: no CRS loaded");
+  if (count == 0) return GS_OK;
+  // the reference panics on empty variable lists: keep it an error
+  if (m == 0 || n == 0) FAIL(GS_EDIM, "verify: empty variable list");
+  if (m > 1 << 20 || n > 1 << 20) FAIL(GS_EDIM, "verify: too many variables");
+  if (!a_consts || !b_consts || !gamma || !target || !xcoms || !ycoms || !pi || !theta || !out_ok_dev) return GS_EARG;
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  verify_shape s = make_verify_shape(type, (int)m, (int)n);
+  for (size_t off = 0; off < count; off += ctx->verify_batch_max) {
+    size_t nprob = count - off < ctx->verify_batch_max ? count - off : ctx->verify_batch_max;
+    Scratch sc(ctx);
+    verify_args v;
+    v.a_consts = (const char*)a_consts + off * n * elem_size_A(type);
+    v.b_consts = (const char*)b_consts + off * m * elem_size_B(type);
+    v.gamma = (const fr*)gamma + off * m * n;
+    v.target = (const char*)target + off * elem_size_T(type);
+    v.xcoms = (const g1_aff*)xcoms + off * m * 2;
+    v.ycoms = (const g2_aff*)ycoms + off * n * 2;
+    v.pi = (const g2_aff*)pi + off * s.cx * 2;
+    v.theta = (const g1_aff*)theta + off * s.cy * 2;
+    g1_aff* X;
+    g2_aff* Y;
+    g1_jac* part;
+    uint8_t* ok4;
+    CUDA_TRY(sc.alloc(&X, 2 * (size_t)s.K * nprob));
+    CUDA_TRY(sc.alloc(&Y, 2 * (size_t)s.K * nprob));
+    CUDA_TRY(sc.alloc(&part, (size_t)s.nchunk * s.n_out * 2 * nprob));
+    CUDA_TRY(sc.alloc(&ok4, 4 * nprob));
+    LAUNCH(k_verify_assemble, nprob * (size_t)s.K, s, v, ctx->crs, X, Y, nprob);
+    g1_aff* vtab;
+    CUDA_TRY(sc.alloc(&vtab, (size_t)s.nbases * 2 * GS_VTAB * nprob));
+    LAUNCH(k_vmsm_tables, nprob * (size_t)s.nbases * 2, s, v, ctx->crs, vtab, nprob);
+    LAUNCH(k_vmsm_partial, nprob * (size_t)s.n_out * 2 * s.nchunk, s, v, vtab, part, nprob);
+    LAUNCH(k_vmsm_reduce, nprob * (size_t)s.n_out * 2, s, v, part, X, nprob);
+    int rc = gsi::run_pairing_product(ctx, sc, X, Y, nprob, s.K, nullptr, ok4, type == GS_PPE ? (const fp12*)v.target : nullptr);
+    if (rc) return rc;
+    LAUNCH(k_and4, nprob, ok4, out_ok_dev + off, nprob);
+  }
+  return GS_OK;
+}
+
+int gs_verify_batch(gs_ctx* ctx, int type, size_t count, size_t m, size_t n, const void* a_consts,
+                    const void* b_consts, const gs_fr* gamma, const void* target, const gs_com1* xcoms,
+                    const gs_com2* ycoms, const gs_com2* pi, const gs_com1* theta, uint8_t* out_ok) {
+  if (!ctx) return GS_EARG;
+  if (type < 0 || type > 3) FAIL(GS_EARG, "verify: bad equation type");
+  if (count == 0) return GS_OK;
+  if (m == 0 || n == 0) FAIL(GS_EDIM, "verify: empty variable list");
+  if (!a_consts || !b_consts || !gamma || !target || !xcoms || !ycoms || !pi || !theta || !out_ok) return GS_EARG;
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  verify_shape s = make_verify_shape(type, (int)m, (int)n);
+  Scratch sc(ctx);
+  uint8_t *dA, *dB, *dT, *dok;
+  fr* dG;
+  g1_aff *dc, *dth;
+  g2_aff *dd, *dpi;
+  CUDA_TRY(upload(ctx, sc, &dA, a_consts, count * n * elem_size_A(type)));
+  CUDA_TRY(upload(ctx, sc, &dB, b_consts, count * m * elem_size_B(type)));
+  CUDA_TRY(upload(ctx, sc, &dG, gamma, count * m * n));
+  CUDA_TRY(upload(ctx, sc, &dT, target, count * elem_size_T(type)));
+  CUDA_TRY(upload(ctx, sc, &dc, xcoms, count * m * 2));
+  CUDA_TRY(upload(ctx, sc, &dd, ycoms, count * n * 2));
+  CUDA_TRY(upload(ctx, sc, &dpi, pi, count * s.cx * 2));
+  CUDA_TRY(upload(ctx, sc, &dth, theta, count * s.cy * 2));
+  CUDA_TRY(sc.alloc(&dok, count));
+  int rc = gs_verify_batch_dev(ctx, type, count, m, n, dA, dB, (const gs_fr*)dG, dT, (const gs_com1*)dc,
+                               (const gs_com2*)dd, (const gs_com2*)dpi, (const gs_com1*)dth, dok);
+  if (rc) return rc;
+  CUDA_TRY(cudaMemcpyAsync(out_ok, dok, count, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  return GS_OK;
+}
+
+}  // extern "C"

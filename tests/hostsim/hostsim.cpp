@@ -10,6 +10,13 @@ using namespace gs;
 #define ST(p, v) memcpy(p, &v, sizeof(v))
 extern "C" {
 void hs_fp_mul(void* r, const void* a, const void* b) { LD(fp, x, a); LD(fp, y, b); fp z; fp::mul(z, x, y); ST(r, z); }
+// mulsum: nt in {1,2,3,4,6,8}; a, b arrays of nt fp
+void hs_fp_mulsum(void* r, int nt, const void* a, const void* b) {
+  const fp* A = (const fp*)a; const fp* B = (const fp*)b; fp z;
+#define MS(NT) case NT: { fp x[NT], y[NT]; for (int i = 0; i < NT; i++) { x[i] = A[i]; y[i] = B[i]; } fp::mulsum<NT>(z, x, y); } break;
+  switch (nt) { MS(1) MS(2) MS(3) MS(4) MS(6) MS(8) default: z.set_zero(); }
+#undef MS
+  ST(r, z); }
 void hs_fp_add(void* r, const void* a, const void* b) { LD(fp, x, a); LD(fp, y, b); fp z; fp::add(z, x, y); ST(r, z); }
 void hs_fp_sub(void* r, const void* a, const void* b) { LD(fp, x, a); LD(fp, y, b); fp z; fp::sub(z, x, y); ST(r, z); }
 void hs_fp_neg(void* r, const void* a) { LD(fp, x, a); fp z; fp::neg(z, x); ST(r, z); }

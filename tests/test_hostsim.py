@@ -44,6 +44,31 @@ def test_fp_ops(L):
     assert fp_i(call(L.hs_fp_inv, 48, fp_b(0))) == 0
 
 
+def test_fp_mulsum(L):
+    """lazy reduction: sum of up to 8 products with one interleaved Montgomery reduction (fp.cuh mulsum)"""
+    Rm = pow(2, 384, P)
+    mont = lambda x: x * Rm % P
+    def raw(x): return x.to_bytes(48, "little")
+    for nt in (1, 2, 3, 4, 6, 8):
+        for it in range(300):
+            if it < 20:
+                a = [P - 1] * nt; b = [P - 1] * nt           # worst case for the running bound
+            else:
+                a = [rfp() for _ in range(nt)]; b = [rfp() for _ in range(nt)]
+            got = fp_i(call(L.hs_fp_mulsum, 48, nt, b"".join(fp_b(x) for x in a), b"".join(fp_b(x) for x in b)))
+            assert got == sum(x * y for x, y in zip(a, b)) % P, (nt, it)
+    # operands that are unreduced sums (< 2p) count two units: 3 terms x 2 units
+    for it in range(200):
+        a = [rfp() for _ in range(3)]; b = [(rfp(), rfp()) for _ in range(3)]
+        if it < 10:
+            a = [P - 1] * 3; b = [(P - 1, P - 1)] * 3
+        # pass the raw limb patterns: mont(a), mont(b0)+mont(b1) unreduced
+        ab = b"".join(raw(mont(x)) for x in a)
+        bb = b"".join(raw(mont(x) + mont(y)) for x, y in b)
+        got = fp_i(call(L.hs_fp_mulsum, 48, 3, ab, bb))
+        assert got == sum(x * (y + z) for x, (y, z) in zip(a, b)) % P
+
+
 def test_fr_ops(L):
     edge = [0, 1, R - 1, 2 ** 254]
     for it in range(3000):
