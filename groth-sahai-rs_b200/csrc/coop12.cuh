@@ -1,0 +1,213 @@
+// Cooperative Fp12 arithmetic: ONE WARP PER w-POWER COEFFICIENT, ONE LANE PER ACCUMULATOR.
+//
+// A block of 6 warps (192 threads) owns 32 independent Fp12 values  f = sum_{k<6} a_k w^k  (a_k in Fp2,
+// w^6 = xi = 1 + u; a_0=c0.c0, a_1=c1.c0, a_2=c0.c1, a_3=c1.c1, a_4=c0.c2, a_5=c1.c2 of the tower form).
+// Warp k computes output coefficient k of all 32 values, so every k-dependent decision (which inputs,
+// where xi is applied) is warp-uniform and all 32 lanes stay busy.  The values live in SHARED memory in
+// the "Q layout" (below); each output coefficient is produced as a SUM OF Fp2 PRODUCTS with lazy reduction:
+//     r.c0 = sum_t ( Y_t.c0 * X_t.c0 - Y_t.c1 * X_t.c1 )        one interleaved Montgomery reduction
+//     r.c1 = sum_t ( Y_t.c0 * X_t.c1 + Y_t.c1 * X_t.c0 )        per Fp component (fp.cuh rowsum_l)
+// with the Y operands held in registers (2 x 12 limbs per term) and the X operands streamed limb-quad by
+// limb-quad out of shared memory (LDS.128, conflict free).  No temporaries outside registers, no local memory.
+//
+// Every op reads one accumulator buffer and writes another one (ping-pong), so a single block barrier per op
+// is enough.  The functions are plain (k, lane) functions over word arrays so that tests/hostsim can run the
+// identical code on the CPU by looping over (k, lane) between "barriers".
+//
+// Replaces: ark-ff Fp12 multiplication / squaring / sparse line multiplication underneath
+// E::multi_miller_loop and E::final_exponentiation (reference call sites src/data_structures.rs:484-502).
+#pragma once
+#include "tower.cuh"
+
+namespace gs {
+
+constexpr int CQ_LANES = 32;
+constexpr int CQ_QUAD = 4 * CQ_LANES;  // words per limb-quad of one Fp over the 32 lanes
+constexpr int CQ_FP = 12 * CQ_LANES;   // words per Fp over the 32 lanes: [quad 0..2][lane][4]
+constexpr int CQ_ACC = 12 * CQ_FP;     // one Fp12 accumulator set: Fp index = 2*coef + component
+
+struct alignas(16) q4 {
+  uint32_t v[4];
+};
+
+// pointer to quad 0 of Fp number `idx` of lane `lane`
+GS_HD GS_INL const uint32_t* cq_ptr(const uint32_t* base, int idx, int lane) { return base + idx * CQ_FP + lane * 4; }
+GS_HD GS_INL uint32_t* cq_ptr(uint32_t* base, int idx, int lane) { return base + idx * CQ_FP + lane * 4; }
+
+GS_HD GS_INL void cq_ld(fp& r, const uint32_t* p) {
+#pragma unroll
+  for (int q = 0; q < 3; q++) {
+    q4 t = *(const q4*)(p + q * CQ_QUAD);
+#pragma unroll
+    for (int i = 0; i < 4; i++) r.l[q * 4 + i] = t.v[i];
+  }
+}
+GS_HD GS_INL void cq_st(uint32_t* p, const fp& a) {
+#pragma unroll
+  for (int q = 0; q < 3; q++) {
+    q4 t;
+#pragma unroll
+    for (int i = 0; i < 4; i++) t.v[i] = a.l[q * 4 + i];
+    *(q4*)(p + q * CQ_QUAD) = t;
+  }
+}
+
+// r = (sum_t a[t] * B_t) / R mod p, B_t streamed from the Q layout (b[t] = pointer to quad 0 of this lane)
+template <int NT>
+GS_HD GS_INL void mulsum_q(fp& r, const fp (&a)[NT], const uint32_t* const (&b)[NT]) {
+  uint32_t E[12], O[12];
+#pragma unroll
+  for (int q = 0; q < 3; q++) {
+    q4 bl[NT];
+#pragma unroll
+    for (int t = 0; t < NT; t++) bl[t] = *(const q4*)(b[t] + q * CQ_QUAD);
+#pragma unroll
+    for (int ii = 0; ii < 4; ii++) {
+      uint32_t lim[NT];
+#pragma unroll
+      for (int t = 0; t < NT; t++) lim[t] = bl[t].v[ii];
+      if ((ii & 1) == 0)
+        fp::rowsum_l<NT>(E, O, a, lim, q == 0 && ii == 0);
+      else
+        fp::rowsum_l<NT>(O, E, a, lim, false);
+    }
+  }
+  fp::mulsum_finish(r, E, O);
+}
+
+// r = sum_{t<NT} Y_t * X_t in Fp2.  y[2t], y[2t+1] = Y_t.c0, Y_t.c1 in registers (y[2t+1] is NEGATED on
+// return); x0[t], x1[t] = Q-layout pointers of X_t.c0, X_t.c1.  All operands canonical; 2*NT <= 8.
+template <int NT>
+GS_HD GS_INL void cq_fp2_dot(fp2& r, fp (&y)[2 * NT], const uint32_t* const (&x0)[NT], const uint32_t* const (&x1)[NT]) {
+  const uint32_t* b[2 * NT];
+#pragma unroll
+  for (int t = 0; t < NT; t++) {
+    b[2 * t] = x1[t];
+    b[2 * t + 1] = x0[t];
+  }
+  mulsum_q<2 * NT>(r.c1, y, b);
+#pragma unroll
+  for (int t = 0; t < NT; t++) {
+    fp::neg(y[2 * t + 1], y[2 * t + 1]);
+    b[2 * t] = x0[t];
+    b[2 * t + 1] = x1[t];
+  }
+  mulsum_q<2 * NT>(r.c0, y, b);
+}
+
+// load coefficient j of the accumulator set `f` into (y0, y1), optionally times xi and/or 2
+GS_HD GS_INL void cq_ld_coef(fp& y0, fp& y1, const uint32_t* f, int j, int lane, bool xi, bool dbl) {
+  cq_ld(y0, cq_ptr(f, 2 * j, lane));
+  cq_ld(y1, cq_ptr(f, 2 * j + 1, lane));
+  if (xi) {
+    fp t0, t1;
+    fp::sub(t0, y0, y1);
+    fp::add(t1, y0, y1);
+    y0 = t0;
+    y1 = t1;
+  }
+  if (dbl) {
+    fp::add(y0, y0, y0);
+    fp::add(y1, y1, y1);
+  }
+}
+GS_HD GS_INL void cq_st_coef(uint32_t* f, int k, int lane, const fp2& r) {
+  cq_st(cq_ptr(f, 2 * k, lane), r.c0);
+  cq_st(cq_ptr(f, 2 * k + 1, lane), r.c1);
+}
+
+// ------------------------------------------------------------------ sparse line multiplication
+// fout.a_k = alpha a_k + beta a_{k-2} + gamma a_{k-3}   (indices mod 6, times xi on wrap-around), i.e.
+// f * (alpha + beta w^2 + gamma w^3): the M-twist line  (= ark-ff mul_by_014 in the w basis).
+// `tile` holds alpha.c0, alpha.c1, beta.c0, beta.c1, gamma.c0, gamma.c1 (6 Fp, Q layout).
+// !active lanes copy their coefficient through unchanged (pair dropped: identity on either side).
+GS_HD GS_INL void cq_line_mul(int k, int lane, const uint32_t* fin, uint32_t* fout, const uint32_t* tile, bool active) {
+  fp y[6];
+  const int j1 = k >= 2 ? k - 2 : k + 4, j2 = k >= 3 ? k - 3 : k + 3;
+  cq_ld_coef(y[0], y[1], fin, k, lane, false, false);
+  cq_ld_coef(y[2], y[3], fin, j1, lane, k < 2, false);
+  cq_ld_coef(y[4], y[5], fin, j2, lane, k < 3, false);
+  const uint32_t* x0[3] = {cq_ptr(tile, 0, lane), cq_ptr(tile, 2, lane), cq_ptr(tile, 4, lane)};
+  const uint32_t* x1[3] = {cq_ptr(tile, 1, lane), cq_ptr(tile, 3, lane), cq_ptr(tile, 5, lane)};
+  fp2 r;
+  cq_fp2_dot<3>(r, y, x0, x1);
+  if (!active) cq_ld_coef(r.c0, r.c1, fin, k, lane, false, false);
+  cq_st_coef(fout, k, lane, r);
+}
+
+// ------------------------------------------------------------------ squaring
+// fout = fin^2:  b_k = sum_{i<=j, i+j = k mod 6} c_ij a_i a_j,  c_ij = (i<j ? 2 : 1) * (i+j >= 6 ? xi : 1).
+// Even k have 4 terms (2 doubled pairs + 2 squares), odd k have 3 doubled pairs; two passes of <= 2 terms.
+GS_HD GS_INL void cq_sqr(int k, int lane, const uint32_t* fin, uint32_t* fout) {
+  int ti[4], tj[4], nt = 0;
+  for (int i = 0; i < 6; i++) {
+    int j = (k - i + 6) % 6;
+    if (i <= j) {
+      ti[nt] = i;
+      tj[nt] = j;
+      nt++;
+    }
+  }
+  fp2 r, r2;
+  {
+    fp y[4];
+    cq_ld_coef(y[0], y[1], fin, tj[0], lane, ti[0] + tj[0] >= 6, ti[0] < tj[0]);
+    cq_ld_coef(y[2], y[3], fin, tj[1], lane, ti[1] + tj[1] >= 6, ti[1] < tj[1]);
+    const uint32_t* x0[2] = {cq_ptr(fin, 2 * ti[0], lane), cq_ptr(fin, 2 * ti[1], lane)};
+    const uint32_t* x1[2] = {cq_ptr(fin, 2 * ti[0] + 1, lane), cq_ptr(fin, 2 * ti[1] + 1, lane)};
+    cq_fp2_dot<2>(r, y, x0, x1);
+  }
+  if (nt == 4) {
+    fp y[4];
+    cq_ld_coef(y[0], y[1], fin, tj[2], lane, ti[2] + tj[2] >= 6, ti[2] < tj[2]);
+    cq_ld_coef(y[2], y[3], fin, tj[3], lane, ti[3] + tj[3] >= 6, ti[3] < tj[3]);
+    const uint32_t* x0[2] = {cq_ptr(fin, 2 * ti[2], lane), cq_ptr(fin, 2 * ti[3], lane)};
+    const uint32_t* x1[2] = {cq_ptr(fin, 2 * ti[2] + 1, lane), cq_ptr(fin, 2 * ti[3] + 1, lane)};
+    cq_fp2_dot<2>(r2, y, x0, x1);
+  } else {
+    fp y[2];
+    cq_ld_coef(y[0], y[1], fin, tj[2], lane, ti[2] + tj[2] >= 6, ti[2] < tj[2]);
+    const uint32_t* x0[1] = {cq_ptr(fin, 2 * ti[2], lane)};
+    const uint32_t* x1[1] = {cq_ptr(fin, 2 * ti[2] + 1, lane)};
+    cq_fp2_dot<1>(r2, y, x0, x1);
+  }
+  fp2::add(r, r, r2);
+  cq_st_coef(fout, k, lane, r);
+}
+
+// ------------------------------------------------------------------ general product
+// fout = f * g:  b_k = sum_i g_i f_{k-i}  (xi on wrap-around).  f on the register side, g streamed.
+GS_HD GS_INL void cq_mul(int k, int lane, const uint32_t* f, const uint32_t* g, uint32_t* fout) {
+  fp2 r, r2;
+#pragma unroll 1
+  for (int h = 0; h < 2; h++) {
+    fp y[6];
+    const uint32_t *x0[3], *x1[3];
+#pragma unroll
+    for (int t = 0; t < 3; t++) {
+      int i = h * 3 + t;
+      int j = (k - i + 6) % 6;
+      cq_ld_coef(y[2 * t], y[2 * t + 1], f, j, lane, i > k, false);
+      x0[t] = cq_ptr(g, 2 * i, lane);
+      x1[t] = cq_ptr(g, 2 * i + 1, lane);
+    }
+    if (h == 0)
+      cq_fp2_dot<3>(r, y, x0, x1);
+    else
+      cq_fp2_dot<3>(r2, y, x0, x1);
+  }
+  fp2::add(r, r, r2);
+  cq_st_coef(fout, k, lane, r);
+}
+
+// ------------------------------------------------------------------ constants / conversion
+GS_HD GS_INL void cq_set_one(int k, int lane, uint32_t* f) {
+  fp2 r;
+  r.set_zero();
+  if (k == 0) fp_one(r.c0);
+  cq_st_coef(f, k, lane, r);
+}
+// position (in Fp2 units) of w-basis coefficient k inside the tower-ordered fp12
+GS_HD GS_INL int cq_tower_pos(int k) { return (k & 1) * 3 + (k >> 1); }
+
+}  // namespace gs

@@ -291,6 +291,45 @@ struct Mont {
     cmad_row_mod<0>(E, m);
     O[N - 1] = addc(O[N - 1], 0u);
   }
+  // ---- the same interleaved sum of products with the b-side limbs supplied row by row (`bl[t]` = limb i of
+  // b[t]), so that the b operands can be streamed out of shared memory a quad at a time instead of being
+  // held in registers (coop12.cuh).  Row i uses rowsum_l(E, O, ...) for even i and rowsum_l(O, E, ...) for odd i;
+  // after the N rows mulsum_finish() produces the canonical value.
+  template <int NT>
+  GS_HD static GS_INL void rowsum_l(uint32_t* E, uint32_t* O, const Mont (&a)[NT], const uint32_t (&bl)[NT], bool first) {
+    if (first) {
+#pragma unroll
+      for (int j = 0; j < N; j += 2) {
+        E[j] = mul_lo(a[0].l[j], bl[0]);
+        E[j + 1] = mul_hi(a[0].l[j], bl[0]);
+        O[j] = mul_lo(a[0].l[j + 1], bl[0]);
+        O[j + 1] = mul_hi(a[0].l[j + 1], bl[0]);
+      }
+    } else {
+      E[0] = add_cc(E[0], O[1]);
+      madc_row_rshift(O, a[0].l + 1, bl[0]);
+      cmad_row(E, a[0].l, bl[0]);
+      O[N - 1] = addc(O[N - 1], 0u);
+    }
+#pragma unroll
+    for (int t = 1; t < NT; t++) {
+      cmad_row(O, a[t].l + 1, bl[t]);
+      cmad_row(E, a[t].l, bl[t]);
+      O[N - 1] = addc(O[N - 1], 0u);
+    }
+    uint32_t m = mul_lo(E[0], PR::M0);
+    cmad_row_mod<1>(O, m);
+    cmad_row_mod<0>(E, m);
+    O[N - 1] = addc(O[N - 1], 0u);
+  }
+  GS_HD static GS_INL void mulsum_finish(Mont& r, const uint32_t* E, const uint32_t* O) {
+    uint32_t t[N];
+    t[0] = add_cc(O[1], E[0]);
+#pragma unroll
+    for (int i = 1; i < N - 1; i++) t[i] = addc_cc(O[i + 1], E[i]);
+    t[N - 1] = addc(0u, E[N - 1]);
+    final_sub(r, t);
+  }
   // plain limb-wise sum without reduction (inputs < p, result < 2p): an operand for mulsum that counts 2 units
   GS_HD static GS_INL void add_noreduce(Mont& r, const Mont& a, const Mont& b) {
     r.l[0] = add_cc(a.l[0], b.l[0]);

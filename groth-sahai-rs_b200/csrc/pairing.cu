@@ -2,7 +2,8 @@
 // ComT entry points of the C ABI (ComT::pairing / pairing_sum / linear_map_*, E::pairing).
 // Reference: src/data_structures.rs:484-540, src/generator.rs:116.
 #include "ctx.h"
-#include "miller_v2.cuh"
+#include "coop12.cuh"
+#include "pairing.cuh"
 
 using namespace gs;
 
@@ -14,90 +15,162 @@ namespace gs {
 // Points are stored SoA over problems so that a warp (32 consecutive problems, same slot, same
 // coordinate) reads contiguous memory:
 //     X[(a*K + k) * nprob + p]   g1_aff        Y[(b*K + k) * nprob + p]   g2_aff
-//     L[(((b*K + k) * 68 + step) * 72 + w) * nprob + p]   32-bit word w of a line triple (k_g2_prepare)
 
-// ------------------------------------------------------------------ G2 preparation
-// one thread per G2 point q = (b*K + k) * nprob + p
-__global__ void __launch_bounds__(128) k_g2_prepare(const g2_aff* __restrict__ Y, uint32_t* __restrict__ L,
-                                                    uint8_t* __restrict__ yinf, size_t npoints, size_t nprob) {
+// ------------------------------------------------------------------ v3: evaluated line tiles + cooperative Miller
+// Accumulator index A = chunk * np + (p - p0) (chunk = slot range [chunk*S, chunk*S+S) of a big statement);
+// 32 consecutive accumulators of one ComT entry e = 2a+b form a block  bid = (A/32)*4 + e.
+// Tile (bid, kk, step): the line of slot kk at Miller step `step`, already evaluated at the G1 point of
+// entry e, as 6 Fp in the Q layout of coop12.cuh (alpha.c0 alpha.c1 beta.c0 beta.c1 gamma.c0 gamma.c1 =
+// c0, c1*xP, c2*yP), 9,216 B, contiguous: written by k_g2_prepare3 with 16-B stores (512 B per warp and
+// quad), copied into shared memory by k_miller3 with cp.async.
+//     tiles[((bid*S + kk)*68 + step) * M3_TILE ...]      masks[bid*S + kk] = lanes whose pair is not dropped
+constexpr int M3_NV = 6;
+constexpr int M3_TILE = M3_NV * CQ_FP;
+constexpr int M3_THREADS = 6 * CQ_LANES;
+constexpr int M3_MAXS = 512;
+constexpr int M3_SMEM = (2 * CQ_ACC + 2 * M3_TILE) * 4 + M3_MAXS * 6 + 16;
+
+// one thread per G2 point q = (b*K + k) * np + pl  (pl = p - p0)
+__global__ void __launch_bounds__(128) k_g2_prepare3(const g1_aff* __restrict__ X, const g2_aff* __restrict__ Y,
+                                                     uint32_t* __restrict__ tiles, uint32_t* __restrict__ masks,
+                                                     size_t nprob, size_t p0, size_t np, int K, int S) {
   size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (q >= npoints) return;
-  g2_aff pt = Y[q];
-  bool inf = pt.is_inf();
-  yinf[q] = inf ? 1 : 0;
-  if (inf) return;
-  size_t bk = q / nprob, p = q % nprob;
-  g2_prepare(L + (bk * GS_NUM_LINES * GS_LINE_WORDS) * nprob + p, nprob, pt);
-}
-
-// ------------------------------------------------------------------ Miller accumulation (v2)
-// thread -> (p, e = 2a+b, chunk);  F[(chunk*4 + e) * nprob + p] = conj( prod over its slots ).
-// The accumulator and the current line triple live in shared memory (miller_v2.cuh): 864 B / thread,
-// 2 blocks of 128 threads per SM, no local-memory temporaries.
-constexpr int GS_MV2_NT = 128;
-constexpr int GS_MV2_SMEM = (144 + 72) * GS_MV2_NT * 4;
-__global__ void __launch_bounds__(GS_MV2_NT, 2) k_miller(const g1_aff* __restrict__ X, const uint8_t* __restrict__ yinf,
-                                                        const uint32_t* __restrict__ L, fp12* __restrict__ F, size_t nprob,
-                                                        int K, int S, int nchunk) {
-  extern __shared__ uint32_t sm[];
-  uint32_t* f = sm + threadIdx.x;
-  uint32_t* lc = sm + 144 * GS_MV2_NT + threadIdx.x;
-  size_t id = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (id >= nprob * 4 * (size_t)nchunk) return;
-  size_t p = id % nprob;
-  int e = (int)((id / nprob) & 3);
-  int ch = (int)(id / (nprob * 4));
-  int a = e >> 1, b = e & 1;
-  int k0 = ch * S, k1 = min(K, k0 + S);
-  bool any = false;
-  for (int k = k0; k < k1; k++) {
-    if (yinf[((size_t)b * K + k) * nprob + p]) continue;
-    if (X[((size_t)a * K + k) * nprob + p].is_inf()) continue;
-    any = true;
+  if (q >= 2 * (size_t)K * np) return;
+  size_t pl = q % np, bk = q / np;
+  int b = (int)(bk / K), k = (int)(bk % K);
+  g2_aff Q = Y[bk * nprob + p0 + pl];
+  if (Q.is_inf()) return;
+  fp px[2], py[2];
+  bool act[2];
+  size_t tbase[2];
+  const int ch = k / S, kk = k % S;
+  const size_t A = (size_t)ch * np + pl;
+  const int lane = (int)(A & 31);
+#pragma unroll
+  for (int a = 0; a < 2; a++) {
+    const g1_aff* P = &X[((size_t)a * K + k) * nprob + p0 + pl];
+    px[a] = P->x;
+    py[a] = P->y;
+    act[a] = !(px[a].is_zero() && py[a].is_zero());
+    size_t bid = (A >> 5) * 4 + (size_t)(2 * a + b);
+    tbase[a] = ((bid * S + kk) * GS_NUM_LINES) * (size_t)M3_TILE;
+    if (act[a]) atomicOr(&masks[bid * S + kk], 1u << lane);
   }
-  fp12 out;
-  if (!any) {
-    out.set_one();
-  } else {
-    f12w_set_one(f, GS_MV2_NT);
-    int idx = 0;
-    for (int bit = 62; bit >= 0; bit--) {
-      if (bit != 62) f12w_sqr(f, lc, GS_MV2_NT);  // f = 1 on the first pass
-      int nl = ((GS_X_ABS >> bit) & 1) ? 2 : 1;
-      for (int t = 0; t < nl; t++, idx++) {
-        for (int k = k0; k < k1; k++) {
-          size_t bk = (size_t)b * K + k;
-          if (yinf[bk * nprob + p]) continue;
-          const g1_aff* P = &X[((size_t)a * K + k) * nprob + p];
-          fp px = P->x, py = P->y;
-          if (px.is_zero() && py.is_zero()) continue;
-          const uint32_t* lp = L + ((bk * GS_NUM_LINES + idx) * GS_LINE_WORDS) * nprob + p;
-          // c0 straight to shared memory; c1 * xP and c2 * yP on the way
-#pragma unroll
-          for (int w = 0; w < 24; w++) lc[w * GS_MV2_NT] = lp[(size_t)w * nprob];
-          fp t0, t1;
-#pragma unroll
-          for (int h = 0; h < 2; h++) {
-#pragma unroll
-            for (int w = 0; w < 12; w++) {
-              t0.l[w] = lp[(size_t)(24 + h * 12 + w) * nprob];
-              t1.l[w] = lp[(size_t)(48 + h * 12 + w) * nprob];
-            }
-            fp::mul(t0, t0, px);
-            fp::mul(t1, t1, py);
-#pragma unroll
-            for (int w = 0; w < 12; w++) {
-              lc[(24 + h * 12 + w) * GS_MV2_NT] = t0.l[w];
-              lc[(48 + h * 12 + w) * GS_MV2_NT] = t1.l[w];
-            }
-          }
-          f12w_mul_line(f, lc, GS_MV2_NT);
-        }
+  if (!act[0] && !act[1]) return;
+  g2_proj t;
+  t.x = Q.x;
+  t.y = Q.y;
+  t.z.set_one();
+  int idx = 0;
+  for (int bit = 62; bit >= 0; bit--) {
+    int nl = ((GS_X_ABS >> bit) & 1) ? 2 : 1;
+    for (int w = 0; w < nl; w++, idx++) {
+      line_coeffs l;
+      if (w == 0)
+        g2_double_step(t, l);
+      else
+        g2_add_step(t, Q, l);
+#pragma unroll 1
+      for (int a = 0; a < 2; a++) {
+        if (!act[a]) continue;
+        uint32_t* o = tiles + tbase[a] + (size_t)idx * M3_TILE;
+        fp v;
+        cq_st(cq_ptr(o, 0, lane), l.c0.c0);
+        cq_st(cq_ptr(o, 1, lane), l.c0.c1);
+        fp::mul(v, l.c1.c0, px[a]);
+        cq_st(cq_ptr(o, 2, lane), v);
+        fp::mul(v, l.c1.c1, px[a]);
+        cq_st(cq_ptr(o, 3, lane), v);
+        fp::mul(v, l.c2.c0, py[a]);
+        cq_st(cq_ptr(o, 4, lane), v);
+        fp::mul(v, l.c2.c1, py[a]);
+        cq_st(cq_ptr(o, 5, lane), v);
       }
     }
-    f12w_store_conj(out, f, GS_MV2_NT);
   }
-  F[((size_t)ch * 4 + e) * nprob + p] = out;
+}
+
+__device__ GS_INL void cp_async16(uint32_t* smem, const uint32_t* g) {
+  unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(g) : "memory");
+}
+__device__ GS_INL void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+// block = 32 accumulators of entry e (bid = blk*4 + e); warp k = w-power coefficient k (coop12.cuh).
+// F[(ch*4 + e) * nprob + p] = conj( prod over the chunk's slots )
+__global__ void __launch_bounds__(M3_THREADS, 2) k_miller3(const uint32_t* __restrict__ tiles, const uint32_t* __restrict__ masks,
+                                                          fp12* __restrict__ F, size_t nprob, size_t p0, size_t np, int S,
+                                                          int nchunk) {
+  extern __shared__ __align__(16) uint32_t sm[];
+  uint32_t* acc = sm;
+  uint32_t* tile = sm + 2 * CQ_ACC;
+  uint32_t* smask = tile + 2 * M3_TILE;
+  uint16_t* slots = (uint16_t*)(smask + M3_MAXS);
+  int* nact_s = (int*)(slots + M3_MAXS);
+  const int k = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const size_t bid = blockIdx.x;
+  if (threadIdx.x == 0) {
+    int n = 0;
+    for (int kk = 0; kk < S; kk++) {
+      uint32_t m = masks[bid * S + kk];
+      if (m) {
+        slots[n] = (uint16_t)kk;
+        smask[n] = m;
+        n++;
+      }
+    }
+    *nact_s = n;
+  }
+  cq_set_one(k, lane, acc);
+  __syncthreads();
+  const int nact = *nact_s;
+  int cur = 0;
+  if (nact > 0) {
+    const int total = GS_NUM_LINES * nact;
+    auto issue = [&](int n, int stage) {
+      int s = n / nact, i = n - s * nact;
+      const uint32_t* src = tiles + ((bid * S + slots[i]) * GS_NUM_LINES + s) * (size_t)M3_TILE;
+      uint32_t* dst = tile + stage * M3_TILE;
+#pragma unroll
+      for (int c = 0; c < M3_TILE / 4 / M3_THREADS; c++) {
+        int w = (c * M3_THREADS + threadIdx.x) * 4;
+        cp_async16(dst + w, src + w);
+      }
+    };
+    issue(0, 0);
+    cp_async_wait_all();
+    __syncthreads();
+    int n = 0;
+    for (int bit = 62; bit >= 0; bit--) {
+      if (bit != 62) {
+        cq_sqr(k, lane, acc + cur * CQ_ACC, acc + (cur ^ 1) * CQ_ACC);
+        __syncthreads();
+        cur ^= 1;
+      }
+      int nl = ((GS_X_ABS >> bit) & 1) ? 2 : 1;
+      for (int i = 0; i < nl * nact; i++, n++) {
+        if (n + 1 < total) issue(n + 1, (n + 1) & 1);
+        int si = i >= nact ? i - nact : i;
+        bool active = (smask[si] >> lane) & 1;
+        cq_line_mul(k, lane, acc + cur * CQ_ACC, acc + (cur ^ 1) * CQ_ACC, tile + (n & 1) * M3_TILE, active);
+        cp_async_wait_all();
+        __syncthreads();
+        cur ^= 1;
+      }
+    }
+  }
+  // conjugate (x < 0) and write out in tower order
+  size_t A = (bid >> 2) * 32 + lane;
+  int e = (int)(bid & 3);
+  if (A < np * (size_t)nchunk) {
+    size_t pl = A % np;
+    int ch = (int)(A / np);
+    fp2 r;
+    cq_ld_coef(r.c0, r.c1, acc + cur * CQ_ACC, k, lane, false, false);
+    if (k & 1) fp2::neg(r, r);
+    fp2* dst = (fp2*)&F[((size_t)ch * 4 + e) * nprob + p0 + pl];
+    dst[cq_tower_pos(k)] = r;
+  }
 }
 
 // ------------------------------------------------------------------ AoS -> slot scatter for ComT ops
@@ -158,49 +231,50 @@ __global__ void k_linear_map_slots(int type, const void* target, const crs_dev* 
 }  // namespace gs
 
 int gsi::pairing_init(gs_ctx* ctx) {
-  CUDA_TRY(cudaFuncSetAttribute(k_miller, cudaFuncAttributeMaxDynamicSharedMemorySize, GS_MV2_SMEM));
+  CUDA_TRY(cudaFuncSetAttribute(k_miller3, cudaFuncAttributeMaxDynamicSharedMemorySize, M3_SMEM));
   return GS_OK;
 }
 
 // ------------------------------------------------------------------ pairing-product pipeline
 // X, Y: device slot arrays [2][K][nprob].  Produces either ComT values (out_comt, AoS [p][4]) or
 // per-entry verdict bytes ok4[4][nprob] (compared with 1 / target).
+// Problems are processed in passes of `pc` so that the evaluated-line tiles stay within ctx->tile_budget
+// bytes of HBM; a pass is sized to a whole number of k_miller3 waves (2 blocks x 148 SMs x 32 accumulators
+// / 4 entries = 2,368 problems per wave) when the batch is large enough.
 int gsi::run_pairing_product(gs_ctx* ctx, Scratch& sc, const g1_aff* X, const g2_aff* Y, size_t nprob, int K,
                                fp12* out_comt, uint8_t* ok4, const fp12* target) {
-  size_t npoints = 2 * (size_t)K * nprob;
-  uint32_t* L;
-  uint8_t* yinf;
-  fp12* F;
-  CUDA_TRY(sc.alloc(&L, npoints * GS_NUM_LINES * GS_LINE_WORDS));
-  CUDA_TRY(sc.alloc(&yinf, npoints));
-  // split the slots over threads when there are few problems (one big statement)
+  const size_t wave = 2368;
+  // split the slots of a big statement over several accumulators when there are few problems
   int S = K, nchunk = 1;
-  size_t want_threads = 148 * 256;
-  if (nprob * 4 < want_threads && K > 2) {
-    size_t c = (want_threads + nprob * 4 - 1) / (nprob * 4);
+  if (nprob < wave && K > 2) {
+    size_t c = (wave + nprob - 1) / nprob;
     if (c > (size_t)(K + 1) / 2) c = (K + 1) / 2;  // at least 2 slots per chunk
     if (c < 1) c = 1;
     S = (int)((K + c - 1) / c);
-    nchunk = (K + S - 1) / S;
   }
+  if (S > M3_MAXS) S = M3_MAXS;
+  nchunk = (K + S - 1) / S;
+  const size_t per_prob = (size_t)4 * nchunk * S * GS_NUM_LINES * M3_TILE * 4 / 32;  // tile bytes per problem
+  size_t pc = ctx->tile_budget / per_prob;
+  if (pc >= nprob) {
+    pc = nprob;
+  } else {
+    if (pc > wave) pc -= pc % wave;
+    if (pc < 32) pc = 32;
+    pc -= pc % 32;
+  }
+  const size_t nblk_max = ((pc * nchunk + 31) / 32) * 4;
+  uint32_t *tiles, *masks;
+  fp12* F;
+  CUDA_TRY(sc.alloc(&tiles, nblk_max * S * GS_NUM_LINES * (size_t)M3_TILE));
+  CUDA_TRY(sc.alloc(&masks, nblk_max * S));
   CUDA_TRY(sc.alloc(&F, (size_t)nchunk * 4 * nprob));
-  LAUNCH(k_g2_prepare, npoints, Y, L, yinf, npoints, nprob);
-  {
-    size_t nt_ = nprob * 4 * (size_t)nchunk;
-    gs_ctx::prof_rec pr_{"k_miller", nullptr, nullptr};
-    if (ctx->profile) {
-      cudaEventCreate(&pr_.e0);
-      cudaEventCreate(&pr_.e1);
-      cudaEventRecord(pr_.e0, ctx->stream);
-    }
-    k_miller<<<(unsigned)((nt_ + GS_MV2_NT - 1) / GS_MV2_NT), GS_MV2_NT, GS_MV2_SMEM, ctx->stream>>>(X, yinf, L, F, nprob, K, S,
-                                                                                                      nchunk);
-    if (ctx->profile) {
-      cudaEventRecord(pr_.e1, ctx->stream);
-      ctx->prof.push_back(pr_);
-    }
-    ctx->launches++;
-    CUDA_TRY(cudaGetLastError());
+  for (size_t p0 = 0; p0 < nprob; p0 += pc) {
+    size_t np = nprob - p0 < pc ? nprob - p0 : pc;
+    size_t nblk = ((np * nchunk + 31) / 32) * 4;
+    CUDA_TRY(cudaMemsetAsync(masks, 0, nblk * S * sizeof(uint32_t), ctx->stream));
+    LAUNCH(k_g2_prepare3, 2 * (size_t)K * np, X, Y, tiles, masks, nprob, p0, np, K, S);
+    LAUNCH_CFG(k_miller3, nblk * M3_THREADS, M3_THREADS, M3_SMEM, tiles, masks, F, nprob, p0, np, S, nchunk);
   }
   return gsi::launch_final_exp(ctx, F, nprob, nchunk, out_comt, ok4, target);
 }

@@ -103,3 +103,82 @@ extern "C" void hs_miller_v2(void* r, int n, const void* g1s, const void* g2s, i
   }
   fp12 out; f12w_store_conj(out, f.data(), stride); ST(r, out);
 }
+
+// ---- v3 cooperative Miller accumulation (coop12.cuh): `lanes` independent accumulators, n pairs each
+// (g1s/g2s indexed [lane*n + i]); the (k, lane) functions are run for all k, lane between "barriers".
+#include "../../groth-sahai-rs_b200/csrc/coop12.cuh"
+extern "C" void hs_miller_v3(void* r, int lanes, int n, const void* g1s, const void* g2s) {
+  const g1_aff* P = (const g1_aff*)g1s; const g2_aff* Q = (const g2_aff*)g2s;
+  const int TILE = 6 * CQ_FP;
+  std::vector<uint32_t> tiles((size_t)n * GS_NUM_LINES * TILE, 0xdeadbeefu);
+  std::vector<uint32_t> mask(n, 0);
+  for (int lane = 0; lane < lanes; lane++)
+    for (int i = 0; i < n; i++) {
+      const g1_aff& p = P[lane * n + i]; const g2_aff& q = Q[lane * n + i];
+      if (p.is_inf() || q.is_inf()) continue;
+      mask[i] |= 1u << lane;
+      g2_proj t; t.x = q.x; t.y = q.y; t.z.set_one();
+      int idx = 0;
+      for (int bit = 62; bit >= 0; bit--) {
+        int nl = ((GS_X_ABS >> bit) & 1) ? 2 : 1;
+        for (int w = 0; w < nl; w++, idx++) {
+          line_coeffs l;
+          if (w == 0) g2_double_step(t, l); else g2_add_step(t, q, l);
+          uint32_t* o = tiles.data() + ((size_t)i * GS_NUM_LINES + idx) * TILE;
+          fp v;
+          cq_st(cq_ptr(o, 0, lane), l.c0.c0); cq_st(cq_ptr(o, 1, lane), l.c0.c1);
+          fp::mul(v, l.c1.c0, p.x); cq_st(cq_ptr(o, 2, lane), v);
+          fp::mul(v, l.c1.c1, p.x); cq_st(cq_ptr(o, 3, lane), v);
+          fp::mul(v, l.c2.c0, p.y); cq_st(cq_ptr(o, 4, lane), v);
+          fp::mul(v, l.c2.c1, p.y); cq_st(cq_ptr(o, 5, lane), v);
+        }
+      }
+    }
+  std::vector<uint32_t> acc(2 * CQ_ACC, 0xdeadbeefu);
+  int cur = 0;
+  for (int k = 0; k < 6; k++) for (int lane = 0; lane < 32; lane++) cq_set_one(k, lane, acc.data());
+  int idx = 0;
+  for (int bit = 62; bit >= 0; bit--) {
+    if (bit != 62) {
+      for (int k = 0; k < 6; k++) for (int lane = 0; lane < lanes; lane++) cq_sqr(k, lane, acc.data() + cur * CQ_ACC, acc.data() + (cur ^ 1) * CQ_ACC);
+      cur ^= 1;
+    }
+    int nl = ((GS_X_ABS >> bit) & 1) ? 2 : 1;
+    for (int w = 0; w < nl; w++, idx++)
+      for (int i = 0; i < n; i++) {
+        if (!mask[i]) continue;
+        const uint32_t* tile = tiles.data() + ((size_t)i * GS_NUM_LINES + idx) * TILE;
+        for (int k = 0; k < 6; k++) for (int lane = 0; lane < lanes; lane++)
+          cq_line_mul(k, lane, acc.data() + cur * CQ_ACC, acc.data() + (cur ^ 1) * CQ_ACC, tile, (mask[i] >> lane) & 1);
+        cur ^= 1;
+      }
+  }
+  fp12* out = (fp12*)r;
+  for (int lane = 0; lane < lanes; lane++)
+    for (int k = 0; k < 6; k++) {
+      fp2 c; cq_ld_coef(c.c0, c.c1, acc.data() + cur * CQ_ACC, k, lane, false, false);
+      if (k & 1) fp2::neg(c, c);
+      ((fp2*)&out[lane])[cq_tower_pos(k)] = c;
+    }
+}
+// fout = f * g and f^2 through the cooperative ops (single lane), tower-ordered in/out
+static void cq_from_tower(uint32_t* acc, int lane, const fp12& x) {
+  for (int k = 0; k < 6; k++) cq_st_coef(acc, k, lane, ((const fp2*)&x)[cq_tower_pos(k)]);
+}
+static void cq_to_tower(fp12& x, const uint32_t* acc, int lane) {
+  for (int k = 0; k < 6; k++) { fp2 c; cq_ld_coef(c.c0, c.c1, acc, k, lane, false, false); ((fp2*)&x)[cq_tower_pos(k)] = c; }
+}
+extern "C" void hs_cq_mul(void* r, const void* a, const void* b, int lane) {
+  LD(fp12, x, a); LD(fp12, y, b);
+  std::vector<uint32_t> f(CQ_ACC), g(CQ_ACC), o(CQ_ACC);
+  cq_from_tower(f.data(), lane, x); cq_from_tower(g.data(), lane, y);
+  for (int k = 0; k < 6; k++) cq_mul(k, lane, f.data(), g.data(), o.data());
+  fp12 z; cq_to_tower(z, o.data(), lane); ST(r, z);
+}
+extern "C" void hs_cq_sqr(void* r, const void* a, int lane) {
+  LD(fp12, x, a);
+  std::vector<uint32_t> f(CQ_ACC), o(CQ_ACC);
+  cq_from_tower(f.data(), lane, x);
+  for (int k = 0; k < 6; k++) cq_sqr(k, lane, f.data(), o.data());
+  fp12 z; cq_to_tower(z, o.data(), lane); ST(r, z);
+}

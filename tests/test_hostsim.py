@@ -157,3 +157,29 @@ def test_miller_v2_matches_v1(L):
     for stride in (1, 5):
         assert call(L.hs_miller_v2, 576, 3, g1s, g2s, stride) == v1
     assert fp12_i(v1) == multi_miller_loop(list(zip(ps, qs)))
+
+
+def test_coop12_mul_sqr(L):
+    """cooperative (warp-per-coefficient) Fp12 product / squaring == the big-int tower product"""
+    for it in range(6):
+        a, b = rfp12(), rfp12()
+        lane = [0, 7, 31][it % 3]
+        assert fp12_i(call(L.hs_cq_mul, 576, fp12_b(a), fp12_b(b), lane)) == a * b
+        assert fp12_i(call(L.hs_cq_sqr, 576, fp12_b(a), lane)) == a * a
+
+
+def test_miller_v3_matches_v1(L):
+    """The cooperative Miller accumulator (evaluated line tiles, lazy-reduced sums of products) must equal the
+    tower one bit for bit, several lanes at once, with dropped (identity) pairs in some lanes only."""
+    lanes, n = 3, 3
+    ps = [[g1_mul(G1_GEN, rng.randrange(R)) for _ in range(n)] for _ in range(lanes)]
+    qs = [[g2_mul(G2_GEN_FP2, rng.randrange(R)) for _ in range(n)] for _ in range(lanes)]
+    ps[1][0] = None            # lane 1 drops pair 0
+    qs[2][2] = None            # lane 2 drops pair 2
+    g1s = b"".join(g1_b(p) for row in ps for p in row)
+    g2s = b"".join(g2_b(q) for row in qs for q in row)
+    got = call(L.hs_miller_v3, 576 * lanes, lanes, n, g1s, g2s)
+    for l in range(lanes):
+        row1 = b"".join(g1_b(p) for p in ps[l]); row2 = b"".join(g2_b(q) for q in qs[l])
+        assert got[576 * l:576 * (l + 1)] == call(L.hs_miller, 576, n, row1, row2)
+        assert fp12_i(got[576 * l:576 * (l + 1)]) == multi_miller_loop(list(zip(ps[l], qs[l])))
