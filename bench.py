@@ -30,23 +30,27 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 M_VARS = N_VARS = 4
 # ---- algorithmic work model (Fp Montgomery products "M"; 1 M = 600 IMAD-equivalents) ----
 IMAD_PER_M = 600
-M_SQR12, M_LINE, M_014 = 36, 4, 39           # Fp12 squaring, line evaluation at P, sparse product
-M_G2_DBL, M_G2_ADD = 25, 37                  # one doubling / addition step of the G2 line walk
+M_SQR12, M_LINE, M_014 = 36, 4, 39           # Fp12 squaring, line evaluation at P, sparse product (tower formulas)
+M_G2_DBL, M_G2_ADD = 21, 37                  # one doubling / addition step of the projective G2 line walk
 M_FE = 8300                                  # final exponentiation (easy ~750 + 5 exp-by-x + products)
 M_G1_DBL, M_G1_MADD, M_FP_INV = 7, 11, 490
 
 
 def work_model(m, n):
-    """Algorithmic M per verified 4x4-shaped PPE proof, per kernel (what the CUDA path really executes)."""
+    """Algorithmic M per verified 4x4-shaped PPE proof, per kernel: the best sequential (tower / Karatsuba)
+    operation counts of SURVEY.md §8d for what each kernel computes -- NOT the instructions it executes
+    (the cooperative kernels trade Karatsuba for lazy-reduced schoolbook sums and execute more)."""
     cx = cy = 2
     pairs = 2 * (n + cx + cy) + 2 * (n + m + cx + cy)            # Miller pairs over the 4 ComT entries
-    g2_points = 2 * n + m + 2 * cx + 2 * cy                        # non-identity G2 coordinates to prepare
+    g2_points = 2 * n + m + 2 * cx + 2 * cy                        # non-identity G2 coordinates to walk
     return {
-        "k_miller": 4 * 63 * M_SQR12 + pairs * 68 * (M_LINE + M_014),
-        "k_g2_prepare": g2_points * (63 * M_G2_DBL + 5 * M_G2_ADD),
+        "k_miller3": 4 * 62 * M_SQR12 + pairs * 68 * M_014,
+        "k_g2_prepare3": g2_points * (63 * M_G2_DBL + 5 * M_G2_ADD) + pairs * 68 * M_LINE,
         "k_final_exp": 4 * M_FE,
-        "k_vmsm_partial": 2 * n * (255 * M_G1_DBL + 127.5 * m * M_G1_MADD),
-        "k_vmsm_reduce": 2 * n * (M_FP_INV + M_G1_MADD + 5),
+        # Straus, signed 4-bit windows: 64 windows x (4 shared doublings + one addition per base, 15/16 non-zero)
+        "k_vmsm_partial": 2 * n * (256 * M_G1_DBL + 64 * m * (15 / 16) * M_G1_MADD),
+        "k_vmsm_tables": 2 * m * (M_G1_DBL + 6 * M_G1_MADD + 8 * 9),
+        "k_vmsm_reduce": 2 * n * (M_G1_MADD + 9),
         "pairs": pairs,
     }
 

@@ -48,6 +48,10 @@ GS_PTX4(madc_hi_cc, "madc.hi.cc.u32")
 GS_PTX4(madc_hi, "madc.hi.u32")
 __device__ GS_INL uint32_t mul_lo(uint32_t a, uint32_t b) { return a * b; }
 __device__ GS_INL uint32_t mul_hi(uint32_t a, uint32_t b) { return __umulhi(a, b); }
+// full 32x32 -> 64 product as ONE IMAD.WIDE (lo, hi land in a register pair)
+__device__ GS_INL void mul_wide(uint32_t& lo, uint32_t& hi, uint32_t a, uint32_t b) {
+  asm volatile("{\n\t.reg .u64 t;\n\tmul.wide.u32 t, %2, %3;\n\tmov.b64 {%0, %1}, t;\n\t}" : "=r"(lo), "=r"(hi) : "r"(a), "r"(b));
+}
 #else
 // host emulation of the PTX condition-code register (tests only)
 static thread_local uint32_t g_cc = 0;
@@ -59,6 +63,7 @@ GS_INL uint32_t subc_cc(uint32_t a, uint32_t b) { uint64_t t = (uint64_t)a - b -
 GS_INL uint32_t subc(uint32_t a, uint32_t b) { return a - b - g_cc; }
 GS_INL uint32_t mul_lo(uint32_t a, uint32_t b) { return a * b; }
 GS_INL uint32_t mul_hi(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * b) >> 32); }
+GS_INL void mul_wide(uint32_t& lo, uint32_t& hi, uint32_t a, uint32_t b) { uint64_t t = (uint64_t)a * b; lo = (uint32_t)t; hi = (uint32_t)(t >> 32); }
 GS_INL uint32_t mad_lo_cc(uint32_t a, uint32_t b, uint32_t c) { return add_cc(mul_lo(a, b), c); }
 GS_INL uint32_t madc_lo_cc(uint32_t a, uint32_t b, uint32_t c) { return addc_cc(mul_lo(a, b), c); }
 GS_INL uint32_t mad_hi_cc(uint32_t a, uint32_t b, uint32_t c) { return add_cc(mul_hi(a, b), c); }
@@ -194,10 +199,8 @@ struct Mont {
     if (first) {
 #pragma unroll
       for (int j = 0; j < N; j += 2) {
-        E[j] = mul_lo(a[j], bi);
-        E[j + 1] = mul_hi(a[j], bi);
-        O[j] = mul_lo(a[j + 1], bi);
-        O[j + 1] = mul_hi(a[j + 1], bi);
+        mul_wide(E[j], E[j + 1], a[j], bi);
+        mul_wide(O[j], O[j + 1], a[j + 1], bi);
       }
     } else {
       // here E is last row's O (already at the right position) and O is last row's E,
@@ -269,10 +272,8 @@ struct Mont {
     if (first) {
 #pragma unroll
       for (int j = 0; j < N; j += 2) {
-        E[j] = mul_lo(a[0].l[j], b[0].l[i]);
-        E[j + 1] = mul_hi(a[0].l[j], b[0].l[i]);
-        O[j] = mul_lo(a[0].l[j + 1], b[0].l[i]);
-        O[j + 1] = mul_hi(a[0].l[j + 1], b[0].l[i]);
+        mul_wide(E[j], E[j + 1], a[0].l[j], b[0].l[i]);
+        mul_wide(O[j], O[j + 1], a[0].l[j + 1], b[0].l[i]);
       }
     } else {
       E[0] = add_cc(E[0], O[1]);
@@ -300,10 +301,8 @@ struct Mont {
     if (first) {
 #pragma unroll
       for (int j = 0; j < N; j += 2) {
-        E[j] = mul_lo(a[0].l[j], bl[0]);
-        E[j + 1] = mul_hi(a[0].l[j], bl[0]);
-        O[j] = mul_lo(a[0].l[j + 1], bl[0]);
-        O[j + 1] = mul_hi(a[0].l[j + 1], bl[0]);
+        mul_wide(E[j], E[j + 1], a[0].l[j], bl[0]);
+        mul_wide(O[j], O[j + 1], a[0].l[j + 1], bl[0]);
       }
     } else {
       E[0] = add_cc(E[0], O[1]);

@@ -36,10 +36,16 @@ GS_HD GS_INL void fp2_mul_b_twist(fp2& r, const fp2& a) {
   fp2::dbl(r, t);
 }
 GS_HD GS_INL void fp_half(fp& r, const fp& a) {
-  fp h;
+  // a/2 mod p = (a + (a odd ? p : 0)) >> 1   (the Montgomery representative halves like the value)
+  uint32_t mask = 0u - (a.l[0] & 1u);
+  uint32_t t[12];
+  t[0] = add_cc(a.l[0], FpParams::mod(0) & mask);
 #pragma unroll
-  for (int i = 0; i < 12; i++) h.l[i] = FP_TWO_INV(i);
-  fp::mul(r, a, h);
+  for (int i = 1; i < 11; i++) t[i] = addc_cc(a.l[i], FpParams::mod(i) & mask);
+  t[11] = addc(a.l[11], FpParams::mod(11) & mask);  // a + p < 2^382: no carry out
+#pragma unroll
+  for (int i = 0; i < 11; i++) r.l[i] = (t[i] >> 1) | (t[i + 1] << 31);
+  r.l[11] = t[11] >> 1;
 }
 GS_HD GS_INL void fp2_half(fp2& r, const fp2& a) {
   fp_half(r.c0, a.c0);

@@ -98,14 +98,35 @@ __global__ void __launch_bounds__(128) k_vmsm_tables(verify_shape s, verify_args
   g1_aff B;
   B.set_inf();
   if (active) B = vmsm_base(s, v, crs, p, i, a);
-  g1_jac acc;
-  acc.from_affine(B);
-  g1_aff* out = tab + ((size_t)(i * 2 + a) * GS_VTAB) * nprob + p;
+  // all GS_VTAB multiples in Jacobian form, then ONE batched inversion (Montgomery's trick over the thread's
+  // own Z values, block_batch_inv over the per-thread products) instead of one Fermat inversion per multiple
+  g1_jac mlt[GS_VTAB];
+  mlt[0].from_affine(B);
+  g1_jac::dbl(mlt[1], mlt[0]);
+  for (int d = 2; d < GS_VTAB; d++) g1_jac::add_mixed(mlt[d], mlt[d - 1], B);
+  fp pre[GS_VTAB], z;
   for (int d = 0; d < GS_VTAB; d++) {
-    if (d == 1) g1_jac::dbl(acc, acc);
-    if (d > 1) g1_jac::add_mixed(acc, acc, B);
+    z = mlt[d].Z;
+    if (z.is_zero()) fp_one(z);
+    if (d == 0)
+      pre[0] = z;
+    else
+      fp::mul(pre[d], pre[d - 1], z);
+  }
+  fp inv = pre[GS_VTAB - 1];
+  block_batch_inv<128>(inv, sm);
+  g1_aff* out = tab + ((size_t)(i * 2 + a) * GS_VTAB) * nprob + p;
+  for (int d = GS_VTAB - 1; d >= 0; d--) {
+    fp zi;
+    if (d > 0)
+      fp::mul(zi, inv, pre[d - 1]);
+    else
+      zi = inv;
+    z = mlt[d].Z;
+    if (z.is_zero()) fp_one(z);
+    fp::mul(inv, inv, z);
     g1_aff e;
-    block_to_affine<128>(e, acc, sm);
+    g1_jac::to_affine_with_zinv(e, mlt[d], zi);
     if (active) out[(size_t)d * nprob] = e;
   }
 }
