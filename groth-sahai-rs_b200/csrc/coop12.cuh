@@ -200,6 +200,221 @@ GS_HD GS_INL void cq_mul(int k, int lane, const uint32_t* f, const uint32_t* g, 
   cq_st_coef(fout, k, lane, r);
 }
 
+// ------------------------------------------------------------------ cyclotomic squaring (Granger-Scott)
+// For f in the cyclotomic subgroup, with the Fp4 pairs (x, y) = (a_0,a_3), (a_1,a_4), (a_2,a_5) (y on w^3):
+//     S_g = x^2 + xi y^2,  P_g = 2 x y     and
+//     a_0' = 3 S_0 - 2 a_0   a_3' = 3 P_0 + 2 a_3
+//     a_2' = 3 S_1 - 2 a_2   a_5' = 3 P_1 + 2 a_5
+//     a_4' = 3 S_2 - 2 a_4   a_1' = 3 xi P_2 + 2 a_1        (= ark-ff cyclotomic_square in the w basis)
+// Balanced over the 6 warps by Fp COMPONENT: warp (g = k % 3, c = k / 3) computes component c of S_g
+// (4 Fp products) and of P_g (2 Fp products), each with one lazy reduction.
+GS_HD GS_INL void cq_cyc_sqr(int k, int lane, const uint32_t* fin, uint32_t* fout) {
+  const int g = k % 3, c = k / 3;
+  const int ix = g, iy = g + 3;
+  const int tS = g == 0 ? 0 : (g == 1 ? 2 : 4), tP = g == 0 ? 3 : (g == 1 ? 5 : 1);
+  fp x0, x1, y0, y1;
+  cq_ld_coef(x0, x1, fin, ix, lane, false, false);
+  cq_ld_coef(y0, y1, fin, iy, lane, false, false);
+  fp S, Pp;
+  {
+    // Y-side for S: (x, xi y);  comp 0: x0*x0 + (-x1)*x1 + e0*y0 + (-e1)*y1 ; comp 1: x0*x1 + x1*x0 + e0*y1 + e1*y0
+    fp a[4];
+    a[0] = x0;
+    a[1] = x1;
+    fp::sub(a[2], y0, y1);
+    fp::add(a[3], y0, y1);
+    const uint32_t* b[4];
+    if (c == 0) {
+      fp::neg(a[1], a[1]);
+      fp::neg(a[3], a[3]);
+      b[0] = cq_ptr(fin, 2 * ix, lane);
+      b[1] = cq_ptr(fin, 2 * ix + 1, lane);
+      b[2] = cq_ptr(fin, 2 * iy, lane);
+      b[3] = cq_ptr(fin, 2 * iy + 1, lane);
+    } else {
+      b[0] = cq_ptr(fin, 2 * ix + 1, lane);
+      b[1] = cq_ptr(fin, 2 * ix, lane);
+      b[2] = cq_ptr(fin, 2 * iy + 1, lane);
+      b[3] = cq_ptr(fin, 2 * iy, lane);
+    }
+    mulsum_q<4>(S, a, b);
+  }
+  {
+    // Y-side for P: X = 2x (times xi for g = 2);  comp 0: X0*y0 + (-X1)*y1 ; comp 1: X0*y1 + X1*y0
+    fp a[2];
+    if (g == 2) {
+      fp::sub(a[0], x0, x1);
+      fp::add(a[1], x0, x1);
+    } else {
+      a[0] = x0;
+      a[1] = x1;
+    }
+    fp::add(a[0], a[0], a[0]);
+    fp::add(a[1], a[1], a[1]);
+    const uint32_t* b[2];
+    if (c == 0) {
+      fp::neg(a[1], a[1]);
+      b[0] = cq_ptr(fin, 2 * iy, lane);
+      b[1] = cq_ptr(fin, 2 * iy + 1, lane);
+    } else {
+      b[0] = cq_ptr(fin, 2 * iy + 1, lane);
+      b[1] = cq_ptr(fin, 2 * iy, lane);
+    }
+    mulsum_q<2>(Pp, a, b);
+  }
+  fp t, o;
+  // 3 S - 2 a_tS
+  cq_ld(t, cq_ptr(fin, 2 * tS + c, lane));
+  fp::sub(o, S, t);
+  fp::add(o, o, o);
+  fp::add(o, o, S);
+  cq_st(cq_ptr(fout, 2 * tS + c, lane), o);
+  // 3 P + 2 a_tP
+  cq_ld(t, cq_ptr(fin, 2 * tP + c, lane));
+  fp::add(o, Pp, t);
+  fp::add(o, o, o);
+  fp::add(o, o, Pp);
+  cq_st(cq_ptr(fout, 2 * tP + c, lane), o);
+}
+
+// ------------------------------------------------------------------ coefficient-local ops (no cross-warp reads)
+GS_HD GS_INL void cq_copy(int k, int lane, const uint32_t* fin, uint32_t* fout) {
+  fp2 r;
+  cq_ld_coef(r.c0, r.c1, fin, k, lane, false, false);
+  cq_st_coef(fout, k, lane, r);
+}
+// conjugation x -> x^(p^6): negate the odd powers of w
+GS_HD GS_INL void cq_conj(int k, int lane, const uint32_t* fin, uint32_t* fout) {
+  fp2 r;
+  cq_ld_coef(r.c0, r.c1, fin, k, lane, false, false);
+  if (k & 1) fp2::neg(r, r);
+  cq_st_coef(fout, k, lane, r);
+}
+// x -> x^(p^K), K = 1, 2:  (a_k w^k)^(p^K) = conj^K(a_k) * FROB_K[k] * w^k
+template <int K>
+GS_HD GS_INL void cq_frob(int k, int lane, const uint32_t* fin, uint32_t* fout) {
+  fp2 t;
+  cq_ld_coef(t.c0, t.c1, fin, k, lane, false, false);
+  if (K & 1) fp::neg(t.c1, t.c1);
+  if (k > 0) {
+    fp2 g, r;
+    for (int j = 0; j < 12; j++) {
+      g.c0.l[j] = frob_coeff(K, k, 0, j);
+      g.c1.l[j] = frob_coeff(K, k, 1, j);
+    }
+    fp s0, s1, t0, t1, t2;
+    fp::add(s0, t.c0, t.c1);
+    fp::add(s1, g.c0, g.c1);
+    fp::mul(t0, t.c0, g.c0);
+    fp::mul(t1, t.c1, g.c1);
+    fp::mul(t2, s0, s1);
+    fp::sub(r.c0, t0, t1);
+    fp::sub(t2, t2, t0);
+    fp::sub(r.c1, t2, t1);
+    t = r;
+  }
+  cq_st_coef(fout, k, lane, t);
+}
+// fout = 1 / N for N in Fp6 = {a_0 + a_2 w^2 + a_4 w^4} (odd coefficients of fin ignored, of fout zeroed).
+// Warp 0 inverts for its 32 lanes with the tower code (one Fermat inversion per lane); the others only zero.
+GS_HD GS_INL void cq_inv6(int k, int lane, const uint32_t* fin, uint32_t* fout) {
+  if (k == 0) {
+    fp6 n, r;
+    cq_ld_coef(n.c0.c0, n.c0.c1, fin, 0, lane, false, false);
+    cq_ld_coef(n.c1.c0, n.c1.c1, fin, 2, lane, false, false);
+    cq_ld_coef(n.c2.c0, n.c2.c1, fin, 4, lane, false, false);
+    fp6::inv(r, n);
+    cq_st_coef(fout, 0, lane, r.c0);
+    cq_st_coef(fout, 2, lane, r.c1);
+    cq_st_coef(fout, 4, lane, r.c2);
+  } else if (k & 1) {
+    fp2 z;
+    z.set_zero();
+    cq_st_coef(fout, k, lane, z);
+  }
+}
+
+// ------------------------------------------------------------------ op programs
+// A cooperative computation is a straight-line PROGRAM of ops over a small set of accumulator buffers; the
+// kernel executes op after op with one block barrier in between, and tests/hostsim executes the same
+// program by looping over (k, lane).  An op never reads a buffer it writes, except the coefficient-local
+// ones (COPY / CONJ / FROB / INV6), which may run in place.
+enum { CQ_OP_MUL = 1, CQ_OP_SQR, CQ_OP_CYC, CQ_OP_COPY, CQ_OP_CONJ, CQ_OP_FROB1, CQ_OP_FROB2, CQ_OP_INV6 };
+GS_HD constexpr uint32_t cq_ins(int op, int dst, int a, int b = 0) {
+  return (uint32_t)op | ((uint32_t)dst << 8) | ((uint32_t)a << 16) | ((uint32_t)b << 24);
+}
+GS_HD GS_INL void cq_exec(uint32_t ins, int k, int lane, uint32_t* bufs) {
+  const int op = ins & 255;
+  uint32_t* d = bufs + ((ins >> 8) & 255) * CQ_ACC;
+  const uint32_t* a = bufs + ((ins >> 16) & 255) * CQ_ACC;
+  const uint32_t* b = bufs + ((ins >> 24) & 255) * CQ_ACC;
+  switch (op) {
+    case CQ_OP_MUL: cq_mul(k, lane, a, b, d); break;
+    case CQ_OP_SQR: cq_sqr(k, lane, a, d); break;
+    case CQ_OP_CYC: cq_cyc_sqr(k, lane, a, d); break;
+    case CQ_OP_COPY: cq_copy(k, lane, a, d); break;
+    case CQ_OP_CONJ: cq_conj(k, lane, a, d); break;
+    case CQ_OP_FROB1: cq_frob<1>(k, lane, a, d); break;
+    case CQ_OP_FROB2: cq_frob<2>(k, lane, a, d); break;
+    case CQ_OP_INV6: cq_inv6(k, lane, a, d); break;
+    default: break;
+  }
+}
+
+// Final exponentiation program (arkworks exponent: easy part, then (x-1)^2 (x+p)(x^2+p^2-1) + 3).
+// Input in buffer 0, result in buffer CQ_FE_OUT; 5 buffers.  Returns the number of ops written (<= CQ_FE_MAXOPS).
+constexpr int CQ_FE_NBUF = 5, CQ_FE_OUT = 3, CQ_FE_MAXOPS = 400;
+inline int cq_build_final_exp(uint32_t* prog) {
+  int n = 0;
+  auto I = [&](int op, int dst, int a, int b = 0) { prog[n++] = cq_ins(op, dst, a, b); };
+  // dst = src^|x| conjugated, via the ping-pong buffers 0/1 (src must not be 0 or 1)
+  auto exp_x = [&](int dst, int src) {
+    I(CQ_OP_COPY, 0, src);
+    int cur = 0;
+    for (int bit = 62; bit >= 0; bit--) {
+      I(CQ_OP_CYC, cur ^ 1, cur);
+      cur ^= 1;
+      if ((0xd201000000010000ull >> bit) & 1) {
+        I(CQ_OP_MUL, cur ^ 1, cur, src);
+        cur ^= 1;
+      }
+    }
+    I(CQ_OP_CONJ, dst, cur);
+  };
+  // easy part: r = f^((p^6-1)(p^2+1)) = frob2(g) * g,  g = conj(f)^2 / (f conj(f))
+  I(CQ_OP_CONJ, 1, 0);
+  I(CQ_OP_MUL, 2, 0, 1);   // N = f * conj(f)  in Fp6
+  I(CQ_OP_INV6, 2, 2);
+  I(CQ_OP_SQR, 3, 1);
+  I(CQ_OP_MUL, 0, 3, 2);   // g
+  I(CQ_OP_FROB2, 1, 0);
+  I(CQ_OP_MUL, 4, 1, 0);   // r  (kept in 4)
+  // a = r^(x-1)
+  exp_x(2, 4);
+  I(CQ_OP_CONJ, 1, 4);
+  I(CQ_OP_MUL, 3, 2, 1);   // a in 3
+  // b = a^(x-1)
+  exp_x(2, 3);
+  I(CQ_OP_CONJ, 1, 3);
+  I(CQ_OP_MUL, 3, 2, 1);   // b in 3  (a dead)
+  // c = b^(x+p)
+  exp_x(2, 3);
+  I(CQ_OP_FROB1, 1, 3);
+  I(CQ_OP_MUL, 3, 2, 1);   // c in 3
+  // d = c^(x^2) * c^(p^2) * conj(c)
+  exp_x(2, 3);
+  exp_x(2, 2);             // copies 2 -> 0 first, so in == out is fine
+  I(CQ_OP_FROB2, 1, 3);
+  I(CQ_OP_MUL, 0, 2, 1);
+  I(CQ_OP_CONJ, 1, 3);
+  I(CQ_OP_MUL, 2, 0, 1);   // d in 2
+  // r^3
+  I(CQ_OP_CYC, 0, 4);
+  I(CQ_OP_MUL, 1, 0, 4);
+  I(CQ_OP_MUL, 3, 2, 1);   // result in 3
+  return n;
+}
+
 // ------------------------------------------------------------------ constants / conversion
 GS_HD GS_INL void cq_set_one(int k, int lane, uint32_t* f) {
   fp2 r;

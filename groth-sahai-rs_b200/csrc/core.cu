@@ -40,7 +40,7 @@ int gs_ctx_create(int device, gs_ctx** out) {
   }
   // deep call chains (Fp12 -> Fp6 -> Fp2) with big local frames
   cudaDeviceSetLimit(cudaLimitStackSize, 32 * 1024);
-  if (gsi::pairing_init(ctx) != GS_OK) {
+  if (gsi::pairing_init(ctx) != GS_OK || gsi::final_exp_init(ctx) != GS_OK) {
     delete ctx;
     return GS_ECUDA;
   }
@@ -55,6 +55,7 @@ void gs_ctx_destroy(gs_ctx* ctx) {
   gsi::fixed_table_release<FpOps>(ctx);
   gsi::fixed_table_release<Fp2Ops>(ctx);
   if (ctx->crs_lines) cudaFree(ctx->crs_lines);
+  if (ctx->fe_prog) cudaFree(ctx->fe_prog);
   cudaFree(ctx->crs);
   cudaStreamDestroy(ctx->stream);
   delete ctx;

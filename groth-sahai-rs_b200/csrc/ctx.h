@@ -30,6 +30,8 @@ struct gs_ctx {
   gs_fixed_table<gs::FpOps> tab1;
   gs_fixed_table<gs::Fp2Ops> tab2;
   uint32_t* crs_lines = nullptr;  // prepared line triples of the fixed G2 points v1.0 v1.1 v2.0 v2.1 W2.0 W2.1 (pairing.cu)
+  uint32_t* fe_prog = nullptr;    // op program of the cooperative final exponentiation (finalexp.cu)
+  int fe_nops = 0;
   uint64_t launches = 0;
   bool profile = false;
   struct prof_rec {
@@ -116,6 +118,7 @@ using namespace gs;
 
 // pairing.cu
 int pairing_init(gs_ctx* ctx);  // per-context kernel attributes
+int final_exp_init(gs_ctx* ctx);
 // X, Y: device slot arrays [2][K][nprob]  ->  ComT values (out_comt, AoS [p][4]) or per-entry verdict
 // bytes ok4[4][nprob] (compared with 1 / target).
 int run_pairing_product(gs_ctx* ctx, Scratch& sc, const g1_aff* X, const g2_aff* Y, size_t nprob, int K, fp12* out_comt,

@@ -2,53 +2,89 @@
 // comparison against the expected ComT entry.  Reference: ark-ec final_exponentiation as reached from
 // src/data_structures.rs:484-502.
 #include "ctx.h"
+#include "coop12.cuh"
 #include "pairing.cuh"
 
 using namespace gs;
 
 namespace gs {
 
-// ------------------------------------------------------------------ final exponentiation (+ compare)
-// thread -> (p, e).  f = prod_chunks F;  g = FE(f).
-//   out_comt != null : out_comt[p].e[e] = g
-//   ok != null       : ok[e*nprob + p] = (g == expected), expected = target[p] for PPE entry 3, else 1
-__global__ void __launch_bounds__(128) k_final_exp(const fp12* __restrict__ F, size_t nprob, int nchunk,
-                                                   fp12* __restrict__ out_comt, uint8_t* __restrict__ ok,
-                                                   const fp12* __restrict__ target) {
-  size_t id = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (id >= nprob * 4) return;
-  size_t p = id % nprob;
-  int e = (int)(id / nprob);
-  fp12 f = F[(size_t)e * nprob + p];
-  for (int ch = 1; ch < nchunk; ch++) {
-    fp12 g = F[((size_t)ch * 4 + e) * nprob + p];
-    fp12::mul(f, f, g);
-  }
-  fp12 one;
-  one.set_one();
-  fp12 g;
-  if (f.equals(one)) {
-    g = one;
-  } else {
-    final_exponentiation(g, f);
-  }
-  if (out_comt) out_comt[p * 4 + e] = g;
-  if (ok) {
-    bool good;
-    if (target != nullptr && e == 3) {
-      fp12 t = target[p];
-      good = g.equals(t);
+// ------------------------------------------------------------------ cooperative final exponentiation (+ compare)
+// block = 32 instances id = p + e*nprob (6 warps, one per w-power coefficient, coop12.cuh); the op program of
+// cq_build_final_exp runs over 5 accumulator buffers in shared memory with one barrier per op.
+constexpr int FE3_THREADS = 6 * CQ_LANES;
+constexpr int FE3_SMEM = CQ_FE_NBUF * CQ_ACC * 4 + CQ_LANES * 4;
+__global__ void __launch_bounds__(FE3_THREADS, 2) k_final_exp3(const fp12* __restrict__ F, size_t nprob, int nchunk,
+                                                              fp12* __restrict__ out_comt, uint8_t* __restrict__ ok,
+                                                              const fp12* __restrict__ target, const uint32_t* __restrict__ prog,
+                                                              int nops) {
+  extern __shared__ __align__(16) uint32_t sm[];
+  uint32_t* bufs = sm;
+  uint32_t* bad = sm + CQ_FE_NBUF * CQ_ACC;
+  const int k = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const size_t id = (size_t)blockIdx.x * CQ_LANES + lane;
+  const bool valid = id < nprob * 4;
+  const size_t p = valid ? id % nprob : 0;
+  const int e = valid ? (int)(id / nprob) : 0;
+  const int pos = cq_tower_pos(k);
+  if (k == 0) bad[lane] = 0;
+  // f = product of the chunk partial products
+  for (int ch = 0; ch < nchunk; ch++) {
+    fp2 c;
+    if (valid) {
+      c = ((const fp2*)&F[((size_t)ch * 4 + e) * nprob + p])[pos];
     } else {
-      good = g.equals(one);
+      c.set_zero();
+      if (k == 0) fp_one(c.c0);
     }
-    ok[(size_t)e * nprob + p] = good ? 1 : 0;
+    cq_st_coef(bufs + (ch == 0 ? 0 : 1) * CQ_ACC, k, lane, c);
+    __syncthreads();
+    if (ch > 0) {
+      cq_mul(k, lane, bufs, bufs + CQ_ACC, bufs + 2 * CQ_ACC);
+      __syncthreads();
+      cq_copy(k, lane, bufs + 2 * CQ_ACC, bufs);
+      __syncthreads();
+    }
   }
+#pragma unroll 1
+  for (int i = 0; i < nops; i++) {
+    cq_exec(prog[i], k, lane, bufs);
+    __syncthreads();
+  }
+  fp2 g;
+  cq_ld_coef(g.c0, g.c1, bufs + CQ_FE_OUT * CQ_ACC, k, lane, false, false);
+  if (valid) {
+    if (out_comt) ((fp2*)&out_comt[p * 4 + e])[pos] = g;
+    if (ok) {
+      fp2 want;
+      if (target != nullptr && e == 3) {
+        want = ((const fp2*)&target[p])[pos];
+      } else {
+        want.set_zero();
+        if (k == 0) fp_one(want.c0);
+      }
+      if (!g.equals(want)) bad[lane] = 1;
+    }
+  }
+  __syncthreads();
+  if (ok && valid && k == 0) ok[(size_t)e * nprob + p] = bad[lane] ? 0 : 1;
 }
-
 
 }  // namespace gs
 
+int gsi::final_exp_init(gs_ctx* ctx) {
+  static uint32_t prog[CQ_FE_MAXOPS];
+  int n = cq_build_final_exp(prog);
+  ctx->fe_nops = n;
+  CUDA_TRY(cudaMalloc(&ctx->fe_prog, n * sizeof(uint32_t)));
+  CUDA_TRY(cudaMemcpy(ctx->fe_prog, prog, n * sizeof(uint32_t), cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaFuncSetAttribute(k_final_exp3, cudaFuncAttributeMaxDynamicSharedMemorySize, FE3_SMEM));
+  return GS_OK;
+}
+
 int gsi::launch_final_exp(gs_ctx* ctx, const fp12* F, size_t nprob, int nchunk, fp12* out_comt, uint8_t* ok4, const fp12* target) {
-  LAUNCH(k_final_exp, nprob * 4, F, nprob, nchunk, out_comt, ok4, target);
+  size_t nblk = (nprob * 4 + CQ_LANES - 1) / CQ_LANES;
+  LAUNCH_CFG(k_final_exp3, nblk * FE3_THREADS, FE3_THREADS, FE3_SMEM, F, nprob, nchunk, out_comt, ok4, target, ctx->fe_prog,
+             ctx->fe_nops);
   return GS_OK;
 }

@@ -182,3 +182,21 @@ extern "C" void hs_cq_sqr(void* r, const void* a, int lane) {
   for (int k = 0; k < 6; k++) cq_sqr(k, lane, f.data(), o.data());
   fp12 z; cq_to_tower(z, o.data(), lane); ST(r, z);
 }
+// the cooperative final-exponentiation op program (finalexp.cu runs the same program on the GPU)
+extern "C" void hs_final_exp3(void* r, const void* a, int lane) {
+  LD(fp12, x, a);
+  std::vector<uint32_t> bufs(CQ_FE_NBUF * CQ_ACC, 0xdeadbeefu);
+  cq_from_tower(bufs.data(), lane, x);
+  static uint32_t prog[CQ_FE_MAXOPS];
+  int n = cq_build_final_exp(prog);
+  for (int i = 0; i < n; i++)
+    for (int k = 0; k < 6; k++) cq_exec(prog[i], k, lane, bufs.data());
+  fp12 z; cq_to_tower(z, bufs.data() + CQ_FE_OUT * CQ_ACC, lane); ST(r, z);
+}
+extern "C" void hs_cq_cyc_sqr(void* r, const void* a, int lane) {
+  LD(fp12, x, a);
+  std::vector<uint32_t> f(CQ_ACC), o(CQ_ACC);
+  cq_from_tower(f.data(), lane, x);
+  for (int k = 0; k < 6; k++) cq_cyc_sqr(k, lane, f.data(), o.data());
+  fp12 z; cq_to_tower(z, o.data(), lane); ST(r, z);
+}

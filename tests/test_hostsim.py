@@ -183,3 +183,15 @@ def test_miller_v3_matches_v1(L):
         row1 = b"".join(g1_b(p) for p in ps[l]); row2 = b"".join(g2_b(q) for q in qs[l])
         assert got[576 * l:576 * (l + 1)] == call(L.hs_miller, 576, n, row1, row2)
         assert fp12_i(got[576 * l:576 * (l + 1)]) == multi_miller_loop(list(zip(ps[l], qs[l])))
+
+
+def test_coop12_final_exp(L):
+    """cooperative cyclotomic squaring and the whole final-exponentiation op program == oracle"""
+    a = rfp12()
+    c = a.conj() * a.inv()
+    c = c.frobenius(2) * c
+    assert fp12_i(call(L.hs_cq_cyc_sqr, 576, fp12_b(c), 5)) == c * c
+    for lane in (0, 17):
+        f = rfp12()
+        assert fp12_i(call(L.hs_final_exp3, 576, fp12_b(f), lane)) == final_exponentiation(f)
+    assert fp12_i(call(L.hs_final_exp3, 576, fp12_b(FP12_ONE), 3)) == FP12_ONE
