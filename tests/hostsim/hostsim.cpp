@@ -21,6 +21,7 @@ void hs_fp_add(void* r, const void* a, const void* b) { LD(fp, x, a); LD(fp, y, 
 void hs_fp_sub(void* r, const void* a, const void* b) { LD(fp, x, a); LD(fp, y, b); fp z; fp::sub(z, x, y); ST(r, z); }
 void hs_fp_neg(void* r, const void* a) { LD(fp, x, a); fp z; fp::neg(z, x); ST(r, z); }
 void hs_fp_inv(void* r, const void* a) { LD(fp, x, a); fp z; fp_inv(z, x); ST(r, z); }
+void hs_fp_inv_fermat(void* r, const void* a) { LD(fp, x, a); fp z; fp_inv_fermat(z, x); ST(r, z); }
 void hs_fr_mul(void* r, const void* a, const void* b) { LD(fr, x, a); LD(fr, y, b); fr z; fr::mul(z, x, y); ST(r, z); }
 void hs_fr_add(void* r, const void* a, const void* b) { LD(fr, x, a); LD(fr, y, b); fr z; fr::add(z, x, y); ST(r, z); }
 void hs_fr_sub(void* r, const void* a, const void* b) { LD(fr, x, a); LD(fr, y, b); fr z; fr::sub(z, x, y); ST(r, z); }
@@ -200,3 +201,5 @@ extern "C" void hs_cq_cyc_sqr(void* r, const void* a, int lane) {
   for (int k = 0; k < 6; k++) cq_cyc_sqr(k, lane, f.data(), o.data());
   fp12 z; cq_to_tower(z, o.data(), lane); ST(r, z);
 }
+// safegcd inversion (modinv.cuh)
+extern "C" void hs_fp_inv_sg(void* r, const void* a) { LD(fp, x, a); fp z; fp_inv_sg(z, x); ST(r, z); }

@@ -38,10 +38,14 @@ def test_fp_ops(L):
         assert fp_i(call(L.hs_fp_add, 48, fp_b(a), fp_b(b))) == (a + b) % P
         assert fp_i(call(L.hs_fp_sub, 48, fp_b(a), fp_b(b))) == (a - b) % P
         assert fp_i(call(L.hs_fp_neg, 48, fp_b(a))) == (-a) % P
-    for it in range(20):
-        a = rfp()
+    # safegcd inversion (modinv.cuh, the product path) and the Fermat chain (independent cross-check)
+    for it in range(400):
+        a = [1, 2, P - 1, P - 2, 2 ** 380, (P - 1) // 2][it] if it < 6 else (rfp() if it % 3 else (rng.randrange(2 ** rng.randrange(1, 381)) or 1))
         assert fp_i(call(L.hs_fp_inv, 48, fp_b(a))) == pow(a, -1, P)
+        if it < 20:
+            assert fp_i(call(L.hs_fp_inv_fermat, 48, fp_b(a))) == pow(a, -1, P)
     assert fp_i(call(L.hs_fp_inv, 48, fp_b(0))) == 0
+    assert fp_i(call(L.hs_fp_inv_fermat, 48, fp_b(0))) == 0
 
 
 def test_fp_mulsum(L):

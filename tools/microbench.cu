@@ -5,6 +5,8 @@
 #include <cstdio>
 #include <cuda_runtime.h>
 #include "../groth-sahai-rs_b200/csrc/fp.cuh"
+#include "../groth-sahai-rs_b200/csrc/tower.cuh"
+#include "../groth-sahai-rs_b200/csrc/modinv.cuh"
 using namespace gs;
 
 __global__ void k_imad_wide(unsigned long long* out, unsigned a, unsigned b, int iters) {
@@ -56,6 +58,29 @@ __global__ void k_fpmul(fp* out, const fp* in, int iters) {
   for (int j = 1; j < ILP; j++) fp::add(r, r, x[j]);
   out[t] = r;
 }
+__global__ void k_fpinv_fermat(fp* out, const fp* in, int iters) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  fp x = in[t];
+  for (int i = 0; i < iters; i++) fp_inv(x, x);
+  out[t] = x;
+}
+__global__ void k_fpinv_safegcd(fp* out, const fp* in, int iters) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  fp x = in[t];
+  for (int i = 0; i < iters; i++) fp_inv_sg(x, x);
+  out[t] = x;
+}
+// safegcd inversions on half of the warps next to fp::mul chains on the other half: do the pipes overlap?
+__global__ void k_mix(fp* out, const fp* in, int iters_inv, int iters_mul) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  fp x = in[t], y = in[t + 1];
+  if ((threadIdx.x >> 5) & 1) {
+    for (int i = 0; i < iters_inv; i++) fp_inv_sg(x, x);
+  } else {
+    for (int i = 0; i < iters_mul; i++) fp::mul(x, x, y);
+  }
+  out[t] = x;
+}
 template <class K, class... A>
 float timeit(K k, dim3 g, dim3 b, A... args) {
   cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
@@ -84,6 +109,23 @@ int main() {
     float m2 = timeit(k_fpmul<2>, g, b, (fp*)buf + (1 << 20), (const fp*)buf, iters);
     double n1 = (double)sms * wps * 32 * iters, n2 = n1 * 2;
     printf("warps/SM %2d: fp::mul ILP1 %.3e M/s   ILP2 %.3e M/s\n", wps, n1 / m1 * 1e3, n2 / m2 * 1e3);
+  }
+  for (int wps : {4, 8, 16, 32}) {
+    dim3 g(sms), b(wps * 32);
+    int iters = 8;
+    float m1 = timeit(k_fpinv_fermat, g, b, (fp*)buf + (1 << 20), (const fp*)buf, iters);
+    float m2 = timeit(k_fpinv_safegcd, g, b, (fp*)buf + (1 << 20), (const fp*)buf, iters);
+    double n = (double)sms * wps * 32 * iters;
+    printf("warps/SM %2d: fp_inv Fermat %.3e inv/s (%.0f M-equivalents each)   safegcd %.3e inv/s (%.0f M-equivalents each)\n", wps,
+           n / m1 * 1e3, 3.08e10 / (n / m1 * 1e3), n / m2 * 1e3, 3.08e10 / (n / m2 * 1e3));
+  }
+  for (int wps : {8, 16, 32}) {
+    dim3 g(sms), b(wps * 32);
+    int ii = 8, im = 8 * 120;
+    float ma = timeit(k_mix, g, b, (fp*)buf + (1 << 20), (const fp*)buf, ii, 0);
+    float mb = timeit(k_mix, g, b, (fp*)buf + (1 << 20), (const fp*)buf, 0, im);
+    float mc = timeit(k_mix, g, b, (fp*)buf + (1 << 20), (const fp*)buf, ii, im);
+    printf("warps/SM %2d: half warps safegcd alone %.3f ms, half warps fp::mul alone %.3f ms, both %.3f ms\n", wps, ma, mb, mc);
   }
   return 0;
 }
