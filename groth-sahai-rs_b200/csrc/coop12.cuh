@@ -135,6 +135,25 @@ GS_HD GS_INL void cq_line_mul(int k, int lane, const uint32_t* fin, uint32_t* fo
   cq_st_coef(fout, k, lane, r);
 }
 
+// Same with gamma = 1 (affine line scaled by 1/yP, pairing.cuh g2_affine_step):
+//     fout.a_k = alpha a_k + beta a_{k-2} + a_{k-3}
+// `tile` holds alpha.c0, alpha.c1, beta.c0, beta.c1 (4 Fp): 8 Fp products + 2 reductions per coefficient
+// instead of 12 + 2, and only two register-side operands.
+GS_HD GS_INL void cq_line_mul_u(int k, int lane, const uint32_t* fin, uint32_t* fout, const uint32_t* tile, bool active) {
+  fp y[4];
+  const int j1 = k >= 2 ? k - 2 : k + 4, j2 = k >= 3 ? k - 3 : k + 3;
+  cq_ld_coef(y[0], y[1], fin, k, lane, false, false);
+  cq_ld_coef(y[2], y[3], fin, j1, lane, k < 2, false);
+  const uint32_t* x0[2] = {cq_ptr(tile, 0, lane), cq_ptr(tile, 2, lane)};
+  const uint32_t* x1[2] = {cq_ptr(tile, 1, lane), cq_ptr(tile, 3, lane)};
+  fp2 r, u;
+  cq_fp2_dot<2>(r, y, x0, x1);
+  cq_ld_coef(u.c0, u.c1, fin, j2, lane, k < 3, false);
+  fp2::add(r, r, u);
+  if (!active) cq_ld_coef(r.c0, r.c1, fin, k, lane, false, false);
+  cq_st_coef(fout, k, lane, r);
+}
+
 // ------------------------------------------------------------------ squaring
 // fout = fin^2:  b_k = sum_{i<=j, i+j = k mod 6} c_ij a_i a_j,  c_ij = (i<j ? 2 : 1) * (i+j >= 6 ? xi : 1).
 // Even k have 4 terms (2 doubled pairs + 2 squares), odd k have 3 doubled pairs; two passes of <= 2 terms.
@@ -156,6 +175,7 @@ GS_HD GS_INL void cq_sqr(int k, int lane, const uint32_t* fin, uint32_t* fout) {
     const uint32_t* x0[2] = {cq_ptr(fin, 2 * ti[0], lane), cq_ptr(fin, 2 * ti[1], lane)};
     const uint32_t* x1[2] = {cq_ptr(fin, 2 * ti[0] + 1, lane), cq_ptr(fin, 2 * ti[1] + 1, lane)};
     cq_fp2_dot<2>(r, y, x0, x1);
+    cq_st_coef(fout, k, lane, r);  // parked in the output slot (nobody reads fout during this op)
   }
   if (nt == 4) {
     fp y[4];
@@ -171,6 +191,7 @@ GS_HD GS_INL void cq_sqr(int k, int lane, const uint32_t* fin, uint32_t* fout) {
     const uint32_t* x1[1] = {cq_ptr(fin, 2 * ti[2] + 1, lane)};
     cq_fp2_dot<1>(r2, y, x0, x1);
   }
+  cq_ld_coef(r.c0, r.c1, fout, k, lane, false, false);
   fp2::add(r, r, r2);
   cq_st_coef(fout, k, lane, r);
 }
@@ -191,11 +212,14 @@ GS_HD GS_INL void cq_mul(int k, int lane, const uint32_t* f, const uint32_t* g, 
       x0[t] = cq_ptr(g, 2 * i, lane);
       x1[t] = cq_ptr(g, 2 * i + 1, lane);
     }
-    if (h == 0)
+    if (h == 0) {
       cq_fp2_dot<3>(r, y, x0, x1);
-    else
+      cq_st_coef(fout, k, lane, r);  // parked in the output slot
+    } else {
       cq_fp2_dot<3>(r2, y, x0, x1);
+    }
   }
+  cq_ld_coef(r.c0, r.c1, fout, k, lane, false, false);
   fp2::add(r, r, r2);
   cq_st_coef(fout, k, lane, r);
 }
@@ -414,6 +438,19 @@ inline int cq_build_final_exp(uint32_t* prog) {
   I(CQ_OP_MUL, 3, 2, 1);   // result in 3
   return n;
 }
+
+// ------------------------------------------------------------------ block shape
+// A thread block holds CQ_GROUPS independent 6-warp groups (12 warps = 3 per SM sub-partition, so the four
+// schedulers of an SM carry the same load: with 6-warp blocks two of them get two warps of every block and
+// the group barrier makes everyone wait for those).  Each group synchronises on its own named barrier.
+constexpr int CQ_GROUPS = 2;
+constexpr int CQ_GROUP_THREADS = 6 * CQ_LANES;
+constexpr int CQ_BLOCK_THREADS = CQ_GROUPS * CQ_GROUP_THREADS;
+#if defined(__CUDACC__)
+__device__ GS_INL void cq_group_sync(int group) {
+  asm volatile("bar.sync %0, %1;" ::"r"(group + 1), "r"(CQ_GROUP_THREADS) : "memory");
+}
+#endif
 
 // ------------------------------------------------------------------ constants / conversion
 GS_HD GS_INL void cq_set_one(int k, int lane, uint32_t* f) {

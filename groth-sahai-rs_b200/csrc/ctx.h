@@ -39,7 +39,7 @@ struct gs_ctx {
     cudaEvent_t e0, e1;
   };
   std::vector<prof_rec> prof;
-  size_t verify_batch_max = 16576;  // problems per verify pass (7 waves of k_miller3)
+  size_t verify_batch_max = 23680;  // problems per verify pass (10 waves of k_miller4)
   size_t tile_budget = (size_t)16 << 30;  // bytes of HBM for the evaluated-line tiles of one pairing pass
   std::string err;
 };

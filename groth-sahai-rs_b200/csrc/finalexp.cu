@@ -12,17 +12,19 @@ namespace gs {
 // ------------------------------------------------------------------ cooperative final exponentiation (+ compare)
 // block = 32 instances id = p + e*nprob (6 warps, one per w-power coefficient, coop12.cuh); the op program of
 // cq_build_final_exp runs over 5 accumulator buffers in shared memory with one barrier per op.
-constexpr int FE3_THREADS = 6 * CQ_LANES;
-constexpr int FE3_SMEM = CQ_FE_NBUF * CQ_ACC * 4 + CQ_LANES * 4;
-__global__ void __launch_bounds__(FE3_THREADS, 2) k_final_exp3(const fp12* __restrict__ F, size_t nprob, int nchunk,
-                                                              fp12* __restrict__ out_comt, uint8_t* __restrict__ ok,
-                                                              const fp12* __restrict__ target, const uint32_t* __restrict__ prog,
-                                                              int nops) {
-  extern __shared__ __align__(16) uint32_t sm[];
-  uint32_t* bufs = sm;
-  uint32_t* bad = sm + CQ_FE_NBUF * CQ_ACC;
-  const int k = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const size_t id = (size_t)blockIdx.x * CQ_LANES + lane;
+constexpr int FE3_SMEM = CQ_FE_NBUF * CQ_ACC * 4 + CQ_LANES * 4;  // per 6-warp group
+__global__ void __launch_bounds__(CQ_BLOCK_THREADS, 1) k_final_exp3(const fp12* __restrict__ F, size_t nprob, int nchunk,
+                                                                   fp12* __restrict__ out_comt, uint8_t* __restrict__ ok,
+                                                                   const fp12* __restrict__ target,
+                                                                   const uint32_t* __restrict__ prog, int nops, size_t ngroups) {
+  extern __shared__ __align__(16) uint32_t sm_all[];
+  const int grp = threadIdx.x / CQ_GROUP_THREADS, tg = threadIdx.x % CQ_GROUP_THREADS;
+  uint32_t* bufs = sm_all + (size_t)grp * (FE3_SMEM / 4);
+  uint32_t* bad = bufs + CQ_FE_NBUF * CQ_ACC;
+  const int k = tg >> 5, lane = tg & 31;
+  const size_t gid = (size_t)blockIdx.x * CQ_GROUPS + grp;
+  if (gid >= ngroups) return;
+  const size_t id = gid * CQ_LANES + lane;
   const bool valid = id < nprob * 4;
   const size_t p = valid ? id % nprob : 0;
   const int e = valid ? (int)(id / nprob) : 0;
@@ -38,18 +40,18 @@ __global__ void __launch_bounds__(FE3_THREADS, 2) k_final_exp3(const fp12* __res
       if (k == 0) fp_one(c.c0);
     }
     cq_st_coef(bufs + (ch == 0 ? 0 : 1) * CQ_ACC, k, lane, c);
-    __syncthreads();
+    cq_group_sync(grp);
     if (ch > 0) {
       cq_mul(k, lane, bufs, bufs + CQ_ACC, bufs + 2 * CQ_ACC);
-      __syncthreads();
+      cq_group_sync(grp);
       cq_copy(k, lane, bufs + 2 * CQ_ACC, bufs);
-      __syncthreads();
+      cq_group_sync(grp);
     }
   }
 #pragma unroll 1
   for (int i = 0; i < nops; i++) {
     cq_exec(prog[i], k, lane, bufs);
-    __syncthreads();
+    cq_group_sync(grp);
   }
   fp2 g;
   cq_ld_coef(g.c0, g.c1, bufs + CQ_FE_OUT * CQ_ACC, k, lane, false, false);
@@ -66,7 +68,7 @@ __global__ void __launch_bounds__(FE3_THREADS, 2) k_final_exp3(const fp12* __res
       if (!g.equals(want)) bad[lane] = 1;
     }
   }
-  __syncthreads();
+  cq_group_sync(grp);
   if (ok && valid && k == 0) ok[(size_t)e * nprob + p] = bad[lane] ? 0 : 1;
 }
 
@@ -78,13 +80,13 @@ int gsi::final_exp_init(gs_ctx* ctx) {
   ctx->fe_nops = n;
   CUDA_TRY(cudaMalloc(&ctx->fe_prog, n * sizeof(uint32_t)));
   CUDA_TRY(cudaMemcpy(ctx->fe_prog, prog, n * sizeof(uint32_t), cudaMemcpyHostToDevice));
-  CUDA_TRY(cudaFuncSetAttribute(k_final_exp3, cudaFuncAttributeMaxDynamicSharedMemorySize, FE3_SMEM));
+  CUDA_TRY(cudaFuncSetAttribute(k_final_exp3, cudaFuncAttributeMaxDynamicSharedMemorySize, CQ_GROUPS * FE3_SMEM));
   return GS_OK;
 }
 
 int gsi::launch_final_exp(gs_ctx* ctx, const fp12* F, size_t nprob, int nchunk, fp12* out_comt, uint8_t* ok4, const fp12* target) {
-  size_t nblk = (nprob * 4 + CQ_LANES - 1) / CQ_LANES;
-  LAUNCH_CFG(k_final_exp3, nblk * FE3_THREADS, FE3_THREADS, FE3_SMEM, F, nprob, nchunk, out_comt, ok4, target, ctx->fe_prog,
-             ctx->fe_nops);
+  size_t ngroups = (nprob * 4 + CQ_LANES - 1) / CQ_LANES;
+  LAUNCH_CFG(k_final_exp3, ((ngroups + CQ_GROUPS - 1) / CQ_GROUPS) * CQ_BLOCK_THREADS, CQ_BLOCK_THREADS, CQ_GROUPS * FE3_SMEM, F, nprob,
+             nchunk, out_comt, ok4, target, ctx->fe_prog, ctx->fe_nops, ngroups);
   return GS_OK;
 }

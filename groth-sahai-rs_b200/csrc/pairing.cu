@@ -2,6 +2,7 @@
 // ComT entry points of the C ABI (ComT::pairing / pairing_sum / linear_map_*, E::pairing).
 // Reference: src/data_structures.rs:484-540, src/generator.rs:116.
 #include "ctx.h"
+#include "batchinv.cuh"
 #include "coop12.cuh"
 #include "pairing.cuh"
 
@@ -16,76 +17,160 @@ namespace gs {
 // coordinate) reads contiguous memory:
 //     X[(a*K + k) * nprob + p]   g1_aff        Y[(b*K + k) * nprob + p]   g2_aff
 
-// ------------------------------------------------------------------ v3: evaluated line tiles + cooperative Miller
+// ------------------------------------------------------------------ evaluated line tiles + cooperative Miller
 // Accumulator index A = chunk * np + (p - p0) (chunk = slot range [chunk*S, chunk*S+S) of a big statement);
 // 32 consecutive accumulators of one ComT entry e = 2a+b form a block  bid = (A/32)*4 + e.
-// Tile (bid, kk, step): the line of slot kk at Miller step `step`, already evaluated at the G1 point of
-// entry e, as 6 Fp in the Q layout of coop12.cuh (alpha.c0 alpha.c1 beta.c0 beta.c1 gamma.c0 gamma.c1 =
-// c0, c1*xP, c2*yP), 9,216 B, contiguous: written by k_g2_prepare3 with 16-B stores (512 B per warp and
-// quad), copied into shared memory by k_miller3 with cp.async.
-//     tiles[((bid*S + kk)*68 + step) * M3_TILE ...]      masks[bid*S + kk] = lanes whose pair is not dropped
-constexpr int M3_NV = 6;
-constexpr int M3_TILE = M3_NV * CQ_FP;
-constexpr int M3_THREADS = 6 * CQ_LANES;
-constexpr int M3_MAXS = 512;
-constexpr int M3_SMEM = (2 * CQ_ACC + 2 * M3_TILE) * 4 + M3_MAXS * 6 + 16;
+// Tile (bid, kk, step): the line of slot kk at Miller step `step`, evaluated at the G1 point of entry e and
+// scaled so that its w^3 coefficient is one:  l' = w^3 + beta w^2 + alpha  with  beta = lam * (-xP/yP),
+// alpha = mu / yP  (pairing.cuh g2_affine_step).  Stored as 4 Fp (alpha.c0 alpha.c1 beta.c0 beta.c1) in the
+// Q layout of coop12.cuh, 6,144 B, contiguous: written by k_g2_prepare4 with 16-B stores (512 B per warp
+// and quad), copied into shared memory by k_miller4 with cp.async.
+//     tiles[((bid*S + kk)*68 + step) * M4_TILE ...]      masks[bid*S + kk] = lanes whose pair is not dropped
+constexpr int M4_NV = 4;
+constexpr int M4_TILE = M4_NV * CQ_FP;
+constexpr int M4_MAXS = 512;
+constexpr int M4_SMEM = (2 * CQ_ACC + 2 * M4_TILE) * 4 + M4_MAXS * 6 + 16;  // per 6-warp group
+constexpr int G2_E = 4;  // G2 points walked per thread (one shared inversion per Miller step)
 
-// one thread per G2 point q = (b*K + k) * np + pl  (pl = p - p0)
-__global__ void __launch_bounds__(128) k_g2_prepare3(const g1_aff* __restrict__ X, const g2_aff* __restrict__ Y,
-                                                     uint32_t* __restrict__ tiles, uint32_t* __restrict__ masks,
-                                                     size_t nprob, size_t p0, size_t np, int K, int S) {
+// per G1 slot point: PW[((a*K + k)*2 + which)*12 + limb][pl] with which = 0: -xP/yP, 1: 1/yP (zero for identity)
+__global__ void __launch_bounds__(128) k_g1_prep(const g1_aff* __restrict__ X, uint32_t* __restrict__ PW, size_t nprob,
+                                                 size_t p0, size_t np, int K) {
+  __shared__ fp sm[2 * 128];
   size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (q >= 2 * (size_t)K * np) return;
-  size_t pl = q % np, bk = q / np;
-  int b = (int)(bk / K), k = (int)(bk % K);
-  g2_aff Q = Y[bk * nprob + p0 + pl];
-  if (Q.is_inf()) return;
-  fp px[2], py[2];
-  bool act[2];
-  size_t tbase[2];
-  const int ch = k / S, kk = k % S;
-  const size_t A = (size_t)ch * np + pl;
-  const int lane = (int)(A & 31);
-#pragma unroll
-  for (int a = 0; a < 2; a++) {
-    const g1_aff* P = &X[((size_t)a * K + k) * nprob + p0 + pl];
-    px[a] = P->x;
-    py[a] = P->y;
-    act[a] = !(px[a].is_zero() && py[a].is_zero());
-    size_t bid = (A >> 5) * 4 + (size_t)(2 * a + b);
-    tbase[a] = ((bid * S + kk) * GS_NUM_LINES) * (size_t)M3_TILE;
-    if (act[a]) atomicOr(&masks[bid * S + kk], 1u << lane);
+  bool in = q < 2 * (size_t)K * np;
+  size_t pl = in ? q % np : 0, ak = in ? q / np : 0;
+  fp x, w;
+  x.set_zero();
+  w.set_zero();
+  if (in) {
+    const g1_aff* P = &X[ak * nprob + p0 + pl];
+    x = P->x;
+    w = P->y;
+    if (x.is_zero() && w.is_zero()) w.set_zero();
   }
-  if (!act[0] && !act[1]) return;
-  g2_proj t;
-  t.x = Q.x;
-  t.y = Q.y;
-  t.z.set_one();
+  block_batch_inv<128>(w, sm);  // 0 stays 0
+  if (!in) return;
+  fp s;
+  fp::mul(s, x, w);
+  fp::neg(s, s);
+  uint32_t* o = PW + (ak * 2 * 12) * np + pl;
+#pragma unroll
+  for (int j = 0; j < 12; j++) {
+    o[(size_t)j * np] = s.l[j];
+    o[(size_t)(12 + j) * np] = w.l[j];
+  }
+}
+
+// one thread per (b, group of G2_E consecutive slots, problem).  The G2_E running points T_i live in shared
+// memory, word-major / thread-minor (conflict free): 768 B per thread, 2 blocks of 128 threads per SM.
+struct g2_pts_smem {  // word w of point i of this thread at base[(i*48 + w) * 128]
+  uint32_t* base;
+  __device__ GS_INL void ld(int i, fp2& X, fp2& Y) const {
+    const uint32_t* p = base + (size_t)i * 48 * 128;
+#pragma unroll
+    for (int j = 0; j < 12; j++) {
+      X.c0.l[j] = p[j * 128];
+      X.c1.l[j] = p[(12 + j) * 128];
+      Y.c0.l[j] = p[(24 + j) * 128];
+      Y.c1.l[j] = p[(36 + j) * 128];
+    }
+  }
+  __device__ GS_INL void st(int i, const fp2& X, const fp2& Y) {
+    uint32_t* p = base + (size_t)i * 48 * 128;
+#pragma unroll
+    for (int j = 0; j < 12; j++) {
+      p[j * 128] = X.c0.l[j];
+      p[(12 + j) * 128] = X.c1.l[j];
+      p[(24 + j) * 128] = Y.c0.l[j];
+      p[(36 + j) * 128] = Y.c1.l[j];
+    }
+  }
+};
+struct g2_pts_gmem {  // the fixed points Q_i (read again at the 5 addition steps only)
+  const g2_aff* q;    // &Y[(b*K + g*G2_E) * nprob + p]
+  size_t stride;      // nprob
+  __device__ GS_INL void ld(int i, fp2& X, fp2& Y) const {
+    const g2_aff* p = q + (size_t)i * stride;
+    X = p->x;
+    Y = p->y;
+  }
+};
+constexpr int G2P_SMEM = G2_E * 48 * 128 * 4;
+__global__ void __launch_bounds__(128, 2) k_g2_prepare4(const uint32_t* __restrict__ PW, const g2_aff* __restrict__ Y,
+                                                        uint32_t* __restrict__ tiles, uint32_t* __restrict__ masks,
+                                                        size_t nprob, size_t p0, size_t np, int K, int S) {
+  extern __shared__ __align__(16) uint32_t sm[];
+  const int G = (K + G2_E - 1) / G2_E;
+  size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool inrange = q < 2 * (size_t)G * np;
+  if (!inrange) q = 0;
+  const size_t pl = q % np;
+  const int g = (int)((q / np) % G), b = (int)(q / (np * G));
+  g2_pts_smem T{sm + threadIdx.x};
+  g2_pts_gmem Q{&Y[((size_t)b * K + (size_t)g * G2_E) * nprob + p0 + pl], nprob};
+  bool act[G2_E], acta[G2_E][2];
+  size_t tb[G2_E][2];
+  int lanes[G2_E];
+  bool any = false;
+#pragma unroll
+  for (int i = 0; i < G2_E; i++) {
+    const int k = g * G2_E + i;
+    act[i] = false;
+    acta[i][0] = acta[i][1] = false;
+    tb[i][0] = tb[i][1] = 0;
+    lanes[i] = 0;
+    if (k >= K || !inrange) continue;
+    fp2 qx, qy;
+    Q.ld(i, qx, qy);
+    if (qx.is_zero() && qy.is_zero()) continue;
+    const int ch = k / S, kk = k % S;
+    const size_t A = (size_t)ch * np + pl;
+    lanes[i] = (int)(A & 31);
+#pragma unroll
+    for (int a = 0; a < 2; a++) {
+      // 1/yP is zero exactly for an identity G1 point
+      const uint32_t* w = PW + ((((size_t)a * K + k) * 2 + 1) * 12) * np + pl;
+      uint32_t nz = 0;
+      for (int j = 0; j < 12; j++) nz |= w[(size_t)j * np];
+      acta[i][a] = nz != 0;
+      size_t bid = (A >> 5) * 4 + (size_t)(2 * a + b);
+      tb[i][a] = ((bid * S + kk) * GS_NUM_LINES) * (size_t)M4_TILE;
+      if (acta[i][a]) atomicOr(&masks[bid * S + kk], 1u << lanes[i]);
+    }
+    act[i] = acta[i][0] || acta[i][1];
+    if (act[i]) T.st(i, qx, qy);
+    any = any || act[i];
+  }
+  if (!__syncthreads_or(any)) return;  // block-uniform: the step barriers below need every thread
   int idx = 0;
-  for (int bit = 62; bit >= 0; bit--) {
-    int nl = ((GS_X_ABS >> bit) & 1) ? 2 : 1;
-    for (int w = 0; w < nl; w++, idx++) {
-      line_coeffs l;
-      if (w == 0)
-        g2_double_step(t, l);
-      else
-        g2_add_step(t, Q, l);
 #pragma unroll 1
-      for (int a = 0; a < 2; a++) {
-        if (!act[a]) continue;
-        uint32_t* o = tiles + tbase[a] + (size_t)idx * M3_TILE;
-        fp v;
-        cq_st(cq_ptr(o, 0, lane), l.c0.c0);
-        cq_st(cq_ptr(o, 1, lane), l.c0.c1);
-        fp::mul(v, l.c1.c0, px[a]);
-        cq_st(cq_ptr(o, 2, lane), v);
-        fp::mul(v, l.c1.c1, px[a]);
-        cq_st(cq_ptr(o, 3, lane), v);
-        fp::mul(v, l.c2.c0, py[a]);
-        cq_st(cq_ptr(o, 4, lane), v);
-        fp::mul(v, l.c2.c1, py[a]);
-        cq_st(cq_ptr(o, 5, lane), v);
-      }
+  for (int bit = 62; bit >= 0; bit--) {
+    const int nl = ((GS_X_ABS >> bit) & 1) ? 2 : 1;
+#pragma unroll 1
+    for (int w = 0; w < nl; w++, idx++) {
+      g2_affine_step<G2_E>(T, Q, act, w == 1, [&](int i, const fp2& lam, const fp2& mu) {
+        const int k = g * G2_E + i;
+#pragma unroll 1
+        for (int a = 0; a < 2; a++) {
+          if (!acta[i][a]) continue;
+          const uint32_t* pw = PW + ((((size_t)a * K + k) * 2) * 12) * np + pl;
+          fp s, wv, v;
+#pragma unroll
+          for (int j = 0; j < 12; j++) {
+            s.l[j] = pw[(size_t)j * np];
+            wv.l[j] = pw[(size_t)(12 + j) * np];
+          }
+          uint32_t* o = tiles + tb[i][a] + (size_t)idx * M4_TILE;
+          fp_mul_n(v, mu.c0, wv);
+          cq_st(cq_ptr(o, 0, lanes[i]), v);
+          fp_mul_n(v, mu.c1, wv);
+          cq_st(cq_ptr(o, 1, lanes[i]), v);
+          fp_mul_n(v, lam.c0, s);
+          cq_st(cq_ptr(o, 2, lanes[i]), v);
+          fp_mul_n(v, lam.c1, s);
+          cq_st(cq_ptr(o, 3, lanes[i]), v);
+        }
+      }, [] { __syncthreads(); });
     }
   }
 }
@@ -96,20 +181,24 @@ __device__ GS_INL void cp_async16(uint32_t* smem, const uint32_t* g) {
 }
 __device__ GS_INL void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
-// block = 32 accumulators of entry e (bid = blk*4 + e); warp k = w-power coefficient k (coop12.cuh).
-// F[(ch*4 + e) * nprob + p] = conj( prod over the chunk's slots )
-__global__ void __launch_bounds__(M3_THREADS, 2) k_miller3(const uint32_t* __restrict__ tiles, const uint32_t* __restrict__ masks,
-                                                          fp12* __restrict__ F, size_t nprob, size_t p0, size_t np, int S,
-                                                          int nchunk) {
-  extern __shared__ __align__(16) uint32_t sm[];
+// group (6 warps) = 32 accumulators of entry e (bid = blk*4 + e); warp k = w-power coefficient k (coop12.cuh);
+// CQ_GROUPS groups per block.   F[(ch*4 + e) * nprob + p] = conj( prod over the chunk's slots )
+__global__ void __launch_bounds__(CQ_BLOCK_THREADS, 1) k_miller4(const uint32_t* __restrict__ tiles,
+                                                                const uint32_t* __restrict__ masks, fp12* __restrict__ F,
+                                                                size_t nprob, size_t p0, size_t np, int S, int nchunk,
+                                                                size_t ngroups) {
+  extern __shared__ __align__(16) uint32_t sm_all[];
+  const int grp = threadIdx.x / CQ_GROUP_THREADS, tg = threadIdx.x % CQ_GROUP_THREADS;
+  uint32_t* sm = sm_all + (size_t)grp * (M4_SMEM / 4);
   uint32_t* acc = sm;
   uint32_t* tile = sm + 2 * CQ_ACC;
-  uint32_t* smask = tile + 2 * M3_TILE;
-  uint16_t* slots = (uint16_t*)(smask + M3_MAXS);
-  int* nact_s = (int*)(slots + M3_MAXS);
-  const int k = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const size_t bid = blockIdx.x;
-  if (threadIdx.x == 0) {
+  uint32_t* smask = tile + 2 * M4_TILE;
+  uint16_t* slots = (uint16_t*)(smask + M4_MAXS);
+  int* nact_s = (int*)(slots + M4_MAXS);
+  const int k = tg >> 5, lane = tg & 31;
+  const size_t bid = (size_t)blockIdx.x * CQ_GROUPS + grp;
+  if (bid >= ngroups) return;
+  if (tg == 0) {
     int n = 0;
     for (int kk = 0; kk < S; kk++) {
       uint32_t m = masks[bid * S + kk];
@@ -122,29 +211,29 @@ __global__ void __launch_bounds__(M3_THREADS, 2) k_miller3(const uint32_t* __res
     *nact_s = n;
   }
   cq_set_one(k, lane, acc);
-  __syncthreads();
+  cq_group_sync(grp);
   const int nact = *nact_s;
   int cur = 0;
   if (nact > 0) {
     const int total = GS_NUM_LINES * nact;
     auto issue = [&](int n, int stage) {
       int s = n / nact, i = n - s * nact;
-      const uint32_t* src = tiles + ((bid * S + slots[i]) * GS_NUM_LINES + s) * (size_t)M3_TILE;
-      uint32_t* dst = tile + stage * M3_TILE;
+      const uint32_t* src = tiles + ((bid * S + slots[i]) * GS_NUM_LINES + s) * (size_t)M4_TILE;
+      uint32_t* dst = tile + stage * M4_TILE;
 #pragma unroll
-      for (int c = 0; c < M3_TILE / 4 / M3_THREADS; c++) {
-        int w = (c * M3_THREADS + threadIdx.x) * 4;
+      for (int c = 0; c < M4_TILE / 4 / CQ_GROUP_THREADS; c++) {
+        int w = (c * CQ_GROUP_THREADS + tg) * 4;
         cp_async16(dst + w, src + w);
       }
     };
     issue(0, 0);
     cp_async_wait_all();
-    __syncthreads();
+    cq_group_sync(grp);
     int n = 0;
     for (int bit = 62; bit >= 0; bit--) {
       if (bit != 62) {
         cq_sqr(k, lane, acc + cur * CQ_ACC, acc + (cur ^ 1) * CQ_ACC);
-        __syncthreads();
+        cq_group_sync(grp);
         cur ^= 1;
       }
       int nl = ((GS_X_ABS >> bit) & 1) ? 2 : 1;
@@ -152,9 +241,9 @@ __global__ void __launch_bounds__(M3_THREADS, 2) k_miller3(const uint32_t* __res
         if (n + 1 < total) issue(n + 1, (n + 1) & 1);
         int si = i >= nact ? i - nact : i;
         bool active = (smask[si] >> lane) & 1;
-        cq_line_mul(k, lane, acc + cur * CQ_ACC, acc + (cur ^ 1) * CQ_ACC, tile + (n & 1) * M3_TILE, active);
+        cq_line_mul_u(k, lane, acc + cur * CQ_ACC, acc + (cur ^ 1) * CQ_ACC, tile + (n & 1) * M4_TILE, active);
         cp_async_wait_all();
-        __syncthreads();
+        cq_group_sync(grp);
         cur ^= 1;
       }
     }
@@ -231,7 +320,8 @@ __global__ void k_linear_map_slots(int type, const void* target, const crs_dev* 
 }  // namespace gs
 
 int gsi::pairing_init(gs_ctx* ctx) {
-  CUDA_TRY(cudaFuncSetAttribute(k_miller3, cudaFuncAttributeMaxDynamicSharedMemorySize, M3_SMEM));
+  CUDA_TRY(cudaFuncSetAttribute(k_miller4, cudaFuncAttributeMaxDynamicSharedMemorySize, CQ_GROUPS * M4_SMEM));
+  CUDA_TRY(cudaFuncSetAttribute(k_g2_prepare4, cudaFuncAttributeMaxDynamicSharedMemorySize, G2P_SMEM));
   return GS_OK;
 }
 
@@ -239,7 +329,7 @@ int gsi::pairing_init(gs_ctx* ctx) {
 // X, Y: device slot arrays [2][K][nprob].  Produces either ComT values (out_comt, AoS [p][4]) or
 // per-entry verdict bytes ok4[4][nprob] (compared with 1 / target).
 // Problems are processed in passes of `pc` so that the evaluated-line tiles stay within ctx->tile_budget
-// bytes of HBM; a pass is sized to a whole number of k_miller3 waves (2 blocks x 148 SMs x 32 accumulators
+// bytes of HBM; a pass is sized to a whole number of k_miller4 waves (2 groups x 148 SMs x 32 accumulators
 // / 4 entries = 2,368 problems per wave) when the batch is large enough.
 int gsi::run_pairing_product(gs_ctx* ctx, Scratch& sc, const g1_aff* X, const g2_aff* Y, size_t nprob, int K,
                                fp12* out_comt, uint8_t* ok4, const fp12* target) {
@@ -252,9 +342,9 @@ int gsi::run_pairing_product(gs_ctx* ctx, Scratch& sc, const g1_aff* X, const g2
     if (c < 1) c = 1;
     S = (int)((K + c - 1) / c);
   }
-  if (S > M3_MAXS) S = M3_MAXS;
+  if (S > M4_MAXS) S = M4_MAXS;
   nchunk = (K + S - 1) / S;
-  const size_t per_prob = (size_t)4 * nchunk * S * GS_NUM_LINES * M3_TILE * 4 / 32;  // tile bytes per problem
+  const size_t per_prob = (size_t)4 * nchunk * S * GS_NUM_LINES * M4_TILE * 4 / 32;  // tile bytes per problem
   size_t pc = ctx->tile_budget / per_prob;
   if (pc >= nprob) {
     pc = nprob;
@@ -264,17 +354,20 @@ int gsi::run_pairing_product(gs_ctx* ctx, Scratch& sc, const g1_aff* X, const g2
     pc -= pc % 32;
   }
   const size_t nblk_max = ((pc * nchunk + 31) / 32) * 4;
-  uint32_t *tiles, *masks;
+  uint32_t *tiles, *masks, *PW;
   fp12* F;
-  CUDA_TRY(sc.alloc(&tiles, nblk_max * S * GS_NUM_LINES * (size_t)M3_TILE));
+  CUDA_TRY(sc.alloc(&PW, 2 * (size_t)K * 24 * pc));
+  CUDA_TRY(sc.alloc(&tiles, nblk_max * S * GS_NUM_LINES * (size_t)M4_TILE));
   CUDA_TRY(sc.alloc(&masks, nblk_max * S));
   CUDA_TRY(sc.alloc(&F, (size_t)nchunk * 4 * nprob));
   for (size_t p0 = 0; p0 < nprob; p0 += pc) {
     size_t np = nprob - p0 < pc ? nprob - p0 : pc;
     size_t nblk = ((np * nchunk + 31) / 32) * 4;
     CUDA_TRY(cudaMemsetAsync(masks, 0, nblk * S * sizeof(uint32_t), ctx->stream));
-    LAUNCH(k_g2_prepare3, 2 * (size_t)K * np, X, Y, tiles, masks, nprob, p0, np, K, S);
-    LAUNCH_CFG(k_miller3, nblk * M3_THREADS, M3_THREADS, M3_SMEM, tiles, masks, F, nprob, p0, np, S, nchunk);
+    LAUNCH(k_g1_prep, 2 * (size_t)K * np, X, PW, nprob, p0, np, K);
+    LAUNCH_CFG(k_g2_prepare4, 2 * (size_t)((K + G2_E - 1) / G2_E) * np, 128, G2P_SMEM, PW, Y, tiles, masks, nprob, p0, np, K, S);
+    LAUNCH_CFG(k_miller4, ((nblk + CQ_GROUPS - 1) / CQ_GROUPS) * CQ_BLOCK_THREADS, CQ_BLOCK_THREADS, CQ_GROUPS * M4_SMEM, tiles, masks,
+               F, nprob, p0, np, S, nchunk, nblk);
   }
   return gsi::launch_final_exp(ctx, F, nprob, nchunk, out_comt, ok4, target);
 }

@@ -113,6 +113,132 @@ inline GS_HD GS_NOINL void g2_add_step(g2_proj& t, const g2_aff& q, line_coeffs&
   l.c2 = lambda;
 }
 
+// ------------------------------------------------------------------ affine line walk, E points per thread
+// One Miller step (doubling: T <- 2T, or addition: T <- T + Q) for E independent G2 points in AFFINE
+// coordinates.  The E slope denominators (2 y_T, or x_T - x_Q) are inverted together: Fp2 norms, Montgomery's
+// trick over the E norms, ONE safegcd inversion (modinv.cuh), so a step costs ~13 + 6 Fp products per point
+// plus 1/E of an inversion that runs on the integer-ALU pipe.  Output per point: the line through T with
+// slope lam on the twist,
+//     l(P) * w^3 = yP w^3 - lam xP w^2 + mu,      mu = lam x_T - y_T
+// which the caller scales by 1/yP (an Fp factor, killed by the final exponentiation) so that the w^3
+// coefficient is ONE:  l' = w^3 + (lam * (-xP/yP)) w^2 + mu * (1/yP).
+// Points with act[i] == false are left untouched.  Inputs must be points of the order-r subgroup (as the
+// reference's G2Affine values are): then no denominator vanishes; a zero denominator yields lam = 0.
+// T / Q are accessor objects (ld(i, x, y), st(i, x, y)): strided shared memory on the GPU, plain arrays in
+// tests/hostsim; emit(i, lam, mu) receives each line as soon as it is known (no per-thread line arrays);
+// sync() is a block barrier on the GPU (keeps the warps of a block in the same code region, which is what
+// lets them share instruction-cache lines) and a no-op in the tests.
+// The walk is latency- and I-cache-sensitive (few warps per SM, every warp at its own place in a long loop
+// body), so the field products are single out-of-line copies: the loop body stays ~3k instructions.
+inline GS_HD GS_NOINL void fp_mul_n(fp& r, const fp& a, const fp& b) { fp::mul(r, a, b); }
+inline GS_HD GS_NOINL void fp2_mul_n(fp2& r, const fp2& a, const fp2& b) {
+  fp t0, t1, t2, s0, s1;
+  fp::add(s0, a.c0, a.c1);
+  fp::add(s1, b.c0, b.c1);
+  fp_mul_n(t0, a.c0, b.c0);
+  fp_mul_n(t1, a.c1, b.c1);
+  fp_mul_n(t2, s0, s1);
+  fp::sub(r.c0, t0, t1);
+  fp::sub(t2, t2, t0);
+  fp::sub(r.c1, t2, t1);
+}
+inline GS_HD GS_NOINL void fp2_sqr_n(fp2& r, const fp2& a) {
+  fp s, d, m;
+  fp::add(s, a.c0, a.c1);
+  fp::sub(d, a.c0, a.c1);
+  fp_mul_n(m, a.c0, a.c1);
+  fp_mul_n(r.c0, s, d);
+  fp::add(r.c1, m, m);
+}
+inline GS_HD GS_NOINL void fp2_sub_n(fp2& r, const fp2& a, const fp2& b) { fp2::sub(r, a, b); }
+inline GS_HD GS_NOINL void fp2_add_n(fp2& r, const fp2& a, const fp2& b) { fp2::add(r, a, b); }
+
+// phase 1 for point i: slope denominator -> its Fp2 norm (1 when the point is inactive or degenerate)
+template <class TS, class QS>
+GS_HD GS_INL void g2_affine_den(fp2& den, fp2& x, fp2& y, fp2& qx, fp2& qy, TS& T, const QS& Q, int i, bool is_add) {
+  T.ld(i, x, y);
+  if (is_add) {
+    Q.ld(i, qx, qy);
+    fp2_sub_n(den, x, qx);
+  } else {
+    fp2_add_n(den, y, y);
+  }
+}
+template <int E, class TS, class QS, class EM, class SY>
+GS_HD GS_INL void g2_affine_step(TS& T, const QS& Q, const bool* act, bool is_add, EM&& emit, SY&& sync) {
+  fp nrm[E], pre[E];
+#pragma unroll 1
+  for (int i = 0; i < E; i++) {
+    fp n;
+    fp_one(n);
+    if (act[i]) {
+      fp2 x, y, qx, qy, den;
+      g2_affine_den(den, x, y, qx, qy, T, Q, i, is_add);
+      fp t;
+      fp_mul_n(n, den.c0, den.c0);
+      fp_mul_n(t, den.c1, den.c1);
+      fp::add(n, n, t);
+      if (n.is_zero()) fp_one(n);
+    }
+    nrm[i] = n;
+    if (i == 0)
+      pre[0] = n;
+    else
+      fp_mul_n(pre[i], pre[i - 1], n);
+  }
+  sync();
+  fp inv;
+  fp_inv(inv, pre[E - 1]);
+  sync();
+#pragma unroll 1
+  for (int i = E - 1; i >= 0; i--) {
+    fp ninv;
+    if (i > 0) {
+      fp_mul_n(ninv, inv, pre[i - 1]);
+      fp_mul_n(inv, inv, nrm[i]);
+    } else {
+      ninv = inv;
+    }
+    if (!act[i]) continue;
+    fp2 x, y, qx, qy, num, sum, dinv, l, t, x3;
+    g2_affine_den(dinv, x, y, qx, qy, T, Q, i, is_add);
+    if (is_add) {
+      fp2_sub_n(num, y, qy);
+      fp2_add_n(sum, x, qx);
+    } else {
+      fp2_sqr_n(t, x);
+      fp2_add_n(num, t, t);
+      fp2_add_n(num, num, t);
+      fp2_add_n(sum, x, x);
+    }
+    // 1/den = conj(den) / |den|^2
+    fp_mul_n(dinv.c0, dinv.c0, ninv);
+    fp_mul_n(dinv.c1, dinv.c1, ninv);
+    fp::neg(dinv.c1, dinv.c1);
+    fp2_mul_n(l, num, dinv);
+    fp2_sqr_n(x3, l);
+    fp2_sub_n(x3, x3, sum);
+    fp2_mul_n(t, l, x);
+    fp2_sub_n(t, t, y);  // mu = lam x_T - y_T
+    emit(i, l, t);
+    fp2_mul_n(num, l, x3);
+    fp2_sub_n(y, t, num);
+    T.st(i, x3, y);
+  }
+}
+// array-backed accessor (host tests)
+struct g2_pts_arr {
+  fp2 *x, *y;
+  GS_HD GS_INL void ld(int i, fp2& X, fp2& Y) const {
+    X = x[i];
+    Y = y[i];
+  }
+  GS_HD GS_INL void st(int i, const fp2& X, const fp2& Y) {
+    x[i] = X;
+    y[i] = Y;
+  }
+};
+
 // Line storage: word-interleaved so that both the writer (one thread per G2 point) and the reader
 // (one thread per accumulator) are perfectly coalesced over consecutive problems:
 //     word w (0..71) of line `idx` of a point lives at  base[(idx*72 + w) * stride]

@@ -203,3 +203,49 @@ extern "C" void hs_cq_cyc_sqr(void* r, const void* a, int lane) {
 }
 // safegcd inversion (modinv.cuh)
 extern "C" void hs_fp_inv_sg(void* r, const void* a) { LD(fp, x, a); fp z; fp_inv_sg(z, x); ST(r, z); }
+
+// ---- v4: affine line walk (4 points per inversion, safegcd) + unit-gamma line multiplication.
+// One accumulator (lane), n <= 4 pairs.  The Miller value differs from hs_miller by Fp2 / Fp factors, so the
+// caller compares after the final exponentiation.
+extern "C" void hs_miller_v4(void* r, int n, const void* g1s, const void* g2s, int lane) {
+  const g1_aff* P = (const g1_aff*)g1s; const g2_aff* Q = (const g2_aff*)g2s;
+  const int TILE = 4 * CQ_FP;
+  fp2 Tx[4], Ty[4], Qx[4], Qy[4], lam[4], mu[4]; bool act[4] = {false, false, false, false};
+  fp s[4], w[4];
+  for (int i = 0; i < n && i < 4; i++) {
+    if (P[i].is_inf() || Q[i].is_inf()) continue;
+    act[i] = true; Tx[i] = Q[i].x; Ty[i] = Q[i].y; Qx[i] = Q[i].x; Qy[i] = Q[i].y;
+    fp_inv(w[i], P[i].y); fp::mul(s[i], P[i].x, w[i]); fp::neg(s[i], s[i]);
+  }
+  std::vector<uint32_t> acc(2 * CQ_ACC, 0xdeadbeefu), tile(TILE, 0xdeadbeefu);
+  int cur = 0;
+  for (int k = 0; k < 6; k++) cq_set_one(k, lane, acc.data());
+  for (int bit = 62; bit >= 0; bit--) {
+    if (bit != 62) {
+      for (int k = 0; k < 6; k++) cq_sqr(k, lane, acc.data() + cur * CQ_ACC, acc.data() + (cur ^ 1) * CQ_ACC);
+      cur ^= 1;
+    }
+    int nl = ((GS_X_ABS >> bit) & 1) ? 2 : 1;
+    for (int t = 0; t < nl; t++) {
+      g2_pts_arr TT{Tx, Ty}, QQ{Qx, Qy};
+      g2_affine_step<4>(TT, QQ, act, t == 1, [&](int i, const fp2& l, const fp2& m) { lam[i] = l; mu[i] = m; }, [] {});
+      for (int i = 3; i >= 0; i--) {
+        if (!act[i]) continue;
+        fp v;
+        fp::mul(v, mu[i].c0, w[i]); cq_st(cq_ptr(tile.data(), 0, lane), v);
+        fp::mul(v, mu[i].c1, w[i]); cq_st(cq_ptr(tile.data(), 1, lane), v);
+        fp::mul(v, lam[i].c0, s[i]); cq_st(cq_ptr(tile.data(), 2, lane), v);
+        fp::mul(v, lam[i].c1, s[i]); cq_st(cq_ptr(tile.data(), 3, lane), v);
+        for (int k = 0; k < 6; k++) cq_line_mul_u(k, lane, acc.data() + cur * CQ_ACC, acc.data() + (cur ^ 1) * CQ_ACC, tile.data(), true);
+        cur ^= 1;
+      }
+    }
+  }
+  fp12 out;
+  for (int k = 0; k < 6; k++) {
+    fp2 c; cq_ld_coef(c.c0, c.c1, acc.data() + cur * CQ_ACC, k, lane, false, false);
+    if (k & 1) fp2::neg(c, c);
+    ((fp2*)&out)[cq_tower_pos(k)] = c;
+  }
+  ST(r, out);
+}

@@ -199,3 +199,17 @@ def test_coop12_final_exp(L):
         f = rfp12()
         assert fp12_i(call(L.hs_final_exp3, 576, fp12_b(f), lane)) == final_exponentiation(f)
     assert fp12_i(call(L.hs_final_exp3, 576, fp12_b(FP12_ONE), 3)) == FP12_ONE
+
+
+def test_miller_v4_affine_lines(L):
+    """Affine line walk (shared safegcd inversion per step) + unit-gamma sparse multiplication: the Miller value
+    differs from the projective one by subfield factors only, i.e. it is identical after the final exponentiation."""
+    ps = [g1_mul(G1_GEN, rng.randrange(R)) for _ in range(4)]
+    qs = [g2_mul(G2_GEN_FP2, rng.randrange(R)) for _ in range(4)]
+    ps[2] = None                       # a dropped pair inside the batch of four
+    g1s = b"".join(g1_b(p) for p in ps)
+    g2s = b"".join(g2_b(q) for q in qs)
+    v4 = call(L.hs_miller_v4, 576, 4, g1s, g2s, 9)
+    want = final_exponentiation(multi_miller_loop(list(zip(ps, qs))))
+    assert fp12_i(call(L.hs_final_exp3, 576, v4, 2)) == want
+    assert fp12_i(call(L.hs_final_exp, 576, v4)) == want
