@@ -61,31 +61,10 @@ __global__ void __launch_bounds__(128) k_g1_prep(const g1_aff* __restrict__ X, u
   }
 }
 
-// one thread per (b, group of G2_E consecutive slots, problem).  The G2_E running points T_i live in shared
-// memory, word-major / thread-minor (conflict free): 768 B per thread, 2 blocks of 128 threads per SM.
-struct g2_pts_smem {  // word w of point i of this thread at base[(i*48 + w) * 128]
-  uint32_t* base;
-  __device__ GS_INL void ld(int i, fp2& X, fp2& Y) const {
-    const uint32_t* p = base + (size_t)i * 48 * 128;
-#pragma unroll
-    for (int j = 0; j < 12; j++) {
-      X.c0.l[j] = p[j * 128];
-      X.c1.l[j] = p[(12 + j) * 128];
-      Y.c0.l[j] = p[(24 + j) * 128];
-      Y.c1.l[j] = p[(36 + j) * 128];
-    }
-  }
-  __device__ GS_INL void st(int i, const fp2& X, const fp2& Y) {
-    uint32_t* p = base + (size_t)i * 48 * 128;
-#pragma unroll
-    for (int j = 0; j < 12; j++) {
-      p[j * 128] = X.c0.l[j];
-      p[(12 + j) * 128] = X.c1.l[j];
-      p[(24 + j) * 128] = Y.c0.l[j];
-      p[(36 + j) * 128] = Y.c1.l[j];
-    }
-  }
-};
+// one thread per (b, group of G2_E consecutive slots, problem).  The G2_E running points T_i (192 B each) live
+// in thread-local memory (L1/L2-resident, lane-interleaved by the hardware): shared memory would cap the
+// kernel at 8 warps per SM, and the walk is latency-bound (long dependent chains in the division steps), so
+// occupancy matters more than the few hundred bytes of local traffic per step.
 struct g2_pts_gmem {  // the fixed points Q_i (read again at the 5 addition steps only)
   const g2_aff* q;    // &Y[(b*K + g*G2_E) * nprob + p]
   size_t stride;      // nprob
@@ -95,18 +74,17 @@ struct g2_pts_gmem {  // the fixed points Q_i (read again at the 5 addition step
     Y = p->y;
   }
 };
-constexpr int G2P_SMEM = G2_E * 48 * 128 * 4;
-__global__ void __launch_bounds__(128, 2) k_g2_prepare4(const uint32_t* __restrict__ PW, const g2_aff* __restrict__ Y,
+__global__ void __launch_bounds__(128, 4) k_g2_prepare4(const uint32_t* __restrict__ PW, const g2_aff* __restrict__ Y,
                                                         uint32_t* __restrict__ tiles, uint32_t* __restrict__ masks,
                                                         size_t nprob, size_t p0, size_t np, int K, int S) {
-  extern __shared__ __align__(16) uint32_t sm[];
   const int G = (K + G2_E - 1) / G2_E;
   size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const bool inrange = q < 2 * (size_t)G * np;
   if (!inrange) q = 0;
   const size_t pl = q % np;
   const int g = (int)((q / np) % G), b = (int)(q / (np * G));
-  g2_pts_smem T{sm + threadIdx.x};
+  fp2 Tx[G2_E], Ty[G2_E];
+  g2_pts_arr T{Tx, Ty};
   g2_pts_gmem Q{&Y[((size_t)b * K + (size_t)g * G2_E) * nprob + p0 + pl], nprob};
   bool act[G2_E], acta[G2_E][2];
   size_t tb[G2_E][2];
@@ -321,7 +299,6 @@ __global__ void k_linear_map_slots(int type, const void* target, const crs_dev* 
 
 int gsi::pairing_init(gs_ctx* ctx) {
   CUDA_TRY(cudaFuncSetAttribute(k_miller4, cudaFuncAttributeMaxDynamicSharedMemorySize, CQ_GROUPS * M4_SMEM));
-  CUDA_TRY(cudaFuncSetAttribute(k_g2_prepare4, cudaFuncAttributeMaxDynamicSharedMemorySize, G2P_SMEM));
   return GS_OK;
 }
 
@@ -365,7 +342,7 @@ int gsi::run_pairing_product(gs_ctx* ctx, Scratch& sc, const g1_aff* X, const g2
     size_t nblk = ((np * nchunk + 31) / 32) * 4;
     CUDA_TRY(cudaMemsetAsync(masks, 0, nblk * S * sizeof(uint32_t), ctx->stream));
     LAUNCH(k_g1_prep, 2 * (size_t)K * np, X, PW, nprob, p0, np, K);
-    LAUNCH_CFG(k_g2_prepare4, 2 * (size_t)((K + G2_E - 1) / G2_E) * np, 128, G2P_SMEM, PW, Y, tiles, masks, nprob, p0, np, K, S);
+    LAUNCH_CFG(k_g2_prepare4, 2 * (size_t)((K + G2_E - 1) / G2_E) * np, 128, 0, PW, Y, tiles, masks, nprob, p0, np, K, S);
     LAUNCH_CFG(k_miller4, ((nblk + CQ_GROUPS - 1) / CQ_GROUPS) * CQ_BLOCK_THREADS, CQ_BLOCK_THREADS, CQ_GROUPS * M4_SMEM, tiles, masks,
                F, nprob, p0, np, S, nchunk, nblk);
   }
