@@ -1,0 +1,164 @@
+"""GPU tests at the sizes of BASELINE.json's configs, through size-independent properties (the big-int
+oracle cannot follow there): completeness + tamper masks for batch verification (C5), a large dense
+statement through the chunked pairing product (C3), linearity of the batched commitments (C2) and the four
+equation types side by side (C4).  Everything goes through the C ABI; comparisons are byte equality."""
+import os
+import sys
+
+import pytest
+
+from gsutil import *  # noqa: F401,F403
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def eng():
+    import groth_sahai_rs_b200 as gsb
+    e = gsb.Engine(0)
+    crs, _ = make_crs(1)
+    e.crs_load(crs_bytes(crs))
+    e._crs = crs
+    return e
+
+
+def _multiples_g1(eng, ks):
+    g = g1_b(eng._crs.g1_gen)
+    out = eng.com1_matmul(len(ks), 1, 1, b"".join(fr_b(k) for k in ks), g + g)
+    return [out[i * 192:i * 192 + 96] for i in range(len(ks))]
+
+
+def _multiples_g2(eng, ks):
+    g = g2_b(eng._crs.g2_gen)
+    out = eng.com2_matmul(len(ks), 1, 1, b"".join(fr_b(k) for k in ks), g + g)
+    return [out[i * 384:i * 384 + 192] for i in range(len(ks))]
+
+
+def _instance(eng, ty, m, n, rng):
+    """A satisfied equation of type `ty` built on the GPU (witnesses = multiples of the generators)."""
+    xs, ys = [rng.fr() for _ in range(m)], [rng.fr() for _ in range(n)]
+    a, b = [rng.fr() for _ in range(n)], [rng.fr() for _ in range(m)]
+    gam = [[rng.fr() for _ in range(n)] for _ in range(m)]
+    val = (sum(a[j] * ys[j] for j in range(n)) + sum(xs[i] * b[i] for i in range(m)) +
+           sum(gam[i][j] * xs[i] * ys[j] for i in range(m) for j in range(n))) % R
+    g1A = ty in (0, 1)
+    g2B = ty in (0, 2)
+    X = b"".join(_multiples_g1(eng, xs)) if g1A else frs_b(xs)
+    A = b"".join(_multiples_g1(eng, a)) if g1A else frs_b(a)
+    Y = b"".join(_multiples_g2(eng, ys)) if g2B else frs_b(ys)
+    B = b"".join(_multiples_g2(eng, b)) if g2B else frs_b(b)
+    if ty == 0:
+        T = eng.pairing(_multiples_g1(eng, [val])[0], g2_b(eng._crs.g2_gen))
+    elif ty == 1:
+        T = _multiples_g1(eng, [val])[0]
+    elif ty == 2:
+        T = _multiples_g2(eng, [val])[0]
+    else:
+        T = fr_b(val)
+    return A, B, frmat_b(gam), T, X, Y
+
+
+def _commit_prove(eng, ty, m, n, inst, rng):
+    A, B, G, T, X, Y = inst
+    cx = 2 if ty in (0, 1) else 1
+    cy = 2 if ty in (0, 2) else 1
+    xr = b"".join(fr_b(rng.fr()) for _ in range(m * cx))
+    yr = b"".join(fr_b(rng.fr()) for _ in range(n * cy))
+    Tr = b"".join(fr_b(rng.fr()) for _ in range(cx * cy))
+    xc = eng.batch_commit_g1(X, xr) if ty in (0, 1) else eng.batch_commit_scalar_b1(X, xr)
+    yc = eng.batch_commit_g2(Y, yr) if ty in (0, 2) else eng.batch_commit_scalar_b2(Y, yr)
+    pi, th = eng.prove(ty, m, n, A, B, G, X, Y, xr, yr, Tr)
+    return [A, B, G, T, xc, yc, pi, th]
+
+
+def test_c5_batch_verify_tamper_mask(eng):
+    """C5 shape: 4x4 PPE proofs, distinct instances tiled to 8,192 proofs, 1 % tampered -> exact mask."""
+    sys.path.insert(0, ROOT)
+    import bench
+    arrays, expected = bench.build_workload(eng, distinct=8, proofs=8192, seed=5)
+    ok = eng.verify_batch(0, 8192, 4, 4, *[a.tobytes() for a in arrays])
+    assert bytes(ok) == expected.tobytes()
+    assert expected.sum() == 8192 - len(range(37, 8192, 100))
+    crs, _ = make_crs(1)
+    eng.crs_load(crs_bytes(crs))           # build_workload loaded its own key
+
+
+@pytest.mark.parametrize("m,n", [(96, 64)])
+def test_c3_large_dense_statement(eng, m, n):
+    """One PPE with a dense Gamma (C3 shape, scaled): K = n + m + 4 slots go through the chunked pairing product."""
+    rng = SeededRng(3)
+    inst = _instance(eng, 0, m, n, rng)
+    arrs = _commit_prove(eng, 0, m, n, inst, rng)
+    assert eng.verify(0, m, n, *arrs) is True
+    bad = list(arrs)
+    g = bytearray(bad[2])
+    g[32 * (5 * n + 7)] ^= 1                         # one bit of Gamma[5][7]
+    bad[2] = bytes(g)
+    assert eng.verify(0, m, n, *bad) is False
+    bad = list(arrs)
+    bad[4] = bad[4][192:384] + bad[4][:192] + bad[4][384:]   # swap two commitments
+    assert eng.verify(0, m, n, *bad) is False
+
+
+def test_pairing_sum_splits(eng):
+    """ComT::pairing_sum over 300 pairs == entry-wise product of the sums over the two halves
+    (data_structures.rs:1381-1407 at a size that uses several accumulator chunks)."""
+    rng = SeededRng(31)
+    k = 300
+    ks = [rng.fr() for _ in range(4 * k)]
+    p = _multiples_g1(eng, ks[:2 * k])
+    q = _multiples_g2(eng, ks[2 * k:])
+    xs = b"".join(p[2 * i] + p[2 * i + 1] for i in range(k))
+    ys = b"".join(q[2 * i] + q[2 * i + 1] for i in range(k))
+    whole = eng.comt_pairing_sum(xs, ys)
+    h = k // 2
+    a = eng.comt_pairing_sum(xs[:h * 192], ys[:h * 384])
+    b = eng.comt_pairing_sum(xs[h * 192:], ys[h * 384:])
+    from oracle.bls12_381 import Fp12  # noqa: F401  (only the GT product of two 576-byte values is done on the host)
+    for e in range(4):
+        prod = fp12_i(a[576 * e:576 * (e + 1)]) * fp12_i(b[576 * e:576 * (e + 1)])
+        assert fp12_b(prod) == whole[576 * e:576 * (e + 1)]
+    # and the discrete-log check of entry (0,0): prod e(x_i g1, y_i g2) = gt^(sum x_i y_i)
+    s = sum(ks[2 * i] * ks[2 * k + 2 * i] for i in range(k)) % R
+    assert whole[:576] == eng.pairing(_multiples_g1(eng, [s])[0], g2_b(eng._crs.g2_gen))
+
+
+def test_c2_batch_commit_linearity(eng):
+    """C2 shape (scaled to 2^14 variables): commit(X, 0) = iota(X); commit(X, R) - commit(X, 0) does not depend
+    on X; and the big-table path (batches >= 8192) equals the small-table path on the same inputs."""
+    rng = SeededRng(2)
+    n = 1 << 14
+    base = _multiples_g1(eng, [rng.fr() for _ in range(64)])
+    X = b"".join(base[i % 64] for i in range(n))
+    Rr = b"".join(fr_b(rng.fr()) for _ in range(128)) * (n // 64)
+    big = eng.batch_commit_g1(X, Rr)
+    zero = eng.batch_commit_g1(X, bytes(64 * n))
+    assert all(zero[192 * i:192 * i + 96] == bytes(96) and zero[192 * i + 96:192 * (i + 1)] == X[96 * i:96 * (i + 1)]
+               for i in range(0, n, 97))
+    small = eng.batch_commit_g1(X[:96 * 64], Rr[:64 * 64])          # 64 variables: c = 8 tables
+    assert small == big[:192 * 64]
+    assert big[192 * 64:192 * 128] == small                          # the inputs repeat with period 64
+    q = _multiples_g2(eng, [rng.fr() for _ in range(64)])
+    Y = b"".join(q[i % 64] for i in range(n))
+    big2 = eng.batch_commit_g2(Y, Rr)
+    small2 = eng.batch_commit_g2(Y[:192 * 64], Rr[:64 * 64])
+    assert small2 == big2[:384 * 64] == big2[384 * 64:384 * 128]
+
+
+@pytest.mark.parametrize("ty", [0, 1, 2, 3])
+def test_c4_mixed_statement_types(eng, ty):
+    """C4 shape (scaled): every equation type at m = n = 16, batch of 6 proofs with one tampered."""
+    rng = SeededRng(40 + ty)
+    m = n = 16
+    rows = [_commit_prove(eng, ty, m, n, _instance(eng, ty, m, n, rng), rng) for _ in range(2)]
+    count = 6
+    cols = [[] for _ in range(8)]
+    for i in range(count):
+        r = list(rows[i % 2])
+        if i == 4:
+            r[5] = r[5][384:768] + r[5][:384] + r[5][768:]           # swap two y-commitments
+        for c in range(8):
+            cols[c].append(r[c])
+    ok = eng.verify_batch(ty, count, m, n, *[b"".join(c) for c in cols])
+    assert list(ok) == [1, 1, 1, 1, 0, 1]
