@@ -74,6 +74,14 @@ struct g2_pts_gmem {  // the fixed points Q_i (read again at the 5 addition step
     Y = p->y;
   }
 };
+// tile stores bypass the usual L2 retention (st.global.cs): the tiles are written once and read once by
+// k_miller4 much later, while the running points in local memory must stay L2-resident -- with default
+// stores one launch moved 43 GB of DRAM writes for 8.6 GB of tiles (profiles/r01b_ncu_full_summary.csv).
+__device__ GS_INL void cq_st_stream(uint32_t* p, const fp& a) {
+#pragma unroll
+  for (int q = 0; q < 3; q++)
+    __stcs((uint4*)(p + q * CQ_QUAD), make_uint4(a.l[q * 4], a.l[q * 4 + 1], a.l[q * 4 + 2], a.l[q * 4 + 3]));
+}
 __global__ void __launch_bounds__(128, 4) k_g2_prepare4(const uint32_t* __restrict__ PW, const g2_aff* __restrict__ Y,
                                                         uint32_t* __restrict__ tiles, uint32_t* __restrict__ masks,
                                                         size_t nprob, size_t p0, size_t np, int K, int S) {
@@ -140,13 +148,13 @@ __global__ void __launch_bounds__(128, 4) k_g2_prepare4(const uint32_t* __restri
           }
           uint32_t* o = tiles + tb[i][a] + (size_t)idx * M4_TILE;
           fp_mul_n(v, mu.c0, wv);
-          cq_st(cq_ptr(o, 0, lanes[i]), v);
+          cq_st_stream(cq_ptr(o, 0, lanes[i]), v);
           fp_mul_n(v, mu.c1, wv);
-          cq_st(cq_ptr(o, 1, lanes[i]), v);
+          cq_st_stream(cq_ptr(o, 1, lanes[i]), v);
           fp_mul_n(v, lam.c0, s);
-          cq_st(cq_ptr(o, 2, lanes[i]), v);
+          cq_st_stream(cq_ptr(o, 2, lanes[i]), v);
           fp_mul_n(v, lam.c1, s);
-          cq_st(cq_ptr(o, 3, lanes[i]), v);
+          cq_st_stream(cq_ptr(o, 3, lanes[i]), v);
         }
       }, [] { __syncthreads(); });
     }
