@@ -219,6 +219,25 @@ class QuadEqu(_Equation):
     equ_type = EquType.Quadratic
 
 
+def prove_batch(equations, xvars, yvars, xcoms, ycoms, crs: CRS, rng) -> List[EquProof]:
+    """Provable::prove for many equations of one type over the SAME committed variables (a multi-equation
+    statement, statement.rs:109) in one GPU pass.  T is drawn equation by equation in the reference's order."""
+    assert equations
+    e0 = equations[0]
+    ty, cx, cy = e0.equ_type, e0._cx(), e0._cy()
+    m, n = len(xvars), len(yvars)
+    for e in equations:
+        assert e.equ_type == ty and len(e.gamma) == m and len(e.gamma[0]) == n
+    assert len(xcoms.rand) == m and len(ycoms.rand) == n and len(xcoms.rand[0]) == cx and len(ycoms.rand[0]) == cy
+    rands = [[[rng.fr() for _ in range(cx)] for _ in range(cy)] for _ in equations]
+    pi, th = crs._use().prove_batch(ty, len(equations), m, n, b"".join(b"".join(e.a_consts) for e in equations),
+                                    b"".join(b"".join(e.b_consts) for e in equations), b"".join(_flat(e.gamma) for e in equations),
+                                    b"".join(xvars), b"".join(yvars), _flat(xcoms.rand), _flat(ycoms.rand),
+                                    b"".join(_flat(r) for r in rands), shared_vars=True)
+    ps, ts = _split(pi, 384 * cx), _split(th, 192 * cy)
+    return [EquProof(_split(p, 384), _split(t, 192), ty, r) for p, t, r in zip(ps, ts, rands)]
+
+
 def verify_batch(equations, proofs, crs: CRS) -> List[bool]:
     """Many independent (equation, CProof) pairs of one type and shape in one GPU pass."""
     assert len(equations) == len(proofs) and equations

@@ -25,6 +25,7 @@ struct gs_fixed_table {
 struct gs_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
+  std::vector<cudaStream_t> pool;  // extra streams for batches of small independent launch chains (gs_prove_batch)
   gs::crs_dev* crs = nullptr;  // device
   bool crs_loaded = false;
   gs_fixed_table<gs::FpOps> tab1;
@@ -121,11 +122,14 @@ int pairing_init(gs_ctx* ctx);  // per-context kernel attributes
 int final_exp_init(gs_ctx* ctx);
 // X, Y: device slot arrays [2][K][nprob]  ->  ComT values (out_comt, AoS [p][4]) or per-entry verdict
 // bytes ok4[4][nprob] (compared with 1 / target).
+// With out_partial (AoS [p][4]) the un-exponentiated Miller products are returned instead (sharded statements).
 int run_pairing_product(gs_ctx* ctx, Scratch& sc, const g1_aff* X, const g2_aff* Y, size_t nprob, int K, fp12* out_comt,
-                        uint8_t* ok4, const fp12* target);
+                        uint8_t* ok4, const fp12* target, fp12* out_partial);
 
 // finalexp.cu: f = prod_chunks F[(ch*4 + e)*nprob + p]; g = FE(f); writes out_comt[p*4+e] and/or ok4[e*nprob + p]
 int launch_final_exp(gs_ctx* ctx, const fp12* F, size_t nprob, int nchunk, fp12* out_comt, uint8_t* ok4, const fp12* target);
+// finalexp.cu: multiplies groups of chunks together (cooperative kernel) until nchunk <= max_out
+int reduce_chunks(gs_ctx* ctx, Scratch& sc, const fp12** F, size_t nprob, int* nchunk, int max_out);
 
 // prover.cu
 int crs_generate_points(gs_ctx* ctx, const gs_g1* p1, const gs_g2* p2, const gs_fr* a1, const gs_fr* a2, const gs_fr* t1,

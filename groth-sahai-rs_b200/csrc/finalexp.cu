@@ -72,7 +72,72 @@ __global__ void __launch_bounds__(CQ_BLOCK_THREADS, 1) k_final_exp3(const fp12* 
   if (ok && valid && k == 0) ok[(size_t)e * nprob + p] = bad[lane] ? 0 : 1;
 }
 
+// ------------------------------------------------------------------ chunk-product tree (big statements)
+// A statement with few problems and many slots is split into up to ~1,000 accumulator chunks (pairing.cu);
+// multiplying them one after the other inside k_final_exp3 cost 23 ms of a 137 ms verify at m = n = 1024.
+// Here 32 lanes x 6 warps multiply L chunks each:  F2[(part*4 + e)*nprob + p] = prod_{ch in part} F[(ch*4 + e)*nprob + p]
+constexpr int CR_SMEM = 3 * CQ_ACC * 4;  // per 6-warp group
+__global__ void __launch_bounds__(CQ_BLOCK_THREADS, 1) k_chunk_reduce(const fp12* __restrict__ F, fp12* __restrict__ F2, size_t nprob,
+                                                                     int nchunk, int L, int nparts, size_t ngroups) {
+  extern __shared__ __align__(16) uint32_t sm_all[];
+  const int grp = threadIdx.x / CQ_GROUP_THREADS, tg = threadIdx.x % CQ_GROUP_THREADS;
+  uint32_t* bufs = sm_all + (size_t)grp * (CR_SMEM / 4);
+  const int k = tg >> 5, lane = tg & 31;
+  const size_t gid = (size_t)blockIdx.x * CQ_GROUPS + grp;
+  if (gid >= ngroups) return;
+  const size_t id = gid * CQ_LANES + lane;
+  const bool valid = id < nprob * 4 * (size_t)nparts;
+  const size_t p = valid ? id % nprob : 0;
+  const int e = valid ? (int)((id / nprob) & 3) : 0;
+  const int part = valid ? (int)(id / (nprob * 4)) : 0;
+  const int pos = cq_tower_pos(k);
+  int cur = 0;
+  for (int i = 0; i < L; i++) {
+    const int ch = part * L + i;
+    fp2 c;
+    if (valid && ch < nchunk) {
+      c = ((const fp2*)&F[((size_t)ch * 4 + e) * nprob + p])[pos];
+    } else {
+      c.set_zero();
+      if (k == 0) fp_one(c.c0);
+    }
+    if (i == 0) {
+      cq_st_coef(bufs, k, lane, c);
+      cq_group_sync(grp);
+    } else {
+      cq_st_coef(bufs + 2 * CQ_ACC, k, lane, c);
+      cq_group_sync(grp);
+      cq_mul(k, lane, bufs + cur * CQ_ACC, bufs + 2 * CQ_ACC, bufs + (cur ^ 1) * CQ_ACC);
+      cq_group_sync(grp);
+      cur ^= 1;
+    }
+  }
+  fp2 g;
+  cq_ld_coef(g.c0, g.c1, bufs + cur * CQ_ACC, k, lane, false, false);
+  if (valid) ((fp2*)&F2[((size_t)part * 4 + e) * nprob + p])[pos] = g;
+}
+
 }  // namespace gs
+
+// Reduces the chunk dimension of F ([nchunk][4][nprob]) until at most `max_out` chunks are left; *F then points
+// at scratch owned by `sc`.
+int gsi::reduce_chunks(gs_ctx* ctx, Scratch& sc, const fp12** F, size_t nprob, int* nchunk, int max_out) {
+  if (max_out < 1) max_out = 1;
+  while (*nchunk > max_out) {
+    int L = 2;
+    while (L * L < *nchunk) L++;  // ~sqrt: serial depth of this pass ~ serial depth left for the consumer
+    if (L > 64) L = 64;
+    const int nparts = (*nchunk + L - 1) / L;
+    fp12* F2;
+    CUDA_TRY(sc.alloc(&F2, (size_t)nparts * 4 * nprob));
+    size_t ngroups = (nprob * 4 * (size_t)nparts + CQ_LANES - 1) / CQ_LANES;
+    LAUNCH_CFG(k_chunk_reduce, ((ngroups + CQ_GROUPS - 1) / CQ_GROUPS) * CQ_BLOCK_THREADS, CQ_BLOCK_THREADS, CQ_GROUPS * CR_SMEM, *F,
+               F2, nprob, *nchunk, L, nparts, ngroups);
+    *F = F2;
+    *nchunk = nparts;
+  }
+  return GS_OK;
+}
 
 int gsi::final_exp_init(gs_ctx* ctx) {
   static uint32_t prog[CQ_FE_MAXOPS];
@@ -81,6 +146,7 @@ int gsi::final_exp_init(gs_ctx* ctx) {
   CUDA_TRY(cudaMalloc(&ctx->fe_prog, n * sizeof(uint32_t)));
   CUDA_TRY(cudaMemcpy(ctx->fe_prog, prog, n * sizeof(uint32_t), cudaMemcpyHostToDevice));
   CUDA_TRY(cudaFuncSetAttribute(k_final_exp3, cudaFuncAttributeMaxDynamicSharedMemorySize, CQ_GROUPS * FE3_SMEM));
+  CUDA_TRY(cudaFuncSetAttribute(k_chunk_reduce, cudaFuncAttributeMaxDynamicSharedMemorySize, CQ_GROUPS * CR_SMEM));
   return GS_OK;
 }
 

@@ -30,7 +30,6 @@ constexpr int M4_NV = 4;
 constexpr int M4_TILE = M4_NV * CQ_FP;
 constexpr int M4_MAXS = 512;
 constexpr int M4_SMEM = (2 * CQ_ACC + 2 * M4_TILE) * 4 + M4_MAXS * 6 + 16;  // per 6-warp group
-constexpr int G2_E = 4;  // G2 points walked per thread (one shared inversion per Miller step)
 
 // per G1 slot point: PW[((a*K + k)*2 + which)*12 + limb][pl] with which = 0: -xP/yP, 1: 1/yP (zero for identity)
 __global__ void __launch_bounds__(128) k_g1_prep(const g1_aff* __restrict__ X, uint32_t* __restrict__ PW, size_t nprob,
@@ -82,25 +81,28 @@ __device__ GS_INL void cq_st_stream(uint32_t* p, const fp& a) {
   for (int q = 0; q < 3; q++)
     __stcs((uint4*)(p + q * CQ_QUAD), make_uint4(a.l[q * 4], a.l[q * 4 + 1], a.l[q * 4 + 2], a.l[q * 4 + 3]));
 }
+// E = G2 points walked per thread (one shared inversion per Miller step): 4 for throughput, 1 when the whole
+// batch is a fraction of one wave and only the length of the serial chain counts (single statements).
+template <int E>
 __global__ void __launch_bounds__(128, 4) k_g2_prepare4(const uint32_t* __restrict__ PW, const g2_aff* __restrict__ Y,
                                                         uint32_t* __restrict__ tiles, uint32_t* __restrict__ masks,
                                                         size_t nprob, size_t p0, size_t np, int K, int S) {
-  const int G = (K + G2_E - 1) / G2_E;
+  const int G = (K + E - 1) / E;
   size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const bool inrange = q < 2 * (size_t)G * np;
   if (!inrange) q = 0;
   const size_t pl = q % np;
   const int g = (int)((q / np) % G), b = (int)(q / (np * G));
-  fp2 Tx[G2_E], Ty[G2_E];
+  fp2 Tx[E], Ty[E];
   g2_pts_arr T{Tx, Ty};
-  g2_pts_gmem Q{&Y[((size_t)b * K + (size_t)g * G2_E) * nprob + p0 + pl], nprob};
-  bool act[G2_E], acta[G2_E][2];
-  size_t tb[G2_E][2];
-  int lanes[G2_E];
+  g2_pts_gmem Q{&Y[((size_t)b * K + (size_t)g * E) * nprob + p0 + pl], nprob};
+  bool act[E], acta[E][2];
+  size_t tb[E][2];
+  int lanes[E];
   bool any = false;
 #pragma unroll
-  for (int i = 0; i < G2_E; i++) {
-    const int k = g * G2_E + i;
+  for (int i = 0; i < E; i++) {
+    const int k = g * E + i;
     act[i] = false;
     acta[i][0] = acta[i][1] = false;
     tb[i][0] = tb[i][1] = 0;
@@ -134,8 +136,8 @@ __global__ void __launch_bounds__(128, 4) k_g2_prepare4(const uint32_t* __restri
     const int nl = ((GS_X_ABS >> bit) & 1) ? 2 : 1;
 #pragma unroll 1
     for (int w = 0; w < nl; w++, idx++) {
-      g2_affine_step<G2_E>(T, Q, act, w == 1, [&](int i, const fp2& lam, const fp2& mu) {
-        const int k = g * G2_E + i;
+      g2_affine_step<E>(T, Q, act, w == 1, [&](int i, const fp2& lam, const fp2& mu) {
+        const int k = g * E + i;
 #pragma unroll 1
         for (int a = 0; a < 2; a++) {
           if (!acta[i][a]) continue;
@@ -267,6 +269,19 @@ __global__ void k_fp12_set_one(fp12* out, size_t n) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) out[i].set_one();
 }
+// out[p*4 + e] = prod_ch F[(ch*4 + e)*nprob + p]   (tower code: a handful of products per problem)
+__global__ void k_chunk_product(const fp12* __restrict__ F, fp12* __restrict__ out, size_t nprob, int nchunk) {
+  size_t id = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (id >= nprob * 4) return;
+  size_t p = id >> 2;
+  int e = (int)(id & 3);
+  fp12 acc = F[(size_t)e * nprob + p];
+  for (int ch = 1; ch < nchunk; ch++) {
+    fp12 t = F[((size_t)ch * 4 + e) * nprob + p];
+    fp12::mul(acc, acc, t);
+  }
+  out[id] = acc;
+}
 // iota_T for PPE: (1, 1, 1, t)            data_structures.rs:509-516
 __global__ void k_linear_map_ppe(const fp12* t, fp12* out) {
   int e = threadIdx.x;
@@ -317,8 +332,13 @@ int gsi::pairing_init(gs_ctx* ctx) {
 // bytes of HBM; a pass is sized to a whole number of k_miller4 waves (2 groups x 148 SMs x 32 accumulators
 // / 4 entries = 2,368 problems per wave) when the batch is large enough.
 int gsi::run_pairing_product(gs_ctx* ctx, Scratch& sc, const g1_aff* X, const g2_aff* Y, size_t nprob, int K,
-                               fp12* out_comt, uint8_t* ok4, const fp12* target) {
+                               fp12* out_comt, uint8_t* ok4, const fp12* target, fp12* out_partial) {
   const size_t wave = 2368;
+  if (K == 0) {  // a shard that owns no slot: empty product
+    if (!out_partial) FAIL(GS_EARG, "pairing product over zero slots");
+    LAUNCH(k_fp12_set_one, nprob * 4, out_partial, nprob * 4);
+    return GS_OK;
+  }
   // split the slots of a big statement over several accumulators when there are few problems
   int S = K, nchunk = 1;
   if (nprob < wave && K > 2) {
@@ -350,11 +370,25 @@ int gsi::run_pairing_product(gs_ctx* ctx, Scratch& sc, const g1_aff* X, const g2
     size_t nblk = ((np * nchunk + 31) / 32) * 4;
     CUDA_TRY(cudaMemsetAsync(masks, 0, nblk * S * sizeof(uint32_t), ctx->stream));
     LAUNCH(k_g1_prep, 2 * (size_t)K * np, X, PW, nprob, p0, np, K);
-    LAUNCH_CFG(k_g2_prepare4, 2 * (size_t)((K + G2_E - 1) / G2_E) * np, 128, 0, PW, Y, tiles, masks, nprob, p0, np, K, S);
+    if (2 * (size_t)((K + 3) / 4) * np < 16384)
+      LAUNCH_CFG(k_g2_prepare4<1>, 2 * (size_t)K * np, 128, 0, PW, Y, tiles, masks, nprob, p0, np, K, S);
+    else
+      LAUNCH_CFG(k_g2_prepare4<4>, 2 * (size_t)((K + 3) / 4) * np, 128, 0, PW, Y, tiles, masks, nprob, p0, np, K, S);
     LAUNCH_CFG(k_miller4, ((nblk + CQ_GROUPS - 1) / CQ_GROUPS) * CQ_BLOCK_THREADS, CQ_BLOCK_THREADS, CQ_GROUPS * M4_SMEM, tiles, masks,
                F, nprob, p0, np, S, nchunk, nblk);
   }
-  return gsi::launch_final_exp(ctx, F, nprob, nchunk, out_comt, ok4, target);
+  const fp12* Fr = F;
+  if (out_partial) {  // sharded statement: hand back the un-exponentiated Miller products, one per ComT entry
+    int rc = gsi::reduce_chunks(ctx, sc, &Fr, nprob, &nchunk, 1);
+    if (rc) return rc;
+    LAUNCH(k_chunk_product, nprob * 4, Fr, out_partial, nprob, nchunk);
+    return GS_OK;
+  }
+  if (nchunk > 12) {
+    int rc = gsi::reduce_chunks(ctx, sc, &Fr, nprob, &nchunk, 12);
+    if (rc) return rc;
+  }
+  return gsi::launch_final_exp(ctx, Fr, nprob, nchunk, out_comt, ok4, target);
 }
 
 static int comt_pairing_impl(gs_ctx* ctx, size_t nprob, int K, const gs_com1* xs, const gs_com2* ys, gs_comt* out) {
@@ -371,7 +405,7 @@ static int comt_pairing_impl(gs_ctx* ctx, size_t nprob, int K, const gs_com1* xs
   CUDA_TRY(sc.alloc(&Y, np * 2));
   CUDA_TRY(sc.alloc(&dout, nprob * 4));
   LAUNCH(k_scatter_pairs, np, dx, dy, X, Y, nprob, K);
-  int rc = gsi::run_pairing_product(ctx, sc, X, Y, nprob, K, dout, nullptr, nullptr);
+  int rc = gsi::run_pairing_product(ctx, sc, X, Y, nprob, K, dout, nullptr, nullptr, nullptr);
   if (rc) return rc;
   CUDA_TRY(cudaMemcpyAsync(out, dout, nprob * 4 * sizeof(fp12), cudaMemcpyDeviceToHost, ctx->stream));
   CUDA_TRY(cudaStreamSynchronize(ctx->stream));
@@ -441,7 +475,7 @@ int gs_comt_linear_map(gs_ctx* ctx, int type, const void* target, gs_comt* out) 
     LAUNCH(k_linear_map_ppe, 4, (const fp12*)dt, dout);
   } else {
     LAUNCH(k_linear_map_slots, 1, type, dt, ctx->crs, X, Y);
-    int rc = gsi::run_pairing_product(ctx, sc, X, Y, 1, 1, dout, nullptr, nullptr);
+    int rc = gsi::run_pairing_product(ctx, sc, X, Y, 1, 1, dout, nullptr, nullptr, nullptr);
     if (rc) return rc;
   }
   CUDA_TRY(cudaMemcpyAsync(out, dout, 4 * sizeof(fp12), cudaMemcpyDeviceToHost, ctx->stream));

@@ -215,9 +215,11 @@ int gs_batch_commit_scalar_b2(gs_ctx* ctx, size_t n, const gs_fr* ys, const gs_f
   return batch_commit_impl<Fp2Ops>(ctx, n, 2, 0, buf.data(), 1, buf.data() + n, 1, 2 * n, nullptr, out);
 }
 
-int gs_prove(gs_ctx* ctx, int type, size_t m, size_t n, const void* a_consts, const void* b_consts, const gs_fr* gamma,
-             const void* xvars, const void* yvars, const gs_fr* x_rand, const gs_fr* y_rand, const gs_fr* pf_rand,
-             gs_com2* out_pi, gs_com1* out_theta) {
+// Enqueues one Provable::prove on ctx->stream (uploads, kernels, download into out_pi / out_theta); the caller
+// synchronises.  `sc` must stay alive until then only in the sense of stream order (frees are stream-ordered).
+static int prove_enqueue(gs_ctx* ctx, Scratch& sc, int type, size_t m, size_t n, const void* a_consts, const void* b_consts,
+                         const gs_fr* gamma, const void* xvars, const void* yvars, const gs_fr* x_rand, const gs_fr* y_rand,
+                         const gs_fr* pf_rand, void* out_pi, void* out_theta) {
   if (!ctx) return GS_EARG;
   if (type < 0 || type > 3) FAIL(GS_EARG, "prove: bad equation type");
   if (!ctx->crs_loaded) FAIL(GS_EARG, "prove: no CRS loaded");
@@ -225,10 +227,8 @@ int gs_prove(gs_ctx* ctx, int type, size_t m, size_t n, const void* a_consts, co
   if (m > 1 << 22 || n > 1 << 22) FAIL(GS_EDIM, "prove: too many variables");
   if (!a_consts || !b_consts || !gamma || !xvars || !yvars || !x_rand || !y_rand || !pf_rand || !out_pi || !out_theta)
     return GS_EARG;
-  CUDA_TRY(cudaSetDevice(ctx->device));
   verify_shape s = make_verify_shape(type, (int)m, (int)n);
   const int cx = s.cx, cy = s.cy;
-  Scratch sc(ctx);
   uint8_t *dA, *dB, *dX, *dY;
   fr *dG, *dR, *dS, *dT;
   CUDA_TRY(upload(ctx, sc, &dA, a_consts, n * elem_size_A(type)));
@@ -275,9 +275,78 @@ int gs_prove(gs_ctx* ctx, int type, size_t m, size_t n, const void* a_consts, co
   if (rc) return rc;
   CUDA_TRY(cudaMemcpyAsync(out_pi, dpi, 2 * cx * sizeof(g2_aff), cudaMemcpyDeviceToHost, ctx->stream));
   CUDA_TRY(cudaMemcpyAsync(out_theta, dth, 2 * cy * sizeof(g1_aff), cudaMemcpyDeviceToHost, ctx->stream));
+  return GS_OK;
+}
+
+int gs_prove(gs_ctx* ctx, int type, size_t m, size_t n, const void* a_consts, const void* b_consts, const gs_fr* gamma,
+             const void* xvars, const void* yvars, const gs_fr* x_rand, const gs_fr* y_rand, const gs_fr* pf_rand,
+             gs_com2* out_pi, gs_com1* out_theta) {
+  if (!ctx) return GS_EARG;
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  Scratch sc(ctx);
+  int rc = prove_enqueue(ctx, sc, type, m, n, a_consts, b_consts, gamma, xvars, yvars, x_rand, y_rand, pf_rand, out_pi, out_theta);
+  if (rc) return rc;
   CUDA_TRY(cudaStreamSynchronize(ctx->stream));
   return GS_OK;
 }
+
+// `count` independent proofs of one type and shape (C4 of SURVEY.md §8d: many equations over shared variable
+// sets).  A single prove is a chain of ~40 small launches whose length is set by ONE serial scalar
+// multiplication per thread, so a batch is spread round-robin over a pool of streams and the chains overlap
+// on the GPU; results come back through a pinned staging buffer (a pageable D2H would serialise the host).
+// Per-proof arrays are laid out like gs_verify_batch's; variables / randomness may be shared (stride 0).
+int gs_prove_batch(gs_ctx* ctx, int type, size_t count, size_t m, size_t n, const void* a_consts, const void* b_consts,
+                   const gs_fr* gamma, const void* xvars, const void* yvars, const gs_fr* x_rand, const gs_fr* y_rand,
+                   const gs_fr* pf_rand, int shared_vars, gs_com2* out_pi, gs_com1* out_theta) {
+  if (!ctx) return GS_EARG;
+  if (type < 0 || type > 3) FAIL(GS_EARG, "prove: bad equation type");
+  if (count == 0) return GS_OK;
+  if (!out_pi || !out_theta) return GS_EARG;
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  verify_shape s = make_verify_shape(type, (int)m, (int)n);
+  const size_t pi_b = 2 * s.cx * sizeof(g2_aff), th_b = 2 * s.cy * sizeof(g1_aff);
+  if (ctx->pool.empty()) {
+    ctx->pool.resize(48);
+    for (auto& st : ctx->pool) CUDA_TRY(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+  }
+  uint8_t* stage = nullptr;
+  CUDA_TRY(cudaMallocHost(&stage, count * (pi_b + th_b)));
+  cudaStream_t main_stream = ctx->stream;
+  // tables / CRS uploads issued earlier on the main stream must be visible to the pool
+  cudaEvent_t ready;
+  cudaEventCreateWithFlags(&ready, cudaEventDisableTiming);
+  cudaEventRecord(ready, main_stream);
+  for (auto& st : ctx->pool) cudaStreamWaitEvent(st, ready, 0);
+  int rc = GS_OK;
+  const size_t sv = shared_vars ? 0 : 1;
+  for (size_t i = 0; i < count && rc == GS_OK; i++) {
+    ctx->stream = ctx->pool[i % ctx->pool.size()];
+    Scratch sc(ctx);
+    rc = prove_enqueue(ctx, sc, type, m, n, (const char*)a_consts + i * n * elem_size_A(type),
+                       (const char*)b_consts + i * m * elem_size_B(type), gamma + i * m * n,
+                       (const char*)xvars + sv * i * m * elem_size_A(type), (const char*)yvars + sv * i * n * elem_size_B(type),
+                       x_rand + sv * i * m * s.cx, y_rand + sv * i * n * s.cy, pf_rand + i * s.cx * s.cy, stage + i * (pi_b + th_b),
+                       stage + i * (pi_b + th_b) + pi_b);
+  }
+  ctx->stream = main_stream;
+  cudaError_t e = cudaSuccess;
+  for (auto& st : ctx->pool) {
+    cudaError_t e2 = cudaStreamSynchronize(st);
+    if (e == cudaSuccess) e = e2;
+  }
+  cudaEventDestroy(ready);
+  if (rc == GS_OK && e == cudaSuccess) {
+    for (size_t i = 0; i < count; i++) {
+      memcpy((char*)out_pi + i * pi_b, stage + i * (pi_b + th_b), pi_b);
+      memcpy((char*)out_theta + i * th_b, stage + i * (pi_b + th_b) + pi_b, th_b);
+    }
+  }
+  cudaFreeHost(stage);
+  if (rc) return rc;
+  CUDA_TRY(e);
+  return GS_OK;
+}
+
 
 int gs_com1_matmul(gs_ctx* ctx, size_t r, size_t k, size_t c, const gs_fr* lhs, const gs_com1* mat, gs_com1* out) {
   return com_matmul_impl<FpOps>(ctx, r, k, c, lhs, mat, out);

@@ -143,10 +143,12 @@ __global__ void __launch_bounds__(128) k_jac_reduce_step(Jac<F>* __restrict__ te
 //   out[i].p[0] =                  sum_l coef[i][l] key_l.0  (+ e_i W.0)
 //   out[i].p[1] = varsum[i]      + sum_l coef[i][l] key_l.1  (+ e_i W.1)
 // thread -> (i, a).  `varsum` = reduced MSM rows (group-typed) or null; `e` = collapsed scalar (scalar-typed) or null.
+// key_l (u_l / v_l) and W are the CRS points the fixed-base window tables hold (bases l and 2): one table
+// lookup + mixed addition per window instead of a 255-step double-and-add in this single thread.
 template <class F>
 __global__ void k_proof_finish(Aff<F>* __restrict__ out, int rows, int ncoef, const fr* __restrict__ coef, size_t coef_rs,
-                               size_t coef_cs, const Aff<F>* __restrict__ key /* [2][2] */, const Jac<F>* __restrict__ varsum,
-                               size_t var_stride, const fr* __restrict__ e, const Aff<F>* __restrict__ W /* [2] */) {
+                               size_t coef_cs, const Aff<F>* __restrict__ tab, int c, int W, size_t H,
+                               const Jac<F>* __restrict__ varsum, size_t var_stride, const fr* __restrict__ e) {
   int id = blockIdx.x * blockDim.x + threadIdx.x;
   if (id >= rows * 2) return;
   int i = id >> 1, a = id & 1;
@@ -156,15 +158,11 @@ __global__ void k_proof_finish(Aff<F>* __restrict__ out, int rows, int ncoef, co
   uint32_t k[8];
   for (int l = 0; l < ncoef; l++) {
     fr_from_mont(k, coef[i * coef_rs + l * coef_cs]);
-    Jac<F> t;
-    scalar_mul<F>(t, key[l * 2 + a], k);
-    Jac<F>::add(acc, acc, t);
+    fixed_base_accumulate<F>(acc, tab + ((size_t)(l * 2 + a) * W) * H, k, c, W, H);
   }
   if (e != nullptr) {
     fr_from_mont(k, e[i]);
-    Jac<F> t;
-    scalar_mul<F>(t, W[a], k);
-    Jac<F>::add(acc, acc, t);
+    fixed_base_accumulate<F>(acc, tab + ((size_t)(2 * 2 + a) * W) * H, k, c, W, H);
   }
   Aff<F> r;
   Jac<F>::to_affine(r, acc);
@@ -298,18 +296,22 @@ int proof_element(gs_ctx* ctx, Scratch& sc, int rows, bool group_typed, const fr
                   const void* dvars, size_t nvars, int ncoef, const fr* coef, size_t coef_rs, const Aff<F>* key,
                   const Aff<F>* W, const fr* e, Aff<F>* dout) {
   size_t nt = nconst + nvars;
+  (void)key;
+  (void)W;
+  const gs_fixed_table<F>& T = table_of<F>(ctx);  // built at CRS load (c = 8) or by a big commit batch (c = 16)
+  if (!T.t) FAIL(GS_EARG, "prove: fixed-base tables missing (no CRS loaded)");
   if (group_typed) {
     Jac<F>* terms;
     CUDA_TRY(sc.alloc(&terms, nt * rows));
     LAUNCH((k_msm_terms<F>), nt * rows, terms, sv, (const Aff<F>*)dconst, nconst, (const Aff<F>*)dvars, nvars, rows);
     int rc = reduce_rows<F>(ctx, terms, nt, nt, rows);
     if (rc) return rc;
-    LAUNCH((k_proof_finish<F>), (size_t)rows * 2, dout, rows, ncoef, coef, coef_rs, (size_t)1, key, terms, nt, (const fr*)nullptr,
-           (const Aff<F>*)nullptr);
+    LAUNCH((k_proof_finish<F>), (size_t)rows * 2, dout, rows, ncoef, coef, coef_rs, (size_t)1, T.t, T.c, T.W, T.H, terms, nt,
+           (const fr*)nullptr);
   } else {
     // scalar-typed side: the caller collapsed the terms into e_i = <sv_i, (consts | vars)> (k_fr_dot, prover.cu)
-    LAUNCH((k_proof_finish<F>), (size_t)rows * 2, dout, rows, ncoef, coef, coef_rs, (size_t)1, key, (const Jac<F>*)nullptr,
-           (size_t)0, e, W);
+    LAUNCH((k_proof_finish<F>), (size_t)rows * 2, dout, rows, ncoef, coef, coef_rs, (size_t)1, T.t, T.c, T.W, T.H,
+           (const Jac<F>*)nullptr, (size_t)0, e);
   }
   return GS_OK;
 }

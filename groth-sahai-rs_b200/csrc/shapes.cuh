@@ -23,6 +23,10 @@ struct verify_shape {  // slot bookkeeping shared by host and device
   int n_out;    // MSM outputs per problem: n (+1 scalar-B) (+1 Quad target)
   int nbases;   // m (+1 when A is scalar: W1 is an extra base)
   int nchunk;   // MSM base chunks
+  int rank, world;  // statement sharding: slot k belongs to rank k % world; 0, 1 = everything
+  GS_HD bool owns(int slot) const { return world <= 1 || slot % world == rank; }
+  // slot that MSM output jj is written to: jj < n -> jj; the scalar-B sum -> sB; the Quad target -> sT
+  GS_HD int out_slot(int jj) const { return jj < n ? jj : ((jj == n && !groupB) ? sB : sT); }
 };
 constexpr int GS_MSM_CHUNK = 16;
 
@@ -44,6 +48,8 @@ inline verify_shape make_verify_shape(int type, int m, int n) {
   s.n_out = n + (s.groupB ? 0 : 1) + (type == 3 ? 1 : 0);
   s.nbases = m + (s.groupA ? 0 : 1);
   s.nchunk = (s.nbases + GS_MSM_CHUNK - 1) / GS_MSM_CHUNK;
+  s.rank = 0;
+  s.world = 1;
   return s;
 }
 

@@ -143,6 +143,7 @@ __global__ void __launch_bounds__(128) k_vmsm_partial(verify_shape s, verify_arg
   r >>= 1;
   int jj = (int)(r % s.n_out);
   int ch = (int)(r / s.n_out);
+  if (!s.owns(s.out_slot(jj))) return;  // sharded statement: that slot's Miller pairs run on another rank
 
   // biased scalars k' = k + 0x88..8 (64 nibbles): digit_w = nibble_w(k') - 8 in [-8, 7], no carries
   uint32_t sc[GS_MSM_CHUNK][9];
@@ -218,6 +219,7 @@ __global__ void __launch_bounds__(128) k_vmsm_reduce(verify_shape s, verify_args
   size_t r = active ? id / nprob : 0;
   int a = (int)(r & 1);
   int jj = (int)(r >> 1);
+  if (active && !s.owns(s.out_slot(jj))) active = false;
   g1_jac acc;
   acc.set_inf();
   int slot = 0;
@@ -245,6 +247,28 @@ __global__ void __launch_bounds__(128) k_vmsm_reduce(verify_shape s, verify_args
   if (active) X[((size_t)a * s.K + slot) * nprob + p] = out;
 }
 
+// sharded statement: keep the slots k = rank, rank + world, ... (K' of them) of the [2][K][nprob] slot arrays
+__global__ void k_gather_owned_slots(const g1_aff* __restrict__ X, const g2_aff* __restrict__ Y, g1_aff* __restrict__ Xo,
+                                     g2_aff* __restrict__ Yo, size_t nprob, int K, int Ko, int rank, int world) {
+  size_t id = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (id >= nprob * (size_t)Ko * 2) return;
+  size_t p = id % nprob;
+  size_t r = id / nprob;
+  int ko = (int)(r % Ko), a = (int)(r / Ko);
+  int k = rank + ko * world;
+  Xo[((size_t)a * Ko + ko) * nprob + p] = X[((size_t)a * K + k) * nprob + p];
+  Yo[((size_t)a * Ko + ko) * nprob + p] = Y[((size_t)a * K + k) * nprob + p];
+}
+// partial[part][p][e] (AoS, as the ranks exchange them)  ->  F[(part*4 + e)*nprob + p] (launch_final_exp's layout)
+__global__ void k_partials_to_chunks(const fp12* __restrict__ partials, fp12* __restrict__ F, size_t nprob, int nparts) {
+  size_t id = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (id >= nprob * 4 * (size_t)nparts) return;
+  int e = (int)(id & 3);
+  size_t p = (id >> 2) % nprob;
+  size_t part = (id >> 2) / nprob;
+  F[(part * 4 + e) * nprob + p] = partials[id];
+}
+
 __global__ void k_and4(const uint8_t* __restrict__ ok4, uint8_t* __restrict__ out, size_t nprob) {
   size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= nprob) return;
@@ -255,19 +279,26 @@ __global__ void k_and4(const uint8_t* __restrict__ ok4, uint8_t* __restrict__ ou
 
 extern "C" {
 
-int gs_verify_batch_dev(gs_ctx* ctx, int type, size_t count, size_t m, size_t n, const void* a_consts,
-                        const void* b_consts, const gs_fr* gamma, const void* target, const gs_com1* xcoms,
-                        const gs_com2* ycoms, const gs_com2* pi, const gs_com1* theta, uint8_t* out_ok_dev) {
+// Shared body of gs_verify_batch_dev (rank 0 of 1, verdicts) and gs_verify_partial_dev (rank r of w: the
+// un-exponentiated Miller products of the slots that rank owns, out_partial[p][4]).
+static int verify_impl(gs_ctx* ctx, int type, size_t count, size_t m, size_t n, const void* a_consts, const void* b_consts,
+                       const gs_fr* gamma, const void* target, const gs_com1* xcoms, const gs_com2* ycoms, const gs_com2* pi,
+                       const gs_com1* theta, int rank, int world, uint8_t* out_ok_dev, fp12* out_partial_dev) {
   if (!ctx) return GS_EARG;
   if (type < 0 || type > 3) FAIL(GS_EARG, "verify: bad equation type");
+  if (world < 1 || rank < 0 || rank >= world) FAIL(GS_EARG, "verify: bad shard (rank, world)");
   if (!ctx->crs_loaded) FAIL(GS_EARG, "verify: no CRS loaded");
   if (count == 0) return GS_OK;
   // the reference panics on empty variable lists: keep it an error
   if (m == 0 || n == 0) FAIL(GS_EDIM, "verify: empty variable list");
   if (m > 1 << 20 || n > 1 << 20) FAIL(GS_EDIM, "verify: too many variables");
-  if (!a_consts || !b_consts || !gamma || !target || !xcoms || !ycoms || !pi || !theta || !out_ok_dev) return GS_EARG;
+  if (!a_consts || !b_consts || !gamma || !target || !xcoms || !ycoms || !pi || !theta) return GS_EARG;
+  if (!out_ok_dev && !out_partial_dev) return GS_EARG;
   CUDA_TRY(cudaSetDevice(ctx->device));
   verify_shape s = make_verify_shape(type, (int)m, (int)n);
+  s.rank = rank;
+  s.world = world;
+  const int Ko = world > 1 ? (s.K - rank + world - 1) / world : s.K;  // slots this rank owns
   for (size_t off = 0; off < count; off += ctx->verify_batch_max) {
     size_t nprob = count - off < ctx->verify_batch_max ? count - off : ctx->verify_batch_max;
     Scratch sc(ctx);
@@ -294,25 +325,81 @@ int gs_verify_batch_dev(gs_ctx* ctx, int type, size_t count, size_t m, size_t n,
     LAUNCH(k_vmsm_tables, nprob * (size_t)s.nbases * 2, s, v, ctx->crs, vtab, nprob);
     LAUNCH(k_vmsm_partial, nprob * (size_t)s.n_out * 2 * s.nchunk, s, v, vtab, part, nprob);
     LAUNCH(k_vmsm_reduce, nprob * (size_t)s.n_out * 2, s, v, part, X, nprob);
-    int rc = gsi::run_pairing_product(ctx, sc, X, Y, nprob, s.K, nullptr, ok4, type == GS_PPE ? (const fp12*)v.target : nullptr);
-    if (rc) return rc;
-    LAUNCH(k_and4, nprob, ok4, out_ok_dev + off, nprob);
+    const g1_aff* Xp = X;
+    const g2_aff* Yp = Y;
+    if (world > 1) {
+      g1_aff* Xo;
+      g2_aff* Yo;
+      CUDA_TRY(sc.alloc(&Xo, 2 * (size_t)(Ko ? Ko : 1) * nprob));
+      CUDA_TRY(sc.alloc(&Yo, 2 * (size_t)(Ko ? Ko : 1) * nprob));
+      LAUNCH(k_gather_owned_slots, nprob * (size_t)Ko * 2, X, Y, Xo, Yo, nprob, s.K, Ko, rank, world);
+      Xp = Xo;
+      Yp = Yo;
+    }
+    int rc;
+    if (out_partial_dev) {
+      rc = gsi::run_pairing_product(ctx, sc, Xp, Yp, nprob, Ko, nullptr, nullptr, nullptr, out_partial_dev + off * 4);
+      if (rc) return rc;
+    } else {
+      rc = gsi::run_pairing_product(ctx, sc, Xp, Yp, nprob, Ko, nullptr, ok4, type == GS_PPE ? (const fp12*)v.target : nullptr,
+                                    nullptr);
+      if (rc) return rc;
+      LAUNCH(k_and4, nprob, ok4, out_ok_dev + off, nprob);
+    }
   }
   return GS_OK;
 }
 
-int gs_verify_batch(gs_ctx* ctx, int type, size_t count, size_t m, size_t n, const void* a_consts,
-                    const void* b_consts, const gs_fr* gamma, const void* target, const gs_com1* xcoms,
-                    const gs_com2* ycoms, const gs_com2* pi, const gs_com1* theta, uint8_t* out_ok) {
+int gs_verify_batch_dev(gs_ctx* ctx, int type, size_t count, size_t m, size_t n, const void* a_consts,
+                        const void* b_consts, const gs_fr* gamma, const void* target, const gs_com1* xcoms,
+                        const gs_com2* ycoms, const gs_com2* pi, const gs_com1* theta, uint8_t* out_ok_dev) {
+  if (!out_ok_dev) return GS_EARG;
+  return verify_impl(ctx, type, count, m, n, a_consts, b_consts, gamma, target, xcoms, ycoms, pi, theta, 0, 1, out_ok_dev, nullptr);
+}
+
+int gs_verify_partial_dev(gs_ctx* ctx, int type, size_t count, size_t m, size_t n, const void* a_consts,
+                          const void* b_consts, const gs_fr* gamma, const void* target, const gs_com1* xcoms,
+                          const gs_com2* ycoms, const gs_com2* pi, const gs_com1* theta, int rank, int world,
+                          gs_gt* out_partial_dev) {
+  if (!out_partial_dev) return GS_EARG;
+  return verify_impl(ctx, type, count, m, n, a_consts, b_consts, gamma, target, xcoms, ycoms, pi, theta, rank, world, nullptr,
+                     (fp12*)out_partial_dev);
+}
+
+int gs_verify_finish_dev(gs_ctx* ctx, int type, size_t count, int nparts, const gs_gt* partials_dev, const void* target_dev,
+                         uint8_t* out_ok_dev) {
+  if (!ctx) return GS_EARG;
+  if (type < 0 || type > 3) FAIL(GS_EARG, "verify_finish: bad equation type");
+  if (nparts < 1 || nparts > 4096) FAIL(GS_EARG, "verify_finish: bad number of partial products");
+  if (count == 0) return GS_OK;
+  if (!partials_dev || !out_ok_dev || (type == GS_PPE && !target_dev)) return GS_EARG;
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  Scratch sc(ctx);
+  fp12* F;
+  uint8_t* ok4;
+  CUDA_TRY(sc.alloc(&F, (size_t)nparts * 4 * count));
+  CUDA_TRY(sc.alloc(&ok4, 4 * count));
+  LAUNCH(k_partials_to_chunks, count * 4 * (size_t)nparts, (const fp12*)partials_dev, F, count, nparts);
+  int rc = gsi::launch_final_exp(ctx, F, count, nparts, nullptr, ok4, type == GS_PPE ? (const fp12*)target_dev : nullptr);
+  if (rc) return rc;
+  LAUNCH(k_and4, count, ok4, out_ok_dev, count);
+  return GS_OK;
+}
+
+// host-buffer front end shared by gs_verify_batch and gs_verify_partial: upload, run, download
+static int verify_host(gs_ctx* ctx, int type, size_t count, size_t m, size_t n, const void* a_consts, const void* b_consts,
+                       const gs_fr* gamma, const void* target, const gs_com1* xcoms, const gs_com2* ycoms, const gs_com2* pi,
+                       const gs_com1* theta, int rank, int world, uint8_t* out_ok, gs_gt* out_partial) {
   if (!ctx) return GS_EARG;
   if (type < 0 || type > 3) FAIL(GS_EARG, "verify: bad equation type");
   if (count == 0) return GS_OK;
   if (m == 0 || n == 0) FAIL(GS_EDIM, "verify: empty variable list");
-  if (!a_consts || !b_consts || !gamma || !target || !xcoms || !ycoms || !pi || !theta || !out_ok) return GS_EARG;
+  if (!a_consts || !b_consts || !gamma || !target || !xcoms || !ycoms || !pi || !theta || (!out_ok && !out_partial)) return GS_EARG;
   CUDA_TRY(cudaSetDevice(ctx->device));
   verify_shape s = make_verify_shape(type, (int)m, (int)n);
   Scratch sc(ctx);
-  uint8_t *dA, *dB, *dT, *dok;
+  uint8_t *dA, *dB, *dT, *dok = nullptr;
+  fp12* dpart = nullptr;
   fr* dG;
   g1_aff *dc, *dth;
   g2_aff *dd, *dpi;
@@ -324,9 +411,53 @@ int gs_verify_batch(gs_ctx* ctx, int type, size_t count, size_t m, size_t n, con
   CUDA_TRY(upload(ctx, sc, &dd, ycoms, count * n * 2));
   CUDA_TRY(upload(ctx, sc, &dpi, pi, count * s.cx * 2));
   CUDA_TRY(upload(ctx, sc, &dth, theta, count * s.cy * 2));
+  if (out_ok)
+    CUDA_TRY(sc.alloc(&dok, count));
+  else
+    CUDA_TRY(sc.alloc(&dpart, count * 4));
+  int rc = verify_impl(ctx, type, count, m, n, dA, dB, (const gs_fr*)dG, dT, (const gs_com1*)dc, (const gs_com2*)dd,
+                       (const gs_com2*)dpi, (const gs_com1*)dth, rank, world, dok, dpart);
+  if (rc) return rc;
+  if (out_ok)
+    CUDA_TRY(cudaMemcpyAsync(out_ok, dok, count, cudaMemcpyDeviceToHost, ctx->stream));
+  else
+    CUDA_TRY(cudaMemcpyAsync(out_partial, dpart, count * 4 * sizeof(fp12), cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  return GS_OK;
+}
+
+int gs_verify_batch(gs_ctx* ctx, int type, size_t count, size_t m, size_t n, const void* a_consts,
+                    const void* b_consts, const gs_fr* gamma, const void* target, const gs_com1* xcoms,
+                    const gs_com2* ycoms, const gs_com2* pi, const gs_com1* theta, uint8_t* out_ok) {
+  if (ctx && count && !out_ok) return GS_EARG;
+  return verify_host(ctx, type, count, m, n, a_consts, b_consts, gamma, target, xcoms, ycoms, pi, theta, 0, 1, out_ok, nullptr);
+}
+
+int gs_verify_partial(gs_ctx* ctx, int type, size_t count, size_t m, size_t n, const void* a_consts,
+                      const void* b_consts, const gs_fr* gamma, const void* target, const gs_com1* xcoms,
+                      const gs_com2* ycoms, const gs_com2* pi, const gs_com1* theta, int rank, int world,
+                      gs_gt* out_partial) {
+  if (ctx && count && !out_partial) return GS_EARG;
+  if (ctx && (world < 1 || rank < 0 || rank >= world)) FAIL(GS_EARG, "verify: bad shard (rank, world)");
+  return verify_host(ctx, type, count, m, n, a_consts, b_consts, gamma, target, xcoms, ycoms, pi, theta, rank, world, nullptr,
+                     out_partial);
+}
+
+int gs_verify_finish(gs_ctx* ctx, int type, size_t count, int nparts, const gs_gt* partials, const void* target,
+                     uint8_t* out_ok) {
+  if (!ctx) return GS_EARG;
+  if (type < 0 || type > 3) FAIL(GS_EARG, "verify_finish: bad equation type");
+  if (nparts < 1 || nparts > 4096) FAIL(GS_EARG, "verify_finish: bad number of partial products");
+  if (count == 0) return GS_OK;
+  if (!partials || !out_ok || (type == GS_PPE && !target)) return GS_EARG;
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  Scratch sc(ctx);
+  fp12 *dp, *dT = nullptr;
+  uint8_t* dok;
+  CUDA_TRY(upload(ctx, sc, &dp, partials, (size_t)nparts * count * 4));
+  if (type == GS_PPE) CUDA_TRY(upload(ctx, sc, &dT, target, count));
   CUDA_TRY(sc.alloc(&dok, count));
-  int rc = gs_verify_batch_dev(ctx, type, count, m, n, dA, dB, (const gs_fr*)dG, dT, (const gs_com1*)dc,
-                               (const gs_com2*)dd, (const gs_com2*)dpi, (const gs_com1*)dth, dok);
+  int rc = gs_verify_finish_dev(ctx, type, count, nparts, (const gs_gt*)dp, dT, dok);
   if (rc) return rc;
   CUDA_TRY(cudaMemcpyAsync(out_ok, dok, count, cudaMemcpyDeviceToHost, ctx->stream));
   CUDA_TRY(cudaStreamSynchronize(ctx->stream));

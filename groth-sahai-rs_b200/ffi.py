@@ -16,7 +16,8 @@ EXPORTED_SYMBOLS = [
     "gs_profile_enable", "gs_profile_read", "gs_diag_fpmul_rate",
     "gs_crs_generate", "gs_crs_load",
     "gs_batch_commit_g1", "gs_batch_commit_g2", "gs_batch_commit_scalar_b1", "gs_batch_commit_scalar_b2",
-    "gs_prove", "gs_verify_batch", "gs_verify_batch_dev",
+    "gs_prove", "gs_prove_batch", "gs_verify_batch", "gs_verify_batch_dev",
+    "gs_verify_partial", "gs_verify_partial_dev", "gs_verify_finish", "gs_verify_finish_dev",
     "gs_comt_pairing", "gs_comt_pairing_sum", "gs_comt_linear_map", "gs_pairing",
     "gs_com1_matmul", "gs_com2_matmul", "gs_fr_matmul",
 ]
@@ -61,8 +62,13 @@ def load_library():
         for f in ("gs_batch_commit_g1", "gs_batch_commit_g2", "gs_batch_commit_scalar_b1", "gs_batch_commit_scalar_b2"):
             getattr(lib, f).argtypes = [vp, sz, vp, vp, vp]
         lib.gs_prove.argtypes = [vp, ci, sz, sz] + [vp] * 10
+        lib.gs_prove_batch.argtypes = [vp, ci, sz, sz, sz] + [vp] * 8 + [ci, vp, vp]
         lib.gs_verify_batch.argtypes = [vp, ci, sz, sz, sz] + [vp] * 9
         lib.gs_verify_batch_dev.argtypes = [vp, ci, sz, sz, sz] + [vp] * 9
+        lib.gs_verify_partial.argtypes = [vp, ci, sz, sz, sz] + [vp] * 8 + [ci, ci, vp]
+        lib.gs_verify_partial_dev.argtypes = [vp, ci, sz, sz, sz] + [vp] * 8 + [ci, ci, vp]
+        lib.gs_verify_finish.argtypes = [vp, ci, sz, ci, vp, vp, vp]
+        lib.gs_verify_finish_dev.argtypes = [vp, ci, sz, ci, vp, vp, vp]
         lib.gs_comt_pairing.argtypes = [vp, sz, vp, vp, vp]
         lib.gs_comt_pairing_sum.argtypes = [vp, sz, vp, vp, vp]
         lib.gs_comt_linear_map.argtypes = [vp, ci, vp, vp]
@@ -199,6 +205,22 @@ class Engine:
                                     ctypes.cast(th, ctypes.c_void_p)))
         return pi.raw, th.raw
 
+    def prove_batch(self, ty, count, m, n, a_consts, b_consts, gamma, xvars, yvars, x_rand, y_rand, pf_rand, shared_vars=False):
+        """`count` independent proofs in one pass (gs_prove_batch); returns (pi bytes, theta bytes), proof-major."""
+        cx, cy = _cx(ty), _cy(ty)
+        reps = 1 if shared_vars else count
+        if count and m and n:
+            assert len(a_consts) == count * n * _a_size(ty) and len(b_consts) == count * m * _b_size(ty)
+            assert len(gamma) == count * m * n * FR and len(pf_rand) == count * cx * cy * FR
+            assert len(xvars) == reps * m * _a_size(ty) and len(yvars) == reps * n * _b_size(ty)
+            assert len(x_rand) == reps * m * cx * FR and len(y_rand) == reps * n * cy * FR
+        pi = ctypes.create_string_buffer(max(1, count * cx * COM2))
+        th = ctypes.create_string_buffer(max(1, count * cy * COM1))
+        ks = [_buf(x) for x in (a_consts, b_consts, gamma, xvars, yvars, x_rand, y_rand, pf_rand)]
+        self._chk(self.lib.gs_prove_batch(self.h, ty, count, m, n, *[k[1] for k in ks], 1 if shared_vars else 0,
+                                          ctypes.cast(pi, ctypes.c_void_p), ctypes.cast(th, ctypes.c_void_p)))
+        return pi.raw[: count * cx * COM2], th.raw[: count * cy * COM1]
+
     def verify_batch(self, ty, count, m, n, a_consts, b_consts, gamma, target, xcoms, ycoms, pi, theta) -> bytes:
         cx, cy = _cx(ty), _cy(ty)
         if count and m and n:
@@ -218,6 +240,24 @@ class Engine:
 
     def verify(self, ty, m, n, a_consts, b_consts, gamma, target, xcoms, ycoms, pi, theta) -> bool:
         return self.verify_batch(ty, 1, m, n, a_consts, b_consts, gamma, target, xcoms, ycoms, pi, theta) == b"\x01"
+
+    # ---- one statement sharded by slot over several GPUs (gs_verify_partial / gs_verify_finish)
+    def verify_partial(self, ty, count, m, n, a_consts, b_consts, gamma, target, xcoms, ycoms, pi, theta, rank, world) -> bytes:
+        """This rank's un-exponentiated Miller products: count x 4 GT values (2304 B per statement)."""
+        out = ctypes.create_string_buffer(max(1, count * COMT))
+        ks = [_buf(x) for x in (a_consts, b_consts, gamma, target, xcoms, ycoms, pi, theta)]
+        self._chk(self.lib.gs_verify_partial(self.h, ty, count, m, n, *[k[1] for k in ks], int(rank), int(world),
+                                             ctypes.cast(out, ctypes.c_void_p)))
+        return out.raw[: count * COMT]
+
+    def verify_finish(self, ty, count, partials: bytes, target: bytes) -> bytes:
+        """partials = the ranks' verify_partial outputs concatenated rank-major; returns count verdict bytes."""
+        assert count and len(partials) % (count * COMT) == 0
+        nparts = len(partials) // (count * COMT)
+        ok = ctypes.create_string_buffer(max(1, count))
+        kp, kt = _buf(partials), _buf(target)
+        self._chk(self.lib.gs_verify_finish(self.h, ty, count, nparts, kp[1], kt[1], ctypes.cast(ok, ctypes.c_void_p)))
+        return ok.raw[:count]
 
     # ---- ComT
     def comt_pairing(self, xs: bytes, ys: bytes) -> bytes:

@@ -55,3 +55,39 @@ def verify_batch_sharded(verify_local, arrays: Sequence, unit_sizes: Sequence[in
     if world == 1:
         return local
     return gather_verdicts(local, count, group)
+
+
+# ---------------------------------------------------------------- one large statement over several GPUs
+PARTIAL_BYTES = 4 * 576   # four un-exponentiated GT values per statement (include/gs_b200.h gs_verify_partial)
+
+
+def owned_slots(num_slots: int, rank: int, world: int) -> range:
+    """Slots of the pairing-product equation evaluated by `rank` (round-robin, as the kernels do)."""
+    if world <= 0 or not 0 <= rank < world:
+        raise ValueError("bad rank / world size")
+    return range(rank, num_slots, world)
+
+
+def gather_partials(local_partial, group=None):
+    """All-gather of the per-rank Miller partial products (uint8 tensor, count * 2304 bytes, the same size on
+    every rank) -> one uint8 tensor, rank-major, ready for gs_verify_finish.  This is the ONLY collective of a
+    sharded statement: 2,304 B per rank and statement."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    parts = [torch.empty_like(local_partial) for _ in range(world)]
+    dist.all_gather(parts, local_partial, group=group)
+    return torch.cat(parts)
+
+
+def verify_statement_sharded(partial_local, finish, count: int, rank: int, world: int, group=None, device="cpu"):
+    """Verifiable::verify of `count` LARGE statements, each split by slot across `world` ranks.
+    `partial_local(rank, world) -> bytes` is Engine.verify_partial bound to the statement(s);
+    `finish(partials_bytes) -> count verdict bytes` is Engine.verify_finish.  Every rank returns the verdicts."""
+    import torch
+    mine = partial_local(rank, world)
+    if len(mine) != count * PARTIAL_BYTES:
+        raise ValueError("verify_partial returned the wrong number of bytes")
+    local = torch.frombuffer(bytearray(mine), dtype=torch.uint8).to(device)
+    allp = local if world == 1 else gather_partials(local, group)
+    return finish(bytes(allp.cpu().numpy().tobytes()))

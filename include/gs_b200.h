@@ -117,6 +117,17 @@ int gs_prove(gs_ctx* ctx, int type, size_t m, size_t n, const void* a_consts, co
              const gs_fr* gamma, const void* xvars, const void* yvars, const gs_fr* x_rand,
              const gs_fr* y_rand, const gs_fr* pf_rand, gs_com2* out_pi, gs_com1* out_theta);
 
+/* `count` independent Provable::prove calls of one type and shape in one pass (the reference proves equation
+ * by equation, prove.rs:92-171; a statement with many equations -- BASELINE.json configs[3] -- is a batch of
+ * those).  Per-proof arrays are contiguous as in gs_verify_batch: a_consts[count][n], b_consts[count][m],
+ * gamma[count][m][n], pf_rand[count][cy][cx]; with shared_vars != 0 the witnesses and their commitment
+ * randomness (xvars, yvars, x_rand, y_rand) are ONE set used by every equation, otherwise [count][...].
+ * out_pi[count][cx], out_theta[count][cy].  Results are identical to `count` gs_prove calls. */
+int gs_prove_batch(gs_ctx* ctx, int type, size_t count, size_t m, size_t n, const void* a_consts,
+                   const void* b_consts, const gs_fr* gamma, const void* xvars, const void* yvars,
+                   const gs_fr* x_rand, const gs_fr* y_rand, const gs_fr* pf_rand, int shared_vars,
+                   gs_com2* out_pi, gs_com1* out_theta);
+
 /* ---- verification (src/verifier.rs) ----------------------------------------------------- */
 /* Verifiable::verify :23-157 for `count` independent (equation, proof) instances of the same
  * type and shape, each laid out contiguously with the given element counts:
@@ -132,6 +143,31 @@ int gs_verify_batch_dev(gs_ctx* ctx, int type, size_t count, size_t m, size_t n,
                         const void* b_consts, const gs_fr* gamma, const void* target,
                         const gs_com1* xcoms, const gs_com2* ycoms, const gs_com2* pi,
                         const gs_com1* theta, uint8_t* out_ok_dev);
+
+/* ---- one large statement sharded over several GPUs --------------------------- */
+/* Verifiable::verify :23-157 split by SLOT: the pairing-product equation of a statement is a product of
+ * K = n + (m or 1) + cx + cy (+1) Miller pairs per ComT entry; rank `rank` of `world` owns the slots
+ * k = rank (mod world), evaluates the statement MSM only for those (columns of Gamma) and returns the
+ * UN-exponentiated Miller products out_partial[count][4].  Inputs are the FULL arrays of gs_verify_batch
+ * on every rank.  The ranks exchange their 4 x 576 B per statement (one all-gather) and any of them
+ * finishes with gs_verify_finish.  The reference has no distributed mode; this replaces its Rayon
+ * parallelism over left_mul outputs (src/data_structures.rs:657-728) for statements too big for one GPU's
+ * latency budget.  rank 0 of world 1 followed by gs_verify_finish(nparts = 1) equals gs_verify_batch. */
+int gs_verify_partial(gs_ctx* ctx, int type, size_t count, size_t m, size_t n, const void* a_consts,
+                      const void* b_consts, const gs_fr* gamma, const void* target, const gs_com1* xcoms,
+                      const gs_com2* ycoms, const gs_com2* pi, const gs_com1* theta, int rank, int world,
+                      gs_gt* out_partial);
+int gs_verify_partial_dev(gs_ctx* ctx, int type, size_t count, size_t m, size_t n, const void* a_consts,
+                          const void* b_consts, const gs_fr* gamma, const void* target, const gs_com1* xcoms,
+                          const gs_com2* ycoms, const gs_com2* pi, const gs_com1* theta, int rank, int world,
+                          gs_gt* out_partial_dev);
+/* partials[nparts][count][4] (the all-gathered out_partial arrays, rank-major): entry-wise product over the
+ * parts, ONE final exponentiation per ComT entry, comparison with iota_T(target) (PPE: target[count] GT
+ * values; the other types carry their target inside a slot, `target` is ignored).  out_ok[count]. */
+int gs_verify_finish(gs_ctx* ctx, int type, size_t count, int nparts, const gs_gt* partials, const void* target,
+                     uint8_t* out_ok);
+int gs_verify_finish_dev(gs_ctx* ctx, int type, size_t count, int nparts, const gs_gt* partials_dev,
+                         const void* target_dev, uint8_t* out_ok_dev);
 
 /* ---- ComT (src/data_structures.rs) ------------------------------------------------------- */
 /* ComT::pairing :484-491, batched: out[i] = F(xs[i], ys[i]) (4 full pairings each) */

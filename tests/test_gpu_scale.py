@@ -23,53 +23,7 @@ def eng():
     return e
 
 
-def _multiples_g1(eng, ks):
-    g = g1_b(eng._crs.g1_gen)
-    out = eng.com1_matmul(len(ks), 1, 1, b"".join(fr_b(k) for k in ks), g + g)
-    return [out[i * 192:i * 192 + 96] for i in range(len(ks))]
-
-
-def _multiples_g2(eng, ks):
-    g = g2_b(eng._crs.g2_gen)
-    out = eng.com2_matmul(len(ks), 1, 1, b"".join(fr_b(k) for k in ks), g + g)
-    return [out[i * 384:i * 384 + 192] for i in range(len(ks))]
-
-
-def _instance(eng, ty, m, n, rng):
-    """A satisfied equation of type `ty` built on the GPU (witnesses = multiples of the generators)."""
-    xs, ys = [rng.fr() for _ in range(m)], [rng.fr() for _ in range(n)]
-    a, b = [rng.fr() for _ in range(n)], [rng.fr() for _ in range(m)]
-    gam = [[rng.fr() for _ in range(n)] for _ in range(m)]
-    val = (sum(a[j] * ys[j] for j in range(n)) + sum(xs[i] * b[i] for i in range(m)) +
-           sum(gam[i][j] * xs[i] * ys[j] for i in range(m) for j in range(n))) % R
-    g1A = ty in (0, 1)
-    g2B = ty in (0, 2)
-    X = b"".join(_multiples_g1(eng, xs)) if g1A else frs_b(xs)
-    A = b"".join(_multiples_g1(eng, a)) if g1A else frs_b(a)
-    Y = b"".join(_multiples_g2(eng, ys)) if g2B else frs_b(ys)
-    B = b"".join(_multiples_g2(eng, b)) if g2B else frs_b(b)
-    if ty == 0:
-        T = eng.pairing(_multiples_g1(eng, [val])[0], g2_b(eng._crs.g2_gen))
-    elif ty == 1:
-        T = _multiples_g1(eng, [val])[0]
-    elif ty == 2:
-        T = _multiples_g2(eng, [val])[0]
-    else:
-        T = fr_b(val)
-    return A, B, frmat_b(gam), T, X, Y
-
-
-def _commit_prove(eng, ty, m, n, inst, rng):
-    A, B, G, T, X, Y = inst
-    cx = 2 if ty in (0, 1) else 1
-    cy = 2 if ty in (0, 2) else 1
-    xr = b"".join(fr_b(rng.fr()) for _ in range(m * cx))
-    yr = b"".join(fr_b(rng.fr()) for _ in range(n * cy))
-    Tr = b"".join(fr_b(rng.fr()) for _ in range(cx * cy))
-    xc = eng.batch_commit_g1(X, xr) if ty in (0, 1) else eng.batch_commit_scalar_b1(X, xr)
-    yc = eng.batch_commit_g2(Y, yr) if ty in (0, 2) else eng.batch_commit_scalar_b2(Y, yr)
-    pi, th = eng.prove(ty, m, n, A, B, G, X, Y, xr, yr, Tr)
-    return [A, B, G, T, xc, yc, pi, th]
+from workloads import multiples_g1 as _multiples_g1, multiples_g2 as _multiples_g2, instance as _instance, commit_prove as _commit_prove  # noqa: E402
 
 
 def test_c5_batch_verify_tamper_mask(eng):
@@ -162,3 +116,53 @@ def test_c4_mixed_statement_types(eng, ty):
             cols[c].append(r[c])
     ok = eng.verify_batch(ty, count, m, n, *[b"".join(c) for c in cols])
     assert list(ok) == [1, 1, 1, 1, 0, 1]
+
+
+@pytest.mark.parametrize("ty,m,n", [(0, 10, 7), (1, 6, 9), (2, 9, 6), (3, 5, 5)])
+def test_sharded_statement_equals_single_gpu(eng, ty, m, n):
+    """SURVEY.md §8e, one statement split by slot: for every world size the entry-wise product of the ranks'
+    Miller partial products, finished with ONE final exponentiation, gives the verdicts of gs_verify_batch
+    (honest / tampered), including world sizes that leave ranks without any slot."""
+    rng = SeededRng(70 + ty)
+    rows = [_commit_prove(eng, ty, m, n, _instance(eng, ty, m, n, rng), rng) for _ in range(2)]
+    bad = list(rows[1])
+    g = bytearray(bad[2])
+    g[32 * (2 * n + 3) + 1] ^= 4                       # one bit of Gamma[2][3] of the second statement
+    bad[2] = bytes(g)
+    cols = [b"".join(c) for c in zip(rows[0], bad, rows[1])]
+    count = 3
+    want = eng.verify_batch(ty, count, m, n, *cols)
+    assert list(want) == [1, 0, 1]
+    K = n + (m if ty in (0, 2) else 1) + (2 if ty in (0, 1) else 1) + (2 if ty in (0, 2) else 1) + (0 if ty == 0 else 1)
+    for world in (1, 2, 3, 8, K + 3):
+        parts = b"".join(eng.verify_partial(ty, count, m, n, *cols, r, world) for r in range(world))
+        assert len(parts) == world * count * 2304
+        assert eng.verify_finish(ty, count, parts, cols[3]) == want, f"world={world}"
+    # a rank that owns no slot contributes the GT identity
+    from oracle.bls12_381 import FP12_ONE
+    last = eng.verify_partial(ty, count, m, n, *cols, K + 2, K + 3)
+    assert last == fp12_b(FP12_ONE) * (4 * count)
+    with pytest.raises(Exception):
+        eng.verify_partial(ty, count, m, n, *cols, 2, 2)
+
+
+@pytest.mark.parametrize("ty", [0, 1, 2, 3])
+def test_prove_batch_equals_single_proves(eng, ty):
+    """gs_prove_batch (stream pool) == one gs_prove per equation, byte for byte: 9 equations over SHARED
+    variables (the C4 shape), and 3 with per-proof variables."""
+    from workloads import instance_many
+    rng = SeededRng(90 + ty)
+    m, n, E = 6, 5, 9
+    A, B, G, T, X, Y, xr, yr, Tr = instance_many(eng, ty, m, n, E, rng)
+    singles = [eng.prove(ty, m, n, A[e], B[e], G[e], X, Y, xr, yr, Tr[e]) for e in range(E)]
+    pi, th = eng.prove_batch(ty, E, m, n, b"".join(A), b"".join(B), b"".join(G), X, Y, xr, yr, b"".join(Tr), shared_vars=True)
+    assert pi == b"".join(s[0] for s in singles) and th == b"".join(s[1] for s in singles)
+    # per-proof variables: three copies of the same witness arrays must give the first three proofs again
+    pi3, th3 = eng.prove_batch(ty, 3, m, n, b"".join(A[:3]), b"".join(B[:3]), b"".join(G[:3]), X * 3, Y * 3, xr * 3, yr * 3,
+                               b"".join(Tr[:3]), shared_vars=False)
+    assert pi3 == b"".join(s[0] for s in singles[:3]) and th3 == b"".join(s[1] for s in singles[:3])
+    # and the proofs verify against commitments of the shared variables
+    xc = eng.batch_commit_g1(X, xr) if ty in (0, 1) else eng.batch_commit_scalar_b1(X, xr)
+    yc = eng.batch_commit_g2(Y, yr) if ty in (0, 2) else eng.batch_commit_scalar_b2(Y, yr)
+    ok = eng.verify_batch(ty, E, m, n, b"".join(A), b"".join(B), b"".join(G), b"".join(T), xc * E, yc * E, pi, th)
+    assert ok == b"\x01" * E

@@ -1,0 +1,313 @@
+#!/usr/bin/env python3
+"""Measured numbers for BASELINE.json configs[0..3] (C1..C4 of SURVEY.md §8d) on one B200 -- the companions of
+bench.py, which carries the headline C5 line.  Every GPU figure is END TO END through the C ABI with host
+buffers (H2D + D2H inside the timed region, wall clock around the synchronous call) plus the per-kernel device
+times the library records with CUDA events; every CPU figure is the oracle's C restatement of the reference
+algorithm on a bounded (down-scaled, stated) sample.  One JSON line per config.
+
+    python tools/bench_configs.py [c1] [c2] [c3] [c4] [--log2n 20] [--c3-size 1024] [--c4-eqs 256] [--no-cpu]
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import numpy as np  # noqa: E402
+
+
+def wall(fn, reps=1):
+    best = None
+    out = None
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        out = fn()
+        dt = time.perf_counter() - t0
+        best = dt if best is None or dt < best else best
+    return best, out
+
+
+def profiled(eng, fn):
+    """Run fn once with the library's per-kernel CUDA-event log on; returns ({kernel: [launches, ms]}, result)."""
+    eng.profile_enable(True)
+    out = fn()
+    prof = eng.profile_read()
+    eng.profile_enable(False)
+    return {k: [v[0], round(v[1], 3)] for k, v in prof.items()}, out
+
+
+def random_fr_bytes(n, seed):
+    """n field elements as arkworks does Fr::rand: random limbs taken as the Montgomery representation
+    (top limb masked below 2^62 so every value is < r)."""
+    rs = np.random.RandomState(seed)
+    a = rs.randint(0, 2 ** 63 - 1, size=(n, 4), dtype=np.int64).astype(np.uint64)
+    a[:, 3] &= np.uint64((1 << 62) - 1)
+    return a.tobytes()
+
+
+def make_engine(seed):
+    import groth_sahai_rs_b200 as gsb
+    from gsutil import make_crs, crs_bytes
+    eng = gsb.Engine(0)
+    crs, draws = make_crs(seed)
+    eng.crs_load(crs_bytes(crs))
+    eng._crs = crs
+    return eng, crs, draws
+
+
+# ------------------------------------------------------------------------------------------------ C1
+def bench_c1(args):
+    from gsutil import SeededRng, crs_bytes, g1_b, g2_b, fr_b
+    from workloads import instance, commit_prove
+    eng, crs, draws = make_engine(1)
+    rng = SeededRng(11)
+    m = n = 4
+    d = [g1_b(draws[0]), g2_b(draws[1])] + [fr_b(x) for x in draws[2:]]
+    t_crs, crsb = wall(lambda: eng.crs_generate(*d), 3)
+    assert crsb == crs_bytes(crs)
+    inst = instance(eng, 0, m, n, rng)
+    A, B, G, T, X, Y = inst
+    xr = b"".join(fr_b(rng.fr()) for _ in range(2 * m))
+    yr = b"".join(fr_b(rng.fr()) for _ in range(2 * n))
+    Tr = b"".join(fr_b(rng.fr()) for _ in range(4))
+    t_c1, xc = wall(lambda: eng.batch_commit_g1(X, xr), 5)
+    t_c2, yc = wall(lambda: eng.batch_commit_g2(Y, yr), 5)
+    t_pr, (pi, th) = wall(lambda: eng.prove(0, m, n, A, B, G, X, Y, xr, yr, Tr), 5)
+    arrs = [A, B, G, T, xc, yc, pi, th]
+    t_v, ok = wall(lambda: eng.verify(0, m, n, *arrs), 5)
+    assert ok is True
+    bad = list(arrs)
+    bad[3] = eng.pairing(g1_b(crs.g1_gen), g2_b(crs.g2_gen))
+    assert eng.verify(0, m, n, *bad) is False
+    prof, _ = profiled(eng, lambda: eng.verify(0, m, n, *arrs))
+    cpu = None
+    if not args.no_cpu:
+        from oracle import cbaseline
+        crsb2 = crs_bytes(crs)
+        tc1, o1 = wall(lambda: cbaseline.batch_commit_g1(X, xr, crsb2), 2)
+        tc2, o2 = wall(lambda: cbaseline.batch_commit_g2(Y, yr, crsb2), 2)
+        assert o1 == xc and o2 == yc, "C1 commitments differ from the C oracle"
+        tv, okc = wall(lambda: cbaseline.verify_ppe_batch(1, m, n, arrs, crsb2, 1), 2)
+        assert okc == b"\x01"
+        cpu = {"kind": "port", "cores": 1, "batch_commit_G1_ms": round(tc1 * 1e3, 2), "batch_commit_G2_ms": round(tc2 * 1e3, 2),
+               "verify_ms": round(tv * 1e3, 2), "sample": "the same single instance, one host thread (C restatement, not arkworks)"}
+    return {"config": "C1: single PPE, 4 G1 + 4 G2 variables (BASELINE.json configs[0])", "unit": "ms (latency, e2e through the C ABI)",
+            "generate_crs_ms": round(t_crs * 1e3, 3), "batch_commit_G1_ms": round(t_c1 * 1e3, 3), "batch_commit_G2_ms": round(t_c2 * 1e3, 3),
+            "prove_ms": round(t_pr * 1e3, 3), "commit_and_prove_ms": round((t_c1 + t_c2 + t_pr) * 1e3, 3), "verify_ms": round(t_v * 1e3, 3),
+            "verify_kernels": prof, "parity": "commitments byte-equal to the C oracle; verify True / tampered target False",
+            "cpu_baseline": cpu}
+
+
+# ------------------------------------------------------------------------------------------------ C2
+def bench_c2(args):
+    from gsutil import SeededRng, crs_bytes
+    from workloads import multiples_g1, multiples_g2
+    eng, crs, _ = make_engine(2)
+    rng = SeededRng(2)
+    n = 1 << args.log2n
+    D = min(n, 1 << 12)                                  # distinct points, tiled to n (scalars are all distinct)
+    p1 = multiples_g1(eng, [rng.fr() for _ in range(D)])
+    p2 = multiples_g2(eng, [rng.fr() for _ in range(D)])
+    X = np.frombuffer(b"".join(p1), dtype=np.uint8).reshape(D, 96)
+    Y = np.frombuffer(b"".join(p2), dtype=np.uint8).reshape(D, 192)
+    idx = np.arange(n) % D
+    Xb, Yb = np.ascontiguousarray(X[idx]), np.ascontiguousarray(Y[idx])
+    Rb, Sb = random_fr_bytes(2 * n, 21), random_fr_bytes(2 * n, 22)
+    import ctypes
+    out1 = np.empty(n * 192, dtype=np.uint8)
+    out2 = np.empty(n * 384, dtype=np.uint8)
+    Rn, Sn = np.frombuffer(Rb, dtype=np.uint8), np.frombuffer(Sb, dtype=np.uint8)
+    vp = ctypes.c_void_p
+
+    def c1():
+        eng._chk(eng.lib.gs_batch_commit_g1(eng.h, n, vp(Xb.ctypes.data), vp(Rn.ctypes.data), vp(out1.ctypes.data)))
+
+    def c2():
+        eng._chk(eng.lib.gs_batch_commit_g2(eng.h, n, vp(Yb.ctypes.data), vp(Sn.ctypes.data), vp(out2.ctypes.data)))
+
+    c1(); c2()                                           # warm-up: builds the big fixed-base tables once
+    t1, _ = wall(c1, 3)
+    t2, _ = wall(c2, 3)
+    prof1, _ = profiled(eng, c1)
+    prof2, _ = profiled(eng, c2)
+    # parity on a sample against the C oracle + linearity (commit(X, R) - commit(X, 0) independent of X is in tests/)
+    cpu = None
+    ns = 64
+    if not args.no_cpu:
+        from oracle import cbaseline
+        crsb = crs_bytes(crs)
+        tc1, o1 = wall(lambda: cbaseline.batch_commit_g1(Xb[:ns].tobytes(), Rb[:ns * 64], crsb))
+        tc2, o2 = wall(lambda: cbaseline.batch_commit_g2(Yb[:ns].tobytes(), Sb[:ns * 64], crsb))
+        assert o1 == out1[:ns * 192].tobytes() and o2 == out2[:ns * 384].tobytes(), "C2 commitments differ from the C oracle"
+        cpu = {"kind": "port", "cores": 1, "g1_commits_per_sec": round(ns / tc1, 1), "g2_commits_per_sec": round(ns / tc2, 1),
+               "sample": f"{ns} variables each (the reference's batch_commit is single-threaded by construction, commit.rs:94,194); "
+                         "C restatement, not arkworks; the GPU's first 64 outputs are byte-equal to it"}
+    k1 = sum(v[1] for v in prof1.values())
+    k2 = sum(v[1] for v in prof2.values())
+    return {"config": f"C2: batch_commit_G1/G2 of 2^{args.log2n} variables each on one B200 (BASELINE.json configs[1])",
+            "unit": "commits/s (e2e: host buffers, H2D+D2H inside)", "n": n, "distinct_points": D,
+            "g1_commits_per_sec": round(n / t1, 1), "g2_commits_per_sec": round(n / t2, 1),
+            "combined_commits_per_sec": round(2 * n / (t1 + t2), 1), "g1_ms": round(t1 * 1e3, 2), "g2_ms": round(t2 * 1e3, 2),
+            "g1_kernel_ms": round(k1, 2), "g2_kernel_ms": round(k2, 2), "g1_kernels": prof1, "g2_kernels": prof2,
+            "hbm_gbs_point_phase": {"g1": round(n * (96 + 64 + 192) / (k1 * 1e-3) / 1e9, 2), "g2": round(n * (192 + 64 + 384) / (k2 * 1e-3) / 1e9, 2)},
+            "cpu_baseline": cpu}
+
+
+# ------------------------------------------------------------------------------------------------ C3
+def bench_c3(args):
+    from gsutil import SeededRng, crs_bytes
+    from workloads import instance, commit_prove
+    eng, crs, _ = make_engine(3)
+    rng = SeededRng(3)
+    m = n = args.c3_size
+    t_gen0 = time.perf_counter()
+    inst = instance(eng, 0, m, n, rng)
+    A, B, G, T, X, Y = inst
+    from gsutil import fr_b
+    xr = b"".join(fr_b(rng.fr()) for _ in range(2 * m))
+    yr = b"".join(fr_b(rng.fr()) for _ in range(2 * n))
+    Tr = b"".join(fr_b(rng.fr()) for _ in range(4))
+    t_gen = time.perf_counter() - t_gen0
+    xc = eng.batch_commit_g1(X, xr)
+    yc = eng.batch_commit_g2(Y, yr)
+    eng.prove(0, m, n, A, B, G, X, Y, xr, yr, Tr)           # warm-up
+    t_pr, (pi, th) = wall(lambda: eng.prove(0, m, n, A, B, G, X, Y, xr, yr, Tr), 3)
+    arrs = [A, B, G, T, xc, yc, pi, th]
+    assert eng.verify(0, m, n, *arrs) is True
+    t_v, ok = wall(lambda: eng.verify(0, m, n, *arrs), 3)
+    g = bytearray(G)
+    g[32 * (5 * n + 7)] ^= 1
+    bad = list(arrs)
+    bad[2] = bytes(g)
+    assert eng.verify(0, m, n, *bad) is False
+    prof_v, _ = profiled(eng, lambda: eng.verify(0, m, n, *arrs))
+    prof_p, _ = profiled(eng, lambda: eng.prove(0, m, n, A, B, G, X, Y, xr, yr, Tr))
+    pairs = 4 * n + 2 * m + 16
+    cpu = None
+    if not args.no_cpu:
+        from oracle import cbaseline
+        ms_ = 16
+        rng2 = SeededRng(33)
+        small = commit_prove(eng, 0, ms_, ms_, instance(eng, 0, ms_, ms_, rng2), rng2)
+        tv, okc = wall(lambda: cbaseline.verify_ppe_batch(1, ms_, ms_, small, crs_bytes(crs), 1))
+        assert okc == b"\x01"
+        cores = cbaseline.host_cores()
+        est = tv * (m * n) / (ms_ * ms_)
+        cpu = {"kind": "port", "cores": 1, "verify_s_at_16x16": round(tv, 3), "verify_s_extrapolated": round(est, 1),
+               "verify_s_extrapolated_all_cores": round(est / cores, 1), "host_cores": cores,
+               "sample": f"one PPE verify at m=n={ms_} on one host thread (reference algorithm: Gamma*d as m*n G2 scalar muls), "
+                         f"scaled by (m n)/(16*16) -- the m*n term dominates; '/cores' assumes ideal Rayon scaling over left_mul outputs"}
+    return {"config": f"C3: one PPE, m=n={m}, dense Gamma (BASELINE.json configs[2]), 1 GPU", "unit": "s (latency, e2e through the C ABI)",
+            "prove_s": round(t_pr, 4), "verify_s": round(t_v, 4), "miller_pairs_per_verify": pairs,
+            "pairings_per_sec_in_verify": round(pairs / t_v, 1), "verify_kernels": prof_v, "prove_kernels": prof_p,
+            "h2d_bytes_verify": sum(len(a) for a in arrs), "instance_build_s": round(t_gen, 1),
+            "parity": "verify True; one flipped bit of Gamma[5][7] -> False", "cpu_baseline": cpu}
+
+
+# ------------------------------------------------------------------------------------------------ C4
+def bench_c4(args):
+    from gsutil import SeededRng, fr_b, frs_b, g2_b, R
+    from workloads import multiples_g1, multiples_g2
+    eng, crs, _ = make_engine(4)
+    rng = SeededRng(4)
+    m = n = 64
+    E = args.c4_eqs
+    xs, ys = [rng.fr() for _ in range(m)], [rng.fr() for _ in range(n)]          # group witnesses (dlogs)
+    xs_s, ys_s = [rng.fr() for _ in range(m)], [rng.fr() for _ in range(n)]      # scalar witnesses
+    Xg, Yg = b"".join(multiples_g1(eng, xs)), b"".join(multiples_g2(eng, ys))
+    Xs, Ys = frs_b(xs_s), frs_b(ys_s)
+    r2 = lambda k: b"".join(fr_b(rng.fr()) for _ in range(k))
+    rx_g, ry_g, rx_s, ry_s = r2(2 * m), r2(2 * n), r2(m), r2(n)
+    t_commit, coms = wall(lambda: (eng.batch_commit_g1(Xg, rx_g), eng.batch_commit_g2(Yg, ry_g),
+                                   eng.batch_commit_scalar_b1(Xs, rx_s), eng.batch_commit_scalar_b2(Ys, ry_s)))
+    cg, dg, cs, ds = coms
+    res = {}
+    total_p = total_v = 0.0
+    for ty in range(4):
+        g1A, g2B = ty in (0, 1), ty in (0, 2)
+        xw, yw = (xs if g1A else xs_s), (ys if g2B else ys_s)
+        Xv, Yv = (Xg if g1A else Xs), (Yg if g2B else Ys)
+        xr, yr = (rx_g if g1A else rx_s), (ry_g if g2B else ry_s)
+        xc, yc = (cg if g1A else cs), (dg if g2B else ds)
+        a = [[rng.fr() for _ in range(n)] for _ in range(E)]
+        b = [[rng.fr() for _ in range(m)] for _ in range(E)]
+        gam = np.frombuffer(random_fr_bytes(E * m * n, 40 + ty), dtype=np.uint8).reshape(E, m * n * 32)
+        from conv import fr_i
+        vals = []
+        for e in range(E):
+            gb = gam[e].tobytes()
+            gi = [fr_i(gb[32 * t:32 * t + 32]) for t in range(m * n)]
+            v = sum(a[e][j] * yw[j] for j in range(n)) + sum(xw[i] * b[e][i] for i in range(m))
+            v += sum(gi[i * n + j] * xw[i] * yw[j] for i in range(m) for j in range(n))
+            vals.append(v % R)
+        flat = lambda rows: [x for r in rows for x in r]
+        Aall = multiples_g1(eng, flat(a)) if g1A else [fr_b(x) for x in flat(a)]
+        Ball = multiples_g2(eng, flat(b)) if g2B else [fr_b(x) for x in flat(b)]
+        if ty == 0:
+            tg = eng.pairing(b"".join(multiples_g1(eng, vals)), g2_b(crs.g2_gen) * E)
+            Tall = [tg[576 * e:576 * (e + 1)] for e in range(E)]
+        elif ty == 1:
+            Tall = multiples_g1(eng, vals)
+        elif ty == 2:
+            Tall = multiples_g2(eng, vals)
+        else:
+            Tall = [fr_b(v) for v in vals]
+        cx, cy = (2 if g1A else 1), (2 if g2B else 1)
+        Trs = [r2(cx * cy) for _ in range(E)]
+        As = [b"".join(Aall[e * n:(e + 1) * n]) for e in range(E)]
+        Bs = [b"".join(Ball[e * m:(e + 1) * m]) for e in range(E)]
+        Gs = [gam[e].tobytes() for e in range(E)]
+        first = eng.prove(ty, m, n, As[0], Bs[0], Gs[0], Xv, Yv, xr, yr, Trs[0])
+        t_one, _ = wall(lambda: eng.prove(ty, m, n, As[1 % E], Bs[1 % E], Gs[1 % E], Xv, Yv, xr, yr, Trs[1 % E]), 2)
+        pb = lambda: eng.prove_batch(ty, E, m, n, b"".join(As), b"".join(Bs), b"".join(Gs), Xv, Yv, xr, yr, b"".join(Trs),
+                                     shared_vars=True)
+        pb()
+        t_p, (pis, ths) = wall(pb, 2)
+        assert (pis[:cx * 384], ths[:cy * 192]) == first, "prove_batch differs from prove"
+        proofs = [(pis[e * cx * 384:(e + 1) * cx * 384], ths[e * cy * 192:(e + 1) * cy * 192]) for e in range(E)]
+        cols = [b"".join(As), b"".join(Bs), b"".join(Gs), b"".join(Tall), xc * E, yc * E,
+                b"".join(p[0] for p in proofs), b"".join(p[1] for p in proofs)]
+        ok = eng.verify_batch(ty, E, m, n, *cols)
+        assert ok == b"\x01" * E, f"type {ty}: {ok.count(1)} of {E} verified"
+        t_v, ok = wall(lambda: eng.verify_batch(ty, E, m, n, *cols), 2)
+        # tamper one equation: swap two gamma rows' worth of bytes of equation 3
+        badG = bytearray(cols[2])
+        o = 3 * m * n * 32
+        badG[o] ^= 1
+        bad = list(cols)
+        bad[2] = bytes(badG)
+        okb = eng.verify_batch(ty, E, m, n, *bad)
+        assert okb == b"\x01" * 3 + b"\x00" + b"\x01" * (E - 4)
+        res[["PPE", "MSMEG1", "MSMEG2", "QuadEqu"][ty]] = {"proved_per_sec": round(E / t_p, 1), "verified_per_sec": round(E / t_v, 1),
+                                                           "prove_single_call_ms": round(t_one * 1e3, 3), "prove_batch_ms": round(t_p * 1e3, 2), "verify_batch_ms": round(t_v * 1e3, 2)}
+        total_p += t_p
+        total_v += t_v
+    return {"config": f"C4: mixed statement, {E} each of PPE/MSMEG1/MSMEG2/QuadEqu over shared variable sets m=n=m'=n'=64 "
+                      "(BASELINE.json configs[3]), 1 GPU", "unit": "equations/s (e2e through the C ABI)",
+            "commit_ms_all_4_sets": round(t_commit * 1e3, 2), "equations": 4 * E,
+            "proved_per_sec": round(4 * E / total_p, 1), "verified_per_sec": round(4 * E / total_v, 1), "per_type": res,
+            "parity": "all honest proofs verify; one flipped Gamma bit in equation 3 of every type is the only rejection"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("which", nargs="*", default=["c1", "c2", "c3", "c4"])
+    ap.add_argument("--log2n", type=int, default=20)
+    ap.add_argument("--c3-size", type=int, default=1024)
+    ap.add_argument("--c4-eqs", type=int, default=256)
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    fns = {"c1": bench_c1, "c2": bench_c2, "c3": bench_c3, "c4": bench_c4}
+    for w in args.which:
+        t0 = time.perf_counter()
+        line = fns[w](args)
+        line["bench_wall_s"] = round(time.perf_counter() - t0, 1)
+        print(json.dumps(line), flush=True)
+
+
+if __name__ == "__main__":
+    main()
