@@ -57,7 +57,6 @@ void gs_ctx_destroy(gs_ctx* ctx) {
   if (ctx->crs_lines) cudaFree(ctx->crs_lines);
   if (ctx->fe_prog) cudaFree(ctx->fe_prog);
   cudaFree(ctx->crs);
-  for (auto st : ctx->pool) cudaStreamDestroy(st);
   cudaStreamDestroy(ctx->stream);
   delete ctx;
 }

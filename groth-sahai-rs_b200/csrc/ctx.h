@@ -25,7 +25,6 @@ struct gs_fixed_table {
 struct gs_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
-  std::vector<cudaStream_t> pool;  // extra streams for batches of small independent launch chains (gs_prove_batch)
   gs::crs_dev* crs = nullptr;  // device
   bool crs_loaded = false;
   gs_fixed_table<gs::FpOps> tab1;
@@ -58,12 +57,13 @@ struct gs_ctx {
     ctx->err = (msg);   \
     return (code);      \
   } while (0)
-// launch `kern` with `nthreads` logical threads in blocks of `bs` and `smem` dynamic shared bytes
-#define LAUNCH_CFG(kern, nthreads, bs, smem, ...)                         \
+// launch `kern` with `nthreads` logical threads in blocks of `bs` and `smem` dynamic shared bytes;
+// `gy` = gridDim.y (batched kernels: blockIdx.y = instance, see prover.cu)
+#define LAUNCH_GRID(kern, nthreads, gy, bs, smem, ...)                    \
   do {                                                                    \
     size_t nt_ = (nthreads);                                              \
-    if (nt_ > 0) {                                                        \
-      unsigned grid_ = (unsigned)((nt_ + (bs)-1) / (bs));                 \
+    if (nt_ > 0 && (gy) > 0) {                                            \
+      dim3 grid_((unsigned)((nt_ + (bs)-1) / (bs)), (unsigned)(gy));      \
       gs_ctx::prof_rec pr_{#kern, nullptr, nullptr};                      \
       if (ctx->profile) {                                                 \
         cudaEventCreate(&pr_.e0);                                         \
@@ -79,7 +79,9 @@ struct gs_ctx {
       CUDA_TRY(cudaGetLastError());                                       \
     }                                                                     \
   } while (0)
-#define LAUNCH(kern, nthreads, ...) LAUNCH_CFG(kern, nthreads, 128, 0, __VA_ARGS__)
+#define LAUNCH_CFG(kern, nthreads, bs, smem, ...) LAUNCH_GRID(kern, nthreads, 1, bs, smem, __VA_ARGS__)
+#define LAUNCH(kern, nthreads, ...) LAUNCH_GRID(kern, nthreads, 1, 128, 0, __VA_ARGS__)
+#define LAUNCH_B(kern, nthreads, nbatch, ...) LAUNCH_GRID(kern, nthreads, nbatch, 128, 0, __VA_ARGS__)
 
 // stream-ordered scratch with RAII release
 struct Scratch {
@@ -152,10 +154,12 @@ template <class F>
 int batch_commit_impl(gs_ctx* ctx, size_t n, int base0, int base1, const gs_fr* s0, size_t s0_stride, const gs_fr* s1,
                       size_t s1_stride, size_t nscal, const void* addend, void* out);
 // one proof element vector (pi: F = G2, theta: F = G1); `e` = collapsed scalar for scalar-typed sides (else null)
+// Batched over `count` proofs (blockIdx.y): per-proof strides are implied by the shapes; `vars_shared` = the
+// variable array is one set used by every proof.
 template <class F>
-int proof_element(gs_ctx* ctx, Scratch& sc, int rows, bool group_typed, const fr* sv, const void* dconst, size_t nconst,
-                  const void* dvars, size_t nvars, int ncoef, const fr* coef, size_t coef_rs, const Aff<F>* key,
-                  const Aff<F>* W, const fr* e, Aff<F>* dout);
+int proof_element(gs_ctx* ctx, Scratch& sc, size_t count, int rows, bool group_typed, const fr* sv, const void* dconst,
+                  size_t nconst, const void* dvars, size_t nvars, bool vars_shared, int ncoef, const fr* coef, size_t coef_rs,
+                  const fr* e, Aff<F>* dout);
 template <class F>
 int com_matmul_impl(gs_ctx* ctx, size_t r, size_t k, size_t c, const gs_fr* lhs, const void* mat, void* out);
 

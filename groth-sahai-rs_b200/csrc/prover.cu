@@ -79,11 +79,15 @@ __global__ void k_crs_derive(crs_dev* c) {
 }
 
 // ------------------------------------------------------------------ Fr matrix algebra
-// out (r x c) = A (r x k) * B (k x c), row-major; optional transposes via strides
+// out (r x c) = A (r x k) * B (k x c), row-major; optional transposes via strides.
+// Every prover kernel is batched over blockIdx.y = proof instance; `*_bs` = elements between instances (0: shared).
 __global__ void k_fr_matmul(fr* __restrict__ out, const fr* __restrict__ A, size_t a_rs, size_t a_cs, const fr* __restrict__ B,
-                            size_t b_rs, size_t b_cs, size_t r, size_t k, size_t c) {
+                            size_t b_rs, size_t b_cs, size_t r, size_t k, size_t c, size_t a_bs, size_t b_bs) {
   size_t id = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (id >= r * c) return;
+  out += (size_t)blockIdx.y * r * c;
+  A += (size_t)blockIdx.y * a_bs;
+  B += (size_t)blockIdx.y * b_bs;
   size_t i = id / c, j = id % c;
   fr acc;
   acc.set_zero();
@@ -97,9 +101,13 @@ __global__ void k_fr_matmul(fr* __restrict__ out, const fr* __restrict__ A, size
 
 // coef_pi[i][l] = (RG * S)[i][l] - T[l][i]            (prove.rs:139-142)   cx x cy
 __global__ void k_coef_pi(fr* __restrict__ out, const fr* __restrict__ RG, const fr* __restrict__ S, const fr* __restrict__ T, int cx,
-                          int cy, size_t n) {
+                          int cy, size_t n, size_t s_bs) {
   int id = blockIdx.x * blockDim.x + threadIdx.x;
   if (id >= cx * cy) return;
+  out += (size_t)blockIdx.y * cx * cy;
+  RG += (size_t)blockIdx.y * cx * n;
+  S += (size_t)blockIdx.y * s_bs;
+  T += (size_t)blockIdx.y * cx * cy;
   int i = id / cy, l = id % cy;
   fr acc;
   acc.set_zero();
@@ -114,18 +122,26 @@ __global__ void k_coef_pi(fr* __restrict__ out, const fr* __restrict__ RG, const
 
 // scalar vectors of the variable-base part of a proof element:
 //   sv[i][t] = R[t][i] (t < m) ; RG[i][t-m] (t >= m)          i < cx
-__global__ void k_concat_scalars(fr* __restrict__ sv, const fr* __restrict__ R, const fr* __restrict__ RG, int cx, size_t m, size_t n) {
+__global__ void k_concat_scalars(fr* __restrict__ sv, const fr* __restrict__ R, const fr* __restrict__ RG, int cx, size_t m, size_t n,
+                                 size_t r_bs) {
   size_t id = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (id >= (size_t)cx * (m + n)) return;
+  sv += (size_t)blockIdx.y * cx * (m + n);
+  R += (size_t)blockIdx.y * r_bs;
+  RG += (size_t)blockIdx.y * cx * n;
   size_t i = id / (m + n), t = id % (m + n);
   sv[id] = t < m ? R[t * cx + i] : RG[i * n + (t - m)];
 }
 
 // dot[i] = sum_t sv[i][t] * w[t]    (scalar-typed constants/variables: everything collapses onto W)
 __global__ void k_fr_dot(fr* __restrict__ out, const fr* __restrict__ sv, const fr* __restrict__ w0, size_t m, const fr* __restrict__ w1,
-                         size_t n, int rows) {
+                         size_t n, int rows, size_t w1_bs) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= rows) return;
+  out += (size_t)blockIdx.y * rows;
+  sv += (size_t)blockIdx.y * rows * (m + n);
+  w0 += (size_t)blockIdx.y * m;
+  w1 += (size_t)blockIdx.y * w1_bs;
   fr acc;
   acc.set_zero();
   for (size_t t = 0; t < m + n; t++) {
@@ -215,138 +231,91 @@ int gs_batch_commit_scalar_b2(gs_ctx* ctx, size_t n, const gs_fr* ys, const gs_f
   return batch_commit_impl<Fp2Ops>(ctx, n, 2, 0, buf.data(), 1, buf.data() + n, 1, 2 * n, nullptr, out);
 }
 
-// Enqueues one Provable::prove on ctx->stream (uploads, kernels, download into out_pi / out_theta); the caller
-// synchronises.  `sc` must stay alive until then only in the sense of stream order (frees are stream-ordered).
-static int prove_enqueue(gs_ctx* ctx, Scratch& sc, int type, size_t m, size_t n, const void* a_consts, const void* b_consts,
-                         const gs_fr* gamma, const void* xvars, const void* yvars, const gs_fr* x_rand, const gs_fr* y_rand,
-                         const gs_fr* pf_rand, void* out_pi, void* out_theta) {
+// `count` independent Provable::prove calls of one type and shape, every kernel batched over blockIdx.y.
+// Per-proof arrays are contiguous ([count][...]); with shared_vars the witnesses and their commitment randomness
+// are one set.  gs_prove is the batch of one.
+static int prove_impl(gs_ctx* ctx, int type, size_t count, size_t m, size_t n, const void* a_consts, const void* b_consts,
+                      const gs_fr* gamma, const void* xvars, const void* yvars, const gs_fr* x_rand, const gs_fr* y_rand,
+                      const gs_fr* pf_rand, bool shared_vars, gs_com2* out_pi, gs_com1* out_theta) {
   if (!ctx) return GS_EARG;
   if (type < 0 || type > 3) FAIL(GS_EARG, "prove: bad equation type");
   if (!ctx->crs_loaded) FAIL(GS_EARG, "prove: no CRS loaded");
+  if (count == 0) return GS_OK;
   if (m == 0 || n == 0) FAIL(GS_EDIM, "prove: empty variable list");  // reference panics
   if (m > 1 << 22 || n > 1 << 22) FAIL(GS_EDIM, "prove: too many variables");
   if (!a_consts || !b_consts || !gamma || !xvars || !yvars || !x_rand || !y_rand || !pf_rand || !out_pi || !out_theta)
     return GS_EARG;
+  CUDA_TRY(cudaSetDevice(ctx->device));
   verify_shape s = make_verify_shape(type, (int)m, (int)n);
   const int cx = s.cx, cy = s.cy;
-  uint8_t *dA, *dB, *dX, *dY;
-  fr *dG, *dR, *dS, *dT;
-  CUDA_TRY(upload(ctx, sc, &dA, a_consts, n * elem_size_A(type)));
-  CUDA_TRY(upload(ctx, sc, &dB, b_consts, m * elem_size_B(type)));
-  CUDA_TRY(upload(ctx, sc, &dX, xvars, m * elem_size_A(type)));
-  CUDA_TRY(upload(ctx, sc, &dY, yvars, n * elem_size_B(type)));
-  CUDA_TRY(upload(ctx, sc, &dG, gamma, m * n));
-  CUDA_TRY(upload(ctx, sc, &dR, x_rand, m * cx));
-  CUDA_TRY(upload(ctx, sc, &dS, y_rand, n * cy));
-  CUDA_TRY(upload(ctx, sc, &dT, pf_rand, (size_t)cx * cy));
-  fr *RG, *SG, *coef_pi, *sv_pi, *sv_th;
-  CUDA_TRY(sc.alloc(&RG, cx * n));
-  CUDA_TRY(sc.alloc(&SG, cy * m));
-  CUDA_TRY(sc.alloc(&coef_pi, (size_t)cx * cy));
-  CUDA_TRY(sc.alloc(&sv_pi, cx * (m + n)));
-  CUDA_TRY(sc.alloc(&sv_th, cy * (m + n)));
-  // RG = R^T Gamma (cx x n)  prove.rs:133 ;  SG = S^T Gamma^T (cy x m)  prove.rs:154
-  LAUNCH(k_fr_matmul, (size_t)cx * n, RG, dR, (size_t)1, (size_t)cx, dG, n, (size_t)1, (size_t)cx, m, n);
-  LAUNCH(k_fr_matmul, (size_t)cy * m, SG, dS, (size_t)1, (size_t)cy, dG, (size_t)1, n, (size_t)cy, n, m);
-  // (R^T Gamma S - T^T)  prove.rs:139-142
-  LAUNCH(k_coef_pi, (size_t)cx * cy, coef_pi, RG, dS, dT, cx, cy, n);
-  LAUNCH(k_concat_scalars, (size_t)cx * (m + n), sv_pi, dR, RG, cx, m, n);
-  LAUNCH(k_concat_scalars, (size_t)cy * (m + n), sv_th, dS, SG, cy, n, m);
-  g2_aff* dpi;
-  g1_aff* dth;
-  CUDA_TRY(sc.alloc(&dpi, 2 * cx));
-  CUDA_TRY(sc.alloc(&dth, 2 * cy));
-  // pi_i = sum_k R[k][i] iota(B_k) + sum_j RG[i][j] iota(Y_j) + sum_l coef_pi[i][l] v_l        (l < cy)
-  fr *e_pi = nullptr, *e_th = nullptr;
-  if (!s.groupB) {  // scalar-typed y side: every term collapses onto W2
-    CUDA_TRY(sc.alloc(&e_pi, cx));
-    LAUNCH(k_fr_dot, (size_t)cx, e_pi, sv_pi, (const fr*)dB, m, (const fr*)dY, n, cx);
+  const size_t szA = elem_size_A(type), szB = elem_size_B(type);
+  const size_t MAXB = 32768;  // gridDim.y limit is 65,535
+  for (size_t off = 0; off < count; off += MAXB) {
+    const size_t nb = count - off < MAXB ? count - off : MAXB;
+    const size_t voff = shared_vars ? 0 : off, nv = shared_vars ? 1 : nb;
+    Scratch sc(ctx);
+    uint8_t *dA, *dB, *dX, *dY;
+    fr *dG, *dR, *dS, *dT;
+    CUDA_TRY(upload(ctx, sc, &dA, (const char*)a_consts + off * n * szA, nb * n * szA));
+    CUDA_TRY(upload(ctx, sc, &dB, (const char*)b_consts + off * m * szB, nb * m * szB));
+    CUDA_TRY(upload(ctx, sc, &dX, (const char*)xvars + voff * m * szA, nv * m * szA));
+    CUDA_TRY(upload(ctx, sc, &dY, (const char*)yvars + voff * n * szB, nv * n * szB));
+    CUDA_TRY(upload(ctx, sc, &dG, gamma + off * m * n, nb * m * n));
+    CUDA_TRY(upload(ctx, sc, &dR, x_rand + voff * m * cx, nv * m * cx));
+    CUDA_TRY(upload(ctx, sc, &dS, y_rand + voff * n * cy, nv * n * cy));
+    CUDA_TRY(upload(ctx, sc, &dT, pf_rand + off * cx * cy, nb * cx * cy));
+    const size_t r_bs = shared_vars ? 0 : m * cx, s_bs = shared_vars ? 0 : n * cy;  // instance strides of R, S
+    fr *RG, *SG, *coef_pi, *sv_pi, *sv_th;
+    CUDA_TRY(sc.alloc(&RG, nb * cx * n));
+    CUDA_TRY(sc.alloc(&SG, nb * cy * m));
+    CUDA_TRY(sc.alloc(&coef_pi, nb * cx * cy));
+    CUDA_TRY(sc.alloc(&sv_pi, nb * cx * (m + n)));
+    CUDA_TRY(sc.alloc(&sv_th, nb * cy * (m + n)));
+    // RG = R^T Gamma (cx x n)  prove.rs:133 ;  SG = S^T Gamma^T (cy x m)  prove.rs:154
+    LAUNCH_B(k_fr_matmul, (size_t)cx * n, nb, RG, dR, (size_t)1, (size_t)cx, dG, n, (size_t)1, (size_t)cx, m, n, r_bs, m * n);
+    LAUNCH_B(k_fr_matmul, (size_t)cy * m, nb, SG, dS, (size_t)1, (size_t)cy, dG, (size_t)1, n, (size_t)cy, n, m, s_bs, m * n);
+    // (R^T Gamma S - T^T)  prove.rs:139-142
+    LAUNCH_B(k_coef_pi, (size_t)cx * cy, nb, coef_pi, RG, dS, dT, cx, cy, n, s_bs);
+    LAUNCH_B(k_concat_scalars, (size_t)cx * (m + n), nb, sv_pi, dR, RG, cx, m, n, r_bs);
+    LAUNCH_B(k_concat_scalars, (size_t)cy * (m + n), nb, sv_th, dS, SG, cy, n, m, s_bs);
+    g2_aff* dpi;
+    g1_aff* dth;
+    CUDA_TRY(sc.alloc(&dpi, nb * 2 * cx));
+    CUDA_TRY(sc.alloc(&dth, nb * 2 * cy));
+    // pi_i = sum_k R[k][i] iota(B_k) + sum_j RG[i][j] iota(Y_j) + sum_l coef_pi[i][l] v_l        (l < cy)
+    fr *e_pi = nullptr, *e_th = nullptr;
+    if (!s.groupB) {  // scalar-typed y side: every term collapses onto W2
+      CUDA_TRY(sc.alloc(&e_pi, nb * cx));
+      LAUNCH_B(k_fr_dot, (size_t)cx, nb, e_pi, sv_pi, (const fr*)dB, m, (const fr*)dY, n, cx, shared_vars ? (size_t)0 : n);
+    }
+    if (!s.groupA) {
+      CUDA_TRY(sc.alloc(&e_th, nb * cy));
+      LAUNCH_B(k_fr_dot, (size_t)cy, nb, e_th, sv_th, (const fr*)dA, n, (const fr*)dX, m, cy, shared_vars ? (size_t)0 : m);
+    }
+    int rc = proof_element<Fp2Ops>(ctx, sc, nb, cx, s.groupB, sv_pi, dB, m, dY, n, shared_vars, cy, coef_pi, (size_t)cy, e_pi, dpi);
+    if (rc) return rc;
+    // theta_i = sum_j S[j][i] iota(A_j) + sum_k SG[i][k] iota(X_k) + sum_l T[i][l] u_l          (l < cx)
+    rc = proof_element<FpOps>(ctx, sc, nb, cy, s.groupA, sv_th, dA, n, dX, m, shared_vars, cx, dT, (size_t)cx, e_th, dth);
+    if (rc) return rc;
+    CUDA_TRY(cudaMemcpyAsync(out_pi + off * cx, dpi, nb * 2 * cx * sizeof(g2_aff), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaMemcpyAsync(out_theta + off * cy, dth, nb * 2 * cy * sizeof(g1_aff), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
   }
-  if (!s.groupA) {
-    CUDA_TRY(sc.alloc(&e_th, cy));
-    LAUNCH(k_fr_dot, (size_t)cy, e_th, sv_th, (const fr*)dA, n, (const fr*)dX, m, cy);
-  }
-  int rc = proof_element<Fp2Ops>(ctx, sc, cx, s.groupB, sv_pi, dB, m, dY, n, cy, coef_pi, (size_t)cy, &ctx->crs->v[0][0],
-                                 &ctx->crs->w2[0], e_pi, dpi);
-  if (rc) return rc;
-  // theta_i = sum_j S[j][i] iota(A_j) + sum_k SG[i][k] iota(X_k) + sum_l T[i][l] u_l          (l < cx)
-  rc = proof_element<FpOps>(ctx, sc, cy, s.groupA, sv_th, dA, n, dX, m, cx, dT, (size_t)cx, &ctx->crs->u[0][0], &ctx->crs->w1[0],
-                            e_th, dth);
-  if (rc) return rc;
-  CUDA_TRY(cudaMemcpyAsync(out_pi, dpi, 2 * cx * sizeof(g2_aff), cudaMemcpyDeviceToHost, ctx->stream));
-  CUDA_TRY(cudaMemcpyAsync(out_theta, dth, 2 * cy * sizeof(g1_aff), cudaMemcpyDeviceToHost, ctx->stream));
   return GS_OK;
 }
 
 int gs_prove(gs_ctx* ctx, int type, size_t m, size_t n, const void* a_consts, const void* b_consts, const gs_fr* gamma,
              const void* xvars, const void* yvars, const gs_fr* x_rand, const gs_fr* y_rand, const gs_fr* pf_rand,
              gs_com2* out_pi, gs_com1* out_theta) {
-  if (!ctx) return GS_EARG;
-  CUDA_TRY(cudaSetDevice(ctx->device));
-  Scratch sc(ctx);
-  int rc = prove_enqueue(ctx, sc, type, m, n, a_consts, b_consts, gamma, xvars, yvars, x_rand, y_rand, pf_rand, out_pi, out_theta);
-  if (rc) return rc;
-  CUDA_TRY(cudaStreamSynchronize(ctx->stream));
-  return GS_OK;
+  return prove_impl(ctx, type, 1, m, n, a_consts, b_consts, gamma, xvars, yvars, x_rand, y_rand, pf_rand, false, out_pi, out_theta);
 }
 
-// `count` independent proofs of one type and shape (C4 of SURVEY.md §8d: many equations over shared variable
-// sets).  A single prove is a chain of ~40 small launches whose length is set by ONE serial scalar
-// multiplication per thread, so a batch is spread round-robin over a pool of streams and the chains overlap
-// on the GPU; results come back through a pinned staging buffer (a pageable D2H would serialise the host).
-// Per-proof arrays are laid out like gs_verify_batch's; variables / randomness may be shared (stride 0).
 int gs_prove_batch(gs_ctx* ctx, int type, size_t count, size_t m, size_t n, const void* a_consts, const void* b_consts,
                    const gs_fr* gamma, const void* xvars, const void* yvars, const gs_fr* x_rand, const gs_fr* y_rand,
                    const gs_fr* pf_rand, int shared_vars, gs_com2* out_pi, gs_com1* out_theta) {
-  if (!ctx) return GS_EARG;
-  if (type < 0 || type > 3) FAIL(GS_EARG, "prove: bad equation type");
-  if (count == 0) return GS_OK;
-  if (!out_pi || !out_theta) return GS_EARG;
-  CUDA_TRY(cudaSetDevice(ctx->device));
-  verify_shape s = make_verify_shape(type, (int)m, (int)n);
-  const size_t pi_b = 2 * s.cx * sizeof(g2_aff), th_b = 2 * s.cy * sizeof(g1_aff);
-  if (ctx->pool.empty()) {
-    ctx->pool.resize(48);
-    for (auto& st : ctx->pool) CUDA_TRY(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
-  }
-  uint8_t* stage = nullptr;
-  CUDA_TRY(cudaMallocHost(&stage, count * (pi_b + th_b)));
-  cudaStream_t main_stream = ctx->stream;
-  // tables / CRS uploads issued earlier on the main stream must be visible to the pool
-  cudaEvent_t ready;
-  cudaEventCreateWithFlags(&ready, cudaEventDisableTiming);
-  cudaEventRecord(ready, main_stream);
-  for (auto& st : ctx->pool) cudaStreamWaitEvent(st, ready, 0);
-  int rc = GS_OK;
-  const size_t sv = shared_vars ? 0 : 1;
-  for (size_t i = 0; i < count && rc == GS_OK; i++) {
-    ctx->stream = ctx->pool[i % ctx->pool.size()];
-    Scratch sc(ctx);
-    rc = prove_enqueue(ctx, sc, type, m, n, (const char*)a_consts + i * n * elem_size_A(type),
-                       (const char*)b_consts + i * m * elem_size_B(type), gamma + i * m * n,
-                       (const char*)xvars + sv * i * m * elem_size_A(type), (const char*)yvars + sv * i * n * elem_size_B(type),
-                       x_rand + sv * i * m * s.cx, y_rand + sv * i * n * s.cy, pf_rand + i * s.cx * s.cy, stage + i * (pi_b + th_b),
-                       stage + i * (pi_b + th_b) + pi_b);
-  }
-  ctx->stream = main_stream;
-  cudaError_t e = cudaSuccess;
-  for (auto& st : ctx->pool) {
-    cudaError_t e2 = cudaStreamSynchronize(st);
-    if (e == cudaSuccess) e = e2;
-  }
-  cudaEventDestroy(ready);
-  if (rc == GS_OK && e == cudaSuccess) {
-    for (size_t i = 0; i < count; i++) {
-      memcpy((char*)out_pi + i * pi_b, stage + i * (pi_b + th_b), pi_b);
-      memcpy((char*)out_theta + i * th_b, stage + i * (pi_b + th_b) + pi_b, th_b);
-    }
-  }
-  cudaFreeHost(stage);
-  if (rc) return rc;
-  CUDA_TRY(e);
-  return GS_OK;
+  return prove_impl(ctx, type, count, m, n, a_consts, b_consts, gamma, xvars, yvars, x_rand, y_rand, pf_rand, shared_vars != 0,
+                    out_pi, out_theta);
 }
-
 
 int gs_com1_matmul(gs_ctx* ctx, size_t r, size_t k, size_t c, const gs_fr* lhs, const gs_com1* mat, gs_com1* out) {
   return com_matmul_impl<FpOps>(ctx, r, k, c, lhs, mat, out);
@@ -363,7 +332,7 @@ int gs_fr_matmul(gs_ctx* ctx, size_t r, size_t k, size_t c, const gs_fr* a, cons
   CUDA_TRY(upload(ctx, sc, &da, a, r * k));
   CUDA_TRY(upload(ctx, sc, &db, b, k * c));
   CUDA_TRY(sc.alloc(&dout, r * c));
-  LAUNCH(k_fr_matmul, r * c, dout, da, k, (size_t)1, db, c, (size_t)1, r, k, c);
+  LAUNCH(k_fr_matmul, r * c, dout, da, k, (size_t)1, db, c, (size_t)1, r, k, c, (size_t)0, (size_t)0);
   CUDA_TRY(cudaMemcpyAsync(out, dout, r * c * sizeof(fr), cudaMemcpyDeviceToHost, ctx->stream));
   CUDA_TRY(cudaStreamSynchronize(ctx->stream));
   return GS_OK;

@@ -111,12 +111,17 @@ __global__ void __launch_bounds__(GS_TAB_NT) k_fixed_commit(const Aff<F>* __rest
 
 // ------------------------------------------------------------------ variable-base MSM (proof elements)
 // terms[row][t] = sv[row][t] * base[t]   (4-bit signed windows per term), bases = two concatenated segments
+// blockIdx.y = proof instance (b1_bs = instance stride of the variable segment, 0 when shared)
 template <class F>
 __global__ void __launch_bounds__(128) k_msm_terms(Jac<F>* __restrict__ terms, const fr* __restrict__ sv, const Aff<F>* __restrict__ b0,
-                                                   size_t n0, const Aff<F>* __restrict__ b1, size_t n1, int rows) {
+                                                   size_t n0, const Aff<F>* __restrict__ b1, size_t n1, int rows, size_t b1_bs) {
   size_t id = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   size_t nt = n0 + n1;
   if (id >= nt * rows) return;
+  terms += (size_t)blockIdx.y * nt * rows;
+  sv += (size_t)blockIdx.y * nt * rows;
+  b0 += (size_t)blockIdx.y * n0;
+  b1 += (size_t)blockIdx.y * b1_bs;
   size_t t = id % nt;
   Aff<F> B = t < n0 ? b0[t] : b1[t - n0];
   uint32_t k[8];
@@ -131,6 +136,7 @@ template <class F>
 __global__ void __launch_bounds__(128) k_jac_reduce_step(Jac<F>* __restrict__ terms, size_t row_stride, size_t cur, size_t half, int rows) {
   size_t id = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (id >= half * rows) return;
+  terms += (size_t)blockIdx.y * row_stride * rows;
   size_t row = id / half, t = id % half;
   if (t + half >= cur) return;
   Jac<F>* base = terms + row * row_stride;
@@ -152,6 +158,10 @@ __global__ void k_proof_finish(Aff<F>* __restrict__ out, int rows, int ncoef, co
   int id = blockIdx.x * blockDim.x + threadIdx.x;
   if (id >= rows * 2) return;
   int i = id >> 1, a = id & 1;
+  out += (size_t)blockIdx.y * rows * 2;
+  coef += (size_t)blockIdx.y * rows * ncoef;
+  if (varsum != nullptr) varsum += (size_t)blockIdx.y * var_stride * rows;
+  if (e != nullptr) e += (size_t)blockIdx.y * rows;
   Jac<F> acc;
   acc.set_inf();
   if (varsum != nullptr && a == 1) acc = varsum[(size_t)i * var_stride];
@@ -280,38 +290,38 @@ int batch_commit_impl(gs_ctx* ctx, size_t n, int base0, int base1, const gs_fr* 
 
 // reduce rows of Jacobian terms in place (row i occupies terms[i*stride .. i*stride+cnt))
 template <class F>
-int reduce_rows(gs_ctx* ctx, Jac<F>* terms, size_t stride, size_t cnt, int rows) {
+int reduce_rows(gs_ctx* ctx, Jac<F>* terms, size_t stride, size_t cnt, int rows, size_t nbatch = 1) {
   size_t cur = cnt;
   while (cur > 1) {
     size_t half = (cur + 1) / 2;
-    LAUNCH((k_jac_reduce_step<F>), half * rows, terms, stride, cur, half, rows);
+    LAUNCH_B((k_jac_reduce_step<F>), half * rows, nbatch, terms, stride, cur, half, rows);
     cur = half;
   }
   return GS_OK;
 }
 
-// one proof element vector (pi: F = G2, theta: F = G1), see k_proof_finish
+// one proof element vector per proof (pi: F = G2, theta: F = G1), see k_proof_finish; batched over `count` proofs
 template <class F>
-int proof_element(gs_ctx* ctx, Scratch& sc, int rows, bool group_typed, const fr* sv, const void* dconst, size_t nconst,
-                  const void* dvars, size_t nvars, int ncoef, const fr* coef, size_t coef_rs, const Aff<F>* key,
-                  const Aff<F>* W, const fr* e, Aff<F>* dout) {
+int proof_element(gs_ctx* ctx, Scratch& sc, size_t count, int rows, bool group_typed, const fr* sv, const void* dconst,
+                  size_t nconst, const void* dvars, size_t nvars, bool vars_shared, int ncoef, const fr* coef, size_t coef_rs,
+                  const fr* e, Aff<F>* dout) {
   size_t nt = nconst + nvars;
-  (void)key;
-  (void)W;
   const gs_fixed_table<F>& T = table_of<F>(ctx);  // built at CRS load (c = 8) or by a big commit batch (c = 16)
   if (!T.t) FAIL(GS_EARG, "prove: fixed-base tables missing (no CRS loaded)");
+  if (coef_rs != (size_t)ncoef) FAIL(GS_EARG, "prove: coefficient matrix must be dense");
   if (group_typed) {
     Jac<F>* terms;
-    CUDA_TRY(sc.alloc(&terms, nt * rows));
-    LAUNCH((k_msm_terms<F>), nt * rows, terms, sv, (const Aff<F>*)dconst, nconst, (const Aff<F>*)dvars, nvars, rows);
-    int rc = reduce_rows<F>(ctx, terms, nt, nt, rows);
+    CUDA_TRY(sc.alloc(&terms, count * nt * rows));
+    LAUNCH_B((k_msm_terms<F>), nt * rows, count, terms, sv, (const Aff<F>*)dconst, nconst, (const Aff<F>*)dvars, nvars, rows,
+             vars_shared ? (size_t)0 : nvars);
+    int rc = reduce_rows<F>(ctx, terms, nt, nt, rows, count);
     if (rc) return rc;
-    LAUNCH((k_proof_finish<F>), (size_t)rows * 2, dout, rows, ncoef, coef, coef_rs, (size_t)1, T.t, T.c, T.W, T.H, terms, nt,
-           (const fr*)nullptr);
+    LAUNCH_B((k_proof_finish<F>), (size_t)rows * 2, count, dout, rows, ncoef, coef, coef_rs, (size_t)1, T.t, T.c, T.W, T.H, terms, nt,
+             (const fr*)nullptr);
   } else {
     // scalar-typed side: the caller collapsed the terms into e_i = <sv_i, (consts | vars)> (k_fr_dot, prover.cu)
-    LAUNCH((k_proof_finish<F>), (size_t)rows * 2, dout, rows, ncoef, coef, coef_rs, (size_t)1, T.t, T.c, T.W, T.H,
-           (const Jac<F>*)nullptr, (size_t)0, e);
+    LAUNCH_B((k_proof_finish<F>), (size_t)rows * 2, count, dout, rows, ncoef, coef, coef_rs, (size_t)1, T.t, T.c, T.W, T.H,
+             (const Jac<F>*)nullptr, (size_t)0, e);
   }
   return GS_OK;
 }
