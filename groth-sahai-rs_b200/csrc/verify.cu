@@ -2,6 +2,7 @@
 // statement MSM (re-association of verifier.rs:39-42), then the pairing-product pipeline.
 #include "batchinv.cuh"
 #include "ctx.h"
+#include "prover_impl.cuh"  // fixed_base_accumulate
 
 using namespace gs;
 
@@ -131,6 +132,22 @@ __global__ void __launch_bounds__(128) k_vmsm_tables(verify_shape s, verify_args
   }
 }
 
+// scalar that multiplies base i in MSM output jj of problem p (false: no such term)
+__device__ GS_INL bool vmsm_scalar(fr& sv, const verify_shape& s, const verify_args& v, size_t p, int i, int jj) {
+  if (jj < s.n) {  // P_j: Gamma column j, plus a_j on the extra base W1 when A is scalar
+    sv = i < s.m ? v.gamma[(p * s.m + i) * s.n + jj] : ((const fr*)v.a_consts)[p * s.n + jj];
+    return true;
+  }
+  if (jj == s.n && !s.groupB) {  // C_B = sum_i b_i c_i
+    if (i >= s.m) return false;
+    sv = ((const fr*)v.b_consts)[p * s.m + i];
+    return true;
+  }
+  if (i != s.m) return false;  // Quad target: t * W1  (W1 is base index m)
+  sv = ((const fr*)v.target)[p];
+  return true;
+}
+
 // thread -> (p, jj, a, chunk)
 __global__ void __launch_bounds__(128) k_vmsm_partial(verify_shape s, verify_args v, const g1_aff* __restrict__ tab,
                                                       g1_jac* __restrict__ part, size_t nprob) {
@@ -152,26 +169,7 @@ __global__ void __launch_bounds__(128) k_vmsm_partial(verify_shape s, verify_arg
   int i0 = ch * GS_MSM_CHUNK, i1 = min(s.nbases, i0 + GS_MSM_CHUNK);
   for (int i = i0; i < i1; i++) {
     fr sv;
-    bool have = false;
-    if (jj < s.n) {
-      if (i < s.m) {
-        sv = v.gamma[(p * s.m + i) * s.n + jj];
-        have = true;
-      } else {  // scalar A: extra base W1 with scalar a_j
-        sv = ((const fr*)v.a_consts)[p * s.n + jj];
-        have = true;
-      }
-    } else if (jj == s.n && !s.groupB) {  // C_B = sum_i b_i c_i
-      if (i < s.m) {
-        sv = ((const fr*)v.b_consts)[p * s.m + i];
-        have = true;
-      }
-    } else {  // Quad target: t * W1  (W1 is base index m)
-      if (i == s.m) {
-        sv = ((const fr*)v.target)[p];
-        have = true;
-      }
-    }
+    bool have = vmsm_scalar(sv, s, v, p, i, jj);
     if (!have || sv.is_zero()) continue;
     uint32_t k[8];
     fr_from_mont(k, sv);
@@ -205,6 +203,117 @@ __global__ void __launch_bounds__(128) k_vmsm_partial(verify_shape s, verify_arg
         g1_jac::add_mixed(acc, acc, e);
       }
     }
+  }
+  part[(((size_t)ch * s.n_out + jj) * 2 + a) * nprob + p] = acc;
+}
+
+// ------------------------------------------------------------------ verify: shared-base window tables
+// When ONE set of commitments c_i serves many MSM outputs (a big statement: n outputs per base; or a batch of
+// equations over the same commitments, C4), the bases get fixed-base treatment: signed 8-bit window tables
+//     T[b][w][d-1] = d * 2^(8w) * base_b,   b = i*2 + a,  w < 32,  d = 1..128      (layout of prover_impl.cuh)
+// are built once (4,096 additions per base coordinate) and every scalar product costs 32 mixed additions and no
+// doubling, against ~60 additions + a share of 256 doublings in the Straus kernel above.  Break-even is at
+// ~160 outputs per base; C3 has 1,024 (2.1 M products: 147 M -> 75 M point additions).
+constexpr int GS_WT_C = 8, GS_WT_W = 32, GS_WT_H = 128;
+// thread -> flat base b: J[b*W + w] = 2^(8w) * base_b   (one Jacobian doubling chain)
+__global__ void __launch_bounds__(128) k_wtab_bases(verify_shape s, verify_args v, const crs_dev* __restrict__ crs,
+                                                    g1_jac* __restrict__ J, int nb) {
+  int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= nb) return;
+  g1_aff B = vmsm_base(s, v, crs, 0, b >> 1, b & 1);
+  g1_jac j;
+  j.from_affine(B);
+  for (int w = 0; w < GS_WT_W; w++) {
+    J[(size_t)b * GS_WT_W + w] = j;
+    if (w + 1 < GS_WT_W)
+      for (int i = 0; i < GS_WT_C; i++) g1_jac::dbl(j, j);
+  }
+}
+// thread -> (row (b, w), run r): the multiples d = r*RUN + 1 .. r*RUN + RUN of the row's base B = tab[row*H]:
+// start (r*RUN + 1) B = B + r * (RUN B) (5 doublings, <= 3 additions), then RUN - 1 mixed additions; 4 runs per row
+// keep the dependent chain short (the kernel is latency-bound: 65 k rows are a fraction of one wave).
+constexpr int GS_WT_RUN = 32;
+__global__ void __launch_bounds__(128) k_wtab_fill(const g1_aff* __restrict__ tab, g1_jac* __restrict__ J, size_t nrows) {
+  constexpr int RUNS = GS_WT_H / GS_WT_RUN;
+  size_t id = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (id >= nrows * RUNS) return;
+  size_t row = id / RUNS;
+  int r = (int)(id % RUNS);
+  g1_aff B = tab[row * GS_WT_H];
+  g1_jac acc;
+  acc.from_affine(B);
+  if (r > 0) {
+    g1_jac step = acc;
+    for (int i = 0; i < 5; i++) g1_jac::dbl(step, step);  // RUN * B
+    for (int i = 0; i < r; i++) g1_jac::add(acc, acc, step);
+  }
+  g1_jac* o = J + row * GS_WT_H + (size_t)r * GS_WT_RUN;
+  o[0] = acc;
+  for (int d = 1; d < GS_WT_RUN; d++) {
+    g1_jac::add_mixed(acc, acc, B);
+    o[d] = acc;
+  }
+}
+// thread -> strip of ST consecutive entries: out[idx * ostride] = affine(in[idx]).  Montgomery's trick inside the
+// strip, then across the block (batchinv.cuh): one field inversion per 128 * ST points.
+template <int ST>
+__global__ void __launch_bounds__(128) k_jac_to_affine_blocks(const g1_jac* __restrict__ in, g1_aff* __restrict__ out, size_t n,
+                                                              size_t ostride) {
+  __shared__ fp sm[2 * 128];
+  const size_t i0 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * ST;
+  fp pre[ST];  // pre[t] = z_0 ... z_t over the strip (infinity / out of range counts as 1)
+  fp acc;
+  fp_one(acc);
+#pragma unroll
+  for (int t = 0; t < ST; t++) {
+    if (i0 + t < n) {
+      fp z = in[i0 + t].Z;
+      if (!z.is_zero()) fp::mul(acc, acc, z);
+    }
+    pre[t] = acc;
+  }
+  block_batch_inv<128>(acc, sm);  // acc = 1 / (z_0 ... z_{ST-1})
+#pragma unroll
+  for (int t = ST - 1; t >= 0; t--) {
+    if (i0 + t >= n) continue;
+    g1_jac j = in[i0 + t];
+    g1_aff a;
+    if (j.Z.is_zero()) {
+      a.set_inf();
+    } else {
+      fp zi;
+      if (t > 0)
+        fp::mul(zi, acc, pre[t - 1]);
+      else
+        zi = acc;
+      fp::mul(acc, acc, j.Z);
+      g1_jac::to_affine_with_zinv(a, j, zi);
+    }
+    out[(i0 + t) * ostride] = a;
+  }
+}
+// thread -> (p, jj, a, chunk): same outputs as k_vmsm_partial, bases looked up in the shared tables
+__global__ void __launch_bounds__(128) k_vmsm_wsum(verify_shape s, verify_args v, const g1_aff* __restrict__ tab,
+                                                   g1_jac* __restrict__ part, size_t nprob) {
+  size_t id = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t total = nprob * (size_t)s.n_out * 2 * s.nchunk;
+  if (id >= total) return;
+  size_t p = id % nprob;
+  size_t r = id / nprob;
+  int a = (int)(r & 1);
+  r >>= 1;
+  int jj = (int)(r % s.n_out);
+  int ch = (int)(r / s.n_out);
+  if (!s.owns(s.out_slot(jj))) return;
+  g1_jac acc;
+  acc.set_inf();
+  int i0 = ch * GS_MSM_CHUNK, i1 = min(s.nbases, i0 + GS_MSM_CHUNK);
+  for (int i = i0; i < i1; i++) {
+    fr sv;
+    if (!vmsm_scalar(sv, s, v, p, i, jj) || sv.is_zero()) continue;
+    uint32_t k[8];
+    fr_from_mont(k, sv);
+    fixed_base_accumulate<FpOps>(acc, tab + ((size_t)(i * 2 + a) * GS_WT_W) * GS_WT_H, k, GS_WT_C, GS_WT_W, (size_t)GS_WT_H);
   }
   part[(((size_t)ch * s.n_out + jj) * 2 + a) * nprob + p] = acc;
 }
@@ -283,7 +392,7 @@ extern "C" {
 // un-exponentiated Miller products of the slots that rank owns, out_partial[p][4]).
 static int verify_impl(gs_ctx* ctx, int type, size_t count, size_t m, size_t n, const void* a_consts, const void* b_consts,
                        const gs_fr* gamma, const void* target, const gs_com1* xcoms, const gs_com2* ycoms, const gs_com2* pi,
-                       const gs_com1* theta, int rank, int world, uint8_t* out_ok_dev, fp12* out_partial_dev) {
+                       const gs_com1* theta, int rank, int world, uint8_t* out_ok_dev, fp12* out_partial_dev, bool shared_x) {
   if (!ctx) return GS_EARG;
   if (type < 0 || type > 3) FAIL(GS_EARG, "verify: bad equation type");
   if (world < 1 || rank < 0 || rank >= world) FAIL(GS_EARG, "verify: bad shard (rank, world)");
@@ -320,10 +429,27 @@ static int verify_impl(gs_ctx* ctx, int type, size_t count, size_t m, size_t n, 
     CUDA_TRY(sc.alloc(&part, (size_t)s.nchunk * s.n_out * 2 * nprob));
     CUDA_TRY(sc.alloc(&ok4, 4 * nprob));
     LAUNCH(k_verify_assemble, nprob * (size_t)s.K, s, v, ctx->crs, X, Y, nprob);
-    g1_aff* vtab;
-    CUDA_TRY(sc.alloc(&vtab, (size_t)s.nbases * 2 * GS_VTAB * nprob));
-    LAUNCH(k_vmsm_tables, nprob * (size_t)s.nbases * 2, s, v, ctx->crs, vtab, nprob);
-    LAUNCH(k_vmsm_partial, nprob * (size_t)s.n_out * 2 * s.nchunk, s, v, vtab, part, nprob);
+    // outputs that share one base coordinate: this rank's MSM outputs x the problems that use the same commitments
+    const size_t owned_out = world > 1 ? ((size_t)s.n_out + world - 1) / world : (size_t)s.n_out;
+    const bool shared_bases = nprob == 1 || shared_x;
+    if (shared_bases && owned_out * nprob >= 256) {
+      const int nb = s.nbases * 2;
+      const size_t nrows = (size_t)nb * GS_WT_W;
+      g1_aff* wtab;
+      g1_jac* J;
+      CUDA_TRY(sc.alloc(&wtab, nrows * GS_WT_H));
+      CUDA_TRY(sc.alloc(&J, nrows * GS_WT_H));
+      LAUNCH(k_wtab_bases, (size_t)nb, s, v, ctx->crs, J, nb);
+      LAUNCH(k_jac_to_affine_blocks<1>, nrows, J, wtab, nrows, (size_t)GS_WT_H);
+      LAUNCH(k_wtab_fill, nrows * (GS_WT_H / GS_WT_RUN), wtab, J, nrows);
+      LAUNCH(k_jac_to_affine_blocks<8>, nrows * GS_WT_H / 8, J, wtab, nrows * GS_WT_H, (size_t)1);
+      LAUNCH(k_vmsm_wsum, nprob * (size_t)s.n_out * 2 * s.nchunk, s, v, wtab, part, nprob);
+    } else {
+      g1_aff* vtab;
+      CUDA_TRY(sc.alloc(&vtab, (size_t)s.nbases * 2 * GS_VTAB * nprob));
+      LAUNCH(k_vmsm_tables, nprob * (size_t)s.nbases * 2, s, v, ctx->crs, vtab, nprob);
+      LAUNCH(k_vmsm_partial, nprob * (size_t)s.n_out * 2 * s.nchunk, s, v, vtab, part, nprob);
+    }
     LAUNCH(k_vmsm_reduce, nprob * (size_t)s.n_out * 2, s, v, part, X, nprob);
     const g1_aff* Xp = X;
     const g2_aff* Yp = Y;
@@ -354,7 +480,7 @@ int gs_verify_batch_dev(gs_ctx* ctx, int type, size_t count, size_t m, size_t n,
                         const void* b_consts, const gs_fr* gamma, const void* target, const gs_com1* xcoms,
                         const gs_com2* ycoms, const gs_com2* pi, const gs_com1* theta, uint8_t* out_ok_dev) {
   if (!out_ok_dev) return GS_EARG;
-  return verify_impl(ctx, type, count, m, n, a_consts, b_consts, gamma, target, xcoms, ycoms, pi, theta, 0, 1, out_ok_dev, nullptr);
+  return verify_impl(ctx, type, count, m, n, a_consts, b_consts, gamma, target, xcoms, ycoms, pi, theta, 0, 1, out_ok_dev, nullptr, false);
 }
 
 int gs_verify_partial_dev(gs_ctx* ctx, int type, size_t count, size_t m, size_t n, const void* a_consts,
@@ -363,7 +489,7 @@ int gs_verify_partial_dev(gs_ctx* ctx, int type, size_t count, size_t m, size_t 
                           gs_gt* out_partial_dev) {
   if (!out_partial_dev) return GS_EARG;
   return verify_impl(ctx, type, count, m, n, a_consts, b_consts, gamma, target, xcoms, ycoms, pi, theta, rank, world, nullptr,
-                     (fp12*)out_partial_dev);
+                     (fp12*)out_partial_dev, false);
 }
 
 int gs_verify_finish_dev(gs_ctx* ctx, int type, size_t count, int nparts, const gs_gt* partials_dev, const void* target_dev,
@@ -415,8 +541,12 @@ static int verify_host(gs_ctx* ctx, int type, size_t count, size_t m, size_t n, 
     CUDA_TRY(sc.alloc(&dok, count));
   else
     CUDA_TRY(sc.alloc(&dpart, count * 4));
+  // a batch of equations over ONE set of x-commitments (a multi-equation statement): detected on the host copy
+  bool shared_x = count > 1;
+  for (size_t i = 1; i < count && shared_x; i++)
+    shared_x = memcmp(xcoms, (const char*)xcoms + i * m * sizeof(gs_com1), m * sizeof(gs_com1)) == 0;
   int rc = verify_impl(ctx, type, count, m, n, dA, dB, (const gs_fr*)dG, dT, (const gs_com1*)dc, (const gs_com2*)dd,
-                       (const gs_com2*)dpi, (const gs_com1*)dth, rank, world, dok, dpart);
+                       (const gs_com2*)dpi, (const gs_com1*)dth, rank, world, dok, dpart, shared_x);
   if (rc) return rc;
   if (out_ok)
     CUDA_TRY(cudaMemcpyAsync(out_ok, dok, count, cudaMemcpyDeviceToHost, ctx->stream));

@@ -81,6 +81,8 @@ def load_library():
 
 def _buf(b):
     """bytes-like -> (keepalive, void*)"""
+    if isinstance(b, bytes) and len(b):   # pass the bytes object's own buffer: no copy (a 1024 x 1024 Gamma is 32 MiB)
+        return b, ctypes.cast(ctypes.c_char_p(b), ctypes.c_void_p)
     if isinstance(b, (bytes, bytearray, memoryview)):
         arr = (ctypes.c_char * len(b)).from_buffer_copy(bytes(b)) if len(b) else (ctypes.c_char * 1)()
         return arr, ctypes.cast(arr, ctypes.c_void_p)

@@ -166,3 +166,46 @@ def test_prove_batch_equals_single_proves(eng, ty):
     yc = eng.batch_commit_g2(Y, yr) if ty in (0, 2) else eng.batch_commit_scalar_b2(Y, yr)
     ok = eng.verify_batch(ty, E, m, n, b"".join(A), b"".join(B), b"".join(G), b"".join(T), xc * E, yc * E, pi, th)
     assert ok == b"\x01" * E
+
+
+@pytest.mark.parametrize("ty,m,n", [(0, 6, 300), (3, 5, 270), (1, 7, 260)])
+def test_shared_base_window_tables_single_statement(eng, ty, m, n):
+    """Statements with >= 256 MSM outputs per commitment take the shared-base window-table path of verify
+    (k_wtab_* / k_vmsm_wsum): honest -> True, any single flipped scalar bit -> False, and the slot-sharded
+    evaluation (where each rank is back on the per-problem Straus tables or on smaller table jobs) agrees."""
+    rng = SeededRng(120 + ty)
+    arrs = _commit_prove(eng, ty, m, n, _instance(eng, ty, m, n, rng), rng)
+    assert eng.verify(ty, m, n, *arrs) is True
+    for (i, j) in ((0, 0), (m - 1, n - 1), (m // 2, 17)):
+        bad = list(arrs)
+        g = bytearray(bad[2])
+        g[32 * (i * n + j) + 3] ^= 0x10
+        bad[2] = bytes(g)
+        assert eng.verify(ty, m, n, *bad) is False
+    for world in (2, 5):
+        parts = b"".join(eng.verify_partial(ty, 1, m, n, *arrs, r, world) for r in range(world))
+        assert eng.verify_finish(ty, 1, parts, arrs[3]) == b"\x01"
+
+
+@pytest.mark.parametrize("ty", [0, 2, 3])
+def test_shared_commitments_batch_uses_tables(eng, ty):
+    """A batch of equations over ONE set of commitments (C4 shape): gs_verify_batch detects the shared x-commitments
+    and builds the window tables once for the whole batch; verdicts equal those of the same equations verified
+    one by one (per-problem Straus path)."""
+    from workloads import instance_many
+    rng = SeededRng(140 + ty)
+    m, n, E = 7, 40, 7                                   # 7 x (40 [+1 +1]) outputs per base >= 256
+    A, B, G, T, X, Y, xr, yr, Tr = instance_many(eng, ty, m, n, E, rng)
+    pi, th = eng.prove_batch(ty, E, m, n, b"".join(A), b"".join(B), b"".join(G), X, Y, xr, yr, b"".join(Tr), shared_vars=True)
+    xc = eng.batch_commit_g1(X, xr) if ty in (0, 1) else eng.batch_commit_scalar_b1(X, xr)
+    yc = eng.batch_commit_g2(Y, yr) if ty in (0, 2) else eng.batch_commit_scalar_b2(Y, yr)
+    Gb = [bytearray(g) for g in G]
+    Gb[4][32 * (3 * n + 5)] ^= 2                         # equation 4 tampered
+    cols = [b"".join(A), b"".join(B), b"".join(bytes(g) for g in Gb), b"".join(T), xc * E, yc * E, pi, th]
+    ok = eng.verify_batch(ty, E, m, n, *cols)
+    assert list(ok) == [1, 1, 1, 1, 0, 1, 1]
+    cx, cy = (2 if ty in (0, 1) else 1), (2 if ty in (0, 2) else 1)
+    for e in (0, 4):
+        one = eng.verify(ty, m, n, A[e], B[e], bytes(Gb[e]), T[e], xc, yc, pi[e * cx * 384:(e + 1) * cx * 384],
+                         th[e * cy * 192:(e + 1) * cy * 192])
+        assert one is bool(ok[e])
