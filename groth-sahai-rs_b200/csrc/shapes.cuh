@@ -22,11 +22,29 @@ struct verify_shape {  // slot bookkeeping shared by host and device
   int sB, nB, sPi, sTh, sT, K;
   int n_out;    // MSM outputs per problem: n (+1 scalar-B) (+1 Quad target)
   int nbases;   // m (+1 when A is scalar: W1 is an extra base)
-  int nchunk;   // MSM base chunks
+  int chunk, nchunk;  // MSM bases per thread (<= GS_MSM_CHUNK) and the number of such chunks
   int rank, world;  // statement sharding: slot k belongs to rank k % world; 0, 1 = everything
   GS_HD bool owns(int slot) const { return world <= 1 || slot % world == rank; }
   // slot that MSM output jj is written to: jj < n -> jj; the scalar-B sum -> sB; the Quad target -> sT
   GS_HD int out_slot(int jj) const { return jj < n ? jj : ((jj == n && !groupB) ? sB : sT); }
+  // the MSM outputs this rank owns, enumerated densely (jo -> jj) so that every lane of a warp has work
+  GS_HD int n_main_owned() const { return world <= 1 ? n : (n > rank ? (n - rank + world - 1) / world : 0); }
+  GS_HD int n_out_owned() const {
+    int c = n_main_owned();
+    for (int jj = n; jj < n_out; jj++) c += owns(out_slot(jj)) ? 1 : 0;
+    return c;
+  }
+  GS_HD int owned_out(int jo) const {
+    const int nm = n_main_owned();
+    if (jo < nm) return world <= 1 ? jo : rank + jo * world;
+    jo -= nm;
+    for (int jj = n; jj < n_out; jj++)
+      if (owns(out_slot(jj))) {
+        if (jo == 0) return jj;
+        jo--;
+      }
+    return -1;
+  }
 };
 constexpr int GS_MSM_CHUNK = 16;
 
@@ -47,10 +65,16 @@ inline verify_shape make_verify_shape(int type, int m, int n) {
   s.K = s.sT + (type == 0 ? 0 : 1);
   s.n_out = n + (s.groupB ? 0 : 1) + (type == 3 ? 1 : 0);
   s.nbases = m + (s.groupA ? 0 : 1);
+  s.chunk = GS_MSM_CHUNK;
   s.nchunk = (s.nbases + GS_MSM_CHUNK - 1) / GS_MSM_CHUNK;
   s.rank = 0;
   s.world = 1;
   return s;
+}
+
+inline void set_msm_chunk(verify_shape& s, int chunk) {
+  s.chunk = chunk < 1 ? 1 : (chunk > GS_MSM_CHUNK ? GS_MSM_CHUNK : chunk);
+  s.nchunk = (s.nbases + s.chunk - 1) / s.chunk;
 }
 
 struct verify_args {

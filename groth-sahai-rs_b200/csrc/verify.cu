@@ -152,21 +152,21 @@ __device__ GS_INL bool vmsm_scalar(fr& sv, const verify_shape& s, const verify_a
 __global__ void __launch_bounds__(128) k_vmsm_partial(verify_shape s, verify_args v, const g1_aff* __restrict__ tab,
                                                       g1_jac* __restrict__ part, size_t nprob) {
   size_t id = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  size_t total = nprob * (size_t)s.n_out * 2 * s.nchunk;
+  const int n_own = s.n_out_owned();  // sharded statement: the other outputs' Miller pairs run on other ranks
+  size_t total = nprob * (size_t)n_own * 2 * s.nchunk;
   if (id >= total) return;
   size_t p = id % nprob;
   size_t r = id / nprob;
   int a = (int)(r & 1);
   r >>= 1;
-  int jj = (int)(r % s.n_out);
-  int ch = (int)(r / s.n_out);
-  if (!s.owns(s.out_slot(jj))) return;  // sharded statement: that slot's Miller pairs run on another rank
+  int jj = s.owned_out((int)(r % n_own));
+  int ch = (int)(r / n_own);
 
   // biased scalars k' = k + 0x88..8 (64 nibbles): digit_w = nibble_w(k') - 8 in [-8, 7], no carries
   uint32_t sc[GS_MSM_CHUNK][9];
   int bidx[GS_MSM_CHUNK];
   int cnt = 0;
-  int i0 = ch * GS_MSM_CHUNK, i1 = min(s.nbases, i0 + GS_MSM_CHUNK);
+  int i0 = ch * s.chunk, i1 = min(s.nbases, i0 + s.chunk);
   for (int i = i0; i < i1; i++) {
     fr sv;
     bool have = vmsm_scalar(sv, s, v, p, i, jj);
@@ -296,18 +296,18 @@ __global__ void __launch_bounds__(128) k_jac_to_affine_blocks(const g1_jac* __re
 __global__ void __launch_bounds__(128) k_vmsm_wsum(verify_shape s, verify_args v, const g1_aff* __restrict__ tab,
                                                    g1_jac* __restrict__ part, size_t nprob) {
   size_t id = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  size_t total = nprob * (size_t)s.n_out * 2 * s.nchunk;
+  const int n_own = s.n_out_owned();  // sharded statement: the other outputs' Miller pairs run on other ranks
+  size_t total = nprob * (size_t)n_own * 2 * s.nchunk;
   if (id >= total) return;
   size_t p = id % nprob;
   size_t r = id / nprob;
   int a = (int)(r & 1);
   r >>= 1;
-  int jj = (int)(r % s.n_out);
-  int ch = (int)(r / s.n_out);
-  if (!s.owns(s.out_slot(jj))) return;
+  int jj = s.owned_out((int)(r % n_own));
+  int ch = (int)(r / n_own);
   g1_jac acc;
   acc.set_inf();
-  int i0 = ch * GS_MSM_CHUNK, i1 = min(s.nbases, i0 + GS_MSM_CHUNK);
+  int i0 = ch * s.chunk, i1 = min(s.nbases, i0 + s.chunk);
   for (int i = i0; i < i1; i++) {
     fr sv;
     if (!vmsm_scalar(sv, s, v, p, i, jj) || sv.is_zero()) continue;
@@ -323,12 +323,11 @@ __global__ void __launch_bounds__(128) k_vmsm_reduce(verify_shape s, verify_args
                                                      g1_aff* __restrict__ X, size_t nprob) {
   __shared__ fp sm[2 * 128];
   size_t id = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  bool active = id < nprob * (size_t)s.n_out * 2;
+  bool active = id < nprob * (size_t)s.n_out_owned() * 2;
   size_t p = active ? id % nprob : 0;
   size_t r = active ? id / nprob : 0;
   int a = (int)(r & 1);
-  int jj = (int)(r >> 1);
-  if (active && !s.owns(s.out_slot(jj))) active = false;
+  int jj = active ? s.owned_out((int)(r >> 1)) : 0;
   g1_jac acc;
   acc.set_inf();
   int slot = 0;
@@ -420,6 +419,18 @@ static int verify_impl(gs_ctx* ctx, int type, size_t count, size_t m, size_t n, 
     v.ycoms = (const g2_aff*)ycoms + off * n * 2;
     v.pi = (const g2_aff*)pi + off * s.cx * 2;
     v.theta = (const g1_aff*)theta + off * s.cy * 2;
+    // outputs that share one base coordinate: this rank's MSM outputs x the problems that use the same commitments
+    const size_t owned_out = (size_t)s.n_out_owned();
+    const bool use_wtab = (nprob == 1 || shared_x) && owned_out * nprob >= 320;  // table build ~ 14.6 ms at m = 1024
+    {
+      // bases per thread: few threads (one statement, or one rank's share of it) -> smaller chunks, so that the
+      // grid is >= 3 waves of the ~296 resident blocks instead of 1.7 (measured: 20.8 ms for half of C3's sums
+      // against 30.8 ms for all of them); the table kernel has no doublings to amortise, Straus keeps >= 8
+      int chunk = GS_MSM_CHUNK;
+      const int floor_chunk = use_wtab ? 2 : 8;
+      while (chunk > floor_chunk && nprob * owned_out * 2 * ((s.nbases + chunk - 1) / chunk) < (size_t)128 * 888) chunk /= 2;
+      set_msm_chunk(s, chunk);
+    }
     g1_aff* X;
     g2_aff* Y;
     g1_jac* part;
@@ -429,10 +440,7 @@ static int verify_impl(gs_ctx* ctx, int type, size_t count, size_t m, size_t n, 
     CUDA_TRY(sc.alloc(&part, (size_t)s.nchunk * s.n_out * 2 * nprob));
     CUDA_TRY(sc.alloc(&ok4, 4 * nprob));
     LAUNCH(k_verify_assemble, nprob * (size_t)s.K, s, v, ctx->crs, X, Y, nprob);
-    // outputs that share one base coordinate: this rank's MSM outputs x the problems that use the same commitments
-    const size_t owned_out = world > 1 ? ((size_t)s.n_out + world - 1) / world : (size_t)s.n_out;
-    const bool shared_bases = nprob == 1 || shared_x;
-    if (shared_bases && owned_out * nprob >= 256) {
+    if (use_wtab) {
       const int nb = s.nbases * 2;
       const size_t nrows = (size_t)nb * GS_WT_W;
       g1_aff* wtab;
@@ -443,14 +451,14 @@ static int verify_impl(gs_ctx* ctx, int type, size_t count, size_t m, size_t n, 
       LAUNCH(k_jac_to_affine_blocks<1>, nrows, J, wtab, nrows, (size_t)GS_WT_H);
       LAUNCH(k_wtab_fill, nrows * (GS_WT_H / GS_WT_RUN), wtab, J, nrows);
       LAUNCH(k_jac_to_affine_blocks<8>, nrows * GS_WT_H / 8, J, wtab, nrows * GS_WT_H, (size_t)1);
-      LAUNCH(k_vmsm_wsum, nprob * (size_t)s.n_out * 2 * s.nchunk, s, v, wtab, part, nprob);
+      LAUNCH(k_vmsm_wsum, nprob * owned_out * 2 * s.nchunk, s, v, wtab, part, nprob);
     } else {
       g1_aff* vtab;
       CUDA_TRY(sc.alloc(&vtab, (size_t)s.nbases * 2 * GS_VTAB * nprob));
       LAUNCH(k_vmsm_tables, nprob * (size_t)s.nbases * 2, s, v, ctx->crs, vtab, nprob);
-      LAUNCH(k_vmsm_partial, nprob * (size_t)s.n_out * 2 * s.nchunk, s, v, vtab, part, nprob);
+      LAUNCH(k_vmsm_partial, nprob * owned_out * 2 * s.nchunk, s, v, vtab, part, nprob);
     }
-    LAUNCH(k_vmsm_reduce, nprob * (size_t)s.n_out * 2, s, v, part, X, nprob);
+    LAUNCH(k_vmsm_reduce, nprob * owned_out * 2, s, v, part, X, nprob);
     const g1_aff* Xp = X;
     const g2_aff* Yp = Y;
     if (world > 1) {

@@ -168,9 +168,9 @@ def test_prove_batch_equals_single_proves(eng, ty):
     assert ok == b"\x01" * E
 
 
-@pytest.mark.parametrize("ty,m,n", [(0, 6, 300), (3, 5, 270), (1, 7, 260)])
+@pytest.mark.parametrize("ty,m,n", [(0, 6, 340), (3, 5, 330), (1, 7, 325)])
 def test_shared_base_window_tables_single_statement(eng, ty, m, n):
-    """Statements with >= 256 MSM outputs per commitment take the shared-base window-table path of verify
+    """Statements with >= 320 MSM outputs per commitment take the shared-base window-table path of verify
     (k_wtab_* / k_vmsm_wsum): honest -> True, any single flipped scalar bit -> False, and the slot-sharded
     evaluation (where each rank is back on the per-problem Straus tables or on smaller table jobs) agrees."""
     rng = SeededRng(120 + ty)
@@ -194,7 +194,7 @@ def test_shared_commitments_batch_uses_tables(eng, ty):
     one by one (per-problem Straus path)."""
     from workloads import instance_many
     rng = SeededRng(140 + ty)
-    m, n, E = 7, 40, 7                                   # 7 x (40 [+1 +1]) outputs per base >= 256
+    m, n, E = 7, 40, 9                                   # 9 x (40 [+1 +1]) outputs per base >= 320
     A, B, G, T, X, Y, xr, yr, Tr = instance_many(eng, ty, m, n, E, rng)
     pi, th = eng.prove_batch(ty, E, m, n, b"".join(A), b"".join(B), b"".join(G), X, Y, xr, yr, b"".join(Tr), shared_vars=True)
     xc = eng.batch_commit_g1(X, xr) if ty in (0, 1) else eng.batch_commit_scalar_b1(X, xr)
@@ -203,7 +203,7 @@ def test_shared_commitments_batch_uses_tables(eng, ty):
     Gb[4][32 * (3 * n + 5)] ^= 2                         # equation 4 tampered
     cols = [b"".join(A), b"".join(B), b"".join(bytes(g) for g in Gb), b"".join(T), xc * E, yc * E, pi, th]
     ok = eng.verify_batch(ty, E, m, n, *cols)
-    assert list(ok) == [1, 1, 1, 1, 0, 1, 1]
+    assert list(ok) == [1, 1, 1, 1, 0, 1, 1, 1, 1]
     cx, cy = (2 if ty in (0, 1) else 1), (2 if ty in (0, 2) else 1)
     for e in (0, 4):
         one = eng.verify(ty, m, n, A[e], B[e], bytes(Gb[e]), T[e], xc, yc, pi[e * cx * 384:(e + 1) * cx * 384],
