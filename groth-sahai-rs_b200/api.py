@@ -253,7 +253,33 @@ def verify_batch(equations, proofs, crs: CRS) -> List[bool]:
 
 
 # ---------------------------------------------------------------- Com1 / Com2 / ComT  (data_structures.rs)
-class Com1:
+class _ComGroup:
+    """Add / Sub / Neg / Sum / Zero of a commitment group (impl_base_commit_groups! :162-255, ComT :391-479).
+    Elements are C-ABI byte strings; lists are processed in one GPU pass."""
+    kind = None
+    size = 0
+
+    @classmethod
+    def _eng(cls, engine): return engine or default_engine()
+    @classmethod
+    def add(cls, a, b, engine=None): return cls._eng(engine).elementwise(cls.kind, "add", a, b)
+    @classmethod
+    def sub(cls, a, b, engine=None): return cls._eng(engine).elementwise(cls.kind, "sub", a, b)
+    @classmethod
+    def neg(cls, a, engine=None): return cls._eng(engine).elementwise(cls.kind, "neg", a)
+    @classmethod
+    def sum(cls, elems, engine=None): return cls._eng(engine).group_sum(cls.kind, b"".join(elems))
+
+    @classmethod
+    def batch_add(cls, xs, ys, engine=None):
+        assert len(xs) == len(ys)
+        return _split(cls._eng(engine).elementwise(cls.kind, "add", b"".join(xs), b"".join(ys)), cls.size)
+
+
+class Com1(_ComGroup):
+    kind, size = "com1", 192
+    @staticmethod
+    def zero(): return bytes(192)                                           # :257-266
     @staticmethod
     def linear_map(x): return G1_ZERO + x                                   # :310-312
     @staticmethod
@@ -262,15 +288,25 @@ class Com1:
     def scalar_linear_map(x, key: CRS):                                     # :323-326  x * (u2 + (O, g1))
         return batch_commit_scalar_b1_norand(key, [x])[0]
     @staticmethod
+    def batch_scalar_linear_map(xs, key: CRS): return batch_commit_scalar_b1_norand(key, xs)   # :328-334
+    @staticmethod
     def scalar_mul(c, s, engine=None):                                      # :336-342
         return (engine or default_engine()).com1_matmul(1, 1, 1, s, c)
 
 
-class Com2:
+class Com2(_ComGroup):
+    kind, size = "com2", 384
+    @staticmethod
+    def zero(): return bytes(384)                                           # :268-277
     @staticmethod
     def linear_map(y): return G2_ZERO + y                                   # :355-357
     @staticmethod
     def batch_linear_map(ys): return [G2_ZERO + y for y in ys]
+    @staticmethod
+    def scalar_linear_map(y, key: CRS):                                     # :368-371  y * (v2 + (O, g2))
+        return batch_commit_scalar_b2_norand(key, [y])[0]
+    @staticmethod
+    def batch_scalar_linear_map(ys, key: CRS): return batch_commit_scalar_b2_norand(key, ys)   # :373-379
     @staticmethod
     def scalar_mul(c, s, engine=None):                                      # :381-387
         return (engine or default_engine()).com2_matmul(1, 1, 1, s, c)
@@ -282,7 +318,18 @@ def batch_commit_scalar_b1_norand(key: CRS, xs):
     return _split(out, 192)
 
 
-class ComT:
+def batch_commit_scalar_b2_norand(key: CRS, ys):
+    """iota_2'(y) = y W2: a scalar commitment with zero randomness."""
+    out = key._use().batch_commit_scalar_b2(b"".join(ys), bytes(FR * len(ys)))
+    return _split(out, 384)
+
+
+class ComT(_ComGroup):
+    kind, size = "comt", 2304
+    @staticmethod
+    def zero(engine=None): return (engine or default_engine()).group_sum("comt", b"")   # four GT identities :412-421
+    @staticmethod
+    def as_matrix(c): return [[c[0:576], c[576:1152]], [c[1152:1728], c[1728:2304]]]     # :1361-1377 row-major
     @staticmethod
     def pairing(x, y, engine=None):                                         # :484-491
         return (engine or default_engine()).comt_pairing(x, y)
@@ -305,6 +352,16 @@ class ComT:
 def _dims(mat): return len(mat), (len(mat[0]) if mat else 0)
 
 
+def _unflat(b, rows, cols, size):
+    return [_split(b[i * cols * size:(i + 1) * cols * size], size) for i in range(rows)]
+
+
+def mat_transpose(mat):
+    """Mat::transpose (:630-643, :809-822): pure data movement, no arithmetic."""
+    r, c = _dims(mat)
+    return [[mat[i][j] for i in range(r)] for j in range(c)]
+
+
 def fr_right_mul(a, rhs, engine=None):
     """Matrix<Fr>::right_mul :824-868 (self * rhs)."""
     (r, k), (k2, c) = _dims(a), _dims(rhs)
@@ -312,12 +369,58 @@ def fr_right_mul(a, rhs, engine=None):
         return []
     assert k == k2
     out = (engine or default_engine()).fr_matmul(r, k, c, _flat(a), _flat(rhs))
-    return [_split(out[i * c * FR:(i + 1) * c * FR], FR) for i in range(r)]
+    return _unflat(out, r, c, FR)
 
 
 def fr_left_mul(a, lhs, engine=None):
     """Matrix<Fr>::left_mul :870-912 (lhs * self)."""
     return fr_right_mul(lhs, a, engine)
+
+
+def fr_add(a, b, engine=None):
+    """Matrix<Fr>::add :771-785 (asserts equal dimensions)."""
+    assert _dims(a) == _dims(b)
+    r, c = _dims(a)
+    return _unflat((engine or default_engine()).elementwise("fr", "add", _flat(a), _flat(b)), r, c, FR)
+
+
+def fr_neg(a, engine=None):
+    """Matrix<Fr>::neg :787-794."""
+    r, c = _dims(a)
+    return _unflat((engine or default_engine()).elementwise("fr", "neg", _flat(a)), r, c, FR)
+
+
+def fr_scalar_mul(a, s, engine=None):
+    """Matrix<Fr>::scalar_mul :796-807."""
+    r, c = _dims(a)
+    return _unflat((engine or default_engine()).fr_scale(s, _flat(a)), r, c, FR)
+
+
+def _com(which): return ("com1", 192) if which == 1 else ("com2", 384)
+
+
+def com_add(a, b, which, engine=None):
+    """Matrix<Com1|Com2>::add :590-603."""
+    assert _dims(a) == _dims(b)
+    kind, size = _com(which)
+    r, c = _dims(a)
+    return _unflat((engine or default_engine()).elementwise(kind, "add", _flat(a), _flat(b)), r, c, size)
+
+
+def com_neg(a, which, engine=None):
+    """Matrix<Com1|Com2>::neg :606-615."""
+    kind, size = _com(which)
+    r, c = _dims(a)
+    return _unflat((engine or default_engine()).elementwise(kind, "neg", _flat(a)), r, c, size)
+
+
+def com_scalar_mul(a, s, which, engine=None):
+    """Matrix<Com1|Com2>::scalar_mul :617-628: every entry times the same scalar."""
+    kind, size = _com(which)
+    r, c = _dims(a)
+    eng = engine or default_engine()
+    fn = eng.com1_matmul if which == 1 else eng.com2_matmul
+    return _unflat(fn(1, 1, r * c, s, _flat(a)), r, c, size)
 
 
 def com_left_mul(mat, lhs, which, engine=None):
@@ -330,4 +433,13 @@ def com_left_mul(mat, lhs, which, engine=None):
     size = 192 if which == 1 else 384
     fn = eng.com1_matmul if which == 1 else eng.com2_matmul
     out = fn(r, k, c, _flat(lhs), _flat(mat))
-    return [_split(out[i * c * size:(i + 1) * c * size], size) for i in range(r)]
+    return _unflat(out, r, c, size)
+
+
+def com_right_mul(mat, rhs, which, engine=None):
+    """Matrix<Com1|Com2>::right_mul :645-694: out[i][j] = sum_k mat[i][k] * rhs[k][j]  (= (rhs^T * mat^T)^T)."""
+    (r, k), (k2, c) = _dims(mat), _dims(rhs)
+    if r == 0 or k == 0 or k2 == 0 or c == 0:
+        return []
+    assert k == k2
+    return mat_transpose(com_left_mul(mat_transpose(mat), mat_transpose(rhs), which, engine))

@@ -318,6 +318,25 @@ __global__ void __launch_bounds__(128) k_vmsm_wsum(verify_shape s, verify_args v
   part[(((size_t)ch * s.n_out + jj) * 2 + a) * nprob + p] = acc;
 }
 
+// thread -> (group g of F chunks, entry e = (jj*2 + a)*nprob + p): out[g][e] = sum_{c < F} part[g*F + c][e]
+__global__ void __launch_bounds__(128) k_vmsm_fold(verify_shape s, const g1_jac* __restrict__ part, g1_jac* __restrict__ out,
+                                                   size_t nprob, int nchunk, int F, int ngroups) {
+  const size_t E = (size_t)s.n_out * 2 * nprob;
+  size_t id = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (id >= E * ngroups) return;
+  size_t e = id % E;
+  int g = (int)(id / E);
+  int jj = (int)(e / (2 * nprob));
+  if (!s.owns(s.out_slot(jj))) return;
+  int c0 = g * F, c1 = min(nchunk, c0 + F);
+  g1_jac acc = part[(size_t)c0 * E + e];
+  for (int c = c0 + 1; c < c1; c++) {
+    g1_jac t = part[(size_t)c * E + e];
+    g1_jac::add(acc, acc, t);
+  }
+  out[(size_t)g * E + e] = acc;
+}
+
 // thread -> (p, jj, a): sum the chunk partials, add iota_1(A_j), negate the Quad target, normalise, write slot
 __global__ void __launch_bounds__(128) k_vmsm_reduce(verify_shape s, verify_args v, const g1_jac* __restrict__ part,
                                                      g1_aff* __restrict__ X, size_t nprob) {
@@ -424,11 +443,12 @@ static int verify_impl(gs_ctx* ctx, int type, size_t count, size_t m, size_t n, 
     const bool use_wtab = (nprob == 1 || shared_x) && owned_out * nprob >= 320;  // table build ~ 14.6 ms at m = 1024
     {
       // bases per thread: few threads (one statement, or one rank's share of it) -> smaller chunks, so that the
-      // grid is >= 3 waves of the ~296 resident blocks instead of 1.7 (measured: 20.8 ms for half of C3's sums
-      // against 30.8 ms for all of them); the table kernel has no doublings to amortise, Straus keeps >= 8
+      // grid is ~8 waves of the ~296 resident blocks instead of 1.7 (measured: 20.8 ms for half of C3's sums against
+      // 30.8 ms for all of them; C4's shared-table batches 91 -> 67 ms); the table kernel has no doublings to
+      // amortise, Straus keeps >= 8.  Many chunks are folded 16 at a time (k_vmsm_fold) before k_vmsm_reduce.
       int chunk = GS_MSM_CHUNK;
-      const int floor_chunk = use_wtab ? 2 : 8;
-      while (chunk > floor_chunk && nprob * owned_out * 2 * ((s.nbases + chunk - 1) / chunk) < (size_t)128 * 888) chunk /= 2;
+      const int floor_chunk = use_wtab ? 4 : 8;
+      while (chunk > floor_chunk && nprob * owned_out * 2 * ((s.nbases + chunk - 1) / chunk) < (size_t)128 * 2368) chunk /= 2;
       set_msm_chunk(s, chunk);
     }
     g1_aff* X;
@@ -458,7 +478,16 @@ static int verify_impl(gs_ctx* ctx, int type, size_t count, size_t m, size_t n, 
       LAUNCH(k_vmsm_tables, nprob * (size_t)s.nbases * 2, s, v, ctx->crs, vtab, nprob);
       LAUNCH(k_vmsm_partial, nprob * owned_out * 2 * s.nchunk, s, v, vtab, part, nprob);
     }
-    LAUNCH(k_vmsm_reduce, nprob * owned_out * 2, s, v, part, X, nprob);
+    const g1_jac* partr = part;
+    if (s.nchunk > 32) {  // fold 16 chunks at a time in parallel; k_vmsm_reduce then walks the few that are left
+      const int F = 16, ng = (s.nchunk + F - 1) / F;
+      g1_jac* part2;
+      CUDA_TRY(sc.alloc(&part2, (size_t)ng * s.n_out * 2 * nprob));
+      LAUNCH(k_vmsm_fold, (size_t)s.n_out * 2 * nprob * ng, s, part, part2, nprob, s.nchunk, F, ng);
+      partr = part2;
+      s.nchunk = ng;
+    }
+    LAUNCH(k_vmsm_reduce, nprob * owned_out * 2, s, v, partr, X, nprob);
     const g1_aff* Xp = X;
     const g2_aff* Yp = Y;
     if (world > 1) {

@@ -20,6 +20,8 @@ EXPORTED_SYMBOLS = [
     "gs_verify_partial", "gs_verify_partial_dev", "gs_verify_finish", "gs_verify_finish_dev",
     "gs_comt_pairing", "gs_comt_pairing_sum", "gs_comt_linear_map", "gs_pairing",
     "gs_com1_matmul", "gs_com2_matmul", "gs_fr_matmul",
+    "gs_com1_add", "gs_com1_sub", "gs_com1_neg", "gs_com1_sum", "gs_com2_add", "gs_com2_sub", "gs_com2_neg", "gs_com2_sum",
+    "gs_comt_add", "gs_comt_sub", "gs_comt_neg", "gs_comt_sum", "gs_fr_add", "gs_fr_sub", "gs_fr_neg", "gs_fr_scale",
 ]
 
 
@@ -75,6 +77,13 @@ def load_library():
         lib.gs_pairing.argtypes = [vp, sz, vp, vp, vp]
         for f in ("gs_com1_matmul", "gs_com2_matmul", "gs_fr_matmul"):
             getattr(lib, f).argtypes = [vp, sz, sz, sz, vp, vp, vp]
+        for g in ("com1", "com2", "comt", "fr"):
+            getattr(lib, f"gs_{g}_add").argtypes = [vp, sz, vp, vp, vp]
+            getattr(lib, f"gs_{g}_sub").argtypes = [vp, sz, vp, vp, vp]
+            getattr(lib, f"gs_{g}_neg").argtypes = [vp, sz, vp, vp]
+        for g in ("com1", "com2", "comt"):
+            getattr(lib, f"gs_{g}_sum").argtypes = [vp, sz, vp, vp]
+        lib.gs_fr_scale.argtypes = [vp, sz, vp, vp, vp]
         _lib = lib
     return _lib
 
@@ -293,6 +302,41 @@ class Engine:
         kp, kq = _buf(ps), _buf(qs)
         self._chk(self.lib.gs_pairing(self.h, n, kp[1], kq[1], ctypes.cast(out, ctypes.c_void_p)))
         return out.raw[: n * GT]
+
+    # ---- entry-wise group arithmetic: kind in ("com1", "com2", "comt", "fr"); element sizes from the ABI
+    _ESIZE = {"com1": COM1, "com2": COM2, "comt": COMT, "fr": FR}
+
+    def elementwise(self, kind, op, a: bytes, b: bytes = None) -> bytes:
+        """op in ("add", "sub", "neg"): out[i] = a[i] op b[i] over len(a) / element-size elements."""
+        es = self._ESIZE[kind]
+        n = len(a) // es
+        assert len(a) == n * es and (op == "neg" or len(b) == len(a))
+        out = ctypes.create_string_buffer(max(1, n * es))
+        ka = _buf(a)
+        fn = getattr(self.lib, f"gs_{kind}_{op}")
+        if op == "neg":
+            self._chk(fn(self.h, n, ka[1], ctypes.cast(out, ctypes.c_void_p)))
+        else:
+            kb = _buf(b)
+            self._chk(fn(self.h, n, ka[1], kb[1], ctypes.cast(out, ctypes.c_void_p)))
+        return out.raw[: n * es]
+
+    def group_sum(self, kind, a: bytes) -> bytes:
+        es = self._ESIZE[kind]
+        n = len(a) // es
+        assert len(a) == n * es and kind != "fr"
+        out = ctypes.create_string_buffer(es)
+        ka = _buf(a)
+        self._chk(getattr(self.lib, f"gs_{kind}_sum")(self.h, n, ka[1], ctypes.cast(out, ctypes.c_void_p)))
+        return out.raw
+
+    def fr_scale(self, s: bytes, a: bytes) -> bytes:
+        n = len(a) // FR
+        assert len(s) == FR and len(a) == n * FR
+        out = ctypes.create_string_buffer(max(1, n * FR))
+        ks, ka = _buf(s), _buf(a)
+        self._chk(self.lib.gs_fr_scale(self.h, n, ks[1], ka[1], ctypes.cast(out, ctypes.c_void_p)))
+        return out.raw[: n * FR]
 
     # ---- Mat
     def _matmul(self, fn, r, k, c, lhs, mat, esize_l, esize_m, esize_o):

@@ -179,6 +179,28 @@ int gs_comt_linear_map(gs_ctx* ctx, int type, const void* target, gs_comt* out);
 /* E::pairing batched: out[i] = e(ps[i], qs[i]) */
 int gs_pairing(gs_ctx* ctx, size_t count, const gs_g1* ps, const gs_g2* qs, gs_gt* out);
 
+/* ---- commitment-group arithmetic (src/data_structures.rs:162-255, 391-479) ----------------------- */
+/* Entry-wise Add / Sub / Neg over n elements and Sum (fold from zero: n = 0 gives the identity) for
+ * Com1 = G1 x G1, Com2 = G2 x G2 (impl_base_commit_groups! :162-255) and ComT = GT^4 (:391-479), where GT is
+ * written additively as arkworks' PairingOutput does: add = Fp12 product, neg = conjugate. */
+int gs_com1_add(gs_ctx* ctx, size_t n, const gs_com1* a, const gs_com1* b, gs_com1* out);
+int gs_com1_sub(gs_ctx* ctx, size_t n, const gs_com1* a, const gs_com1* b, gs_com1* out);
+int gs_com1_neg(gs_ctx* ctx, size_t n, const gs_com1* a, gs_com1* out);
+int gs_com1_sum(gs_ctx* ctx, size_t n, const gs_com1* a, gs_com1* out);
+int gs_com2_add(gs_ctx* ctx, size_t n, const gs_com2* a, const gs_com2* b, gs_com2* out);
+int gs_com2_sub(gs_ctx* ctx, size_t n, const gs_com2* a, const gs_com2* b, gs_com2* out);
+int gs_com2_neg(gs_ctx* ctx, size_t n, const gs_com2* a, gs_com2* out);
+int gs_com2_sum(gs_ctx* ctx, size_t n, const gs_com2* a, gs_com2* out);
+int gs_comt_add(gs_ctx* ctx, size_t n, const gs_comt* a, const gs_comt* b, gs_comt* out);
+int gs_comt_sub(gs_ctx* ctx, size_t n, const gs_comt* a, const gs_comt* b, gs_comt* out);
+int gs_comt_neg(gs_ctx* ctx, size_t n, const gs_comt* a, gs_comt* out);
+int gs_comt_sum(gs_ctx* ctx, size_t n, const gs_comt* a, gs_comt* out);
+/* Matrix<Fr> element-wise parts of the Mat trait (:771-807): add, (sub), neg, scalar_mul over n entries */
+int gs_fr_add(gs_ctx* ctx, size_t n, const gs_fr* a, const gs_fr* b, gs_fr* out);
+int gs_fr_sub(gs_ctx* ctx, size_t n, const gs_fr* a, const gs_fr* b, gs_fr* out);
+int gs_fr_neg(gs_ctx* ctx, size_t n, const gs_fr* a, gs_fr* out);
+int gs_fr_scale(gs_ctx* ctx, size_t n, const gs_fr* s, const gs_fr* a, gs_fr* out);
+
 /* ---- Mat (src/data_structures.rs:645-742, 768-913) ---------------------------------------- */
 /* out (r x c) = lhs (r x k, Fr) * mat (k x c, Com1) -- Matrix<Com1>::left_mul */
 int gs_com1_matmul(gs_ctx* ctx, size_t r, size_t k, size_t c, const gs_fr* lhs, const gs_com1* mat, gs_com1* out);

@@ -228,3 +228,103 @@ def test_error_behaviour(eng, crs_pair):
         eng.verify_batch(0, 1, 0, 0, b"", b"", b"", bytes(576), b"", b"", bytes(768), bytes(384))
     with pytest.raises(gsb.GsError):   # pairing_sum length mismatch (data_structures.rs:495)
         eng.comt_pairing_sum(bytes(192), b"")
+
+
+# ---------------------------------------------------------------- commitment-group arithmetic
+def test_com_group_ops_match_oracle(eng):
+    """Com1 / Com2 Add, Sub, Neg, Sum (impl_base_commit_groups!, data_structures.rs:162-255) incl. the
+    exceptional cases: identity operands, P + P, P + (-P)."""
+    rng = SeededRng(21)
+    p, q = rng.g1(), rng.g1()
+    xs = [(p, q), (None, q), (p, None), (None, None), (p, q), (rng.g1(), rng.g1())]
+    ys = [(q, p), (p, None), (None, q), (None, None), (p, ogs.G1.neg(q)), (rng.g1(), rng.g1())]
+    xb, yb = b"".join(com1_b(x) for x in xs), b"".join(com1_b(y) for y in ys)
+    add = eng.elementwise("com1", "add", xb, yb)
+    sub = eng.elementwise("com1", "sub", xb, yb)
+    neg = eng.elementwise("com1", "neg", xb)
+    for i, (x, y) in enumerate(zip(xs, ys)):
+        assert com1_i(add[192 * i:192 * (i + 1)]) == ogs.com1_add(x, y), i
+        assert com1_i(sub[192 * i:192 * (i + 1)]) == ogs.com1_add(x, ogs.com1_neg(y)), i
+        assert com1_i(neg[192 * i:192 * (i + 1)]) == ogs.com1_neg(x), i
+    acc = (None, None)
+    for x in xs:
+        acc = ogs.com1_add(acc, x)
+    assert com1_i(eng.group_sum("com1", xb)) == acc
+    assert eng.group_sum("com1", b"") == bytes(192)                      # Sum of nothing = Com1::zero()
+    u, v = rng.g2(), rng.g2()
+    as_ = [(u, v), (None, v), (u, u), (rng.g2(), rng.g2()), (rng.g2(), None)]
+    bs_ = [(v, u), (u, None), (u, ogs.G2.neg(u)), (rng.g2(), rng.g2()), (None, None)]
+    ab, bb = b"".join(com2_b(x) for x in as_), b"".join(com2_b(y) for y in bs_)
+    add, sub, neg = eng.elementwise("com2", "add", ab, bb), eng.elementwise("com2", "sub", ab, bb), eng.elementwise("com2", "neg", ab)
+    for i, (x, y) in enumerate(zip(as_, bs_)):
+        assert com2_i(add[384 * i:384 * (i + 1)]) == ogs.com2_add(x, y), i
+        assert com2_i(sub[384 * i:384 * (i + 1)]) == ogs.com2_add(x, ogs.com2_neg(y)), i
+        assert com2_i(neg[384 * i:384 * (i + 1)]) == ogs.com2_neg(x), i
+    acc = (None, None)
+    for x in as_:
+        acc = ogs.com2_add(acc, x)
+    assert com2_i(eng.group_sum("com2", ab)) == acc
+
+
+def test_comt_group_ops_match_oracle(eng):
+    """ComT Add (GT product), Sub, Neg (conjugate), Sum, Zero (data_structures.rs:391-479)."""
+    rng = SeededRng(22)
+    xs = [(rng.g1(), rng.g1()) for _ in range(3)]
+    ys = [(rng.g2(), rng.g2()) for _ in range(3)]
+    t = eng.comt_pairing(b"".join(com1_b(x) for x in xs), b"".join(com2_b(y) for y in ys))
+    ts = [comt_i(t[2304 * i:2304 * (i + 1)]) for i in range(3)]
+    a, b = t[:2 * 2304], t[2304:]
+    add, sub, neg = eng.elementwise("comt", "add", a, b), eng.elementwise("comt", "sub", a, b), eng.elementwise("comt", "neg", a)
+    for i in range(2):
+        assert comt_i(add[2304 * i:2304 * (i + 1)]) == ogs.comt_add(ts[i], ts[i + 1])
+        assert comt_i(sub[2304 * i:2304 * (i + 1)]) == ogs.comt_add(ts[i], ogs.comt_neg(ts[i + 1]))
+        assert comt_i(neg[2304 * i:2304 * (i + 1)]) == ogs.comt_neg(ts[i])
+    acc = ogs.comt_zero()
+    for x in ts:
+        acc = ogs.comt_add(acc, x)
+    assert comt_i(eng.group_sum("comt", t)) == acc
+    # sum of pairings == pairing_sum (data_structures.rs:1381-1407), now entirely on the device
+    assert eng.group_sum("comt", t) == eng.comt_pairing_sum(b"".join(com1_b(x) for x in xs), b"".join(com2_b(y) for y in ys))
+    assert comt_i(eng.group_sum("comt", b"")) == ogs.comt_zero()
+    # x - x = zero
+    assert comt_i(eng.elementwise("comt", "sub", a, a)[:2304]) == ogs.comt_zero()
+
+
+def test_mat_trait_mirror(eng, crs_pair):
+    """The element-wise and structural parts of the Mat trait (data_structures.rs:588-643, 768-823) through
+    api.py: add, neg, scalar_mul, transpose, right_mul for Matrix<Fr> and Matrix<Com1|Com2>."""
+    from groth_sahai_rs_b200 import api
+    rng = SeededRng(23)
+    A = [[rng.fr() for _ in range(3)] for _ in range(2)]
+    B = [[rng.fr() for _ in range(3)] for _ in range(2)]
+    enc = lambda m: [[fr_b(x) for x in r] for r in m]
+    dec = lambda m: [[fr_i(x) for x in r] for r in m]
+    assert dec(api.fr_add(enc(A), enc(B), eng)) == ogs.fr_add(A, B)
+    assert dec(api.fr_neg(enc(A), eng)) == ogs.fr_neg(A)
+    s = rng.fr()
+    assert dec(api.fr_scalar_mul(enc(A), fr_b(s), eng)) == ogs.fr_scalar_mul(A, s)
+    assert dec(api.mat_transpose(enc(A))) == ogs.fr_transpose(A)
+    with pytest.raises(AssertionError):
+        api.fr_add(enc(A), enc(ogs.fr_transpose(B)), eng)
+    C = [[(rng.g1(), rng.g1()) for _ in range(2)] for _ in range(3)]          # 3 x 2 Com1
+    D = [[(rng.g1(), None) for _ in range(2)] for _ in range(3)]
+    e1 = lambda m: [[com1_b(x) for x in r] for r in m]
+    d1 = lambda m: [[com1_i(x) for x in r] for r in m]
+    assert d1(api.com_add(e1(C), e1(D), 1, eng)) == ogs.com_mat_add(C, D, 1)
+    assert d1(api.com_neg(e1(C), 1, eng)) == [[ogs.com1_neg(x) for x in r] for r in C]
+    assert d1(api.com_scalar_mul(e1(C), fr_b(s), 1, eng)) == [[ogs.com1_scalar_mul(x, s) for x in r] for r in C]
+    rhs = [[rng.fr() for _ in range(4)] for _ in range(2)]                     # 2 x 4 scalars
+    assert d1(api.com_right_mul(e1(C), enc(rhs), 1, eng)) == ogs.com_right_mul(C, rhs, 1)
+    E2 = [[(rng.g2(), rng.g2())] for _ in range(2)]                            # 2 x 1 Com2
+    e2 = lambda m: [[com2_b(x) for x in r] for r in m]
+    d2 = lambda m: [[com2_i(x) for x in r] for r in m]
+    lhs = [[rng.fr(), rng.fr()] for _ in range(3)]
+    assert d2(api.com_left_mul(e2(E2), enc(lhs), 2, eng)) == ogs.com_left_mul(E2, lhs, 2)
+    assert d2(api.com_scalar_mul(e2(E2), fr_b(s), 2, eng)) == [[ogs.com2_scalar_mul(x, s) for x in r] for r in E2]
+    # the reference's scalar_linear_map through the mirror (W recomputed per element upstream, :325)
+    crs, _ = crs_pair
+    from groth_sahai_rs_b200.api import CRS as ApiCRS
+    key = ApiCRS.from_bytes(crs_bytes(crs), eng)
+    x = rng.fr()
+    assert com1_i(api.Com1.scalar_linear_map(fr_b(x), key)) == ogs.com1_scalar_linear_map(x, crs)
+    assert com2_i(api.Com2.scalar_linear_map(fr_b(x), key)) == ogs.com2_scalar_linear_map(x, crs)

@@ -81,6 +81,48 @@ __global__ void k_mix(fp* out, const fp* in, int iters_inv, int iters_mul) {
   }
   out[t] = x;
 }
+// FP64 pipe: independent DFMA chains; and DFMA on half of the warps next to IMAD.WIDE on the other half
+__global__ void k_dfma(double* out, double a, double b, int iters) {
+  double x0 = threadIdx.x, x1 = a, x2 = b, x3 = a + b, x4 = 5, x5 = 6, x6 = 7, x7 = 8;
+  for (int i = 0; i < iters; i++) {
+#pragma unroll
+    for (int j = 0; j < 16; j++) {
+      x0 = __fma_rz(x0, a, b); x1 = __fma_rz(x1, a, b); x2 = __fma_rz(x2, a, b); x3 = __fma_rz(x3, a, b);
+      x4 = __fma_rz(x4, a, b); x5 = __fma_rz(x5, a, b); x6 = __fma_rz(x6, a, b); x7 = __fma_rz(x7, a, b);
+    }
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
+}
+__global__ void k_dfma_imad_mix(unsigned long long* out, double a, double b, unsigned ua, int it_d, int it_i) {
+  if ((threadIdx.x >> 5) & 1) {
+    double x0 = threadIdx.x, x1 = a, x2 = b, x3 = a + b, x4 = 5, x5 = 6, x6 = 7, x7 = 8;
+    for (int i = 0; i < it_d; i++) {
+#pragma unroll
+      for (int j = 0; j < 16; j++) {
+        x0 = __fma_rz(x0, a, b); x1 = __fma_rz(x1, a, b); x2 = __fma_rz(x2, a, b); x3 = __fma_rz(x3, a, b);
+        x4 = __fma_rz(x4, a, b); x5 = __fma_rz(x5, a, b); x6 = __fma_rz(x6, a, b); x7 = __fma_rz(x7, a, b);
+      }
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = (unsigned long long)(x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7);
+  } else {
+    unsigned long long x0 = threadIdx.x, x1 = ua, x2 = 3, x3 = 4, x4 = 5, x5 = 6, x6 = 7, x7 = 8;
+    unsigned m = ua | 1;
+    for (int i = 0; i < it_i; i++) {
+#pragma unroll
+      for (int j = 0; j < 16; j++) {
+        asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(x0) : "r"(m), "r"((unsigned)x1));
+        asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(x1) : "r"(m), "r"((unsigned)x2));
+        asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(x2) : "r"(m), "r"((unsigned)x3));
+        asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(x3) : "r"(m), "r"((unsigned)x4));
+        asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(x4) : "r"(m), "r"((unsigned)x5));
+        asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(x5) : "r"(m), "r"((unsigned)x6));
+        asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(x6) : "r"(m), "r"((unsigned)x7));
+        asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(x7) : "r"(m), "r"((unsigned)x0));
+      }
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = x0 ^ x1 ^ x2 ^ x3 ^ x4 ^ x5 ^ x6 ^ x7;
+  }
+}
 template <class K, class... A>
 float timeit(K k, dim3 g, dim3 b, A... args) {
   cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
@@ -126,6 +168,17 @@ int main() {
     float mb = timeit(k_mix, g, b, (fp*)buf + (1 << 20), (const fp*)buf, 0, im);
     float mc = timeit(k_mix, g, b, (fp*)buf + (1 << 20), (const fp*)buf, ii, im);
     printf("warps/SM %2d: half warps safegcd alone %.3f ms, half warps fp::mul alone %.3f ms, both %.3f ms\n", wps, ma, mb, mc);
+  }
+  for (int wps : {8, 16, 32}) {
+    int iters = 4096;
+    dim3 g(sms), b(wps * 32);
+    float ms = timeit(k_dfma, g, b, (double*)buf, 1.0000001, 0.5, iters);
+    double ops = (double)sms * wps * 32 * iters * 128;
+    printf("warps/SM %2d: DFMA %.3e/s (%.1f /clk/SM @1.9GHz)\n", wps, ops / ms * 1e3, ops / ms * 1e3 / sms / 1.9e9);
+    float ma = timeit(k_dfma_imad_mix, g, b, (unsigned long long*)buf, 1.0000001, 0.5, 3u, iters, 0);
+    float mb = timeit(k_dfma_imad_mix, g, b, (unsigned long long*)buf, 1.0000001, 0.5, 3u, 0, iters);
+    float mc = timeit(k_dfma_imad_mix, g, b, (unsigned long long*)buf, 1.0000001, 0.5, 3u, iters, iters);
+    printf("warps/SM %2d: half warps DFMA alone %.3f ms, half warps IMAD.WIDE alone %.3f ms, both %.3f ms\n", wps, ma, mb, mc);
   }
   return 0;
 }
