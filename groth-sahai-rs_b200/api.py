@@ -443,3 +443,125 @@ def com_right_mul(mat, rhs, which, engine=None):
         return []
     assert k == k2
     return mat_transpose(com_left_mul(mat_transpose(mat), mat_transpose(rhs), which, engine))
+
+
+# ---------------------------------------------------------------- canonical serialisation (ark-serialize layout)
+# serialize_compressed of the reference's derived types: fields in declaration order, Vec<T> = u64-LE length then the
+# items, Com1 / Com2 = two compressed points, Fr = 32 B LE, PairingOutput = 576 B LE, EquType = one byte
+# (generator.rs:35-42, prover/commit.rs:18-28, prover/prove.rs:55-61, statement.rs:61-97).  The framing is host
+# logic; every element conversion (compression, decompression + subgroup check, Montgomery <-> canonical) is one
+# batched GPU call per element kind.
+class SerializationError(ValueError):
+    """ark_serialize::SerializationError::InvalidData."""
+
+
+def _u64(n): return int(n).to_bytes(8, "little")
+
+
+class _Reader:
+    def __init__(self, b):
+        self.b, self.o = b, 0
+
+    def take(self, n):
+        if self.o + n > len(self.b):
+            raise SerializationError("unexpected end of input")
+        out = self.b[self.o:self.o + n]
+        self.o += n
+        return out
+
+    def u64(self): return int.from_bytes(self.take(8), "little")
+
+
+def _ser_points(eng, kind, pts): return eng.serialize(kind, b"".join(pts)) if pts else b""
+
+
+def _de(eng, kind, wire, what):
+    out, ok = eng.deserialize(kind, wire)
+    if ok != b"\x01" * len(ok):
+        raise SerializationError(f"invalid {what} encoding at element {ok.index(0)}")
+    return out
+
+
+def _ser_matrix(eng, mat):
+    flat = eng.serialize("fr", _flat(mat)) if mat and mat[0] else b""
+    out, o = _u64(len(mat)), 0
+    for row in mat:
+        out += _u64(len(row)) + flat[o:o + 32 * len(row)]
+        o += 32 * len(row)
+    return out
+
+
+def _de_matrix(eng, rd):
+    rows = rd.u64()
+    lens, wire = [], b""
+    for _ in range(rows):
+        k = rd.u64()
+        lens.append(k)
+        wire += rd.take(32 * k)
+    vals = _split(_de(eng, "fr", wire, "Fr"), FR) if wire else []
+    out, o = [], 0
+    for k in lens:
+        out.append(vals[o:o + k])
+        o += k
+    return out
+
+
+def _com_points(coms, size): return [c[i * size:(i + 1) * size] for c in coms for i in range(2)]
+
+
+def _ser_coms(eng, coms, which):
+    kind, size = ("g1", G1) if which == 1 else ("g2", G2)
+    return _u64(len(coms)) + _ser_points(eng, kind, _com_points(coms, size))
+
+
+def _de_coms(eng, rd, which):
+    kind, size, wsz = ("g1", G1, 48) if which == 1 else ("g2", G2, 96)
+    n = rd.u64()
+    pts = _de(eng, kind, rd.take(2 * n * wsz), "G1" if which == 1 else "G2") if n else b""
+    return _split(pts, 2 * size)
+
+
+def serialize_crs(crs: CRS) -> bytes:
+    """CRS::serialize_compressed: 1,312 bytes (SURVEY.md §8a a11)."""
+    eng = crs.engine or default_engine()
+    return (_ser_coms(eng, crs.u, 1) + _ser_coms(eng, crs.v, 2) + eng.serialize("g1", crs.g1_gen) +
+            eng.serialize("g2", crs.g2_gen) + eng.serialize("gt", crs.gt_gen))
+
+
+def deserialize_crs(b: bytes, engine: Engine = None) -> CRS:
+    eng = engine or default_engine()
+    rd = _Reader(b)
+    u, v = _de_coms(eng, rd, 1), _de_coms(eng, rd, 2)
+    g1 = _de(eng, "g1", rd.take(48), "G1")
+    g2 = _de(eng, "g2", rd.take(96), "G2")
+    gt = _de(eng, "gt", rd.take(576), "GT")
+    if len(u) != 2 or len(v) != 2:
+        raise SerializationError("CRS keys must hold two commitments each")
+    return CRS.from_bytes(b"".join(u) + b"".join(v) + g1 + g2 + gt, eng)
+
+
+def serialize_commit(c: _Commit) -> bytes:
+    eng = default_engine()
+    return _ser_coms(eng, c.coms, 1 if isinstance(c, Commit1) else 2) + _ser_matrix(eng, c.rand)
+
+
+def deserialize_commit(b: bytes, which: int, engine: Engine = None):
+    eng = engine or default_engine()
+    rd = _Reader(b)
+    coms = _de_coms(eng, rd, which)
+    return (Commit1 if which == 1 else Commit2)(coms, _de_matrix(eng, rd))
+
+
+def serialize_equ_proof(p: EquProof, engine: Engine = None) -> bytes:
+    eng = engine or default_engine()
+    return _ser_coms(eng, p.pi, 2) + _ser_coms(eng, p.theta, 1) + bytes([p.equ_type]) + _ser_matrix(eng, p.rand)
+
+
+def deserialize_equ_proof(b: bytes, engine: Engine = None) -> EquProof:
+    eng = engine or default_engine()
+    rd = _Reader(b)
+    pi, theta = _de_coms(eng, rd, 2), _de_coms(eng, rd, 1)
+    ty = rd.take(1)[0]
+    if ty > 3:
+        raise SerializationError("bad EquType byte")       # statement.rs:88-95
+    return EquProof(pi, theta, ty, _de_matrix(eng, rd))

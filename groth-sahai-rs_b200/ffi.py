@@ -22,6 +22,8 @@ EXPORTED_SYMBOLS = [
     "gs_com1_matmul", "gs_com2_matmul", "gs_fr_matmul",
     "gs_com1_add", "gs_com1_sub", "gs_com1_neg", "gs_com1_sum", "gs_com2_add", "gs_com2_sub", "gs_com2_neg", "gs_com2_sum",
     "gs_comt_add", "gs_comt_sub", "gs_comt_neg", "gs_comt_sum", "gs_fr_add", "gs_fr_sub", "gs_fr_neg", "gs_fr_scale",
+    "gs_g1_compress", "gs_g1_decompress", "gs_g2_compress", "gs_g2_decompress",
+    "gs_fr_to_bytes", "gs_fr_from_bytes", "gs_gt_to_bytes", "gs_gt_from_bytes",
 ]
 
 
@@ -84,6 +86,12 @@ def load_library():
         for g in ("com1", "com2", "comt"):
             getattr(lib, f"gs_{g}_sum").argtypes = [vp, sz, vp, vp]
         lib.gs_fr_scale.argtypes = [vp, sz, vp, vp, vp]
+        for f in ("gs_g1_compress", "gs_g2_compress", "gs_fr_to_bytes", "gs_gt_to_bytes"):
+            getattr(lib, f).argtypes = [vp, sz, vp, vp]
+        for f in ("gs_g1_decompress", "gs_g2_decompress"):
+            getattr(lib, f).argtypes = [vp, sz, vp, ci, vp, vp]
+        for f in ("gs_fr_from_bytes", "gs_gt_from_bytes"):
+            getattr(lib, f).argtypes = [vp, sz, vp, vp, vp]
         _lib = lib
     return _lib
 
@@ -337,6 +345,36 @@ class Engine:
         ks, ka = _buf(s), _buf(a)
         self._chk(self.lib.gs_fr_scale(self.h, n, ks[1], ka[1], ctypes.cast(out, ctypes.c_void_p)))
         return out.raw[: n * FR]
+
+    # ---- wire formats: kind in ("g1", "g2") for points, ("fr", "gt") for canonical integers
+    _WIRE = {"g1": (G1, 48), "g2": (G2, 96), "fr": (FR, 32), "gt": (GT, 576)}
+
+    def serialize(self, kind, elems: bytes) -> bytes:
+        """ABI elements -> wire bytes (compressed points / canonical little-endian integers)."""
+        esz, wsz = self._WIRE[kind]
+        n = len(elems) // esz
+        assert len(elems) == n * esz
+        out = ctypes.create_string_buffer(max(1, n * wsz))
+        k = _buf(elems)
+        fn = getattr(self.lib, f"gs_{kind}_compress" if kind in ("g1", "g2") else f"gs_{kind}_to_bytes")
+        self._chk(fn(self.h, n, k[1], ctypes.cast(out, ctypes.c_void_p)))
+        return out.raw[: n * wsz]
+
+    def deserialize(self, kind, wire: bytes, check_subgroup=True):
+        """wire bytes -> (ABI elements, verdict bytes); invalid encodings give verdict 0 and a zeroed element."""
+        esz, wsz = self._WIRE[kind]
+        n = len(wire) // wsz
+        assert len(wire) == n * wsz
+        out = ctypes.create_string_buffer(max(1, n * esz))
+        ok = ctypes.create_string_buffer(max(1, n))
+        k = _buf(wire)
+        if kind in ("g1", "g2"):
+            self._chk(getattr(self.lib, f"gs_{kind}_decompress")(self.h, n, k[1], 1 if check_subgroup else 0,
+                                                               ctypes.cast(out, ctypes.c_void_p), ctypes.cast(ok, ctypes.c_void_p)))
+        else:
+            self._chk(getattr(self.lib, f"gs_{kind}_from_bytes")(self.h, n, k[1], ctypes.cast(out, ctypes.c_void_p),
+                                                               ctypes.cast(ok, ctypes.c_void_p)))
+        return out.raw[: n * esz], ok.raw[:n]
 
     # ---- Mat
     def _matmul(self, fn, r, k, c, lhs, mat, esize_l, esize_m, esize_o):

@@ -201,6 +201,23 @@ int gs_fr_sub(gs_ctx* ctx, size_t n, const gs_fr* a, const gs_fr* b, gs_fr* out)
 int gs_fr_neg(gs_ctx* ctx, size_t n, const gs_fr* a, gs_fr* out);
 int gs_fr_scale(gs_ctx* ctx, size_t n, const gs_fr* s, const gs_fr* a, gs_fr* out);
 
+/* ---- wire formats (ark-serialize as derived at generator.rs:35, commit.rs:18-28, prove.rs:55-61) ---- */
+/* Point compression in ark-bls12-381's zcash / IETF encoding: G1 48 B = big-endian x, G2 96 B = x.c1 || x.c0,
+ * top bits of byte 0: 0x80 compressed, 0x40 infinity, 0x20 y is the lexicographically largest of {y, -y}.
+ * Decompression validates like CanonicalDeserialize with Validate::Yes: out_ok[i] = 0 (and out[i] = identity)
+ * when the flag byte is not a compressed encoding, x >= p, x is not on the curve, or -- with check_subgroup
+ * != 0 -- the point is outside the order-r subgroup.  A set infinity flag yields the identity. */
+int gs_g1_compress(gs_ctx* ctx, size_t n, const gs_g1* pts, uint8_t* out /* 48 n */);
+int gs_g1_decompress(gs_ctx* ctx, size_t n, const uint8_t* in, int check_subgroup, gs_g1* out, uint8_t* out_ok);
+int gs_g2_compress(gs_ctx* ctx, size_t n, const gs_g2* pts, uint8_t* out /* 96 n */);
+int gs_g2_decompress(gs_ctx* ctx, size_t n, const uint8_t* in, int check_subgroup, gs_g2* out, uint8_t* out_ok);
+/* Fr <-> 32 B little-endian canonical integer; GT <-> 12 x 48 B little-endian canonical, tower order.
+ * from_bytes rejects integers >= the modulus (out_ok[i] = 0, value zeroed). */
+int gs_fr_to_bytes(gs_ctx* ctx, size_t n, const gs_fr* in, uint8_t* out);
+int gs_fr_from_bytes(gs_ctx* ctx, size_t n, const uint8_t* in, gs_fr* out, uint8_t* out_ok);
+int gs_gt_to_bytes(gs_ctx* ctx, size_t n, const gs_gt* in, uint8_t* out);
+int gs_gt_from_bytes(gs_ctx* ctx, size_t n, const uint8_t* in, gs_gt* out, uint8_t* out_ok);
+
 /* ---- Mat (src/data_structures.rs:645-742, 768-913) ---------------------------------------- */
 /* out (r x c) = lhs (r x k, Fr) * mat (k x c, Com1) -- Matrix<Com1>::left_mul */
 int gs_com1_matmul(gs_ctx* ctx, size_t r, size_t k, size_t c, const gs_fr* lhs, const gs_com1* mat, gs_com1* out);

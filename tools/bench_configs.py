@@ -293,6 +293,34 @@ def bench_c4(args):
             "parity": "all honest proofs verify; one flipped Gamma bit in equation 3 of every type is the only rejection"}
 
 
+# ------------------------------------------------------------------------------------------------ wire formats
+def bench_ser(args):
+    """Decompression + on-curve + subgroup validation of the points a C5 batch carries."""
+    from gsutil import SeededRng
+    from workloads import multiples_g1, multiples_g2
+    eng, crs, _ = make_engine(6)
+    rng = SeededRng(6)
+    n = 1 << 16
+    D = 1 << 10
+    p1 = b"".join(multiples_g1(eng, [rng.fr() for _ in range(D)])) * (n // D)
+    p2 = b"".join(multiples_g2(eng, [rng.fr() for _ in range(D)])) * (n // D)
+    t_c1, w1 = wall(lambda: eng.serialize("g1", p1), 2)
+    t_c2, w2 = wall(lambda: eng.serialize("g2", p2), 2)
+    t_d1, (b1, ok1) = wall(lambda: eng.deserialize("g1", w1), 2)
+    t_d2, (b2, ok2) = wall(lambda: eng.deserialize("g2", w2), 2)
+    assert b1 == p1 and b2 == p2 and ok1 == b"\x01" * n and ok2 == b"\x01" * n
+    t_n1, _ = wall(lambda: eng.deserialize("g1", w1, check_subgroup=False), 2)
+    t_n2, _ = wall(lambda: eng.deserialize("g2", w2, check_subgroup=False), 2)
+    per_proof = 16 * t_d1 / n + 12 * t_d2 / n       # a 4x4 PPE instance: 16 G1 + 12 G2 points (A, c, theta; B, d, pi)
+    return {"config": "wire formats: zcash-compressed G1 / G2, 65,536 points each (e2e through the C ABI)", "unit": "points/s",
+            "g1_compress_per_sec": round(n / t_c1, 1), "g2_compress_per_sec": round(n / t_c2, 1),
+            "g1_decompress_validated_per_sec": round(n / t_d1, 1), "g2_decompress_validated_per_sec": round(n / t_d2, 1),
+            "g1_decompress_no_subgroup_check_per_sec": round(n / t_n1, 1), "g2_decompress_no_subgroup_check_per_sec": round(n / t_n2, 1),
+            "c5_deserialise_share": f"decoding the 28 points of one 4x4 PPE instance costs {per_proof * 1e6:.1f} us "
+                                    f"=> {1.0 / per_proof:.0f} instances/s",
+            "parity": "round trip byte-equal; encodings equal to oracle/serialize.py in tests/test_gpu_serialize.py"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("which", nargs="*", default=["c1", "c2", "c3", "c4"])
@@ -301,7 +329,7 @@ def main():
     ap.add_argument("--c4-eqs", type=int, default=256)
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
-    fns = {"c1": bench_c1, "c2": bench_c2, "c3": bench_c3, "c4": bench_c4}
+    fns = {"c1": bench_c1, "c2": bench_c2, "c3": bench_c3, "c4": bench_c4, "ser": bench_ser}
     for w in args.which:
         t0 = time.perf_counter()
         line = fns[w](args)
