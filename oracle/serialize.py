@@ -69,6 +69,33 @@ def in_subgroup_g2(pt) -> bool:
     return pt is None or G2.mul(pt, R) is None
 
 
+# the endomorphism membership tests ark-bls12-381 runs (Scott, ePrint 2021/1130 Sections 6 and 4); the constants
+# are fixed by phi(G) = -[x^2] G and psi(G2) = [x] G2 on the generators
+from .bls12_381 import X_ABS, G1_GEN, G2_GEN_FP2  # noqa: E402
+_XI = Fp2(1, 1)
+PSI_CX = _XI.pow((P - 1) // 3).inv()
+PSI_CY = _XI.pow((P - 1) // 2).inv()
+ENDO_BETA = 0x5F19672FDF76CE51BA69C6076A0F77EADDB3A93BE6F89688DE17D813620A00022E01FFFFFFFEFFFE
+
+
+def in_subgroup_g1_fast(pt) -> bool:
+    if pt is None:
+        return True
+    t1 = G1.mul(pt, X_ABS)
+    if t1 == pt:
+        return False
+    t2 = G1.mul(t1, X_ABS)
+    return t2 == (ENDO_BETA * pt[0] % P, -pt[1] % P)
+
+
+def in_subgroup_g2_fast(pt) -> bool:
+    if pt is None:
+        return True
+    t = G2.mul(pt, X_ABS)
+    psi = (pt[0].conj() * PSI_CX, pt[1].conj() * PSI_CY)
+    return t == G2.neg(psi)
+
+
 # ---------------------------------------------------------------- G1
 def g1_compress(pt) -> bytes:
     if pt is None:

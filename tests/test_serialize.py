@@ -87,3 +87,33 @@ def test_fp2_sqrt_and_scalars():
     assert ser.fp2_sqrt(Fp2(P - 1, 0)) is not None              # -1 = u^2
     assert ser.fr_from_bytes(ser.fr_to_bytes(12345)) == (True, 12345)
     assert ser.fr_from_bytes(R.to_bytes(32, "little"))[0] is False
+
+
+def test_endomorphism_membership_tests_agree_with_definition():
+    """The 64-bit endomorphism tests (what arkworks and serial.cu run) == [r]P = O, inside and outside G1 / G2."""
+    rnd = random.Random(11)
+    for _ in range(3):
+        assert ser.in_subgroup_g1_fast(g1_mul(G1_GEN, rnd.randrange(1, R)))
+        assert ser.in_subgroup_g2_fast(g2_mul(G2_GEN_FP2, rnd.randrange(1, R)))
+    found = 0
+    x = 1
+    while found < 6:
+        x += 1
+        y = ser.fp_sqrt((x ** 3 + 4) % P)
+        if y is None:
+            continue
+        slow = ser.in_subgroup_g1((x, y))
+        assert ser.in_subgroup_g1_fast((x, y)) == slow
+        found += 0 if slow else 1
+    # a point of the subgroup plus a point of small cofactor order is outside: h1 = (x-1)^2/3 has the factor 3
+    found = 0
+    c0 = 0
+    while found < 4:
+        c0 += 1
+        xx = Fp2(c0, 2)
+        yy = ser.fp2_sqrt(xx * xx * xx + Fp2(4, 4))
+        if yy is None:
+            continue
+        slow = ser.in_subgroup_g2((xx, yy))
+        assert ser.in_subgroup_g2_fast((xx, yy)) == slow
+        found += 0 if slow else 1
