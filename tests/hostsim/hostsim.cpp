@@ -3,7 +3,9 @@
 // that the CUDA kernels execute, against oracle/ (a separately written big-int restatement).
 #include <cstring>
 #include <vector>
+#include <cfenv>
 #include "../../groth-sahai-rs_b200/csrc/pairing.cuh"
+#include "../../groth-sahai-rs_b200/csrc/fpd.cuh"
 using namespace gs;
 
 #define LD(T, v, p) T v; memcpy(&v, p, sizeof(T))
@@ -249,3 +251,15 @@ extern "C" void hs_miller_v4(void* r, int n, const void* g1s, const void* g2s, i
   }
   ST(r, out);
 }
+
+// FP64-pipe sum of products (fpd.cuh): the host stand-in for __fma_rz is fma() under FE_TOWARDZERO
+extern "C" void hs_fp_mulsum_dfma(void* r, int nt, const void* a, const void* b) {
+  const fp* A = (const fp*)a; const fp* B = (const fp*)b; fp z;
+  const int old = fegetround();
+  fesetround(FE_TOWARDZERO);
+#define MS(NT) case NT: { fp x[NT], y[NT]; for (int i = 0; i < NT; i++) { x[i] = A[i]; y[i] = B[i]; } mulsum_dfma<NT>(z, x, y); \
+    fp z2; mulsum_dfma_rolled<NT>(z2, x, [&](int t, int w) { return (uint64_t)y[t].l[w]; }); if (!z2.equals(z)) z.set_zero(); } break;
+  switch (nt) { MS(1) MS(2) MS(3) MS(4) MS(6) MS(8) default: z.set_zero(); }
+#undef MS
+  fesetround(old);
+  ST(r, z); }

@@ -13,7 +13,7 @@ SO = os.path.join(HERE, "hostsim", "libhostsim.so")
 @pytest.fixture(scope="module")
 def L():
     src = os.path.join(HERE, "hostsim", "hostsim.cpp")
-    subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-o", SO, src])
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-frounding-math", "-shared", "-fPIC", "-o", SO, src])
     return ctypes.CDLL(SO)
 
 
@@ -70,6 +70,35 @@ def test_fp_mulsum(L):
         ab = b"".join(raw(mont(x)) for x in a)
         bb = b"".join(raw(mont(x) + mont(y)) for x, y in b)
         got = fp_i(call(L.hs_fp_mulsum, 48, 3, ab, bb))
+        assert got == sum(x * (y + z) for x, (y, z) in zip(a, b)) % P
+
+
+def test_fp_mulsum_dfma(L):
+    """fpd.cuh: the same sums of products computed with FP64 FMAs in round-toward-zero on 8 x 48-bit limbs
+    (the experimental FP64-pipe building block) must equal the big-int value AND the integer mulsum bit for bit."""
+    Rm = pow(2, 384, P)
+    mont = lambda x: x * Rm % P
+    def raw(x): return x.to_bytes(48, "little")
+    for nt in (1, 2, 3, 4, 6, 8):
+        for it in range(300):
+            if it < 20:
+                a = [P - 1] * nt; b = [P - 1] * nt
+            elif it < 40:
+                a = [rng.choice([0, 1, P - 1, 2 ** 48 - 1, 2 ** 48, 2 ** 380]) for _ in range(nt)]
+                b = [rng.choice([0, 1, P - 1, 2 ** 96 - 1, 2 ** 380]) for _ in range(nt)]
+            else:
+                a = [rfp() for _ in range(nt)]; b = [rfp() for _ in range(nt)]
+            ab, bb = b"".join(fp_b(x) for x in a), b"".join(fp_b(x) for x in b)
+            got = call(L.hs_fp_mulsum_dfma, 48, nt, ab, bb)
+            assert fp_i(got) == sum(x * y for x, y in zip(a, b)) % P, (nt, it)
+            assert got == call(L.hs_fp_mulsum, 48, nt, ab, bb)
+    for it in range(200):                                    # unreduced operands (< 2p), 3 terms x 2 units
+        a = [rfp() for _ in range(3)]; b = [(rfp(), rfp()) for _ in range(3)]
+        if it < 10:
+            a = [P - 1] * 3; b = [(P - 1, P - 1)] * 3
+        ab = b"".join(raw(mont(x)) for x in a)
+        bb = b"".join(raw(mont(x) + mont(y)) for x, y in b)
+        got = fp_i(call(L.hs_fp_mulsum_dfma, 48, 3, ab, bb))
         assert got == sum(x * (y + z) for x, (y, z) in zip(a, b)) % P
 
 

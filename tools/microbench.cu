@@ -7,6 +7,7 @@
 #include "../groth-sahai-rs_b200/csrc/fp.cuh"
 #include "../groth-sahai-rs_b200/csrc/tower.cuh"
 #include "../groth-sahai-rs_b200/csrc/modinv.cuh"
+#include "../groth-sahai-rs_b200/csrc/fpd.cuh"
 using namespace gs;
 
 __global__ void k_imad_wide(unsigned long long* out, unsigned a, unsigned b, int iters) {
@@ -123,6 +124,60 @@ __global__ void k_dfma_imad_mix(unsigned long long* out, double a, double b, uns
     out[blockIdx.x * blockDim.x + threadIdx.x] = x0 ^ x1 ^ x2 ^ x3 ^ x4 ^ x5 ^ x6 ^ x7;
   }
 }
+// sums of 4 Fp products with one Montgomery reduction: integer pipe (fp::mulsum) vs FP64 pipe (fpd.cuh), and
+// both at once on alternating warps.  mode: 0 = all warps integer, 1 = all warps FP64, 2 = odd warps FP64;
+// `it_i` / `it_d` = chain length of the integer / FP64 warps (0 switches that half off).
+template <int mode>
+__global__ void __launch_bounds__(128) k_mulsum_mix(fp* out, const fp* in, int it_i, int it_d) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  fp a[4], b[4];
+  for (int j = 0; j < 4; j++) {
+    a[j] = in[t + j];
+    b[j] = in[t + 4 + j];
+  }
+  const bool dfma = mode == 1 || (mode == 2 && ((threadIdx.x >> 5) & 1));
+  fp r = a[0];
+  if (dfma) {
+    for (int i = 0; i < it_d; i++) {
+      mulsum_dfma<4>(r, a, b);
+      a[i & 3] = r;
+    }
+  } else {
+    for (int i = 0; i < it_i; i++) {
+      fp::mulsum<4>(r, a, b);
+      a[i & 3] = r;
+    }
+  }
+  out[t] = r;
+}
+// the same with the ROLLED FP64 form (b operands in shared memory, word-major / thread-minor):
+// mode 3 = all warps FP64 rolled, 4 = odd warps FP64 rolled + even warps integer
+template <int mode>
+__global__ void __launch_bounds__(128) k_mulsum_mix_r(fp* out, const fp* in, int it_i, int it_d) {
+  __shared__ uint32_t sb[4 * 12 * 128];
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  fp a[4], b[4];
+  for (int j = 0; j < 4; j++) {
+    a[j] = in[t + j];
+    b[j] = in[t + 4 + j];
+    for (int w = 0; w < 12; w++) sb[(j * 12 + w) * 128 + threadIdx.x] = b[j].l[w];
+  }
+  __syncthreads();
+  const bool dfma = mode == 3 || (mode == 4 && ((threadIdx.x >> 5) & 1));
+  fp r = a[0];
+  if (dfma) {
+    for (int i = 0; i < it_d; i++) {
+      mulsum_dfma_rolled<4>(r, a, [&](int tt, int w) { return (uint64_t)sb[(tt * 12 + w) * 128 + threadIdx.x]; });
+      a[i & 3] = r;
+    }
+  } else {
+    for (int i = 0; i < it_i; i++) {
+      fp::mulsum<4>(r, a, b);
+      a[i & 3] = r;
+    }
+  }
+  out[t] = r;
+}
 template <class K, class... A>
 float timeit(K k, dim3 g, dim3 b, A... args) {
   cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
@@ -168,6 +223,25 @@ int main() {
     float mb = timeit(k_mix, g, b, (fp*)buf + (1 << 20), (const fp*)buf, 0, im);
     float mc = timeit(k_mix, g, b, (fp*)buf + (1 << 20), (const fp*)buf, ii, im);
     printf("warps/SM %2d: half warps safegcd alone %.3f ms, half warps fp::mul alone %.3f ms, both %.3f ms\n", wps, ma, mb, mc);
+  }
+  for (int wps : {4, 8, 12, 16}) {  // 4-warp blocks, wps / 4 blocks per SM (as many as the registers allow)
+    dim3 g(sms * (wps / 4)), b(128);
+    int it = 400;
+    fp* o = (fp*)buf + (1 << 20);
+    float mi = timeit(k_mulsum_mix<0>, g, b, o, (const fp*)buf, it, it);
+    float md = timeit(k_mulsum_mix<1>, g, b, o, (const fp*)buf, it, it);
+    float hi = timeit(k_mulsum_mix<2>, g, b, o, (const fp*)buf, it, 0);
+    float hd = timeit(k_mulsum_mix<2>, g, b, o, (const fp*)buf, 0, it);
+    float hb = timeit(k_mulsum_mix<2>, g, b, o, (const fp*)buf, it, it);
+    double n = (double)sms * wps * 32 * it;
+    printf("warps/SM %2d: mulsum<4> integer %.3e/s   FP64 %.3e/s   | half warps: integer alone %.3f ms, FP64 alone %.3f ms, both %.3f ms "
+           "=> %.3e/s combined\n", wps, n / mi * 1e3, n / md * 1e3, hi, hd, hb, n / hb * 1e3);
+    float rd = timeit(k_mulsum_mix_r<3>, g, b, o, (const fp*)buf, it, it);
+    float ri = timeit(k_mulsum_mix_r<4>, g, b, o, (const fp*)buf, it, 0);
+    float rdd = timeit(k_mulsum_mix_r<4>, g, b, o, (const fp*)buf, 0, it);
+    float rb = timeit(k_mulsum_mix_r<4>, g, b, o, (const fp*)buf, it, it);
+    printf("             rolled FP64 form: all warps %.3e/s   | half warps: integer alone %.3f ms, FP64 alone %.3f ms, both %.3f ms "
+           "=> %.3e/s combined\n", n / rd * 1e3, ri, rdd, rb, n / rb * 1e3);
   }
   for (int wps : {8, 16, 32}) {
     int iters = 4096;
