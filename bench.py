@@ -42,10 +42,12 @@ def work_model(m, n):
     (the cooperative kernels trade Karatsuba for lazy-reduced schoolbook sums and execute more)."""
     cx = cy = 2
     pairs = 2 * (n + cx + cy) + 2 * (n + m + cx + cy)            # Miller pairs over the 4 ComT entries
-    g2_points = 2 * n + m + 2 * cx + 2 * cy                        # non-identity G2 coordinates to walk
+    g2_points = 2 * n + m + 2 * cx                                 # G2 coordinates walked per proof (the CRS points
+    fixed_pairs = 2 * 2 * cy                                       # v_1, v_2 have their lines stored at key load)
     return {
         "k_miller4": 4 * 62 * M_SQR12 + pairs * 68 * M_014,
-        "k_g2_prepare4": g2_points * (63 * M_G2_DBL + 5 * M_G2_ADD) + pairs * 68 * M_LINE,
+        "k_g2_prepare4": g2_points * (63 * M_G2_DBL + 5 * M_G2_ADD) + (pairs - fixed_pairs) * 68 * M_LINE,
+        "k_fixed_tiles": fixed_pairs * 68 * M_LINE,
         "k_final_exp3": 4 * M_FE,
         # Straus, signed 4-bit windows: 64 windows x (4 shared doublings + one addition per base, 15/16 non-zero)
         "k_vmsm_partial": 2 * n * (256 * M_G1_DBL + 64 * m * (15 / 16) * M_G1_MADD),

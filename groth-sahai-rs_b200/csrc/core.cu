@@ -168,6 +168,8 @@ static int load_crs_device(gs_ctx* ctx, const gs_crs* crs) {
   if (rc) return rc;
   rc = gsi::fixed_table_rebuild<Fp2Ops>(ctx, 8);
   if (rc) return rc;
+  rc = gsi::crs_lines_build(ctx);  // (lambda, mu) of the Miller walk of v1, v2, W2: they never change with the proof
+  if (rc) return rc;
   CUDA_TRY(cudaStreamSynchronize(ctx->stream));
   ctx->crs_loaded = true;
   return GS_OK;

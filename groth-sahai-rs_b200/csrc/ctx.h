@@ -29,7 +29,8 @@ struct gs_ctx {
   bool crs_loaded = false;
   gs_fixed_table<gs::FpOps> tab1;
   gs_fixed_table<gs::Fp2Ops> tab2;
-  uint32_t* crs_lines = nullptr;  // prepared line triples of the fixed G2 points v1.0 v1.1 v2.0 v2.1 W2.0 W2.1 (pairing.cu)
+  gs::fp2* crs_lines = nullptr;   // (lambda, mu) per Miller step of the fixed G2 points v1.0 v1.1 v2.0 v2.1 W2.0 W2.1:
+                                  // crs_lines[(pid*68 + step)*2 + {0,1}]  (pairing.cu crs_lines_build)
   uint32_t* fe_prog = nullptr;    // op program of the cooperative final exponentiation (finalexp.cu)
   int fe_nops = 0;
   uint64_t launches = 0;
@@ -125,8 +126,13 @@ int final_exp_init(gs_ctx* ctx);
 // X, Y: device slot arrays [2][K][nprob]  ->  ComT values (out_comt, AoS [p][4]) or per-entry verdict
 // bytes ok4[4][nprob] (compared with 1 / target).
 // With out_partial (AoS [p][4]) the un-exponentiated Miller products are returned instead (sharded statements).
+// slot_kind (host, K entries, or null = all GS_SLOT_WALK) tells what is known about Y_k from the shape alone.
+constexpr uint8_t GS_SLOT_WALK = 0;     // arbitrary Com2: walk both coordinates
+constexpr uint8_t GS_SLOT_WALK_B1 = 1;  // Y_k = (O, y): only coordinate 1 exists (iota_2)
+constexpr uint8_t GS_SLOT_FIXED = 2;    // GS_SLOT_FIXED + j: Y_k is the CRS element v_1 (j = 0), v_2 (1) or W2 (2)
 int run_pairing_product(gs_ctx* ctx, Scratch& sc, const g1_aff* X, const g2_aff* Y, size_t nprob, int K, fp12* out_comt,
-                        uint8_t* ok4, const fp12* target, fp12* out_partial);
+                        uint8_t* ok4, const fp12* target, fp12* out_partial, const uint8_t* slot_kind = nullptr);
+int crs_lines_build(gs_ctx* ctx);
 
 // finalexp.cu: f = prod_chunks F[(ch*4 + e)*nprob + p]; g = FE(f); writes out_comt[p*4+e] and/or ok4[e*nprob + p]
 int launch_final_exp(gs_ctx* ctx, const fp12* F, size_t nprob, int nchunk, fp12* out_comt, uint8_t* ok4, const fp12* target);

@@ -64,50 +64,54 @@ __global__ void __launch_bounds__(128) k_g1_prep(const g1_aff* __restrict__ X, u
 // in thread-local memory (L1/L2-resident, lane-interleaved by the hardware): shared memory would cap the
 // kernel at 8 warps per SM, and the walk is latency-bound (long dependent chains in the division steps), so
 // occupancy matters more than the few hundred bytes of local traffic per step.
-struct g2_pts_gmem {  // the fixed points Q_i (read again at the 5 addition steps only)
-  const g2_aff* q;    // &Y[(b*K + g*G2_E) * nprob + p]
-  size_t stride;      // nprob
-  __device__ GS_INL void ld(int i, fp2& X, fp2& Y) const {
-    const g2_aff* p = q + (size_t)i * stride;
-    X = p->x;
-    Y = p->y;
-  }
-};
-// tile stores bypass the usual L2 retention (st.global.cs): the tiles are written once and read once by
-// k_miller4 much later, while the running points in local memory must stay L2-resident -- with default
-// stores one launch moved 43 GB of DRAM writes for 8.6 GB of tiles (profiles/r01b_ncu_full_summary.csv).
+// tile stores bypass the usual L2 retention (st.global.cs): the tiles are written once and read once by k_miller4
+// much later, while the running points in local memory should stay L2-resident.
 __device__ GS_INL void cq_st_stream(uint32_t* p, const fp& a) {
 #pragma unroll
   for (int q = 0; q < 3; q++)
     __stcs((uint4*)(p + q * CQ_QUAD), make_uint4(a.l[q * 4], a.l[q * 4 + 1], a.l[q * 4 + 2], a.l[q * 4 + 3]));
 }
-// E = G2 points walked per thread (one shared inversion per Miller step): 4 for throughput, 1 when the whole
-// batch is a fraction of one wave and only the length of the serial chain counts (single statements).
+// walk[e] = (b << 31) | k: the (coordinate, slot) pairs that have a G2 point to walk, packed so that every thread's E
+// points exist (slots known to be iota_2 images contribute only b = 1, CRS slots none: k_fixed_tiles serves them).
+struct g2_pts_list {  // the fixed points Q_i of one thread (read again at the 5 addition steps only)
+  const g2_aff* q[8];
+  __device__ GS_INL void ld(int i, fp2& X, fp2& Y) const {
+    X = q[i]->x;
+    Y = q[i]->y;
+  }
+};
 template <int E>
 __global__ void __launch_bounds__(128, 4) k_g2_prepare4(const uint32_t* __restrict__ PW, const g2_aff* __restrict__ Y,
                                                         uint32_t* __restrict__ tiles, uint32_t* __restrict__ masks,
-                                                        size_t nprob, size_t p0, size_t np, int K, int S) {
-  const int G = (K + E - 1) / E;
+                                                        size_t nprob, size_t p0, size_t np, int K, int S,
+                                                        const uint32_t* __restrict__ walk, int nwalk) {
+  const int G = (nwalk + E - 1) / E;
   size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const bool inrange = q < 2 * (size_t)G * np;
+  const bool inrange = q < (size_t)G * np;
   if (!inrange) q = 0;
   const size_t pl = q % np;
-  const int g = (int)((q / np) % G), b = (int)(q / (np * G));
+  const int g = (int)(q / np);
   fp2 Tx[E], Ty[E];
   g2_pts_arr T{Tx, Ty};
-  g2_pts_gmem Q{&Y[((size_t)b * K + (size_t)g * E) * nprob + p0 + pl], nprob};
+  g2_pts_list Q;
   bool act[E], acta[E][2];
   size_t tb[E][2];
-  int lanes[E];
+  int lanes[E], kslot[E];
   bool any = false;
 #pragma unroll
   for (int i = 0; i < E; i++) {
-    const int k = g * E + i;
+    const int e = g * E + i;
     act[i] = false;
     acta[i][0] = acta[i][1] = false;
     tb[i][0] = tb[i][1] = 0;
     lanes[i] = 0;
-    if (k >= K || !inrange) continue;
+    kslot[i] = 0;
+    Q.q[i] = Y;
+    if (e >= nwalk || !inrange) continue;
+    const uint32_t we = walk[e];
+    const int b = (int)(we >> 31), k = (int)(we & 0x7FFFFFFFu);
+    kslot[i] = k;
+    Q.q[i] = &Y[((size_t)b * K + k) * nprob + p0 + pl];
     fp2 qx, qy;
     Q.ld(i, qx, qy);
     if (qx.is_zero() && qy.is_zero()) continue;
@@ -137,7 +141,7 @@ __global__ void __launch_bounds__(128, 4) k_g2_prepare4(const uint32_t* __restri
 #pragma unroll 1
     for (int w = 0; w < nl; w++, idx++) {
       g2_affine_step<E>(T, Q, act, w == 1, [&](int i, const fp2& lam, const fp2& mu) {
-        const int k = g * E + i;
+        const int k = kslot[i];
 #pragma unroll 1
         for (int a = 0; a < 2; a++) {
           if (!acta[i][a]) continue;
@@ -159,6 +163,85 @@ __global__ void __launch_bounds__(128, 4) k_g2_prepare4(const uint32_t* __restri
           cq_st_stream(cq_ptr(o, 3, lanes[i]), v);
         }
       }, [] { __syncthreads(); });
+    }
+  }
+}
+
+// ------------------------------------------------------------------ CRS points: the walk is done once per key
+// thread pid (< 6) walks v1.0 v1.1 v2.0 v2.1 W2.0 W2.1 and stores (lambda, mu) of every Miller step
+__global__ void k_crs_lines(const crs_dev* __restrict__ crs, fp2* __restrict__ out) {
+  const int pid = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pid >= 6) return;
+  const g2_aff P = pid < 4 ? crs->v[pid >> 1][pid & 1] : crs->w2[pid & 1];
+  fp2 Tx[1] = {P.x}, Ty[1] = {P.y}, Qx[1] = {P.x}, Qy[1] = {P.y};
+  g2_pts_arr T{Tx, Ty}, Qa{Qx, Qy};
+  bool act[1] = {!P.is_inf()};
+  int idx = 0;
+  for (int bit = 62; bit >= 0; bit--) {
+    const int nl = ((GS_X_ABS >> bit) & 1) ? 2 : 1;
+    for (int w = 0; w < nl; w++, idx++) {
+      fp2 l, m;
+      l.set_zero();
+      m.set_zero();
+      g2_affine_step<1>(T, Qa, act, w == 1, [&](int, const fp2& lam, const fp2& mu) {
+        l = lam;
+        m = mu;
+      }, [] {});
+      out[((size_t)pid * GS_NUM_LINES + idx) * 2] = l;
+      out[((size_t)pid * GS_NUM_LINES + idx) * 2 + 1] = m;
+    }
+  }
+}
+// thread -> (fixed slot f, coordinate b, problem): the tiles of slot fk[f] from the stored (lambda, mu) of CRS point
+// fpid[f]*2 + b, evaluated at the two G1 coordinates of the slot: 8 Fp products per step, no walk, no inversion
+struct fixed_slots {
+  int n;
+  int k[4];
+  int pid[4];
+};
+__global__ void __launch_bounds__(128) k_fixed_tiles(const uint32_t* __restrict__ PW, const fp2* __restrict__ lines,
+                                                     const crs_dev* __restrict__ crs, uint32_t* __restrict__ tiles,
+                                                     uint32_t* __restrict__ masks, size_t p0, size_t np, int K, int S,
+                                                     fixed_slots fs) {
+  size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= (size_t)fs.n * 2 * np) return;
+  (void)p0;
+  const size_t pl = q % np;
+  const int b = (int)((q / np) & 1), f = (int)(q / (2 * np));
+  const int k = fs.k[f], pt = fs.pid[f] * 2 + b;
+  const g2_aff P = pt < 4 ? crs->v[pt >> 1][pt & 1] : crs->w2[pt & 1];
+  if (P.is_inf()) return;
+  const int ch = k / S, kk = k % S;
+  const size_t A = (size_t)ch * np + pl;
+  const int lane = (int)(A & 31);
+#pragma unroll 1
+  for (int a = 0; a < 2; a++) {
+    const uint32_t* pw = PW + ((((size_t)a * K + k) * 2) * 12) * np + pl;
+    fp s, wv;
+    uint32_t nz = 0;
+#pragma unroll
+    for (int j = 0; j < 12; j++) {
+      s.l[j] = pw[(size_t)j * np];
+      wv.l[j] = pw[(size_t)(12 + j) * np];
+      nz |= wv.l[j];
+    }
+    if (!nz) continue;  // identity G1 point: pair dropped
+    const size_t bid = (A >> 5) * 4 + (size_t)(2 * a + b);
+    atomicOr(&masks[bid * S + kk], 1u << lane);
+    uint32_t* o = tiles + ((bid * S + kk) * GS_NUM_LINES) * (size_t)M4_TILE;
+    const fp2* L = lines + (size_t)pt * GS_NUM_LINES * 2;
+#pragma unroll 1
+    for (int idx = 0; idx < GS_NUM_LINES; idx++, o += M4_TILE) {
+      const fp2 lam = L[idx * 2], mu = L[idx * 2 + 1];
+      fp v;
+      fp_mul_n(v, mu.c0, wv);
+      cq_st_stream(cq_ptr(o, 0, lane), v);
+      fp_mul_n(v, mu.c1, wv);
+      cq_st_stream(cq_ptr(o, 1, lane), v);
+      fp_mul_n(v, lam.c0, s);
+      cq_st_stream(cq_ptr(o, 2, lane), v);
+      fp_mul_n(v, lam.c1, s);
+      cq_st_stream(cq_ptr(o, 3, lane), v);
     }
   }
 }
@@ -320,6 +403,12 @@ __global__ void k_linear_map_slots(int type, const void* target, const crs_dev* 
 
 }  // namespace gs
 
+int gsi::crs_lines_build(gs_ctx* ctx) {
+  if (!ctx->crs_lines) CUDA_TRY(cudaMalloc(&ctx->crs_lines, (size_t)6 * GS_NUM_LINES * 2 * sizeof(fp2)));
+  LAUNCH_CFG(k_crs_lines, 6, 32, 0, ctx->crs, ctx->crs_lines);
+  return GS_OK;
+}
+
 int gsi::pairing_init(gs_ctx* ctx) {
   CUDA_TRY(cudaFuncSetAttribute(k_miller4, cudaFuncAttributeMaxDynamicSharedMemorySize, CQ_GROUPS * M4_SMEM));
   return GS_OK;
@@ -332,7 +421,7 @@ int gsi::pairing_init(gs_ctx* ctx) {
 // bytes of HBM; a pass is sized to a whole number of k_miller4 waves (2 groups x 148 SMs x 32 accumulators
 // / 4 entries = 2,368 problems per wave) when the batch is large enough.
 int gsi::run_pairing_product(gs_ctx* ctx, Scratch& sc, const g1_aff* X, const g2_aff* Y, size_t nprob, int K,
-                               fp12* out_comt, uint8_t* ok4, const fp12* target, fp12* out_partial) {
+                               fp12* out_comt, uint8_t* ok4, const fp12* target, fp12* out_partial, const uint8_t* slot_kind) {
   const size_t wave = 2368;
   if (K == 0) {  // a shard that owns no slot: empty product
     if (!out_partial) FAIL(GS_EARG, "pairing product over zero slots");
@@ -359,6 +448,30 @@ int gsi::run_pairing_product(gs_ctx* ctx, Scratch& sc, const g1_aff* X, const g2
     pc -= pc % 32;
   }
   const size_t nblk_max = ((pc * nchunk + 31) / 32) * 4;
+  // which (coordinate, slot) pairs have a point to walk; which slots are CRS points with stored lines
+  std::vector<uint32_t> hwalk;
+  fixed_slots fs;
+  fs.n = 0;
+  int nfixed = 0;
+  for (int k = 0; slot_kind && k < K; k++) nfixed += slot_kind[k] >= GS_SLOT_FIXED ? 1 : 0;
+  const bool use_fixed = ctx->crs_lines && nfixed > 0 && nfixed <= 4;  // no shape has more than 4 CRS slots
+  for (int b = 0; b < 2; b++)
+    for (int k = 0; k < K; k++) {
+      const uint8_t kind = slot_kind ? slot_kind[k] : GS_SLOT_WALK;
+      if (kind >= GS_SLOT_FIXED && use_fixed) {
+        if (b == 0) {
+          fs.k[fs.n] = k;
+          fs.pid[fs.n] = kind - GS_SLOT_FIXED;
+          fs.n++;
+        }
+        continue;
+      }
+      if (kind == GS_SLOT_WALK_B1 && b == 0) continue;
+      hwalk.push_back(((uint32_t)b << 31) | (uint32_t)k);
+    }
+  const int nwalk = (int)hwalk.size();
+  uint32_t* dwalk;
+  CUDA_TRY(upload(ctx, sc, &dwalk, hwalk.data(), hwalk.size()));
   uint32_t *tiles, *masks, *PW;
   fp12* F;
   CUDA_TRY(sc.alloc(&PW, 2 * (size_t)K * 24 * pc));
@@ -372,10 +485,11 @@ int gsi::run_pairing_product(gs_ctx* ctx, Scratch& sc, const g1_aff* X, const g2
     LAUNCH(k_g1_prep, 2 * (size_t)K * np, X, PW, nprob, p0, np, K);
     // (6 points per thread was measured too: 162.6 ms vs 151.0 ms per 65,536 proofs -- the extra local memory costs
     // more than the shared inversion saves)
-    if (2 * (size_t)((K + 3) / 4) * np < 16384)
-      LAUNCH_CFG(k_g2_prepare4<1>, 2 * (size_t)K * np, 128, 0, PW, Y, tiles, masks, nprob, p0, np, K, S);
+    if (fs.n) LAUNCH(k_fixed_tiles, (size_t)fs.n * 2 * np, PW, ctx->crs_lines, ctx->crs, tiles, masks, p0, np, K, S, fs);
+    if ((size_t)((nwalk + 3) / 4) * np < 16384)
+      LAUNCH_CFG(k_g2_prepare4<1>, (size_t)nwalk * np, 128, 0, PW, Y, tiles, masks, nprob, p0, np, K, S, dwalk, nwalk);
     else
-      LAUNCH_CFG(k_g2_prepare4<4>, 2 * (size_t)((K + 3) / 4) * np, 128, 0, PW, Y, tiles, masks, nprob, p0, np, K, S);
+      LAUNCH_CFG(k_g2_prepare4<4>, (size_t)((nwalk + 3) / 4) * np, 128, 0, PW, Y, tiles, masks, nprob, p0, np, K, S, dwalk, nwalk);
     LAUNCH_CFG(k_miller4, ((nblk + CQ_GROUPS - 1) / CQ_GROUPS) * CQ_BLOCK_THREADS, CQ_BLOCK_THREADS, CQ_GROUPS * M4_SMEM, tiles, masks,
                F, nprob, p0, np, S, nchunk, nblk);
   }

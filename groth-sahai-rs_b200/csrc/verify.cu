@@ -499,13 +499,21 @@ static int verify_impl(gs_ctx* ctx, int type, size_t count, size_t m, size_t n, 
       Xp = Xo;
       Yp = Yo;
     }
+    // what the shape alone says about the G2 side of every slot (k_verify_assemble): CRS points have stored lines,
+    // iota_2 images have no first coordinate
+    std::vector<uint8_t> kind_all(s.K, gsi::GS_SLOT_WALK), kind;
+    for (int k = s.sB; k < s.sPi; k++) kind_all[k] = s.groupB ? gsi::GS_SLOT_WALK_B1 : (uint8_t)(gsi::GS_SLOT_FIXED + 2);
+    for (int j = 0; j < s.cy; j++) kind_all[s.sTh + j] = (uint8_t)(gsi::GS_SLOT_FIXED + j);
+    if (type == 1 || type == 3) kind_all[s.sT] = (uint8_t)(gsi::GS_SLOT_FIXED + 2);
+    if (type == 2) kind_all[s.sT] = gsi::GS_SLOT_WALK_B1;
+    for (int k = world > 1 ? rank : 0; k < s.K; k += world > 1 ? world : 1) kind.push_back(kind_all[k]);
     int rc;
     if (out_partial_dev) {
-      rc = gsi::run_pairing_product(ctx, sc, Xp, Yp, nprob, Ko, nullptr, nullptr, nullptr, out_partial_dev + off * 4);
+      rc = gsi::run_pairing_product(ctx, sc, Xp, Yp, nprob, Ko, nullptr, nullptr, nullptr, out_partial_dev + off * 4, kind.data());
       if (rc) return rc;
     } else {
       rc = gsi::run_pairing_product(ctx, sc, Xp, Yp, nprob, Ko, nullptr, ok4, type == GS_PPE ? (const fp12*)v.target : nullptr,
-                                    nullptr);
+                                    nullptr, kind.data());
       if (rc) return rc;
       LAUNCH(k_and4, nprob, ok4, out_ok_dev + off, nprob);
     }
