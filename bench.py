@@ -49,8 +49,9 @@ def work_model(m, n):
         "k_g2_prepare4": g2_points * (63 * M_G2_DBL + 5 * M_G2_ADD) + (pairs - fixed_pairs) * 68 * M_LINE,
         "k_fixed_tiles": fixed_pairs * 68 * M_LINE,
         "k_final_exp3": 4 * M_FE,
-        # Straus, signed 4-bit windows: 64 windows x (4 shared doublings + one addition per base, 15/16 non-zero)
-        "k_vmsm_partial": 2 * n * (256 * M_G1_DBL + 64 * m * (15 / 16) * M_G1_MADD),
+        # Straus over the GLV halves, signed 4-bit windows: 32 windows x (4 shared doublings + one addition per
+        # half-scalar, 15/16 non-zero)
+        "k_vmsm_partial": 2 * n * (128 * M_G1_DBL + 32 * 2 * m * (15 / 16) * M_G1_MADD),
         "k_vmsm_tables": 2 * m * (M_G1_DBL + 6 * M_G1_MADD + 8 * 9),
         "k_vmsm_reduce": 2 * n * (M_G1_MADD + 9),
         "pairs": pairs,

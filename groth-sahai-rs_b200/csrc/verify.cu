@@ -88,8 +88,88 @@ __device__ GS_INL g1_aff vmsm_base(const verify_shape& s, const verify_args& v, 
   return crs->w1[a];
 }
 // thread -> (p, i, a): tab[((i*2 + a)*8 + d) * nprob + p] = (d+1) * base
+// GLV: k P = k1 P + k2 (-phi(P)) with k = k1 + k2 x^2 (k1, k2 < 2^128), phi(x, y) = (beta x, y) = -[x^2] P on G1
+// (the relation serial.cu's membership test uses).  The multiples of -phi(B) share y (negated) with those of B and
+// have x' = beta x, stored in tabx by k_vmsm_tables; the Straus loop then runs 32 windows instead of 64.
+static __device__ __constant__ uint32_t VM_BETA[12] = {0x798a64e8u, 0x30f1361bu, 0x7ece5a2au, 0xf3b8ddabu, 0xc61577f7u, 0x16a8ca3au,
+                                                       0x74fd029bu, 0xc26a2ff8u, 0x60701c6eu, 0x3636b766u, 0x241b6160u, 0x051ba4abu};
+static __device__ __constant__ uint32_t VM_X2[4] = {0x00000000u, 0x00000001u, 0x0001a402u, 0xac45a401u};                 // x^2
+static __device__ __constant__ uint32_t VM_MU[5] = {0xf6cfee2eu, 0x63f6e522u, 0xe01faaddu, 0x7c6becf1u, 0x00000001u};   // 2^256 / x^2
+// k (canonical, < r) -> k1 = k mod x^2, k2 = k div x^2
+__device__ GS_NOINL void glv_split(uint32_t k1[4], uint32_t k2[4], const uint32_t k[8]) {
+  uint32_t t[13];
+  for (int i = 0; i < 13; i++) t[i] = 0;
+  for (int i = 0; i < 8; i++) {
+    uint32_t carry = 0;
+    for (int j = 0; j < 5; j++) {
+      uint64_t vv = (uint64_t)k[i] * VM_MU[j] + t[i + j] + carry;
+      t[i + j] = (uint32_t)vv;
+      carry = (uint32_t)(vv >> 32);
+    }
+    t[i + 5] = carry;
+  }
+  uint32_t q[4] = {t[8], t[9], t[10], t[11]};  // floor(k mu / 2^256) in {k div x^2 - 1, k div x^2}
+  uint32_t pr[8];
+  for (int i = 0; i < 8; i++) pr[i] = 0;
+  for (int i = 0; i < 4; i++) {
+    uint32_t carry = 0;
+    for (int j = 0; j < 4; j++) {
+      uint64_t vv = (uint64_t)q[i] * VM_X2[j] + pr[i + j] + carry;
+      pr[i + j] = (uint32_t)vv;
+      carry = (uint32_t)(vv >> 32);
+    }
+    pr[i + 4] = carry;
+  }
+  uint32_t rem[8];
+  uint32_t borrow = 0;
+  for (int i = 0; i < 8; i++) {
+    uint64_t d = (uint64_t)k[i] - pr[i] - borrow;
+    rem[i] = (uint32_t)d;
+    borrow = (uint32_t)(d >> 63);
+  }
+  for (int it = 0; it < 2; it++) {
+    bool ge = (rem[4] | rem[5] | rem[6] | rem[7]) != 0;
+    if (!ge) {
+      ge = true;
+      for (int i = 3; i >= 0; i--)
+        if (rem[i] != VM_X2[i]) {
+          ge = rem[i] > VM_X2[i];
+          break;
+        }
+    }
+    if (!ge) break;
+    borrow = 0;
+    for (int i = 0; i < 8; i++) {
+      uint64_t d = (uint64_t)rem[i] - (i < 4 ? VM_X2[i] : 0u) - borrow;
+      rem[i] = (uint32_t)d;
+      borrow = (uint32_t)(d >> 63);
+    }
+    uint32_t c = 1;
+    for (int i = 0; i < 4; i++) {
+      uint64_t a = (uint64_t)q[i] + c;
+      q[i] = (uint32_t)a;
+      c = (uint32_t)(a >> 32);
+    }
+  }
+  for (int i = 0; i < 4; i++) {
+    k1[i] = rem[i];
+    k2[i] = q[i];
+  }
+}
+// biased 128-bit scalar k' = k + 0x88..8 (32 nibbles): digit_w = nibble_w(k') - 8 in [-8, 7] for w < 32, digit_32 = carry
+__device__ GS_INL void glv_bias(uint32_t out[5], const uint32_t k[4]) {
+  uint32_t carry = 0;
+#pragma unroll
+  for (int w = 0; w < 4; w++) {
+    uint64_t t = (uint64_t)k[w] + 0x88888888u + carry;
+    out[w] = (uint32_t)t;
+    carry = (uint32_t)(t >> 32);
+  }
+  out[4] = carry;
+}
+
 __global__ void __launch_bounds__(128) k_vmsm_tables(verify_shape s, verify_args v, const crs_dev* __restrict__ crs,
-                                                     g1_aff* __restrict__ tab, size_t nprob) {
+                                                     g1_aff* __restrict__ tab, fp* __restrict__ tabx, size_t nprob) {
   __shared__ fp sm[2 * 128];
   size_t id = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   bool active = id < nprob * (size_t)s.nbases * 2;
@@ -128,7 +208,14 @@ __global__ void __launch_bounds__(128) k_vmsm_tables(verify_shape s, verify_args
     fp::mul(inv, inv, z);
     g1_aff e;
     g1_jac::to_affine_with_zinv(e, mlt[d], zi);
-    if (active) out[(size_t)d * nprob] = e;
+    fp beta, bx;
+#pragma unroll
+    for (int j = 0; j < 12; j++) beta.l[j] = VM_BETA[j];
+    fp::mul(bx, e.x, beta);
+    if (active) {
+      out[(size_t)d * nprob] = e;
+      tabx[((size_t)(i * 2 + a) * GS_VTAB + d) * nprob + p] = bx;
+    }
   }
 }
 
@@ -150,7 +237,7 @@ __device__ GS_INL bool vmsm_scalar(fr& sv, const verify_shape& s, const verify_a
 
 // thread -> (p, jj, a, chunk)
 __global__ void __launch_bounds__(128) k_vmsm_partial(verify_shape s, verify_args v, const g1_aff* __restrict__ tab,
-                                                      g1_jac* __restrict__ part, size_t nprob) {
+                                                      const fp* __restrict__ tabx, g1_jac* __restrict__ part, size_t nprob) {
   size_t id = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int n_own = s.n_out_owned();  // sharded statement: the other outputs' Miller pairs run on other ranks
   size_t total = nprob * (size_t)n_own * 2 * s.nchunk;
@@ -162,8 +249,8 @@ __global__ void __launch_bounds__(128) k_vmsm_partial(verify_shape s, verify_arg
   int jj = s.owned_out((int)(r % n_own));
   int ch = (int)(r / n_own);
 
-  // biased scalars k' = k + 0x88..8 (64 nibbles): digit_w = nibble_w(k') - 8 in [-8, 7], no carries
-  uint32_t sc[GS_MSM_CHUNK][9];
+  // GLV halves of every scalar, biased for the signed 4-bit recoding (glv_bias): entry 2c = k1 (base B), 2c + 1 = k2 (-phi(B))
+  uint32_t sc[2 * GS_MSM_CHUNK][5];
   int bidx[GS_MSM_CHUNK];
   int cnt = 0;
   int i0 = ch * s.chunk, i1 = min(s.nbases, i0 + s.chunk);
@@ -171,36 +258,55 @@ __global__ void __launch_bounds__(128) k_vmsm_partial(verify_shape s, verify_arg
     fr sv;
     bool have = vmsm_scalar(sv, s, v, p, i, jj);
     if (!have || sv.is_zero()) continue;
-    uint32_t k[8];
+    uint32_t k[8], k1[4], k2[4];
     fr_from_mont(k, sv);
-    uint32_t carry = 0;
-#pragma unroll
-    for (int w = 0; w < 8; w++) {
-      uint64_t t = (uint64_t)k[w] + 0x88888888u + carry;
-      sc[cnt][w] = (uint32_t)t;
-      carry = (uint32_t)(t >> 32);
-    }
-    sc[cnt][8] = carry;
+    glv_split(k1, k2, k);
+    glv_bias(sc[2 * cnt], k1);
+    glv_bias(sc[2 * cnt + 1], k2);
     bidx[cnt] = i;
     cnt++;
   }
   g1_jac acc;
   acc.set_inf();
   if (cnt > 0) {
-    for (int w = 64; w >= 0; w--) {
-      if (w != 64) {
+    // The table entry of step (w, i) is fetched one step ahead: its address depends only on the digits, and the
+    // load then overlaps the previous (out-of-line) addition instead of stalling in front of its own.
+    g1_aff cur, nxt;
+    bool cur_nz = false, cur_neg = false, nxt_nz = false, nxt_neg = false;
+    auto fetch = [&](int w, int i, g1_aff& e, bool& nz, bool& ng) {
+      const int d = (int)((sc[i][w >> 3] >> ((w & 7) * 4)) & 15u) - (w == 32 ? 0 : 8);
+      nz = d != 0;
+      if (!nz) return;
+      const int mag = d < 0 ? -d : d;
+      const bool phi = i & 1;
+      const size_t at = ((size_t)(bidx[i >> 1] * 2 + a) * GS_VTAB + (mag - 1)) * nprob + p;
+      e.y = tab[at].y;
+      e.x = phi ? tabx[at] : tab[at].x;
+      ng = (d < 0) != phi;  // the phi half adds multiples of -phi(B) = (beta x, -y)
+    };
+    fetch(32, 0, cur, cur_nz, cur_neg);
+    for (int w = 32; w >= 0; w--) {
+      if (w != 32) {
         g1_jac::dbl(acc, acc);
         g1_jac::dbl(acc, acc);
         g1_jac::dbl(acc, acc);
         g1_jac::dbl(acc, acc);
       }
-      for (int i = 0; i < cnt; i++) {
-        int d = (int)((sc[i][w >> 3] >> ((w & 7) * 4)) & 15u) - (w == 64 ? 0 : 8);
-        if (d == 0) continue;
-        int mag = d < 0 ? -d : d;
-        g1_aff e = tab[((size_t)(bidx[i] * 2 + a) * GS_VTAB + (mag - 1)) * nprob + p];
-        if (d < 0) fp::neg(e.y, e.y);
-        g1_jac::add_mixed(acc, acc, e);
+      for (int i = 0; i < 2 * cnt; i++) {
+        int ni = i + 1, nw = w;
+        if (ni == 2 * cnt) {
+          ni = 0;
+          nw = w - 1;
+        }
+        nxt_nz = false;
+        if (nw >= 0) fetch(nw, ni, nxt, nxt_nz, nxt_neg);
+        if (cur_nz) {
+          if (cur_neg) fp::neg(cur.y, cur.y);
+          g1_jac::add_mixed(acc, acc, cur);
+        }
+        cur = nxt;
+        cur_nz = nxt_nz;
+        cur_neg = nxt_neg;
       }
     }
   }
@@ -474,9 +580,11 @@ static int verify_impl(gs_ctx* ctx, int type, size_t count, size_t m, size_t n, 
       LAUNCH(k_vmsm_wsum, nprob * owned_out * 2 * s.nchunk, s, v, wtab, part, nprob);
     } else {
       g1_aff* vtab;
+      fp* vtabx;
       CUDA_TRY(sc.alloc(&vtab, (size_t)s.nbases * 2 * GS_VTAB * nprob));
-      LAUNCH(k_vmsm_tables, nprob * (size_t)s.nbases * 2, s, v, ctx->crs, vtab, nprob);
-      LAUNCH(k_vmsm_partial, nprob * owned_out * 2 * s.nchunk, s, v, vtab, part, nprob);
+      CUDA_TRY(sc.alloc(&vtabx, (size_t)s.nbases * 2 * GS_VTAB * nprob));
+      LAUNCH(k_vmsm_tables, nprob * (size_t)s.nbases * 2, s, v, ctx->crs, vtab, vtabx, nprob);
+      LAUNCH(k_vmsm_partial, nprob * owned_out * 2 * s.nchunk, s, v, vtab, vtabx, part, nprob);
     }
     const g1_jac* partr = part;
     if (s.nchunk > 32) {  // fold 16 chunks at a time in parallel; k_vmsm_reduce then walks the few that are left
