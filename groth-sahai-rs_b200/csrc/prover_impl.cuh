@@ -70,17 +70,31 @@ GS_HD GS_INL uint32_t get_bits(const uint32_t k[8], int bit, int c) {
 template <class F>
 GS_HD GS_INL void fixed_base_accumulate(Jac<F>& acc, const Aff<F>* __restrict__ T /* [W][H] */, const uint32_t k[8], int c,
                                         int W, size_t H) {
+  // digits recoded into (-2^(c-1), 2^(c-1)]; the table entry of window w + 1 is fetched before the (out-of-line)
+  // addition of window w runs, so the dependent load never stalls in front of its own addition
   uint32_t carry = 0;
   const uint32_t half = 1u << (c - 1);
+  Aff<F> cur, nxt;
+  bool cur_nz = false, cur_neg = false, nxt_nz = false, nxt_neg = false;
+  auto fetch = [&](int w, Aff<F>& e, bool& nz, bool& ng) {
+    uint32_t d = get_bits(k, w * c, c) + carry;
+    ng = d > half;
+    carry = ng ? 1u : 0u;
+    uint32_t mag = ng ? (1u << c) - d : d;
+    nz = mag != 0;
+    if (nz) e = T[(size_t)w * H + (mag - 1)];
+  };
+  fetch(0, cur, cur_nz, cur_neg);
   for (int w = 0; w < W; w++) {
-    uint32_t d = get_bits(k, w * c, c) + carry;   // digits recoded into (-2^(c-1), 2^(c-1)]
-    bool negd = d > half;
-    carry = negd ? 1u : 0u;
-    uint32_t mag = negd ? (1u << c) - d : d;
-    if (mag == 0) continue;
-    Aff<F> e = T[(size_t)w * H + (mag - 1)];
-    if (negd) F::neg(e.y, e.y);
-    Jac<F>::add_mixed(acc, acc, e);
+    nxt_nz = false;
+    if (w + 1 < W) fetch(w + 1, nxt, nxt_nz, nxt_neg);
+    if (cur_nz) {
+      if (cur_neg) F::neg(cur.y, cur.y);
+      Jac<F>::add_mixed(acc, acc, cur);
+    }
+    cur = nxt;
+    cur_nz = nxt_nz;
+    cur_neg = nxt_neg;
   }
 }
 
