@@ -57,6 +57,7 @@ void gs_ctx_destroy(gs_ctx* ctx) {
   if (ctx->crs_lines) cudaFree(ctx->crs_lines);
   if (ctx->fe_prog) cudaFree(ctx->fe_prog);
   cudaFree(ctx->crs);
+  if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
   cudaStreamDestroy(ctx->stream);
   delete ctx;
 }

@@ -25,6 +25,7 @@ struct gs_fixed_table {
 struct gs_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t stream2 = nullptr;  // second stream of chunked batches (copy / compute overlap), created on first use
   gs::crs_dev* crs = nullptr;  // device
   bool crs_loaded = false;
   gs_fixed_table<gs::FpOps> tab1;

@@ -286,6 +286,64 @@ int batch_commit_impl(gs_ctx* ctx, size_t n, int base0, int base1, const gs_fr* 
     int rc = fixed_table_rebuild<F>(ctx, want_c);
     if (rc) return rc;
   }
+  // Big batches (C2: 2^20 variables = 160 MB in, 192 MB out for G1) are cut into chunks that alternate between two
+  // streams: while the host stages chunk i+1 in and chunk i-1 out (pageable copies block the host, not the GPU),
+  // the kernel of chunk i runs.  Only the interleaved-randomness layout (batch_commit_G1/G2) is chunked.
+  const size_t CH = (size_t)1 << 16;
+  if (n > 2 * CH && s0_stride == 2 && (const fr*)s1 == (const fr*)s0 + 1 && nscal == 2 * n && addend) {
+    if (!ctx->stream2) CUDA_TRY(cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking));
+    cudaStream_t main_stream = ctx->stream;
+    CUDA_TRY(cudaStreamSynchronize(main_stream));  // table build (if any) is done before the second stream reads it
+    struct pending_t {
+      Scratch* sc = nullptr;
+      Aff<F>* dout = nullptr;
+      size_t off = 0, cnt = 0;
+      cudaStream_t st = nullptr;
+    } prev;
+    int rc = GS_OK;
+    cudaError_t ce = cudaSuccess;
+    auto drain = [&](pending_t& pd) {  // D2H of a finished chunk (blocks until its kernel is done), then release
+      if (!pd.sc) return;
+      ctx->stream = pd.st;
+      cudaError_t e2 = cudaMemcpyAsync((Aff<F>*)out + 2 * pd.off, pd.dout, 2 * pd.cnt * sizeof(Aff<F>), cudaMemcpyDeviceToHost, pd.st);
+      if (e2 == cudaSuccess) e2 = cudaStreamSynchronize(pd.st);
+      if (ce == cudaSuccess) ce = e2;
+      delete pd.sc;
+      pd.sc = nullptr;
+    };
+    size_t idx = 0;
+    for (size_t off = 0; off < n && rc == GS_OK && ce == cudaSuccess; off += CH, idx++) {
+      const size_t cnt = n - off < CH ? n - off : CH;
+      pending_t cur;
+      cur.st = (idx & 1) ? ctx->stream2 : main_stream;
+      cur.off = off;
+      cur.cnt = cnt;
+      ctx->stream = cur.st;
+      cur.sc = new Scratch(ctx);
+      fr* ds;
+      Aff<F>* dadd;
+      cudaError_t e2 = upload(ctx, *cur.sc, &ds, (const fr*)s0 + 2 * off, 2 * cnt);
+      if (e2 == cudaSuccess) e2 = upload(ctx, *cur.sc, &dadd, (const Aff<F>*)addend + off, cnt);
+      if (e2 == cudaSuccess) e2 = cur.sc->alloc(&cur.dout, 2 * cnt);
+      if (e2 != cudaSuccess) {
+        ce = e2;
+        delete cur.sc;
+        break;
+      }
+      rc = [&]() -> int {
+        LAUNCH((k_fixed_commit<F>), 2 * cnt, T.t, T.c, T.W, T.H, base0, base1, (const fr*)ds, (size_t)2, (const fr*)ds + 1, (size_t)2,
+               dadd, cur.dout, cnt);
+        return GS_OK;
+      }();
+      drain(prev);  // overlaps with the kernel just launched on the other stream
+      prev = cur;
+    }
+    drain(prev);
+    ctx->stream = main_stream;
+    if (rc) return rc;
+    CUDA_TRY(ce);
+    return GS_OK;
+  }
   Scratch sc(ctx);
   fr* ds;
   Aff<F>* dadd = nullptr;

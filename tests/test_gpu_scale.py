@@ -209,3 +209,24 @@ def test_shared_commitments_batch_uses_tables(eng, ty):
         one = eng.verify(ty, m, n, A[e], B[e], bytes(Gb[e]), T[e], xc, yc, pi[e * cx * 384:(e + 1) * cx * 384],
                          th[e * cy * 192:(e + 1) * cy * 192])
         assert one is bool(ok[e])
+
+
+def test_c2_chunked_two_stream_commit(eng):
+    """Batches above 2^17 variables are committed chunk by chunk on two streams (copy / compute overlap): the
+    result must be the concatenation of the results of its halves, each of which takes the single-pass path."""
+    rng = SeededRng(222)
+    n = (1 << 17) + 777
+    base = _multiples_g1(eng, [rng.fr() for _ in range(32)])
+    X = b"".join(base[(7 * i) % 32] for i in range(n))
+    import numpy as np
+    rs = np.random.RandomState(5)
+    Rr = rs.randint(0, 2 ** 63 - 1, size=(2 * n, 4), dtype=np.int64).astype(np.uint64)
+    Rr[:, 3] &= np.uint64((1 << 62) - 1)
+    Rr = Rr.tobytes()
+    whole = eng.batch_commit_g1(X, Rr)
+    h = n // 2
+    assert whole == eng.batch_commit_g1(X[:96 * h], Rr[:64 * h]) + eng.batch_commit_g1(X[96 * h:], Rr[64 * h:])
+    q = _multiples_g2(eng, [rng.fr() for _ in range(8)])
+    Y = b"".join(q[(3 * i) % 8] for i in range(n))
+    whole2 = eng.batch_commit_g2(Y, Rr)
+    assert whole2 == eng.batch_commit_g2(Y[:192 * h], Rr[:64 * h]) + eng.batch_commit_g2(Y[192 * h:], Rr[64 * h:])
