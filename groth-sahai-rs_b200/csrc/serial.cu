@@ -8,6 +8,7 @@
 // One thread per point: x -> y by a field square root, sign by the flag, membership by the endomorphism tests
 // arkworks itself uses (two 64-bit scalar multiplications instead of [r]P = O).
 #include "ctx.h"
+#include "endo.cuh"
 
 using namespace gs;
 
@@ -144,15 +145,6 @@ __device__ GS_NOINL bool fp2_sqrt(fp2& x, const fp2& a) {
 //   G2 (Section 4):  psi(Q) = [x] Q,     psi(x, y) = (conj(x) cx, conj(y) cy)  (untwist-Frobenius-twist)
 // beta, cx, cy below were derived from those relations on the generators (tests/test_serialize.py checks the
 // oracle versions against the definition [r]P = O on points inside and outside the subgroups).
-static __device__ __constant__ uint32_t ENDO_BETA[12] = {0x798a64e8u, 0x30f1361bu, 0x7ece5a2au, 0xf3b8ddabu, 0xc61577f7u, 0x16a8ca3au,
-                                                         0x74fd029bu, 0xc26a2ff8u, 0x60701c6eu, 0x3636b766u, 0x241b6160u, 0x051ba4abu};
-static __device__ __constant__ uint32_t PSI_CX_C1[12] = {0x867545c3u, 0x890dc9e4u, 0x3285a5d5u, 0x2af32253u, 0x309b7e2cu, 0x50880866u,
-                                                         0x7e881024u, 0xa20d1b8cu, 0xe2db9068u, 0x14e4f04fu, 0x1564853au, 0x14e56d3fu};  // cx = (0, c1)
-static __device__ __constant__ uint32_t PSI_CY_C0[12] = {0xa55c9ad1u, 0x3e2f585du, 0x86c18183u, 0x4294213du, 0x8b623732u, 0x382844c8u,
-                                                         0x19103e18u, 0x92ad2afdu, 0xac7cf0b9u, 0x1d794e4fu, 0x7d825ec8u, 0x0bd592fcu};
-static __device__ __constant__ uint32_t PSI_CY_C1[12] = {0x5aa30fdau, 0x7bcfa7a2u, 0x2a927e7cu, 0xdc17dec1u, 0x6b4ebef1u, 0x2f088dd8u,
-                                                         0xda74d4a7u, 0xd1ca2087u, 0x96cebc1du, 0x2da25966u, 0xbbfd87d2u, 0x0e2b7eedu};
-
 // r = [|x|] b, |x| = 0xd201000000010000 (63 doublings, 5 additions)
 template <class F>
 __device__ GS_NOINL void mul_x_abs(Jac<F>& r, const Jac<F>& b) {

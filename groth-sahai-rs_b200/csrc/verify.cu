@@ -2,6 +2,7 @@
 // statement MSM (re-association of verifier.rs:39-42), then the pairing-product pipeline.
 #include "batchinv.cuh"
 #include "ctx.h"
+#include "endo.cuh"
 #include "prover_impl.cuh"  // fixed_base_accumulate
 
 using namespace gs;
@@ -91,71 +92,6 @@ __device__ GS_INL g1_aff vmsm_base(const verify_shape& s, const verify_args& v, 
 // GLV: k P = k1 P + k2 (-phi(P)) with k = k1 + k2 x^2 (k1, k2 < 2^128), phi(x, y) = (beta x, y) = -[x^2] P on G1
 // (the relation serial.cu's membership test uses).  The multiples of -phi(B) share y (negated) with those of B and
 // have x' = beta x, stored in tabx by k_vmsm_tables; the Straus loop then runs 32 windows instead of 64.
-static __device__ __constant__ uint32_t VM_BETA[12] = {0x798a64e8u, 0x30f1361bu, 0x7ece5a2au, 0xf3b8ddabu, 0xc61577f7u, 0x16a8ca3au,
-                                                       0x74fd029bu, 0xc26a2ff8u, 0x60701c6eu, 0x3636b766u, 0x241b6160u, 0x051ba4abu};
-static __device__ __constant__ uint32_t VM_X2[4] = {0x00000000u, 0x00000001u, 0x0001a402u, 0xac45a401u};                 // x^2
-static __device__ __constant__ uint32_t VM_MU[5] = {0xf6cfee2eu, 0x63f6e522u, 0xe01faaddu, 0x7c6becf1u, 0x00000001u};   // 2^256 / x^2
-// k (canonical, < r) -> k1 = k mod x^2, k2 = k div x^2
-__device__ GS_NOINL void glv_split(uint32_t k1[4], uint32_t k2[4], const uint32_t k[8]) {
-  uint32_t t[13];
-  for (int i = 0; i < 13; i++) t[i] = 0;
-  for (int i = 0; i < 8; i++) {
-    uint32_t carry = 0;
-    for (int j = 0; j < 5; j++) {
-      uint64_t vv = (uint64_t)k[i] * VM_MU[j] + t[i + j] + carry;
-      t[i + j] = (uint32_t)vv;
-      carry = (uint32_t)(vv >> 32);
-    }
-    t[i + 5] = carry;
-  }
-  uint32_t q[4] = {t[8], t[9], t[10], t[11]};  // floor(k mu / 2^256) in {k div x^2 - 1, k div x^2}
-  uint32_t pr[8];
-  for (int i = 0; i < 8; i++) pr[i] = 0;
-  for (int i = 0; i < 4; i++) {
-    uint32_t carry = 0;
-    for (int j = 0; j < 4; j++) {
-      uint64_t vv = (uint64_t)q[i] * VM_X2[j] + pr[i + j] + carry;
-      pr[i + j] = (uint32_t)vv;
-      carry = (uint32_t)(vv >> 32);
-    }
-    pr[i + 4] = carry;
-  }
-  uint32_t rem[8];
-  uint32_t borrow = 0;
-  for (int i = 0; i < 8; i++) {
-    uint64_t d = (uint64_t)k[i] - pr[i] - borrow;
-    rem[i] = (uint32_t)d;
-    borrow = (uint32_t)(d >> 63);
-  }
-  for (int it = 0; it < 2; it++) {
-    bool ge = (rem[4] | rem[5] | rem[6] | rem[7]) != 0;
-    if (!ge) {
-      ge = true;
-      for (int i = 3; i >= 0; i--)
-        if (rem[i] != VM_X2[i]) {
-          ge = rem[i] > VM_X2[i];
-          break;
-        }
-    }
-    if (!ge) break;
-    borrow = 0;
-    for (int i = 0; i < 8; i++) {
-      uint64_t d = (uint64_t)rem[i] - (i < 4 ? VM_X2[i] : 0u) - borrow;
-      rem[i] = (uint32_t)d;
-      borrow = (uint32_t)(d >> 63);
-    }
-    uint32_t c = 1;
-    for (int i = 0; i < 4; i++) {
-      uint64_t a = (uint64_t)q[i] + c;
-      q[i] = (uint32_t)a;
-      c = (uint32_t)(a >> 32);
-    }
-  }
-  for (int i = 0; i < 4; i++) {
-    k1[i] = rem[i];
-    k2[i] = q[i];
-  }
-}
 // biased 128-bit scalar k' = k + 0x88..8 (32 nibbles): digit_w = nibble_w(k') - 8 in [-8, 7] for w < 32, digit_32 = carry
 __device__ GS_INL void glv_bias(uint32_t out[5], const uint32_t k[4]) {
   uint32_t carry = 0;
@@ -208,10 +144,8 @@ __global__ void __launch_bounds__(128) k_vmsm_tables(verify_shape s, verify_args
     fp::mul(inv, inv, z);
     g1_aff e;
     g1_jac::to_affine_with_zinv(e, mlt[d], zi);
-    fp beta, bx;
-#pragma unroll
-    for (int j = 0; j < 12; j++) beta.l[j] = VM_BETA[j];
-    fp::mul(bx, e.x, beta);
+    fp bx;
+    endo_phi_x(bx, e.x);
     if (active) {
       out[(size_t)d * nprob] = e;
       tabx[((size_t)(i * 2 + a) * GS_VTAB + d) * nprob + p] = bx;
