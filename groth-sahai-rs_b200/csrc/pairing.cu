@@ -81,7 +81,7 @@ struct g2_pts_list {  // the fixed points Q_i of one thread (read again at the 5
   }
 };
 template <int E>
-__global__ void __launch_bounds__(128, 5) k_g2_prepare4(const uint32_t* __restrict__ PW, const g2_aff* __restrict__ Y,
+__global__ void __launch_bounds__(128, E == 1 ? 2 : 5) k_g2_prepare4(const uint32_t* __restrict__ PW, const g2_aff* __restrict__ Y,
                                                         uint32_t* __restrict__ tiles, uint32_t* __restrict__ masks,
                                                         size_t nprob, size_t p0, size_t np, int K, int S,
                                                         const uint32_t* __restrict__ walk, int nwalk) {

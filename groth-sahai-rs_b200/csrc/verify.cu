@@ -487,7 +487,9 @@ static int verify_impl(gs_ctx* ctx, int type, size_t count, size_t m, size_t n, 
       // 30.8 ms for all of them; C4's shared-table batches 91 -> 67 ms); the table kernel has no doublings to
       // amortise, Straus keeps >= 8.  Many chunks are folded 16 at a time (k_vmsm_fold) before k_vmsm_reduce.
       int chunk = GS_MSM_CHUNK;
-      const int floor_chunk = use_wtab ? 4 : 8;
+      // (a lone small statement is pure latency: one base per thread there)
+      const bool tiny = nprob * owned_out * 2 * ((s.nbases + 7) / 8) < 16384;
+      const int floor_chunk = use_wtab ? 4 : (tiny ? 1 : 8);
       while (chunk > floor_chunk && nprob * owned_out * 2 * ((s.nbases + chunk - 1) / chunk) < (size_t)128 * 2368) chunk /= 2;
       set_msm_chunk(s, chunk);
     }
