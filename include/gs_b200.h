@@ -17,6 +17,10 @@
  *   ComT : four GT, row-major [e(x0,y0), e(x0,y1), e(x1,y0), e(x1,y1)]        (2304 B)
  *   Matrix<Fr> : dense row-major.
  *
+ * Group elements must lie in the order-r subgroups (what arkworks' validated deserialisation guarantees for
+ * every G1Affine / G2Affine; gs_g1_decompress / gs_g2_decompress check it): the kernels use the curve
+ * endomorphisms, which act as scalars only there.
+ *
  * All pointers are HOST pointers unless the function name ends in `_dev`.  Randomness is
  * always supplied by the caller, drawn in the reference's order (commit.rs:85-88,
  * prove.rs:123-126), which is what makes results bit-reproducible.
