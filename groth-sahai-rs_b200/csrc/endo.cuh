@@ -12,27 +12,41 @@
 
 namespace gs {
 
+#define GS_TBL_ENDO_BETA {0x798a64e8u, 0x30f1361bu, 0x7ece5a2au, 0xf3b8ddabu, 0xc61577f7u, 0x16a8ca3au, 0x74fd029bu, 0xc26a2ff8u, 0x60701c6eu, 0x3636b766u, 0x241b6160u, 0x051ba4abu}
+#define GS_TBL_PSI_CX_C1 {0x867545c3u, 0x890dc9e4u, 0x3285a5d5u, 0x2af32253u, 0x309b7e2cu, 0x50880866u, 0x7e881024u, 0xa20d1b8cu, 0xe2db9068u, 0x14e4f04fu, 0x1564853au, 0x14e56d3fu}
+#define GS_TBL_PSI_CY_C0 {0xa55c9ad1u, 0x3e2f585du, 0x86c18183u, 0x4294213du, 0x8b623732u, 0x382844c8u, 0x19103e18u, 0x92ad2afdu, 0xac7cf0b9u, 0x1d794e4fu, 0x7d825ec8u, 0x0bd592fcu}
+#define GS_TBL_PSI_CY_C1 {0x5aa30fdau, 0x7bcfa7a2u, 0x2a927e7cu, 0xdc17dec1u, 0x6b4ebef1u, 0x2f088dd8u, 0xda74d4a7u, 0xd1ca2087u, 0x96cebc1du, 0x2da25966u, 0xbbfd87d2u, 0x0e2b7eedu}
+#define GS_TBL_GLV_X2 {0x00000000u, 0x00000001u, 0x0001a402u, 0xac45a401u}               /* x^2 */
+#define GS_TBL_GLV_MU {0xf6cfee2eu, 0x63f6e522u, 0xe01faaddu, 0x7c6becf1u, 0x00000001u}  /* 2^256 / x^2 */
+// every table exists twice (host array for tests/hostsim, __constant__ array for the kernels), as in constants.cuh
 #if defined(__CUDACC__)
-static __device__ __constant__ uint32_t ENDO_BETA[12] = {0x798a64e8u, 0x30f1361bu, 0x7ece5a2au, 0xf3b8ddabu, 0xc61577f7u, 0x16a8ca3au,
-                                                         0x74fd029bu, 0xc26a2ff8u, 0x60701c6eu, 0x3636b766u, 0x241b6160u, 0x051ba4abu};
-static __device__ __constant__ uint32_t PSI_CX_C1[12] = {0x867545c3u, 0x890dc9e4u, 0x3285a5d5u, 0x2af32253u, 0x309b7e2cu, 0x50880866u,
-                                                         0x7e881024u, 0xa20d1b8cu, 0xe2db9068u, 0x14e4f04fu, 0x1564853au, 0x14e56d3fu};  // cx = (0, c1)
-static __device__ __constant__ uint32_t PSI_CY_C0[12] = {0xa55c9ad1u, 0x3e2f585du, 0x86c18183u, 0x4294213du, 0x8b623732u, 0x382844c8u,
-                                                         0x19103e18u, 0x92ad2afdu, 0xac7cf0b9u, 0x1d794e4fu, 0x7d825ec8u, 0x0bd592fcu};
-static __device__ __constant__ uint32_t PSI_CY_C1[12] = {0x5aa30fdau, 0x7bcfa7a2u, 0x2a927e7cu, 0xdc17dec1u, 0x6b4ebef1u, 0x2f088dd8u,
-                                                         0xda74d4a7u, 0xd1ca2087u, 0x96cebc1du, 0x2da25966u, 0xbbfd87d2u, 0x0e2b7eedu};
-static __device__ __constant__ uint32_t GLV_X2[4] = {0x00000000u, 0x00000001u, 0x0001a402u, 0xac45a401u};                 // x^2
-static __device__ __constant__ uint32_t GLV_MU[5] = {0xf6cfee2eu, 0x63f6e522u, 0xe01faaddu, 0x7c6becf1u, 0x00000001u};   // 2^256 / x^2
+#define GS_ENDO_TABLE(name, n)                                        \
+  static const uint32_t h_##name[n] = GS_TBL_##name;                  \
+  static __device__ __constant__ uint32_t d_##name[n] = GS_TBL_##name;
+#else
+#define GS_ENDO_TABLE(name, n) static const uint32_t h_##name[n] = GS_TBL_##name;
+#endif
+#if defined(__CUDA_ARCH__)
+#define GS_ENDO_AT(name, i) d_##name[i]
+#else
+#define GS_ENDO_AT(name, i) h_##name[i]
+#endif
+GS_ENDO_TABLE(ENDO_BETA, 12)
+GS_ENDO_TABLE(PSI_CX_C1, 12)
+GS_ENDO_TABLE(PSI_CY_C0, 12)
+GS_ENDO_TABLE(PSI_CY_C1, 12)
+GS_ENDO_TABLE(GLV_X2, 4)
+GS_ENDO_TABLE(GLV_MU, 5)
 constexpr uint64_t GS_X_ABS64 = 0xd201000000010000ull;
 
-static __device__ GS_INL void endo_phi_x(fp& bx, const fp& x) {  // beta * x
+static GS_HD GS_INL void endo_phi_x(fp& bx, const fp& x) {  // beta * x
   fp beta;
 #pragma unroll
-  for (int j = 0; j < 12; j++) beta.l[j] = ENDO_BETA[j];
+  for (int j = 0; j < 12; j++) beta.l[j] = GS_ENDO_AT(ENDO_BETA, j);
   fp::mul(bx, x, beta);
 }
 // q = psi(p)
-static __device__ GS_NOINL void endo_psi(g2_aff& q, const g2_aff& p) {
+static GS_HD GS_NOINL void endo_psi(g2_aff& q, const g2_aff& p) {
   if (p.is_inf()) {
     q = p;
     return;
@@ -41,9 +55,9 @@ static __device__ GS_NOINL void endo_psi(g2_aff& q, const g2_aff& p) {
   fp2 cy, t;
 #pragma unroll
   for (int j = 0; j < 12; j++) {
-    c1.l[j] = PSI_CX_C1[j];
-    cy.c0.l[j] = PSI_CY_C0[j];
-    cy.c1.l[j] = PSI_CY_C1[j];
+    c1.l[j] = GS_ENDO_AT(PSI_CX_C1, j);
+    cy.c0.l[j] = GS_ENDO_AT(PSI_CY_C0, j);
+    cy.c1.l[j] = GS_ENDO_AT(PSI_CY_C1, j);
   }
   // conj(x) * (c1 u) = x.c1 c1 + x.c0 c1 u
   fp a, b;
@@ -56,13 +70,13 @@ static __device__ GS_NOINL void endo_psi(g2_aff& q, const g2_aff& p) {
 }
 
 // k (canonical, < r) -> k1 = k mod x^2, k2 = k div x^2   (Barrett with mu = 2^256 / x^2, at most two corrections)
-static __device__ GS_NOINL void glv_split(uint32_t k1[4], uint32_t k2[4], const uint32_t k[8]) {
+static GS_HD GS_NOINL void glv_split(uint32_t k1[4], uint32_t k2[4], const uint32_t k[8]) {
   uint32_t t[13];
   for (int i = 0; i < 13; i++) t[i] = 0;
   for (int i = 0; i < 8; i++) {
     uint32_t carry = 0;
     for (int j = 0; j < 5; j++) {
-      uint64_t vv = (uint64_t)k[i] * GLV_MU[j] + t[i + j] + carry;
+      uint64_t vv = (uint64_t)k[i] * GS_ENDO_AT(GLV_MU, j) + t[i + j] + carry;
       t[i + j] = (uint32_t)vv;
       carry = (uint32_t)(vv >> 32);
     }
@@ -74,7 +88,7 @@ static __device__ GS_NOINL void glv_split(uint32_t k1[4], uint32_t k2[4], const 
   for (int i = 0; i < 4; i++) {
     uint32_t carry = 0;
     for (int j = 0; j < 4; j++) {
-      uint64_t vv = (uint64_t)q[i] * GLV_X2[j] + pr[i + j] + carry;
+      uint64_t vv = (uint64_t)q[i] * GS_ENDO_AT(GLV_X2, j) + pr[i + j] + carry;
       pr[i + j] = (uint32_t)vv;
       carry = (uint32_t)(vv >> 32);
     }
@@ -92,15 +106,15 @@ static __device__ GS_NOINL void glv_split(uint32_t k1[4], uint32_t k2[4], const 
     if (!ge) {
       ge = true;
       for (int i = 3; i >= 0; i--)
-        if (rem[i] != GLV_X2[i]) {
-          ge = rem[i] > GLV_X2[i];
+        if (rem[i] != GS_ENDO_AT(GLV_X2, i)) {
+          ge = rem[i] > GS_ENDO_AT(GLV_X2, i);
           break;
         }
     }
     if (!ge) break;
     borrow = 0;
     for (int i = 0; i < 8; i++) {
-      uint64_t d = (uint64_t)rem[i] - (i < 4 ? GLV_X2[i] : 0u) - borrow;
+      uint64_t d = (uint64_t)rem[i] - (i < 4 ? GS_ENDO_AT(GLV_X2, i) : 0u) - borrow;
       rem[i] = (uint32_t)d;
       borrow = (uint32_t)(d >> 63);
     }
@@ -118,7 +132,7 @@ static __device__ GS_NOINL void glv_split(uint32_t k1[4], uint32_t k2[4], const 
 }
 
 // k (canonical, < r < |x|^4) -> digits c_0..c_3 in base |x|
-static __device__ GS_NOINL void gls_split(uint64_t c[4], const uint32_t k[8]) {
+static GS_HD GS_NOINL void gls_split(uint64_t c[4], const uint32_t k[8]) {
   uint32_t t[8];
   for (int i = 0; i < 8; i++) t[i] = k[i];
   for (int j = 0; j < 3; j++) {
@@ -136,7 +150,7 @@ static __device__ GS_NOINL void gls_split(uint64_t c[4], const uint32_t k[8]) {
 
 // r = k * p for a short scalar: `nwin` signed 4-bit windows over the low 4*nwin bits of k (limbs beyond are ignored)
 template <class F>
-__device__ GS_NOINL void scalar_mul_win(Jac<F>& r, const Aff<F>& p, const uint32_t* k, int nwin) {
+GS_HD GS_NOINL void scalar_mul_win(Jac<F>& r, const Aff<F>& p, const uint32_t* k, int nwin) {
   Jac<F> acc;
   acc.set_inf();
   if (p.is_inf()) {
@@ -185,7 +199,7 @@ struct EndoSplit;
 template <>
 struct EndoSplit<FpOps> {
   static constexpr int PARTS = 2;
-  __device__ static GS_INL void part(g1_jac& r, const g1_aff& base, const uint32_t k[8], int j) {
+  GS_HD static GS_INL void part(g1_jac& r, const g1_aff& base, const uint32_t k[8], int j) {
     uint32_t k1[4], k2[4];
     glv_split(k1, k2, k);
     g1_aff b = base;
@@ -199,7 +213,7 @@ struct EndoSplit<FpOps> {
 template <>
 struct EndoSplit<Fp2Ops> {
   static constexpr int PARTS = 4;
-  __device__ static GS_INL void part(g2_jac& r, const g2_aff& base, const uint32_t k[8], int j) {
+  GS_HD static GS_INL void part(g2_jac& r, const g2_aff& base, const uint32_t k[8], int j) {
     uint64_t c[4];
     gls_split(c, k);
     g2_aff b = base;
@@ -213,6 +227,4 @@ struct EndoSplit<Fp2Ops> {
     scalar_mul_win<Fp2Ops>(r, b, kk, 16);
   }
 };
-#endif  // __CUDACC__
-
 }  // namespace gs

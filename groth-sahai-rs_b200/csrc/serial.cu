@@ -174,9 +174,8 @@ __device__ GS_NOINL bool in_subgroup_g1(const g1_aff& p) {
   mul_x_abs<FpOps>(t1, b);
   if (jac_equals_affine<FpOps>(t1, p.x, p.y)) return false;  // [x]P = P
   mul_x_abs<FpOps>(t2, t1);                                  // [x^2] P
-  fp beta, bx, ny;
-  for (int j = 0; j < 12; j++) beta.l[j] = ENDO_BETA[j];
-  fp::mul(bx, p.x, beta);
+  fp bx, ny;
+  endo_phi_x(bx, p.x);
   fp::neg(ny, p.y);
   return jac_equals_affine<FpOps>(t2, bx, ny);               // [x^2]P = -phi(P)
 }
@@ -184,18 +183,10 @@ __device__ GS_NOINL bool in_subgroup_g2(const g2_aff& q) {
   g2_jac b, t;
   b.from_affine(q);
   mul_x_abs<Fp2Ops>(t, b);                                   // [|x|] Q = -[x] Q
-  fp2 cx, cy, px, py;
-  cx.c0.set_zero();
-  for (int j = 0; j < 12; j++) {
-    cx.c1.l[j] = PSI_CX_C1[j];
-    cy.c0.l[j] = PSI_CY_C0[j];
-    cy.c1.l[j] = PSI_CY_C1[j];
-  }
-  fp2::conj(px, q.x);
-  fp2::conj(py, q.y);
-  fp2::mul(px, px, cx);
-  fp2::mul(py, py, cy);
-  fp2::neg(py, py);
+  g2_aff ps;
+  endo_psi(ps, q);
+  fp2 px = ps.x, py;
+  fp2::neg(py, ps.y);
   return jac_equals_affine<Fp2Ops>(t, px, py);               // [|x|]Q = -psi(Q)
 }
 

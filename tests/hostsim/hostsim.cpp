@@ -6,6 +6,7 @@
 #include <cfenv>
 #include "../../groth-sahai-rs_b200/csrc/pairing.cuh"
 #include "../../groth-sahai-rs_b200/csrc/fpd.cuh"
+#include "../../groth-sahai-rs_b200/csrc/endo.cuh"
 using namespace gs;
 
 #define LD(T, v, p) T v; memcpy(&v, p, sizeof(T))
@@ -263,3 +264,19 @@ extern "C" void hs_fp_mulsum_dfma(void* r, int nt, const void* a, const void* b)
 #undef MS
   fesetround(old);
   ST(r, z); }
+
+// endomorphism splittings (endo.cuh): the decompositions and the per-part scalar multiplications
+extern "C" void hs_glv_split(void* k1k2 /* 2 x 16 B */, const void* k_mont) {
+  LD(fr, k, k_mont); uint32_t kk[8], a[4], b[4]; fr_from_mont(kk, k); glv_split(a, b, kk); memcpy(k1k2, a, 16); memcpy((char*)k1k2 + 16, b, 16); }
+extern "C" void hs_gls_split(void* c /* 4 x 8 B */, const void* k_mont) {
+  LD(fr, k, k_mont); uint32_t kk[8]; uint64_t d[4]; fr_from_mont(kk, k); gls_split(d, kk); memcpy(c, d, 32); }
+extern "C" void hs_endo_psi(void* r, const void* a) { LD(g2_aff, p, a); g2_aff q; endo_psi(q, p); ST(r, q); }
+// sum over the parts of EndoSplit<F>::part == k * base
+extern "C" void hs_g1_mul_split(void* r, const void* a, const void* k_mont) {
+  LD(g1_aff, p, a); LD(fr, k, k_mont); uint32_t kk[8]; fr_from_mont(kk, k); g1_jac acc; acc.set_inf();
+  for (int j = 0; j < EndoSplit<FpOps>::PARTS; j++) { g1_jac t; EndoSplit<FpOps>::part(t, p, kk, j); g1_jac::add(acc, acc, t); }
+  g1_aff o; g1_jac::to_affine(o, acc); ST(r, o); }
+extern "C" void hs_g2_mul_split(void* r, const void* a, const void* k_mont) {
+  LD(g2_aff, p, a); LD(fr, k, k_mont); uint32_t kk[8]; fr_from_mont(kk, k); g2_jac acc; acc.set_inf();
+  for (int j = 0; j < EndoSplit<Fp2Ops>::PARTS; j++) { g2_jac t; EndoSplit<Fp2Ops>::part(t, p, kk, j); g2_jac::add(acc, acc, t); }
+  g2_aff o; g2_jac::to_affine(o, acc); ST(r, o); }

@@ -242,3 +242,27 @@ def test_miller_v4_affine_lines(L):
     want = final_exponentiation(multi_miller_loop(list(zip(ps, qs))))
     assert fp12_i(call(L.hs_final_exp3, 576, v4, 2)) == want
     assert fp12_i(call(L.hs_final_exp, 576, v4)) == want
+
+
+def test_endomorphism_splittings(L):
+    """endo.cuh on the host: GLV split k = k1 + k2 x^2 (both < 2^128), base-|x| digits, psi(Q) = [x] Q, and the
+    per-part scalar multiplications of the prover summing to k * base on both groups (edge scalars included)."""
+    X2 = 0xD201000000010000 ** 2
+    XA = 0xD201000000010000
+    ks = [0, 1, 2, X2 - 1, X2, X2 + 1, R - 1, R - 2, XA, XA - 1, XA ** 3, (R - 1) // 2] + [rng.randrange(R) for _ in range(200)]
+    for k in ks:
+        out = call(L.hs_glv_split, 32, fr_b(k))
+        k1, k2 = int.from_bytes(out[:16], "little"), int.from_bytes(out[16:], "little")
+        assert k1 < X2 and k1 + k2 * X2 == k
+        d = call(L.hs_gls_split, 32, fr_b(k))
+        c = [int.from_bytes(d[8 * i:8 * i + 8], "little") for i in range(4)]
+        assert all(x < XA for x in c) and sum(x * XA ** i for i, x in enumerate(c)) == k
+    q = g2_mul(G2_GEN_FP2, rng.randrange(R))
+    assert g2_i(call(L.hs_endo_psi, 192, g2_b(q))) == g2_mul(q, (-XA) % R)          # psi acts as [x], x < 0
+    assert call(L.hs_endo_psi, 192, g2_b(None)) == g2_b(None)
+    p = g1_mul(G1_GEN, rng.randrange(R))
+    for k in ks[:14] + ks[-6:]:
+        assert g1_i(call(L.hs_g1_mul_split, 96, g1_b(p), fr_b(k))) == g1_mul(p, k), k
+    for k in ks[:8] + ks[-3:]:
+        assert g2_i(call(L.hs_g2_mul_split, 192, g2_b(q), fr_b(k))) == g2_mul(q, k), k
+    assert call(L.hs_g1_mul_split, 96, g1_b(None), fr_b(5)) == g1_b(None)
