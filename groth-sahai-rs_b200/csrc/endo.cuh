@@ -4,7 +4,7 @@
 // (x = -0xd201000000010000 is the curve parameter; both relations hold on the order-r subgroups, which is where every
 // G1Affine / G2Affine value of the reference lives: arkworks checks membership when such a value is deserialised, and
 // gs_g1_decompress / gs_g2_decompress do the same here.)  The constants were derived from the relations on the
-// generators (oracle/serialize.py, tests/test_serialize.py).
+// generators (the serialisation oracle and tests/test_serialize.py).
 // Used by: verify.cu (Straus MSM over the GLV halves), prover_impl.cuh (one thread per sub-scalar of an MSM term),
 // serial.cu (membership tests).
 #pragma once
