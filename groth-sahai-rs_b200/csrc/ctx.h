@@ -131,8 +131,16 @@ int final_exp_init(gs_ctx* ctx);
 constexpr uint8_t GS_SLOT_WALK = 0;     // arbitrary Com2: walk both coordinates
 constexpr uint8_t GS_SLOT_WALK_B1 = 1;  // Y_k = (O, y): only coordinate 1 exists (iota_2)
 constexpr uint8_t GS_SLOT_FIXED = 2;    // GS_SLOT_FIXED + j: Y_k is the CRS element v_1 (j = 0), v_2 (1) or W2 (2)
+struct walk_ahead {  // G2 walks started early on the second stream (lone statements), see g2_walk_ahead
+  fp2* lines = nullptr;
+  uint32_t* dwalk = nullptr;
+  int nwalk = 0;
+  cudaEvent_t done = nullptr;
+};
+int g2_walk_ahead(gs_ctx* ctx, Scratch& sc, const g2_aff* Y, size_t nprob, int K, const uint8_t* slot_kind, walk_ahead* wa);
 int run_pairing_product(gs_ctx* ctx, Scratch& sc, const g1_aff* X, const g2_aff* Y, size_t nprob, int K, fp12* out_comt,
-                        uint8_t* ok4, const fp12* target, fp12* out_partial, const uint8_t* slot_kind = nullptr);
+                        uint8_t* ok4, const fp12* target, fp12* out_partial, const uint8_t* slot_kind = nullptr,
+                        const walk_ahead* wa = nullptr);
 int crs_lines_build(gs_ctx* ctx);
 
 // finalexp.cu: f = prod_chunks F[(ch*4 + e)*nprob + p]; g = FE(f); writes out_comt[p*4+e] and/or ok4[e*nprob + p]

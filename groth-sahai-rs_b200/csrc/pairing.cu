@@ -246,6 +246,86 @@ __global__ void __launch_bounds__(128) k_fixed_tiles(const uint32_t* __restrict_
   }
 }
 
+// ------------------------------------------------------------------ lone statements: walk ahead, evaluate later
+// The walk of a G2 point (lambda, mu per step) does not depend on the G1 side; for a lone statement it is started on
+// a second stream while the statement MSM -- which produces some of the G1 slots -- still runs (verify.cu), and the
+// lines are evaluated at the G1 points afterwards.  lines[((e*np + pl)*68 + step)*2 + {0,1}], e = walk-list entry.
+__global__ void __launch_bounds__(128, 2) k_g2_walk(const g2_aff* __restrict__ Y, fp2* __restrict__ lines, size_t nprob, size_t np,
+                                                    int K, const uint32_t* __restrict__ walk, int nwalk) {
+  size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool inrange = q < (size_t)nwalk * np;
+  if (!inrange) q = 0;
+  const size_t pl = q % np;
+  const int e = (int)(q / np);
+  const uint32_t we = walk[e];
+  const int b = (int)(we >> 31), k = (int)(we & 0x7FFFFFFFu);
+  const g2_aff P = Y[((size_t)b * K + k) * nprob + pl];
+  fp2 Tx[1] = {P.x}, Ty[1] = {P.y}, Qx[1] = {P.x}, Qy[1] = {P.y};
+  g2_pts_arr T{Tx, Ty}, Qa{Qx, Qy};
+  bool act[1] = {inrange && !P.is_inf()};
+  if (!__syncthreads_or(act[0])) return;
+  fp2* out = lines + ((size_t)e * np + pl) * GS_NUM_LINES * 2;
+  int idx = 0;
+#pragma unroll 1
+  for (int bit = 62; bit >= 0; bit--) {
+    const int nl = ((GS_X_ABS >> bit) & 1) ? 2 : 1;
+#pragma unroll 1
+    for (int w = 0; w < nl; w++, idx++) {
+      g2_affine_step<1>(T, Qa, act, w == 1, [&](int, const fp2& lam, const fp2& mu) {
+        out[idx * 2] = lam;
+        out[idx * 2 + 1] = mu;
+      }, [] { __syncthreads(); });
+    }
+  }
+}
+// thread -> (walk entry e, problem): the tiles of slot k, coordinate b from the lines walked ahead
+__global__ void __launch_bounds__(128) k_eval_tiles(const uint32_t* __restrict__ PW, const g2_aff* __restrict__ Y,
+                                                    const fp2* __restrict__ lines, uint32_t* __restrict__ tiles,
+                                                    uint32_t* __restrict__ masks, size_t nprob, size_t np, int K, int S,
+                                                    const uint32_t* __restrict__ walk, int nwalk) {
+  size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= (size_t)nwalk * np) return;
+  const size_t pl = q % np;
+  const int e = (int)(q / np);
+  const uint32_t we = walk[e];
+  const int b = (int)(we >> 31), k = (int)(we & 0x7FFFFFFFu);
+  const g2_aff* P = &Y[((size_t)b * K + k) * nprob + pl];
+  if (P->x.is_zero() && P->y.is_zero()) return;
+  const int ch = k / S, kk = k % S;
+  const size_t A = (size_t)ch * np + pl;
+  const int lane = (int)(A & 31);
+  const fp2* L = lines + ((size_t)e * np + pl) * GS_NUM_LINES * 2;
+#pragma unroll 1
+  for (int a = 0; a < 2; a++) {
+    const uint32_t* pw = PW + ((((size_t)a * K + k) * 2) * 12) * np + pl;
+    fp s, wv;
+    uint32_t nz = 0;
+#pragma unroll
+    for (int j = 0; j < 12; j++) {
+      s.l[j] = pw[(size_t)j * np];
+      wv.l[j] = pw[(size_t)(12 + j) * np];
+      nz |= wv.l[j];
+    }
+    if (!nz) continue;  // identity G1 point: pair dropped
+    const size_t bid = (A >> 5) * 4 + (size_t)(2 * a + b);
+    atomicOr(&masks[bid * S + kk], 1u << lane);
+    uint32_t* o = tiles + ((bid * S + kk) * GS_NUM_LINES) * (size_t)M4_TILE;
+#pragma unroll 1
+    for (int idx = 0; idx < GS_NUM_LINES; idx++, o += M4_TILE) {
+      const fp2 lam = L[idx * 2], mu = L[idx * 2 + 1];
+      fp v;
+      fp_mul_n(v, mu.c0, wv);
+      cq_st_stream(cq_ptr(o, 0, lane), v);
+      fp_mul_n(v, mu.c1, wv);
+      cq_st_stream(cq_ptr(o, 1, lane), v);
+      fp_mul_n(v, lam.c0, s);
+      cq_st_stream(cq_ptr(o, 2, lane), v);
+      fp_mul_n(v, lam.c1, s);
+      cq_st_stream(cq_ptr(o, 3, lane), v);
+    }
+  }
+}
+
 __device__ GS_INL void cp_async16(uint32_t* smem, const uint32_t* g) {
   unsigned s = (unsigned)__cvta_generic_to_shared(smem);
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(g) : "memory");
@@ -414,43 +494,9 @@ int gsi::pairing_init(gs_ctx* ctx) {
   return GS_OK;
 }
 
-// ------------------------------------------------------------------ pairing-product pipeline
-// X, Y: device slot arrays [2][K][nprob].  Produces either ComT values (out_comt, AoS [p][4]) or
-// per-entry verdict bytes ok4[4][nprob] (compared with 1 / target).
-// Problems are processed in passes of `pc` so that the evaluated-line tiles stay within ctx->tile_budget
-// bytes of HBM; a pass is sized to a whole number of k_miller4 waves (2 groups x 148 SMs x 32 accumulators
-// / 4 entries = 2,368 problems per wave) when the batch is large enough.
-int gsi::run_pairing_product(gs_ctx* ctx, Scratch& sc, const g1_aff* X, const g2_aff* Y, size_t nprob, int K,
-                               fp12* out_comt, uint8_t* ok4, const fp12* target, fp12* out_partial, const uint8_t* slot_kind) {
-  const size_t wave = 2368;
-  if (K == 0) {  // a shard that owns no slot: empty product
-    if (!out_partial) FAIL(GS_EARG, "pairing product over zero slots");
-    LAUNCH(k_fp12_set_one, nprob * 4, out_partial, nprob * 4);
-    return GS_OK;
-  }
-  // split the slots of a big statement over several accumulators when there are few problems
-  int S = K, nchunk = 1;
-  if (nprob < wave && K > 2) {
-    size_t c = (wave + nprob - 1) / nprob;
-    if (c > (size_t)(K + 1) / 2) c = (K + 1) / 2;  // at least 2 slots per chunk
-    if (c < 1) c = 1;
-    S = (int)((K + c - 1) / c);
-  }
-  if (S > M4_MAXS) S = M4_MAXS;
-  nchunk = (K + S - 1) / S;
-  const size_t per_prob = (size_t)4 * nchunk * S * GS_NUM_LINES * M4_TILE * 4 / 32;  // tile bytes per problem
-  size_t pc = ctx->tile_budget / per_prob;
-  if (pc >= nprob) {
-    pc = nprob;
-  } else {
-    if (pc > wave) pc -= pc % wave;
-    if (pc < 32) pc = 32;
-    pc -= pc % 32;
-  }
-  const size_t nblk_max = ((pc * nchunk + 31) / 32) * 4;
-  // which (coordinate, slot) pairs have a point to walk; which slots are CRS points with stored lines
-  std::vector<uint32_t> hwalk;
-  fixed_slots fs;
+// (coordinate, slot) pairs to walk and the CRS slots with stored lines, from what the shape says about every slot
+static void build_walk_list(gs_ctx* ctx, int K, const uint8_t* slot_kind, std::vector<uint32_t>& hwalk, fixed_slots& fs) {
+  using namespace gsi;
   fs.n = 0;
   int nfixed = 0;
   for (int k = 0; slot_kind && k < K; k++) nfixed += slot_kind[k] >= GS_SLOT_FIXED ? 1 : 0;
@@ -469,9 +515,90 @@ int gsi::run_pairing_product(gs_ctx* ctx, Scratch& sc, const g1_aff* X, const g2
       if (kind == GS_SLOT_WALK_B1 && b == 0) continue;
       hwalk.push_back(((uint32_t)b << 31) | (uint32_t)k);
     }
+}
+
+// Starts the G2 walks of a lone statement on the context's second stream (the Y slots must be complete on the main
+// stream); run_pairing_product picks the lines up through `wa`.  No-op (wa->lines = null) outside the latency regime.
+int gsi::g2_walk_ahead(gs_ctx* ctx, Scratch& sc, const g2_aff* Y, size_t nprob, int K, const uint8_t* slot_kind, walk_ahead* wa) {
+  wa->lines = nullptr;
+  std::vector<uint32_t> hwalk;
+  fixed_slots fs;
+  build_walk_list(ctx, K, slot_kind, hwalk, fs);
   const int nwalk = (int)hwalk.size();
+  if (nwalk == 0 || (size_t)((nwalk + 3) / 4) * nprob >= 16384) return GS_OK;
+  if (!ctx->stream2) CUDA_TRY(cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking));
+  CUDA_TRY(upload(ctx, sc, &wa->dwalk, hwalk.data(), hwalk.size()));
+  fp2* lines;
+  CUDA_TRY(sc.alloc(&lines, (size_t)nwalk * nprob * GS_NUM_LINES * 2));
+  cudaEvent_t fork;
+  CUDA_TRY(cudaEventCreateWithFlags(&fork, cudaEventDisableTiming));
+  CUDA_TRY(cudaEventCreateWithFlags(&wa->done, cudaEventDisableTiming));
+  CUDA_TRY(cudaEventRecord(fork, ctx->stream));
+  CUDA_TRY(cudaStreamWaitEvent(ctx->stream2, fork, 0));
+  cudaStream_t main_stream = ctx->stream;
+  ctx->stream = ctx->stream2;
+  int rc = [&]() -> int {
+    LAUNCH(k_g2_walk, (size_t)nwalk * nprob, Y, lines, nprob, nprob, K, wa->dwalk, nwalk);
+    return GS_OK;
+  }();
+  ctx->stream = main_stream;
+  cudaEventDestroy(fork);
+  if (rc) return rc;
+  CUDA_TRY(cudaEventRecord(wa->done, ctx->stream2));
+  wa->lines = lines;
+  wa->nwalk = nwalk;
+  return GS_OK;
+}
+
+// ------------------------------------------------------------------ pairing-product pipeline
+// X, Y: device slot arrays [2][K][nprob].  Produces either ComT values (out_comt, AoS [p][4]) or
+// per-entry verdict bytes ok4[4][nprob] (compared with 1 / target).
+// Problems are processed in passes of `pc` so that the evaluated-line tiles stay within ctx->tile_budget
+// bytes of HBM; a pass is sized to a whole number of k_miller4 waves (2 groups x 148 SMs x 32 accumulators
+// / 4 entries = 2,368 problems per wave) when the batch is large enough.
+int gsi::run_pairing_product(gs_ctx* ctx, Scratch& sc, const g1_aff* X, const g2_aff* Y, size_t nprob, int K,
+                               fp12* out_comt, uint8_t* ok4, const fp12* target, fp12* out_partial, const uint8_t* slot_kind,
+                               const walk_ahead* wa) {
+  const size_t wave = 2368;
+  if (K == 0) {  // a shard that owns no slot: empty product
+    if (!out_partial) FAIL(GS_EARG, "pairing product over zero slots");
+    LAUNCH(k_fp12_set_one, nprob * 4, out_partial, nprob * 4);
+    return GS_OK;
+  }
+  // split the slots of a big statement over several accumulators when there are few problems
+  int S = K, nchunk = 1;
+  if (nprob < wave && K > 2) {
+    size_t c = (wave + nprob - 1) / nprob;
+    // at least 2 slots per chunk -- unless one slot per accumulator still fits a single wave: then the Miller chain
+    // of a lone statement is 62 squarings + 68 line steps instead of 62 + 136 (latency form)
+    const size_t cmax = nprob * (size_t)K <= wave ? (size_t)K : (size_t)(K + 1) / 2;
+    if (c > cmax) c = cmax;
+    if (c < 1) c = 1;
+    S = (int)((K + c - 1) / c);
+  }
+  if (S > M4_MAXS) S = M4_MAXS;
+  nchunk = (K + S - 1) / S;
+  const size_t per_prob = (size_t)4 * nchunk * S * GS_NUM_LINES * M4_TILE * 4 / 32;  // tile bytes per problem
+  size_t pc = ctx->tile_budget / per_prob;
+  if (pc >= nprob) {
+    pc = nprob;
+  } else {
+    if (pc > wave) pc -= pc % wave;
+    if (pc < 32) pc = 32;
+    pc -= pc % 32;
+  }
+  const size_t nblk_max = ((pc * nchunk + 31) / 32) * 4;
+  // which (coordinate, slot) pairs have a point to walk; which slots are CRS points with stored lines
+  std::vector<uint32_t> hwalk;
+  fixed_slots fs;
+  build_walk_list(ctx, K, slot_kind, hwalk, fs);
+  const int nwalk = (int)hwalk.size();
+  if (wa && (!wa->lines || wa->nwalk != nwalk || pc < nprob)) wa = nullptr;  // lines walked ahead only for a single pass
   uint32_t* dwalk;
-  CUDA_TRY(upload(ctx, sc, &dwalk, hwalk.data(), hwalk.size()));
+  if (wa)
+    dwalk = wa->dwalk;
+  else
+    CUDA_TRY(upload(ctx, sc, &dwalk, hwalk.data(), hwalk.size()));
   uint32_t *tiles, *masks, *PW;
   fp12* F;
   CUDA_TRY(sc.alloc(&PW, 2 * (size_t)K * 24 * pc));
@@ -486,7 +613,10 @@ int gsi::run_pairing_product(gs_ctx* ctx, Scratch& sc, const g1_aff* X, const g2
     // (6 points per thread was measured too: 162.6 ms vs 151.0 ms per 65,536 proofs -- the extra local memory costs
     // more than the shared inversion saves)
     if (fs.n) LAUNCH(k_fixed_tiles, (size_t)fs.n * 2 * np, PW, ctx->crs_lines, ctx->crs, tiles, masks, p0, np, K, S, fs);
-    if ((size_t)((nwalk + 3) / 4) * np < 16384)
+    if (wa) {
+      CUDA_TRY(cudaStreamWaitEvent(ctx->stream, wa->done, 0));
+      LAUNCH(k_eval_tiles, (size_t)nwalk * np, PW, Y, wa->lines, tiles, masks, nprob, np, K, S, dwalk, nwalk);
+    } else if ((size_t)((nwalk + 3) / 4) * np < 16384)
       LAUNCH_CFG(k_g2_prepare4<1>, (size_t)nwalk * np, 128, 0, PW, Y, tiles, masks, nprob, p0, np, K, S, dwalk, nwalk);
     else
       LAUNCH_CFG(k_g2_prepare4<4>, (size_t)((nwalk + 3) / 4) * np, 128, 0, PW, Y, tiles, masks, nprob, p0, np, K, S, dwalk, nwalk);

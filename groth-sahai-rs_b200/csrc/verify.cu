@@ -416,15 +416,16 @@ __global__ void __launch_bounds__(128) k_vmsm_reduce(verify_shape s, verify_args
 
 // sharded statement: keep the slots k = rank, rank + world, ... (K' of them) of the [2][K][nprob] slot arrays
 __global__ void k_gather_owned_slots(const g1_aff* __restrict__ X, const g2_aff* __restrict__ Y, g1_aff* __restrict__ Xo,
-                                     g2_aff* __restrict__ Yo, size_t nprob, int K, int Ko, int rank, int world) {
+                                     g2_aff* __restrict__ Yo, size_t nprob, int K, int Ko, int rank, int world, int do_x,
+                                     int do_y) {
   size_t id = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (id >= nprob * (size_t)Ko * 2) return;
   size_t p = id % nprob;
   size_t r = id / nprob;
   int ko = (int)(r % Ko), a = (int)(r / Ko);
   int k = rank + ko * world;
-  Xo[((size_t)a * Ko + ko) * nprob + p] = X[((size_t)a * K + k) * nprob + p];
-  Yo[((size_t)a * Ko + ko) * nprob + p] = Y[((size_t)a * K + k) * nprob + p];
+  if (do_x) Xo[((size_t)a * Ko + ko) * nprob + p] = X[((size_t)a * K + k) * nprob + p];
+  if (do_y) Yo[((size_t)a * Ko + ko) * nprob + p] = Y[((size_t)a * K + k) * nprob + p];
 }
 // partial[part][p][e] (AoS, as the ranks exchange them)  ->  F[(part*4 + e)*nprob + p] (launch_final_exp's layout)
 __global__ void k_partials_to_chunks(const fp12* __restrict__ partials, fp12* __restrict__ F, size_t nprob, int nparts) {
@@ -502,6 +503,29 @@ static int verify_impl(gs_ctx* ctx, int type, size_t count, size_t m, size_t n, 
     CUDA_TRY(sc.alloc(&part, (size_t)s.nchunk * s.n_out * 2 * nprob));
     CUDA_TRY(sc.alloc(&ok4, 4 * nprob));
     LAUNCH(k_verify_assemble, nprob * (size_t)s.K, s, v, ctx->crs, X, Y, nprob);
+    // what the shape alone says about the G2 side of every slot (k_verify_assemble): CRS points have stored lines,
+    // iota_2 images have no first coordinate
+    std::vector<uint8_t> kind_all(s.K, gsi::GS_SLOT_WALK), kind;
+    for (int k = s.sB; k < s.sPi; k++) kind_all[k] = s.groupB ? gsi::GS_SLOT_WALK_B1 : (uint8_t)(gsi::GS_SLOT_FIXED + 2);
+    for (int j = 0; j < s.cy; j++) kind_all[s.sTh + j] = (uint8_t)(gsi::GS_SLOT_FIXED + j);
+    if (type == 1 || type == 3) kind_all[s.sT] = (uint8_t)(gsi::GS_SLOT_FIXED + 2);
+    if (type == 2) kind_all[s.sT] = gsi::GS_SLOT_WALK_B1;
+    for (int k = world > 1 ? rank : 0; k < s.K; k += world > 1 ? world : 1) kind.push_back(kind_all[k]);
+    // the G2 side is final now: a lone statement starts its line walks on the second stream, next to the MSM below
+    g1_aff* Xo = nullptr;
+    g2_aff* Yo = nullptr;
+    const g2_aff* Yp = Y;
+    if (world > 1) {
+      CUDA_TRY(sc.alloc(&Xo, 2 * (size_t)(Ko ? Ko : 1) * nprob));
+      CUDA_TRY(sc.alloc(&Yo, 2 * (size_t)(Ko ? Ko : 1) * nprob));
+      LAUNCH(k_gather_owned_slots, nprob * (size_t)Ko * 2, X, Y, Xo, Yo, nprob, s.K, Ko, rank, world, 0, 1);
+      Yp = Yo;
+    }
+    gsi::walk_ahead wa;
+    if (Ko > 0) {
+      int rcw = gsi::g2_walk_ahead(ctx, sc, Yp, nprob, Ko, kind.data(), &wa);
+      if (rcw) return rcw;
+    }
     if (use_wtab) {
       const int nb = s.nbases * 2;
       const size_t nrows = (size_t)nb * GS_WT_W;
@@ -533,31 +557,25 @@ static int verify_impl(gs_ctx* ctx, int type, size_t count, size_t m, size_t n, 
     }
     LAUNCH(k_vmsm_reduce, nprob * owned_out * 2, s, v, partr, X, nprob);
     const g1_aff* Xp = X;
-    const g2_aff* Yp = Y;
     if (world > 1) {
-      g1_aff* Xo;
-      g2_aff* Yo;
-      CUDA_TRY(sc.alloc(&Xo, 2 * (size_t)(Ko ? Ko : 1) * nprob));
-      CUDA_TRY(sc.alloc(&Yo, 2 * (size_t)(Ko ? Ko : 1) * nprob));
-      LAUNCH(k_gather_owned_slots, nprob * (size_t)Ko * 2, X, Y, Xo, Yo, nprob, s.K, Ko, rank, world);
+      LAUNCH(k_gather_owned_slots, nprob * (size_t)Ko * 2, X, Y, Xo, Yo, nprob, s.K, Ko, rank, world, 1, 0);
       Xp = Xo;
-      Yp = Yo;
     }
-    // what the shape alone says about the G2 side of every slot (k_verify_assemble): CRS points have stored lines,
-    // iota_2 images have no first coordinate
-    std::vector<uint8_t> kind_all(s.K, gsi::GS_SLOT_WALK), kind;
-    for (int k = s.sB; k < s.sPi; k++) kind_all[k] = s.groupB ? gsi::GS_SLOT_WALK_B1 : (uint8_t)(gsi::GS_SLOT_FIXED + 2);
-    for (int j = 0; j < s.cy; j++) kind_all[s.sTh + j] = (uint8_t)(gsi::GS_SLOT_FIXED + j);
-    if (type == 1 || type == 3) kind_all[s.sT] = (uint8_t)(gsi::GS_SLOT_FIXED + 2);
-    if (type == 2) kind_all[s.sT] = gsi::GS_SLOT_WALK_B1;
-    for (int k = world > 1 ? rank : 0; k < s.K; k += world > 1 ? world : 1) kind.push_back(kind_all[k]);
     int rc;
     if (out_partial_dev) {
-      rc = gsi::run_pairing_product(ctx, sc, Xp, Yp, nprob, Ko, nullptr, nullptr, nullptr, out_partial_dev + off * 4, kind.data());
+      rc = gsi::run_pairing_product(ctx, sc, Xp, Yp, nprob, Ko, nullptr, nullptr, nullptr, out_partial_dev + off * 4, kind.data(), &wa);
+      if (wa.done) {  // the scratch the walk writes to is freed on the main stream: order it after the walk in any case
+        cudaStreamWaitEvent(ctx->stream, wa.done, 0);
+        cudaEventDestroy(wa.done);
+      }
       if (rc) return rc;
     } else {
       rc = gsi::run_pairing_product(ctx, sc, Xp, Yp, nprob, Ko, nullptr, ok4, type == GS_PPE ? (const fp12*)v.target : nullptr,
-                                    nullptr, kind.data());
+                                    nullptr, kind.data(), &wa);
+      if (wa.done) {  // the scratch the walk writes to is freed on the main stream: order it after the walk in any case
+        cudaStreamWaitEvent(ctx->stream, wa.done, 0);
+        cudaEventDestroy(wa.done);
+      }
       if (rc) return rc;
       LAUNCH(k_and4, nprob, ok4, out_ok_dev + off, nprob);
     }
