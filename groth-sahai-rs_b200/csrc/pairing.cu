@@ -60,10 +60,10 @@ __global__ void __launch_bounds__(128) k_g1_prep(const g1_aff* __restrict__ X, u
   }
 }
 
-// one thread per (b, group of G2_E consecutive slots, problem).  The G2_E running points T_i (192 B each) live
-// in thread-local memory (L1/L2-resident, lane-interleaved by the hardware): shared memory would cap the
+// k_g2_prepare4<E>: one thread per (group of E walk-list entries, problem).  The E running points T_i (192 B each)
+// live in thread-local memory (L1/L2-resident, lane-interleaved by the hardware): shared memory would cap the
 // kernel at 8 warps per SM, and the walk is latency-bound (long dependent chains in the division steps), so
-// occupancy matters more than the few hundred bytes of local traffic per step.
+// occupancy matters more than the few hundred bytes of local traffic per step (20 warps/SM at 96 registers).
 // tile stores bypass the usual L2 retention (st.global.cs): the tiles are written once and read once by k_miller4
 // much later, while the running points in local memory should stay L2-resident.
 __device__ GS_INL void cq_st_stream(uint32_t* p, const fp& a) {

@@ -1,12 +1,15 @@
 // Optimal-ate pairing on BLS12-381, split the B200 way:
 //
-//   (1) g2_prepare_*   one thread per G2 point: walks T <- 2T / T+Q over the 63+5 steps of
-//                      |x| = 0xd201000000010000 and emits the 68 line-coefficient triples
-//                      (3 x Fp2 = 288 B each, 19,584 B per point) into HBM.  Small state
-//                      (T = 72 words), shared by every ComT entry that uses the point.
-//   (2) miller_*       one thread per GT accumulator: f <- f^2 * prod_k line_k(P_k); the only
-//                      wide state is f itself; line triples are streamed from HBM.
-//   (3) final_exp      easy part + the arkworks hard part (x-1)^2 (x+p)(x^2+p^2-1) + 3.
+//   (1) line walk      a thread walks E G2 points in AFFINE coordinates over the 63+5 steps of
+//                      |x| = 0xd201000000010000 (g2_affine_step below: one shared safegcd inversion per
+//                      step), evaluates every line at the slot's two G1 coordinates and writes the
+//                      unit-w^3 tiles that the Miller kernel consumes (pairing.cu k_g2_prepare4).
+//   (2) Miller         6 warps = 32 GT accumulators, one warp per w-power coefficient (coop12.cuh):
+//                      f <- f^2 * prod_k line_k(P_k), tiles streamed from HBM with cp.async.
+//   (3) final exp      easy part + the arkworks hard part (x-1)^2 (x+p)(x^2+p^2-1) + 3 as an op
+//                      program over shared-memory buffers (finalexp.cu).
+// The homogeneous-projective steps and the thread-per-accumulator tower code below are the first
+// generation, kept because tests/hostsim uses them as an independent cross-check of the cooperative path.
 //
 // Replaces: ark-ec `Bls12::multi_miller_loop` + `final_exponentiation` as reached from
 // ComT::pairing / ComT::pairing_sum (src/data_structures.rs:484-502) and generator.rs:116.
