@@ -274,6 +274,8 @@ def bench_c4(args):
         ok = eng.verify_batch(ty, E, m, n, *cols)
         assert ok == b"\x01" * E, f"type {ty}: {ok.count(1)} of {E} verified"
         t_v, ok = wall(lambda: eng.verify_batch(ty, E, m, n, *cols), 2)
+        kprof_p, _ = profiled(eng, pb)
+        kprof_v, _ = profiled(eng, lambda: eng.verify_batch(ty, E, m, n, *cols))
         # tamper one equation: swap two gamma rows' worth of bytes of equation 3
         badG = bytearray(cols[2])
         o = 3 * m * n * 32
@@ -283,6 +285,7 @@ def bench_c4(args):
         okb = eng.verify_batch(ty, E, m, n, *bad)
         assert okb == b"\x01" * 3 + b"\x00" + b"\x01" * (E - 4)
         res[["PPE", "MSMEG1", "MSMEG2", "QuadEqu"][ty]] = {"proved_per_sec": round(E / t_p, 1), "verified_per_sec": round(E / t_v, 1),
+                                                           "prove_kernels": kprof_p, "verify_kernels": kprof_v,
                                                            "prove_single_call_ms": round(t_one * 1e3, 3), "prove_batch_ms": round(t_p * 1e3, 2), "verify_batch_ms": round(t_v * 1e3, 2)}
         total_p += t_p
         total_v += t_v
