@@ -284,6 +284,93 @@ __global__ void __launch_bounds__(128) k_g2_decompress(const uint8_t* __restrict
   ok[i] = good ? 1 : 0;
 }
 
+// ------------------------------------------------------------------ uncompressed encodings (serialize_uncompressed)
+// G1: 96 B = x || y big-endian, G2: 192 B = x.c1 || x.c0 || y.c1 || y.c0; flag bits of byte 0: 0x80 must be clear,
+// 0x40 = infinity (0x20, the sort flag, is not used).  Reading validates: coordinates < p, on the curve, in the subgroup.
+__global__ void __launch_bounds__(128) k_g1_uncompressed(const g1_aff* __restrict__ in, uint8_t* __restrict__ out, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  g1_aff p = in[i];
+  uint8_t b[96];
+  for (int j = 0; j < 96; j++) b[j] = 0;
+  if (p.is_inf()) {
+    b[0] = 0x40;
+  } else {
+    fp_to_be(b, p.x);
+    fp_to_be(b + 48, p.y);
+  }
+  for (int j = 0; j < 96; j++) out[i * 96 + j] = b[j];
+}
+__global__ void __launch_bounds__(128) k_g1_from_uncompressed(const uint8_t* __restrict__ in, g1_aff* __restrict__ out,
+                                                              uint8_t* __restrict__ ok, size_t n, int check_subgroup) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint8_t b[96];
+  for (int j = 0; j < 96; j++) b[j] = in[i * 96 + j];
+  g1_aff p;
+  p.set_inf();
+  bool good = (b[0] & 0x80) == 0;
+  if (good && !(b[0] & 0x40)) {
+    good = (b[0] & 0x20) == 0 && (b[48] & 0xE0) == 0 && fp_from_be(p.x, b) && fp_from_be(p.y, b + 48);
+    if (good) {
+      fp lhs, rhs, four;
+      fp::sqr(lhs, p.y);
+      fp::sqr(rhs, p.x);
+      fp::mul(rhs, rhs, p.x);
+      for (int j = 0; j < 12; j++) four.l[j] = FP_FOUR(j);
+      fp::add(rhs, rhs, four);
+      good = lhs.equals(rhs);
+      if (good && check_subgroup) good = in_subgroup_g1(p);
+    }
+    if (!good) p.set_inf();
+  }
+  out[i] = p;
+  ok[i] = good ? 1 : 0;
+}
+__global__ void __launch_bounds__(128) k_g2_uncompressed(const g2_aff* __restrict__ in, uint8_t* __restrict__ out, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  g2_aff p = in[i];
+  uint8_t b[192];
+  for (int j = 0; j < 192; j++) b[j] = 0;
+  if (p.is_inf()) {
+    b[0] = 0x40;
+  } else {
+    fp_to_be(b, p.x.c1);
+    fp_to_be(b + 48, p.x.c0);
+    fp_to_be(b + 96, p.y.c1);
+    fp_to_be(b + 144, p.y.c0);
+  }
+  for (int j = 0; j < 192; j++) out[i * 192 + j] = b[j];
+}
+__global__ void __launch_bounds__(128) k_g2_from_uncompressed(const uint8_t* __restrict__ in, g2_aff* __restrict__ out,
+                                                              uint8_t* __restrict__ ok, size_t n, int check_subgroup) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint8_t b[192];
+  for (int j = 0; j < 192; j++) b[j] = in[i * 192 + j];
+  g2_aff p;
+  p.set_inf();
+  bool good = (b[0] & 0x80) == 0;
+  if (good && !(b[0] & 0x40)) {
+    good = (b[0] & 0x20) == 0 && ((b[48] | b[96] | b[144]) & 0xE0) == 0 && fp_from_be(p.x.c1, b) && fp_from_be(p.x.c0, b + 48) &&
+           fp_from_be(p.y.c1, b + 96) && fp_from_be(p.y.c0, b + 144);
+    if (good) {
+      fp2 lhs, rhs, bt;
+      fp2::sqr(lhs, p.y);
+      fp2::sqr(rhs, p.x);
+      fp2::mul(rhs, rhs, p.x);
+      for (int j = 0; j < 12; j++) bt.c0.l[j] = bt.c1.l[j] = FP_FOUR(j);
+      fp2::add(rhs, rhs, bt);
+      good = lhs.equals(rhs);
+      if (good && check_subgroup) good = in_subgroup_g2(p);
+    }
+    if (!good) p.set_inf();
+  }
+  out[i] = p;
+  ok[i] = good ? 1 : 0;
+}
+
 // ------------------------------------------------------------------ scalars and GT: canonical little-endian integers
 // Fr: 32 B LE (ark-ff CanonicalSerialize for Fp<4 limbs>); out-of-range input is rejected
 __global__ void k_fr_to_bytes(const fr* __restrict__ in, uint32_t* __restrict__ out, size_t n) {
@@ -390,6 +477,32 @@ int gs_g2_decompress(gs_ctx* ctx, size_t n, const uint8_t* in, int check_subgrou
   if (n && !out_ok) return GS_EARG;
   return convert(ctx, n, in, 96, out, sizeof(gs_g2), out_ok, [&](uint8_t* di, uint8_t* dout, uint8_t* dok) {
     LAUNCH(k_g2_decompress, n, di, (g2_aff*)dout, dok, n, check_subgroup);
+    return GS_OK;
+  });
+}
+int gs_g1_serialize_uncompressed(gs_ctx* ctx, size_t n, const gs_g1* pts, uint8_t* out) {
+  return convert(ctx, n, pts, sizeof(gs_g1), out, 96, nullptr, [&](uint8_t* di, uint8_t* dout, uint8_t*) {
+    LAUNCH(k_g1_uncompressed, n, (const g1_aff*)di, dout, n);
+    return GS_OK;
+  });
+}
+int gs_g1_deserialize_uncompressed(gs_ctx* ctx, size_t n, const uint8_t* in, int check_subgroup, gs_g1* out, uint8_t* out_ok) {
+  if (n && !out_ok) return GS_EARG;
+  return convert(ctx, n, in, 96, out, sizeof(gs_g1), out_ok, [&](uint8_t* di, uint8_t* dout, uint8_t* dok) {
+    LAUNCH(k_g1_from_uncompressed, n, di, (g1_aff*)dout, dok, n, check_subgroup);
+    return GS_OK;
+  });
+}
+int gs_g2_serialize_uncompressed(gs_ctx* ctx, size_t n, const gs_g2* pts, uint8_t* out) {
+  return convert(ctx, n, pts, sizeof(gs_g2), out, 192, nullptr, [&](uint8_t* di, uint8_t* dout, uint8_t*) {
+    LAUNCH(k_g2_uncompressed, n, (const g2_aff*)di, dout, n);
+    return GS_OK;
+  });
+}
+int gs_g2_deserialize_uncompressed(gs_ctx* ctx, size_t n, const uint8_t* in, int check_subgroup, gs_g2* out, uint8_t* out_ok) {
+  if (n && !out_ok) return GS_EARG;
+  return convert(ctx, n, in, 192, out, sizeof(gs_g2), out_ok, [&](uint8_t* di, uint8_t* dout, uint8_t* dok) {
+    LAUNCH(k_g2_from_uncompressed, n, di, (g2_aff*)dout, dok, n, check_subgroup);
     return GS_OK;
   });
 }

@@ -24,6 +24,7 @@ EXPORTED_SYMBOLS = [
     "gs_comt_add", "gs_comt_sub", "gs_comt_neg", "gs_comt_sum", "gs_fr_add", "gs_fr_sub", "gs_fr_neg", "gs_fr_scale",
     "gs_g1_compress", "gs_g1_decompress", "gs_g2_compress", "gs_g2_decompress",
     "gs_fr_to_bytes", "gs_fr_from_bytes", "gs_gt_to_bytes", "gs_gt_from_bytes",
+    "gs_g1_serialize_uncompressed", "gs_g1_deserialize_uncompressed", "gs_g2_serialize_uncompressed", "gs_g2_deserialize_uncompressed",
 ]
 
 
@@ -88,8 +89,10 @@ def load_library():
         lib.gs_fr_scale.argtypes = [vp, sz, vp, vp, vp]
         for f in ("gs_g1_compress", "gs_g2_compress", "gs_fr_to_bytes", "gs_gt_to_bytes"):
             getattr(lib, f).argtypes = [vp, sz, vp, vp]
-        for f in ("gs_g1_decompress", "gs_g2_decompress"):
+        for f in ("gs_g1_decompress", "gs_g2_decompress", "gs_g1_deserialize_uncompressed", "gs_g2_deserialize_uncompressed"):
             getattr(lib, f).argtypes = [vp, sz, vp, ci, vp, vp]
+        for f in ("gs_g1_serialize_uncompressed", "gs_g2_serialize_uncompressed"):
+            getattr(lib, f).argtypes = [vp, sz, vp, vp]
         for f in ("gs_fr_from_bytes", "gs_gt_from_bytes"):
             getattr(lib, f).argtypes = [vp, sz, vp, vp, vp]
         _lib = lib
@@ -349,8 +352,10 @@ class Engine:
     # ---- wire formats: kind in ("g1", "g2") for points, ("fr", "gt") for canonical integers
     _WIRE = {"g1": (G1, 48), "g2": (G2, 96), "fr": (FR, 32), "gt": (GT, 576)}
 
-    def serialize(self, kind, elems: bytes) -> bytes:
-        """ABI elements -> wire bytes (compressed points / canonical little-endian integers)."""
+    def serialize(self, kind, elems: bytes, compressed=True) -> bytes:
+        """ABI elements -> wire bytes (compressed / uncompressed points, canonical little-endian integers)."""
+        if not compressed and kind in ("g1", "g2"):
+            return self._uncompressed(kind, elems)
         esz, wsz = self._WIRE[kind]
         n = len(elems) // esz
         assert len(elems) == n * esz
@@ -360,8 +365,27 @@ class Engine:
         self._chk(fn(self.h, n, k[1], ctypes.cast(out, ctypes.c_void_p)))
         return out.raw[: n * wsz]
 
-    def deserialize(self, kind, wire: bytes, check_subgroup=True):
+    def _uncompressed(self, kind, elems):
+        esz = self._WIRE[kind][0]
+        n = len(elems) // esz
+        assert len(elems) == n * esz
+        out = ctypes.create_string_buffer(max(1, n * esz))
+        k = _buf(elems)
+        self._chk(getattr(self.lib, f"gs_{kind}_serialize_uncompressed")(self.h, n, k[1], ctypes.cast(out, ctypes.c_void_p)))
+        return out.raw[: n * esz]
+
+    def deserialize(self, kind, wire: bytes, check_subgroup=True, compressed=True):
         """wire bytes -> (ABI elements, verdict bytes); invalid encodings give verdict 0 and a zeroed element."""
+        if not compressed and kind in ("g1", "g2"):
+            esz = self._WIRE[kind][0]
+            n = len(wire) // esz
+            assert len(wire) == n * esz
+            out = ctypes.create_string_buffer(max(1, n * esz))
+            ok = ctypes.create_string_buffer(max(1, n))
+            k = _buf(wire)
+            self._chk(getattr(self.lib, f"gs_{kind}_deserialize_uncompressed")(self.h, n, k[1], 1 if check_subgroup else 0,
+                                                                               ctypes.cast(out, ctypes.c_void_p), ctypes.cast(ok, ctypes.c_void_p)))
+            return out.raw[: n * esz], ok.raw[:n]
         esz, wsz = self._WIRE[kind]
         n = len(wire) // wsz
         assert len(wire) == n * wsz

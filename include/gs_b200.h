@@ -215,6 +215,12 @@ int gs_g1_compress(gs_ctx* ctx, size_t n, const gs_g1* pts, uint8_t* out /* 48 n
 int gs_g1_decompress(gs_ctx* ctx, size_t n, const uint8_t* in, int check_subgroup, gs_g1* out, uint8_t* out_ok);
 int gs_g2_compress(gs_ctx* ctx, size_t n, const gs_g2* pts, uint8_t* out /* 96 n */);
 int gs_g2_decompress(gs_ctx* ctx, size_t n, const uint8_t* in, int check_subgroup, gs_g2* out, uint8_t* out_ok);
+/* serialize_uncompressed: G1 96 B = x || y, G2 192 B = x.c1 || x.c0 || y.c1 || y.c0 (big-endian), byte 0: 0x80 clear,
+ * 0x40 infinity.  Reading validates coordinates < p, the curve equation and (check_subgroup != 0) the subgroup. */
+int gs_g1_serialize_uncompressed(gs_ctx* ctx, size_t n, const gs_g1* pts, uint8_t* out /* 96 n */);
+int gs_g1_deserialize_uncompressed(gs_ctx* ctx, size_t n, const uint8_t* in, int check_subgroup, gs_g1* out, uint8_t* out_ok);
+int gs_g2_serialize_uncompressed(gs_ctx* ctx, size_t n, const gs_g2* pts, uint8_t* out /* 192 n */);
+int gs_g2_deserialize_uncompressed(gs_ctx* ctx, size_t n, const uint8_t* in, int check_subgroup, gs_g2* out, uint8_t* out_ok);
 /* Fr <-> 32 B little-endian canonical integer; GT <-> 12 x 48 B little-endian canonical, tower order.
  * from_bytes rejects integers >= the modulus (out_ok[i] = 0, value zeroed). */
 int gs_fr_to_bytes(gs_ctx* ctx, size_t n, const gs_fr* in, uint8_t* out);

@@ -132,7 +132,45 @@ def g1_serialize_uncompressed(pt) -> bytes:
     return (pt[0] % P).to_bytes(48, "big") + (pt[1] % P).to_bytes(48, "big")
 
 
+def g1_deserialize_uncompressed(b: bytes):
+    assert len(b) == 96
+    if b[0] & 0x80:
+        return False, None
+    if b[0] & 0x40:
+        return True, None
+    if b[0] & 0x20:
+        return False, None
+    x, y = int.from_bytes(b[:48], "big"), int.from_bytes(b[48:], "big")
+    if x >= P or y >= P or (y * y - x * x * x - 4) % P != 0:
+        return False, None
+    return (True, (x, y)) if in_subgroup_g1((x, y)) else (False, None)
+
+
 # ---------------------------------------------------------------- G2
+def g2_serialize_uncompressed(pt) -> bytes:
+    if pt is None:
+        return bytes([0x40]) + bytes(191)
+    x, y = pt
+    return b"".join((v % P).to_bytes(48, "big") for v in (x.c1, x.c0, y.c1, y.c0))
+
+
+def g2_deserialize_uncompressed(b: bytes):
+    assert len(b) == 192
+    if b[0] & 0x80:
+        return False, None
+    if b[0] & 0x40:
+        return True, None
+    if b[0] & 0x20:
+        return False, None
+    v = [int.from_bytes(b[48 * i:48 * (i + 1)], "big") for i in range(4)]
+    if any(t >= P for t in v):
+        return False, None
+    x, y = Fp2(v[1], v[0]), Fp2(v[3], v[2])
+    if not y * y == x * x * x + Fp2(4, 4):
+        return False, None
+    return (True, (x, y)) if in_subgroup_g2((x, y)) else (False, None)
+
+
 def g2_compress(pt) -> bytes:
     if pt is None:
         return bytes([0xC0]) + bytes(95)

@@ -163,3 +163,38 @@ def test_struct_serialisation_round_trip(eng):
         api.deserialize_equ_proof(bytes(bad), eng)
     with pytest.raises(api.SerializationError):
         api.deserialize_equ_proof(wp[:-3], eng)
+
+
+def test_uncompressed_encodings(eng):
+    """serialize_uncompressed / deserialize_uncompressed (the reference round-trips both modes,
+    data_structures.rs:1269-1309): bytes equal the oracle's, round trip, and the rejections of Validate::Yes."""
+    rng = SeededRng(81)
+    p1 = [G1_GEN, None] + [rng.g1() for _ in range(6)]
+    w1 = eng.serialize("g1", b"".join(g1_b(p) for p in p1), compressed=False)
+    assert w1 == b"".join(ser.g1_serialize_uncompressed(p) for p in p1)
+    back, ok = eng.deserialize("g1", w1, compressed=False)
+    assert ok == b"\x01" * len(p1) and back == b"".join(g1_b(p) for p in p1)
+    p2 = [G2_GEN_FP2, None] + [rng.g2() for _ in range(4)]
+    w2 = eng.serialize("g2", b"".join(g2_b(p) for p in p2), compressed=False)
+    assert w2 == b"".join(ser.g2_serialize_uncompressed(p) for p in p2)
+    back, ok = eng.deserialize("g2", w2, compressed=False)
+    assert ok == b"\x01" * len(p2) and back == b"".join(g2_b(p) for p in p2)
+    # rejections: compressed flag set, y off the curve, coordinate >= p, curve point outside the subgroup
+    g = ser.g1_serialize_uncompressed(G1_GEN)
+    bad = [bytes([g[0] | 0x80]) + g[1:], g[:95] + bytes([g[95] ^ 1]), P.to_bytes(48, "big") + g[48:]]
+    x = 2
+    while True:
+        x += 1
+        y = ser.fp_sqrt((x ** 3 + 4) % P)
+        if y is not None and not ser.in_subgroup_g1((x, y)):
+            break
+    bad.append(x.to_bytes(48, "big") + y.to_bytes(48, "big"))
+    back, ok = eng.deserialize("g1", b"".join(bad), compressed=False)
+    assert ok == bytes(4) and back == bytes(96 * 4)
+    for b_ in bad:
+        assert ser.g1_deserialize_uncompressed(b_)[0] is False
+    assert eng.deserialize("g1", bad[3], check_subgroup=False, compressed=False)[1] == b"\x01"
+    g2w = ser.g2_serialize_uncompressed(G2_GEN_FP2)
+    bad2 = [g2w[:191] + bytes([g2w[191] ^ 1]), g2w[:96] + P.to_bytes(48, "big") + g2w[144:]]
+    assert eng.deserialize("g2", b"".join(bad2), compressed=False)[1] == bytes(2)
+    assert all(ser.g2_deserialize_uncompressed(b_)[0] is False for b_ in bad2)
