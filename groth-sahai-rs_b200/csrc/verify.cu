@@ -254,32 +254,39 @@ __global__ void __launch_bounds__(128) k_vmsm_partial(verify_shape s, verify_arg
 // are built once (4,096 additions per base coordinate) and every scalar product costs 32 mixed additions and no
 // doubling, against ~60 additions + a share of 256 doublings in the Straus kernel above.  Break-even is at
 // ~160 outputs per base; C3 has 1,024 (2.1 M products: 147 M -> 75 M point additions).
-constexpr int GS_WT_C = 8, GS_WT_W = 32, GS_WT_H = 128;
+// Window width: c = 8 (32 windows x 128 entries), or c = 10 (26 x 512) when a base serves >= 4,096 outputs -- a batch of
+// equations over shared commitments (C4: 16,384 outputs per base) -- where 19 % fewer additions outweigh the 3x table.
+struct wt_geom {
+  int c, W, H;
+};
+static inline wt_geom wt_choose(size_t outputs_per_base) {
+  return outputs_per_base >= 4096 ? wt_geom{10, 26, 512} : wt_geom{8, 32, 128};
+}
 // thread -> flat base b: J[b*W + w] = 2^(8w) * base_b   (one Jacobian doubling chain)
 __global__ void __launch_bounds__(128) k_wtab_bases(verify_shape s, verify_args v, const crs_dev* __restrict__ crs,
-                                                    g1_jac* __restrict__ J, int nb) {
+                                                    g1_jac* __restrict__ J, int nb, wt_geom g) {
   int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= nb) return;
   g1_aff B = vmsm_base(s, v, crs, 0, b >> 1, b & 1);
   g1_jac j;
   j.from_affine(B);
-  for (int w = 0; w < GS_WT_W; w++) {
-    J[(size_t)b * GS_WT_W + w] = j;
-    if (w + 1 < GS_WT_W)
-      for (int i = 0; i < GS_WT_C; i++) g1_jac::dbl(j, j);
+  for (int w = 0; w < g.W; w++) {
+    J[(size_t)b * g.W + w] = j;
+    if (w + 1 < g.W)
+      for (int i = 0; i < g.c; i++) g1_jac::dbl(j, j);
   }
 }
 // thread -> (row (b, w), run r): the multiples d = r*RUN + 1 .. r*RUN + RUN of the row's base B = tab[row*H]:
 // start (r*RUN + 1) B = B + r * (RUN B) (5 doublings, <= 3 additions), then RUN - 1 mixed additions; 4 runs per row
 // keep the dependent chain short (the kernel is latency-bound: 65 k rows are a fraction of one wave).
 constexpr int GS_WT_RUN = 32;
-__global__ void __launch_bounds__(128) k_wtab_fill(const g1_aff* __restrict__ tab, g1_jac* __restrict__ J, size_t nrows) {
-  constexpr int RUNS = GS_WT_H / GS_WT_RUN;
+__global__ void __launch_bounds__(128) k_wtab_fill(const g1_aff* __restrict__ tab, g1_jac* __restrict__ J, size_t nrows, int H) {
+  const int RUNS = H / GS_WT_RUN;
   size_t id = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (id >= nrows * RUNS) return;
   size_t row = id / RUNS;
   int r = (int)(id % RUNS);
-  g1_aff B = tab[row * GS_WT_H];
+  g1_aff B = tab[row * H];
   g1_jac acc;
   acc.from_affine(B);
   if (r > 0) {
@@ -287,7 +294,7 @@ __global__ void __launch_bounds__(128) k_wtab_fill(const g1_aff* __restrict__ ta
     for (int i = 0; i < 5; i++) g1_jac::dbl(step, step);  // RUN * B
     for (int i = 0; i < r; i++) g1_jac::add(acc, acc, step);
   }
-  g1_jac* o = J + row * GS_WT_H + (size_t)r * GS_WT_RUN;
+  g1_jac* o = J + row * H + (size_t)r * GS_WT_RUN;
   o[0] = acc;
   for (int d = 1; d < GS_WT_RUN; d++) {
     g1_jac::add_mixed(acc, acc, B);
@@ -334,7 +341,7 @@ __global__ void __launch_bounds__(128) k_jac_to_affine_blocks(const g1_jac* __re
 }
 // thread -> (p, jj, a, chunk): same outputs as k_vmsm_partial, bases looked up in the shared tables
 __global__ void __launch_bounds__(128) k_vmsm_wsum(verify_shape s, verify_args v, const g1_aff* __restrict__ tab,
-                                                   g1_jac* __restrict__ part, size_t nprob) {
+                                                   g1_jac* __restrict__ part, size_t nprob, wt_geom g) {
   size_t id = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int n_own = s.n_out_owned();  // sharded statement: the other outputs' Miller pairs run on other ranks
   size_t total = nprob * (size_t)n_own * 2 * s.nchunk;
@@ -353,7 +360,7 @@ __global__ void __launch_bounds__(128) k_vmsm_wsum(verify_shape s, verify_args v
     if (!vmsm_scalar(sv, s, v, p, i, jj) || sv.is_zero()) continue;
     uint32_t k[8];
     fr_from_mont(k, sv);
-    fixed_base_accumulate<FpOps>(acc, tab + ((size_t)(i * 2 + a) * GS_WT_W) * GS_WT_H, k, GS_WT_C, GS_WT_W, (size_t)GS_WT_H);
+    fixed_base_accumulate<FpOps>(acc, tab + ((size_t)(i * 2 + a) * g.W) * g.H, k, g.c, g.W, (size_t)g.H);
   }
   part[(((size_t)ch * s.n_out + jj) * 2 + a) * nprob + p] = acc;
 }
@@ -528,16 +535,17 @@ static int verify_impl(gs_ctx* ctx, int type, size_t count, size_t m, size_t n, 
     }
     if (use_wtab) {
       const int nb = s.nbases * 2;
-      const size_t nrows = (size_t)nb * GS_WT_W;
+      const wt_geom g = wt_choose(owned_out * nprob);
+      const size_t nrows = (size_t)nb * g.W;
       g1_aff* wtab;
       g1_jac* J;
-      CUDA_TRY(sc.alloc(&wtab, nrows * GS_WT_H));
-      CUDA_TRY(sc.alloc(&J, nrows * GS_WT_H));
-      LAUNCH(k_wtab_bases, (size_t)nb, s, v, ctx->crs, J, nb);
-      LAUNCH(k_jac_to_affine_blocks<1>, nrows, J, wtab, nrows, (size_t)GS_WT_H);
-      LAUNCH(k_wtab_fill, nrows * (GS_WT_H / GS_WT_RUN), wtab, J, nrows);
-      LAUNCH(k_jac_to_affine_blocks<8>, nrows * GS_WT_H / 8, J, wtab, nrows * GS_WT_H, (size_t)1);
-      LAUNCH(k_vmsm_wsum, nprob * owned_out * 2 * s.nchunk, s, v, wtab, part, nprob);
+      CUDA_TRY(sc.alloc(&wtab, nrows * g.H));
+      CUDA_TRY(sc.alloc(&J, nrows * g.H));
+      LAUNCH(k_wtab_bases, (size_t)nb, s, v, ctx->crs, J, nb, g);
+      LAUNCH(k_jac_to_affine_blocks<1>, nrows, J, wtab, nrows, (size_t)g.H);
+      LAUNCH(k_wtab_fill, nrows * (g.H / GS_WT_RUN), wtab, J, nrows, g.H);
+      LAUNCH(k_jac_to_affine_blocks<8>, nrows * g.H / 8, J, wtab, nrows * g.H, (size_t)1);
+      LAUNCH(k_vmsm_wsum, nprob * owned_out * 2 * s.nchunk, s, v, wtab, part, nprob, g);
     } else {
       g1_aff* vtab;
       fp* vtabx;

@@ -230,3 +230,22 @@ def test_c2_chunked_two_stream_commit(eng):
     Y = b"".join(q[(3 * i) % 8] for i in range(n))
     whole2 = eng.batch_commit_g2(Y, Rr)
     assert whole2 == eng.batch_commit_g2(Y[:192 * h], Rr[:64 * h]) + eng.batch_commit_g2(Y[192 * h:], Rr[64 * h:])
+
+
+def test_shared_commitments_wide_window_tables(eng):
+    """>= 4,096 MSM outputs per shared commitment (70 equations x 64 columns): the c = 10 window tables (26 windows x
+    512 entries) must give the verdicts of the per-equation path; one tampered Gamma entry is the only rejection."""
+    from workloads import instance_many
+    rng = SeededRng(160)
+    ty, m, n, E = 0, 3, 64, 70
+    A, B, G, T, X, Y, xr, yr, Tr = instance_many(eng, ty, m, n, E, rng)
+    pi, th = eng.prove_batch(ty, E, m, n, b"".join(A), b"".join(B), b"".join(G), X, Y, xr, yr, b"".join(Tr), shared_vars=True)
+    xc, yc = eng.batch_commit_g1(X, xr), eng.batch_commit_g2(Y, yr)
+    Gb = [bytearray(g) for g in G]
+    Gb[33][32 * (2 * n + 63) + 31] ^= 0x20                 # top byte of the last entry of equation 33
+    cols = [b"".join(A), b"".join(B), b"".join(bytes(g) for g in Gb), b"".join(T), xc * E, yc * E, pi, th]
+    ok = eng.verify_batch(ty, E, m, n, *cols)
+    assert list(ok) == [0 if e == 33 else 1 for e in range(E)]
+    for e in (0, 33, 69):
+        one = eng.verify(ty, m, n, A[e], B[e], bytes(Gb[e]), T[e], xc, yc, pi[e * 768:(e + 1) * 768], th[e * 384:(e + 1) * 384])
+        assert one is bool(ok[e])
