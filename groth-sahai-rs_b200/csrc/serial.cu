@@ -8,201 +8,18 @@
 // One thread per point: x -> y by a field square root, sign by the flag, membership by the endomorphism tests
 // arkworks itself uses (two 64-bit scalar multiplications instead of [r]P = O).
 #include "ctx.h"
-#include "endo.cuh"
+#include "wire.cuh"
 
 using namespace gs;
 
 namespace gs {
 
-static __device__ __constant__ uint32_t EXP_P14[12] = {0xffffeaabu, 0xee7fbfffu, 0xac54ffffu, 0x07aaffffu, 0x3dac3d89u, 0xd9cc34a8u,
-                                  0x3ce144afu, 0xd91dd2e1u, 0x90d2eb35u, 0x92c6e9edu, 0x8e5ff9a6u, 0x0680447au};   // (p+1)/4
-static __device__ __constant__ uint32_t EXP_PM34[12] = {0xffffeaaau, 0xee7fbfffu, 0xac54ffffu, 0x07aaffffu, 0x3dac3d89u, 0xd9cc34a8u,
-                                   0x3ce144afu, 0xd91dd2e1u, 0x90d2eb35u, 0x92c6e9edu, 0x8e5ff9a6u, 0x0680447au};  // (p-3)/4
-static __device__ __constant__ uint32_t EXP_PM12[12] = {0xffffd555u, 0xdcff7fffu, 0x58a9ffffu, 0x0f55ffffu, 0x7b587b12u, 0xb3986950u,
-                                   0x79c2895fu, 0xb23ba5c2u, 0x21a5d66bu, 0x258dd3dbu, 0x1cbff34du, 0x0d0088f5u};  // (p-1)/2
-
-enum { EXP_SEL_P14 = 0, EXP_SEL_PM34 = 1, EXP_SEL_PM12 = 2 };
-__device__ GS_INL uint32_t exp_limb(int sel, int i) {
-  return sel == EXP_SEL_P14 ? EXP_P14[i] : (sel == EXP_SEL_PM34 ? EXP_PM34[i] : EXP_PM12[i]);
-}
-
-// r = a^e, e one of the three 381-bit constants above (left-to-right binary; the exponents are public)
-template <class F>
-__device__ GS_NOINL void pow_const(typename F::T& r, const typename F::T& a, int sel) {
-  typename F::T acc;
-  F::set_one(acc);
-  bool started = false;
-#pragma unroll 1
-  for (int i = 11; i >= 0; i--) {
-    const uint32_t w = exp_limb(sel, i);
-#pragma unroll 1
-    for (int b = 31; b >= 0; b--) {
-      if (started) F::sqr(acc, acc);
-      if ((w >> b) & 1) {
-        if (started)
-          F::mul(acc, acc, a);
-        else
-          acc = a;
-        started = true;
-      }
-    }
-  }
-  r = acc;
-}
-
-// canonical (non-Montgomery) limbs of a
-__device__ GS_INL void fp_canon(uint32_t out[12], const fp& a) {
-  fp one_raw, t;
-  one_raw.set_zero();
-  one_raw.l[0] = 1;
-  fp::mul(t, a, one_raw);
-#pragma unroll
-  for (int i = 0; i < 12; i++) out[i] = t.l[i];
-}
-__device__ GS_INL bool limbs_gt(const uint32_t* a, const uint32_t* b, int n) {  // a > b
-  for (int i = n - 1; i >= 0; i--) {
-    if (a[i] != b[i]) return a[i] > b[i];
-  }
-  return false;
-}
-__device__ GS_INL bool fp_is_largest(const fp& y) {  // y > (p-1)/2  <=>  y > -y as integers
-  uint32_t c[12];
-  fp_canon(c, y);
-  return limbs_gt(c, EXP_PM12, 12);
-}
-__device__ GS_INL bool fp2_is_largest(const fp2& y) {  // Fp2 ordered with c1 most significant (ark-ff Ord, zcash)
-  if (!y.c1.is_zero()) return fp_is_largest(y.c1);
-  return fp_is_largest(y.c0);
-}
-// 48 big-endian bytes (top three bits of byte 0 masked off) -> Montgomery Fp; false when the integer is >= p
-__device__ GS_INL bool fp_from_be(fp& r, const uint8_t* b) {
-  uint32_t l[12], m[12];
-#pragma unroll
-  for (int j = 0; j < 12; j++) {
-    const uint8_t* q = b + 44 - 4 * j;
-    uint32_t hi = q[0];
-    if (j == 11) hi &= 0x1Fu;
-    l[j] = (hi << 24) | ((uint32_t)q[1] << 16) | ((uint32_t)q[2] << 8) | q[3];
-    m[j] = FpParams::mod(j);
-  }
-  if (!limbs_gt(m, l, 12)) return false;
-  fp raw, r2;
-#pragma unroll
-  for (int j = 0; j < 12; j++) {
-    raw.l[j] = l[j];
-    r2.l[j] = FP_R2(j);
-  }
-  fp::mul(r, raw, r2);
-  return true;
-}
-__device__ GS_INL void fp_to_be(uint8_t* b, const fp& a) {
-  uint32_t c[12];
-  fp_canon(c, a);
-#pragma unroll
-  for (int j = 0; j < 12; j++) {
-    uint8_t* q = b + 44 - 4 * j;
-    q[0] = (uint8_t)(c[j] >> 24);
-    q[1] = (uint8_t)(c[j] >> 16);
-    q[2] = (uint8_t)(c[j] >> 8);
-    q[3] = (uint8_t)c[j];
-  }
-}
-
-__device__ GS_INL bool fp_sqrt(fp& y, const fp& a) {  // p = 3 mod 4
-  pow_const<FpOps>(y, a, EXP_SEL_P14);
-  fp t;
-  fp::sqr(t, y);
-  return t.equals(a);
-}
-// Adj - Rodriguez-Henriquez, "Square root computation over even extension fields", Alg. 9 (q = 3 mod 4)
-__device__ GS_NOINL bool fp2_sqrt(fp2& x, const fp2& a) {
-  fp2 a1, alpha, x0, t, minus_one;
-  pow_const<Fp2Ops>(a1, a, EXP_SEL_PM34);
-  fp2::mul(x0, a1, a);        // a^((q+1)/4)
-  fp2::mul(alpha, a1, x0);    // a^((q-1)/2)
-  minus_one.set_zero();
-  fp_one(minus_one.c0);
-  fp::neg(minus_one.c0, minus_one.c0);
-  if (alpha.equals(minus_one)) {  // x = u * x0
-    fp::neg(x.c0, x0.c1);
-    x.c1 = x0.c0;
-  } else {
-    fp2 b;
-    t = alpha;
-    fp one;
-    fp_one(one);
-    fp::add(t.c0, t.c0, one);
-    pow_const<Fp2Ops>(b, t, EXP_SEL_PM12);
-    fp2::mul(x, b, x0);
-  }
-  fp2::sqr(t, x);
-  return t.equals(a);  // also rejects non-residues (Alg. 9's a0 = -1 test)
-}
-
-// ------------------------------------------------------------------ subgroup membership (Scott, ePrint 2021/1130)
-// The tests ark-bls12-381 runs in is_in_correct_subgroup_assuming_on_curve, 64-bit scalars instead of [r]P:
-//   G1 (Section 6):  phi(P) = -[x^2] P,  phi(x, y) = (beta x, y);  additionally [x]P = P (P != O) is rejected
-//   G2 (Section 4):  psi(Q) = [x] Q,     psi(x, y) = (conj(x) cx, conj(y) cy)  (untwist-Frobenius-twist)
-// beta, cx, cy below were derived from those relations on the generators (tests/test_serialize.py checks the
-// oracle versions against the definition [r]P = O on points inside and outside the subgroups).
-// r = [|x|] b, |x| = 0xd201000000010000 (63 doublings, 5 additions)
-template <class F>
-__device__ GS_NOINL void mul_x_abs(Jac<F>& r, const Jac<F>& b) {
-  Jac<F> acc = b;
-#pragma unroll 1
-  for (int bit = 62; bit >= 0; bit--) {
-    Jac<F>::dbl(acc, acc);
-    if ((0xd201000000010000ull >> bit) & 1) Jac<F>::add(acc, acc, b);
-  }
-  r = acc;
-}
-// Jacobian j == affine (ax, ay) ?   (j finite)
-template <class F>
-__device__ GS_INL bool jac_equals_affine(const Jac<F>& j, const typename F::T& ax, const typename F::T& ay) {
-  if (j.is_inf()) return false;
-  typename F::T z2, z3, t;
-  F::sqr(z2, j.Z);
-  F::mul(z3, z2, j.Z);
-  F::mul(t, ax, z2);
-  if (!t.equals(j.X)) return false;
-  F::mul(t, ay, z3);
-  return t.equals(j.Y);
-}
-__device__ GS_NOINL bool in_subgroup_g1(const g1_aff& p) {
-  g1_jac b, t1, t2;
-  b.from_affine(p);
-  mul_x_abs<FpOps>(t1, b);
-  if (jac_equals_affine<FpOps>(t1, p.x, p.y)) return false;  // [x]P = P
-  mul_x_abs<FpOps>(t2, t1);                                  // [x^2] P
-  fp bx, ny;
-  endo_phi_x(bx, p.x);
-  fp::neg(ny, p.y);
-  return jac_equals_affine<FpOps>(t2, bx, ny);               // [x^2]P = -phi(P)
-}
-__device__ GS_NOINL bool in_subgroup_g2(const g2_aff& q) {
-  g2_jac b, t;
-  b.from_affine(q);
-  mul_x_abs<Fp2Ops>(t, b);                                   // [|x|] Q = -[x] Q
-  g2_aff ps;
-  endo_psi(ps, q);
-  fp2 px = ps.x, py;
-  fp2::neg(py, ps.y);
-  return jac_equals_affine<Fp2Ops>(t, px, py);               // [|x|]Q = -psi(Q)
-}
-
-// ------------------------------------------------------------------ G1
+// ------------------------------------------------------------------ compressed points: one thread per point (wire.cuh)
 __global__ void __launch_bounds__(128) k_g1_compress(const g1_aff* __restrict__ in, uint8_t* __restrict__ out, size_t n) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  g1_aff p = in[i];
   uint8_t b[48];
-  if (p.is_inf()) {
-    for (int j = 0; j < 48; j++) b[j] = 0;
-    b[0] = 0xC0;
-  } else {
-    fp_to_be(b, p.x);
-    b[0] |= 0x80 | (fp_is_largest(p.y) ? 0x20 : 0);
-  }
+  g1_compress_point(b, in[i]);
   for (int j = 0; j < 48; j++) out[i * 48 + j] = b[j];
 }
 __global__ void __launch_bounds__(128) k_g1_decompress(const uint8_t* __restrict__ in, g1_aff* __restrict__ out, uint8_t* __restrict__ ok,
@@ -212,42 +29,15 @@ __global__ void __launch_bounds__(128) k_g1_decompress(const uint8_t* __restrict
   uint8_t b[48];
   for (int j = 0; j < 48; j++) b[j] = in[i * 48 + j];
   g1_aff p;
-  p.set_inf();
-  bool good = (b[0] & 0x80) != 0;
-  if (good && !(b[0] & 0x40)) {
-    good = fp_from_be(p.x, b);
-    if (good) {
-      fp rhs, four;
-      fp::sqr(rhs, p.x);
-      fp::mul(rhs, rhs, p.x);
-      for (int j = 0; j < 12; j++) four.l[j] = FP_FOUR(j);
-      fp::add(rhs, rhs, four);
-      good = fp_sqrt(p.y, rhs);
-      if (good) {
-        if (fp_is_largest(p.y) != ((b[0] & 0x20) != 0)) fp::neg(p.y, p.y);
-        if (check_subgroup) good = in_subgroup_g1(p);
-      }
-    }
-    if (!good) p.set_inf();
-  }
+  const bool good = g1_decompress_point(p, b, check_subgroup);
   out[i] = p;
   ok[i] = good ? 1 : 0;
 }
-
-// ------------------------------------------------------------------ G2
 __global__ void __launch_bounds__(128) k_g2_compress(const g2_aff* __restrict__ in, uint8_t* __restrict__ out, size_t n) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  g2_aff p = in[i];
   uint8_t b[96];
-  if (p.is_inf()) {
-    for (int j = 0; j < 96; j++) b[j] = 0;
-    b[0] = 0xC0;
-  } else {
-    fp_to_be(b, p.x.c1);
-    fp_to_be(b + 48, p.x.c0);
-    b[0] |= 0x80 | (fp2_is_largest(p.y) ? 0x20 : 0);
-  }
+  g2_compress_point(b, in[i]);
   for (int j = 0; j < 96; j++) out[i * 96 + j] = b[j];
 }
 __global__ void __launch_bounds__(128) k_g2_decompress(const uint8_t* __restrict__ in, g2_aff* __restrict__ out, uint8_t* __restrict__ ok,
@@ -257,29 +47,7 @@ __global__ void __launch_bounds__(128) k_g2_decompress(const uint8_t* __restrict
   uint8_t b[96];
   for (int j = 0; j < 96; j++) b[j] = in[i * 96 + j];
   g2_aff p;
-  p.set_inf();
-  bool good = (b[0] & 0x80) != 0;
-  if (good && !(b[0] & 0x40)) {
-    good = fp_from_be(p.x.c1, b);
-    uint8_t save = b[48];
-    if (good) {
-      // the second coordinate has no flag bits: a set top bit means >= p
-      good = (save & 0xE0) == 0 && fp_from_be(p.x.c0, b + 48);
-    }
-    if (good) {
-      fp2 rhs, bt;
-      fp2::sqr(rhs, p.x);
-      fp2::mul(rhs, rhs, p.x);
-      for (int j = 0; j < 12; j++) bt.c0.l[j] = bt.c1.l[j] = FP_FOUR(j);  // b' = 4 (1 + u)
-      fp2::add(rhs, rhs, bt);
-      good = fp2_sqrt(p.y, rhs);
-      if (good) {
-        if (fp2_is_largest(p.y) != ((b[0] & 0x20) != 0)) fp2::neg(p.y, p.y);
-        if (check_subgroup) good = in_subgroup_g2(p);
-      }
-    }
-    if (!good) p.set_inf();
-  }
+  const bool good = g2_decompress_point(p, b, check_subgroup);
   out[i] = p;
   ok[i] = good ? 1 : 0;
 }

@@ -7,6 +7,7 @@
 #include "../../groth-sahai-rs_b200/csrc/pairing.cuh"
 #include "../../groth-sahai-rs_b200/csrc/fpd.cuh"
 #include "../../groth-sahai-rs_b200/csrc/endo.cuh"
+#include "../../groth-sahai-rs_b200/csrc/wire.cuh"
 using namespace gs;
 
 #define LD(T, v, p) T v; memcpy(&v, p, sizeof(T))
@@ -280,3 +281,10 @@ extern "C" void hs_g2_mul_split(void* r, const void* a, const void* k_mont) {
   LD(g2_aff, p, a); LD(fr, k, k_mont); uint32_t kk[8]; fr_from_mont(kk, k); g2_jac acc; acc.set_inf();
   for (int j = 0; j < EndoSplit<Fp2Ops>::PARTS; j++) { g2_jac t; EndoSplit<Fp2Ops>::part(t, p, kk, j); g2_jac::add(acc, acc, t); }
   g2_aff o; g2_jac::to_affine(o, acc); ST(r, o); }
+
+// wire formats (wire.cuh): the one-point (de)compression the serialisation kernels run
+extern "C" void hs_g1_compress(void* out48, const void* a) { LD(g1_aff, p, a); g1_compress_point((uint8_t*)out48, p); }
+extern "C" int hs_g1_decompress(void* out, const void* in48, int check) { g1_aff p; bool ok = g1_decompress_point(p, (const uint8_t*)in48, check); ST(out, p); return ok; }
+extern "C" void hs_g2_compress(void* out96, const void* a) { LD(g2_aff, p, a); g2_compress_point((uint8_t*)out96, p); }
+extern "C" int hs_g2_decompress(void* out, const void* in96, int check) { g2_aff p; bool ok = g2_decompress_point(p, (const uint8_t*)in96, check); ST(out, p); return ok; }
+extern "C" int hs_fp2_sqrt(void* r, const void* a) { LD(fp2, x, a); fp2 y; bool ok = fp2_sqrt(y, x); ST(r, y); return ok; }

@@ -266,3 +266,57 @@ def test_endomorphism_splittings(L):
     for k in ks[:8] + ks[-3:]:
         assert g2_i(call(L.hs_g2_mul_split, 192, g2_b(q), fr_b(k))) == g2_mul(q, k), k
     assert call(L.hs_g1_mul_split, 96, g1_b(None), fr_b(5)) == g1_b(None)
+
+
+def test_wire_format_device_code(L):
+    """wire.cuh on the host: one-point (de)compression with validation == the serialisation oracle, incl. the public
+    generator encodings, identity, off-curve / off-subgroup / out-of-range inputs; Fp2 square roots."""
+    from oracle import serialize as ser
+    from test_serialize import G1_GEN_COMPRESSED, G2_GEN_COMPRESSED
+    assert call(L.hs_g1_compress, 48, g1_b(G1_GEN)) == G1_GEN_COMPRESSED
+    assert call(L.hs_g2_compress, 96, g2_b(G2_GEN_FP2)) == G2_GEN_COMPRESSED
+    pts = [None, G1_GEN, G1.neg(G1_GEN)] + [g1_mul(G1_GEN, rng.randrange(R)) for _ in range(4)]
+    for p_ in pts:
+        w = call(L.hs_g1_compress, 48, g1_b(p_))
+        assert w == ser.g1_compress(p_)
+        out = ctypes.create_string_buffer(96)
+        assert L.hs_g1_decompress(out, w, 1) == 1 and g1_i(out.raw) == p_
+    for x in range(2, 14):                                     # small x: mostly off-curve or off-subgroup
+        e = bytearray(x.to_bytes(48, "big")); e[0] |= 0x80
+        want_ok, want_pt = ser.g1_decompress(bytes(e))
+        out = ctypes.create_string_buffer(96)
+        assert bool(L.hs_g1_decompress(out, bytes(e), 1)) == want_ok
+        assert g1_i(out.raw) == (want_pt if want_ok else None)
+    bad = bytearray(P.to_bytes(48, "big")); bad[0] |= 0x80
+    out = ctypes.create_string_buffer(96)
+    assert L.hs_g1_decompress(out, bytes(bad), 1) == 0
+    for q in [None, G2_GEN_FP2, g2_mul(G2_GEN_FP2, rng.randrange(R))]:
+        w = call(L.hs_g2_compress, 96, g2_b(q))
+        assert w == ser.g2_compress(q)
+        out = ctypes.create_string_buffer(192)
+        assert L.hs_g2_decompress(out, w, 1) == 1 and g2_i(out.raw) == q
+    c0 = 0
+    while True:                                                # a G2 curve point outside the subgroup
+        c0 += 1
+        xx = Fp2(c0, 1)
+        yy = ser.fp2_sqrt(xx * xx * xx + Fp2(4, 4))
+        if yy is not None:
+            e = bytearray((1).to_bytes(48, "big") + c0.to_bytes(48, "big")); e[0] |= 0x80
+            out = ctypes.create_string_buffer(192)
+            assert bool(L.hs_g2_decompress(out, bytes(e), 1)) == ser.g2_decompress(bytes(e))[0]
+            assert L.hs_g2_decompress(out, bytes(e), 0) == 1
+            break
+    for _ in range(6):
+        a = rfp2()
+        sq = a * a
+        out = ctypes.create_string_buffer(96)
+        assert L.hs_fp2_sqrt(out, fp2_b(sq)) == 1
+        r_ = fp2_i(out.raw)
+        assert r_ * r_ == sq
+    out = ctypes.create_string_buffer(96)
+    nonres = None
+    while nonres is None:
+        a = rfp2()
+        if ser.fp2_sqrt(a) is None:
+            nonres = a
+    assert L.hs_fp2_sqrt(out, fp2_b(nonres)) == 0
