@@ -133,17 +133,20 @@ __global__ void __launch_bounds__(GS_TAB_NT) k_fixed_commit(const Aff<F>* __rest
 template <class F>
 __global__ void __launch_bounds__(128) k_msm_terms(Jac<F>* __restrict__ terms, const fr* __restrict__ sv, const Aff<F>* __restrict__ b0,
                                                    size_t n0, const Aff<F>* __restrict__ b1, size_t n1, int rows, size_t b1_bs,
-                                                   int PARTS /* EndoSplit<F>::PARTS, or 1 = whole scalar per thread */) {
+                                                   int PARTS /* EndoSplit<F>::PARTS, or 1 = whole scalar per thread */,
+                                                   size_t nt /* terms per row in `terms` / `sv`: n0 + n1, or more when the
+                                                                variable segment is filled from shared-base tables */) {
   size_t id = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  size_t nt = n0 + n1;
-  if (id >= nt * rows * PARTS) return;
+  const size_t nc = n0 + n1;  // terms this launch computes per row
+  if (id >= nc * rows * PARTS) return;
   const int j = (int)(id % PARTS);
-  const size_t term = id / PARTS;
+  const size_t tr = id / PARTS;
+  const size_t t = tr % nc, row = tr / nc;
+  const size_t term = row * nt + t;
   terms += (size_t)blockIdx.y * nt * rows * PARTS;
   sv += (size_t)blockIdx.y * nt * rows;
   b0 += (size_t)blockIdx.y * n0;
   b1 += (size_t)blockIdx.y * b1_bs;
-  size_t t = term % nt;
   Aff<F> B = t < n0 ? b0[t] : b1[t - n0];
   uint32_t k[8];
   fr_from_mont(k, sv[term]);
@@ -152,7 +155,77 @@ __global__ void __launch_bounds__(128) k_msm_terms(Jac<F>* __restrict__ terms, c
     scalar_mul<F>(r, B, k);
   else
     EndoSplit<F>::part(r, B, k, j);
-  terms[id] = r;
+  terms[term * PARTS + j] = r;
+}
+
+// ------------------------------------------------------------------ shared-variable window tables (many equations, one witness set)
+// A multi-equation statement proves every equation over the SAME variables (C4): sum_j RG[i][j] iota(Y_j) has shared
+// bases and per-equation scalars, so the nvars bases get signed 8-bit window tables once per batch
+//     T[(j*W + w)*H + d-1] = d * 2^(8w) * V_j      (W = 32, H = 128)
+// and a variable term costs 32 mixed additions instead of a 255-bit double-and-add.
+constexpr int GS_PT_C = 8, GS_PT_W = 32, GS_PT_H = 128, GS_PT_RUN = 32;
+template <class F>
+__global__ void __launch_bounds__(128) k_ptab_bases(const Aff<F>* __restrict__ bases, Jac<F>* __restrict__ J, int nb) {
+  int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= nb) return;
+  Jac<F> j;
+  j.from_affine(bases[b]);
+  for (int w = 0; w < GS_PT_W; w++) {
+    J[(size_t)b * GS_PT_W + w] = j;
+    if (w + 1 < GS_PT_W)
+      for (int i = 0; i < GS_PT_C; i++) Jac<F>::dbl(j, j);
+  }
+}
+// thread -> (row (j, w), run r): multiples r*RUN + 1 .. r*RUN + RUN of the row's base tab[row*H]
+template <class F>
+__global__ void __launch_bounds__(128) k_ptab_fill(const Aff<F>* __restrict__ tab, Jac<F>* __restrict__ J, size_t nrows) {
+  constexpr int RUNS = GS_PT_H / GS_PT_RUN;
+  size_t id = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (id >= nrows * RUNS) return;
+  size_t row = id / RUNS;
+  int r = (int)(id % RUNS);
+  Aff<F> B = tab[row * GS_PT_H];
+  Jac<F> acc;
+  acc.from_affine(B);
+  if (r > 0) {
+    Jac<F> step = acc;
+    for (int i = 0; i < 5; i++) Jac<F>::dbl(step, step);  // RUN * B
+    for (int i = 0; i < r; i++) Jac<F>::add(acc, acc, step);
+  }
+  Jac<F>* o = J + row * GS_PT_H + (size_t)r * GS_PT_RUN;
+  o[0] = acc;
+  for (int d = 1; d < GS_PT_RUN; d++) {
+    Jac<F>::add_mixed(acc, acc, B);
+    o[d] = acc;
+  }
+}
+// thread -> entry: out[idx * ostride] = affine(in[idx]), one field inversion per block
+template <class F>
+__global__ void __launch_bounds__(128) k_ptab_to_affine(const Jac<F>* __restrict__ in, Aff<F>* __restrict__ out, size_t n, size_t ostride) {
+  __shared__ fp sm[2 * 128];
+  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  Jac<F> j;
+  j.set_inf();
+  if (idx < n) j = in[idx];
+  Aff<F> a;
+  block_to_affine<128>(a, j, sm);
+  if (idx < n) out[idx * ostride] = a;
+}
+// thread -> (row, variable t) of proof blockIdx.y: terms[row][n0 + t] = sv[row][n0 + t] * V_t from the tables
+template <class F>
+__global__ void __launch_bounds__(128) k_msm_var_terms_tab(Jac<F>* __restrict__ terms, const fr* __restrict__ sv,
+                                                           const Aff<F>* __restrict__ tab, size_t n0, size_t n1, int rows) {
+  size_t id = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (id >= n1 * rows) return;
+  const size_t nt = n0 + n1;
+  const size_t t = id % n1, row = id / n1;
+  const size_t at = (size_t)blockIdx.y * nt * rows + row * nt + n0 + t;
+  uint32_t k[8];
+  fr_from_mont(k, sv[at]);
+  Jac<F> acc;
+  acc.set_inf();
+  fixed_base_accumulate<F>(acc, tab + (t * GS_PT_W) * GS_PT_H, k, GS_PT_C, GS_PT_W, (size_t)GS_PT_H);
+  terms[at] = acc;
 }
 
 // in-place pairwise tree reduction: terms[row][t] += terms[row][t + half] for t < half (one launch per level)
@@ -394,12 +467,53 @@ int proof_element(gs_ctx* ctx, Scratch& sc, size_t count, int rows, bool group_t
   if (group_typed) {
     // few terms (a lone statement): split every scalar multiplication over PARTS threads to shorten the serial chain;
     // big batches are throughput-bound and keep one thread per term (measured on C4: the split costs ~5 % there)
-    const int PARTS = count * nt * rows < 32768 ? EndoSplit<F>::PARTS : 1;
+    // many equations over one witness set: the variable terms come from shared-base window tables (break-even ~20 uses
+    // of a base; required here: 64) and every thread takes a whole scalar
+    const bool var_tables = vars_shared && nvars > 0 && count * rows >= 64;
+    const int PARTS = (!var_tables && count * nt * rows < 32768) ? EndoSplit<F>::PARTS : 1;
     const size_t ntp = nt * PARTS;
     Jac<F>* terms;
     CUDA_TRY(sc.alloc(&terms, count * ntp * rows));
-    LAUNCH_B((k_msm_terms<F>), ntp * rows, count, terms, sv, (const Aff<F>*)dconst, nconst, (const Aff<F>*)dvars, nvars, rows,
-             vars_shared ? (size_t)0 : nvars, PARTS);
+    if (!var_tables) {
+      LAUNCH_B((k_msm_terms<F>), ntp * rows, count, terms, sv, (const Aff<F>*)dconst, nconst, (const Aff<F>*)dvars, nvars, rows,
+               vars_shared ? (size_t)0 : nvars, PARTS, nt);
+    } else {
+      // the tables are built on the second stream while the constant terms (latency-bound scalar multiplications)
+      // run on the main one
+      const size_t nrows = nvars * GS_PT_W;
+      Aff<F>* ptab;
+      Jac<F>* J;
+      CUDA_TRY(sc.alloc(&ptab, nrows * GS_PT_H));
+      CUDA_TRY(sc.alloc(&J, nrows * GS_PT_H));
+      if (!ctx->stream2) CUDA_TRY(cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking));
+      cudaEvent_t fork, join;
+      CUDA_TRY(cudaEventCreateWithFlags(&fork, cudaEventDisableTiming));
+      CUDA_TRY(cudaEventCreateWithFlags(&join, cudaEventDisableTiming));
+      CUDA_TRY(cudaEventRecord(fork, ctx->stream));
+      CUDA_TRY(cudaStreamWaitEvent(ctx->stream2, fork, 0));
+      cudaStream_t main_stream = ctx->stream;
+      ctx->stream = ctx->stream2;
+      int rct = [&]() -> int {
+        LAUNCH((k_ptab_bases<F>), nvars, (const Aff<F>*)dvars, J, (int)nvars);
+        LAUNCH((k_ptab_to_affine<F>), nrows, J, ptab, nrows, (size_t)GS_PT_H);
+        LAUNCH((k_ptab_fill<F>), nrows * (GS_PT_H / GS_PT_RUN), ptab, J, nrows);
+        LAUNCH((k_ptab_to_affine<F>), nrows * GS_PT_H, J, ptab, nrows * GS_PT_H, (size_t)1);
+        LAUNCH_B((k_msm_var_terms_tab<F>), nvars * rows, count, terms, sv, ptab, nconst, nvars, rows);
+        return GS_OK;
+      }();
+      cudaEventRecord(join, ctx->stream2);
+      ctx->stream = main_stream;
+      int rcc = [&]() -> int {
+        LAUNCH_B((k_msm_terms<F>), nconst * rows, count, terms, sv, (const Aff<F>*)dconst, nconst, (const Aff<F>*)dvars, (size_t)0, rows,
+                 (size_t)0, 1, nt);
+        return GS_OK;
+      }();
+      cudaStreamWaitEvent(ctx->stream, join, 0);
+      cudaEventDestroy(fork);
+      cudaEventDestroy(join);
+      if (rct) return rct;
+      if (rcc) return rcc;
+    }
     int rc = reduce_rows<F>(ctx, terms, ntp, ntp, rows, count);
     if (rc) return rc;
     LAUNCH_B((k_proof_finish<F>), (size_t)rows * 2, count, dout, rows, ncoef, coef, coef_rs, (size_t)1, T.t, T.c, T.W, T.H, terms, ntp,
