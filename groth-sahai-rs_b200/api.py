@@ -67,6 +67,17 @@ class CRS:
         a1, a2, t1, t2 = rng.fr(), rng.fr(), rng.fr(), rng.fr()
         return CRS.from_bytes(eng.crs_generate(p1, p2, a1, a2, t1, t2), eng, loaded=True)
 
+    @staticmethod
+    def generate_hiding_crs(rng, engine: Engine = None) -> "CRS":
+        """The simulated (perfectly hiding) key of generator.rs:62-77 -- dead code upstream (`#[allow(dead_code)]`),
+        offered here because it is what a zero-knowledge simulator needs.  Same RNG draws as
+        generate_crs; the only difference is the last entry of each key: u[1].1 = t1*q1 - g1, v[1].1 = t2*q2 - g2,
+        i.e. u[1] - iota_1(g1) and v[1] - iota_2(g2) on the device (gs_com1_sub / gs_com2_sub)."""
+        crs = CRS.generate_crs(rng, engine)
+        u1 = Com1.sub(crs.u[1], Com1.linear_map(crs.g1_gen), crs.engine)
+        v1 = Com2.sub(crs.v[1], Com2.linear_map(crs.g2_gen), crs.engine)
+        return CRS.from_bytes(crs.u[0] + u1 + crs.v[0] + v1 + crs.g1_gen + crs.g2_gen + crs.gt_gen, crs.engine)
+
     def to_bytes(self) -> bytes:
         return b"".join(self.u) + b"".join(self.v) + self.g1_gen + self.g2_gen + self.gt_gen
 
@@ -565,3 +576,38 @@ def deserialize_equ_proof(b: bytes, engine: Engine = None) -> EquProof:
     if ty > 3:
         raise SerializationError("bad EquType byte")       # statement.rs:88-95
     return EquProof(pi, theta, ty, _de_matrix(eng, rd))
+
+
+# equations (statement.rs:117-185): a_consts, b_consts, gamma, target in declaration order; constants and targets are
+# G1 / G2 / Fr / PairingOutput depending on the equation type (the type itself is NOT on the wire: the caller
+# names the struct it deserialises, as in Rust).
+_A_KIND = {0: "g1", 1: "g1", 2: "fr", 3: "fr"}
+_B_KIND = {0: "g2", 1: "fr", 2: "g2", 3: "fr"}
+_T_KIND = {0: "gt", 1: "g1", 2: "g2", 3: "fr"}
+_WIRE = {"g1": 48, "g2": 96, "fr": 32, "gt": 576}
+_MEM = {"g1": G1, "g2": G2, "fr": FR, "gt": GT}
+
+
+def _ser_vec(eng, kind, items):
+    return _u64(len(items)) + (eng.serialize(kind, b"".join(items)) if items else b"")
+
+
+def _de_vec(eng, rd, kind):
+    n = rd.u64()
+    return _split(_de(eng, kind, rd.take(n * _WIRE[kind]), kind), _MEM[kind]) if n else []
+
+
+def serialize_equation(e: _Equation, engine: Engine = None) -> bytes:
+    """PPE / MSMEG1 / MSMEG2 / QuadEqu ::serialize_compressed (statement.rs:117-185)."""
+    eng, ty = engine or default_engine(), e.equ_type
+    return (_ser_vec(eng, _A_KIND[ty], e.a_consts) + _ser_vec(eng, _B_KIND[ty], e.b_consts) +
+            _ser_matrix(eng, e.gamma) + eng.serialize(_T_KIND[ty], e.target))
+
+
+def deserialize_equation(b: bytes, equ_type: int, engine: Engine = None) -> _Equation:
+    eng = engine or default_engine()
+    rd = _Reader(b)
+    a, bc = _de_vec(eng, rd, _A_KIND[equ_type]), _de_vec(eng, rd, _B_KIND[equ_type])
+    gamma = _de_matrix(eng, rd)
+    t = _de(eng, _T_KIND[equ_type], rd.take(_WIRE[_T_KIND[equ_type]]), "target")
+    return (PPE, MSMEG1, MSMEG2, QuadEqu)[equ_type](a, bc, gamma, t)

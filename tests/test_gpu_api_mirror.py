@@ -55,6 +55,33 @@ def test_crs_draw_order_and_binding_key(env):
     assert crs.gt_gen != fp12_b(FP12_ONE)                                   # non-degeneracy
 
 
+def test_hiding_crs_differs_only_in_the_last_key_entries():
+    """generator.rs:62-77 (prepare_simulated_hinding_key, dead code upstream): same draws as the binding key; only
+    u[1].1 = t1*q1 - g1 and v[1].1 = t2*q2 - g2 change, so W1 = u[1] + iota_1(g1) = t1*u[0] (scalar commitments
+    carry no information) while gt_gen, the generators and u[0], v[0] are untouched."""
+    import groth_sahai_rs_b200 as gsb
+    from groth_sahai_rs_b200 import api
+    eng = gsb.Engine(0)
+    r1, r2 = ReplayRng(44), ReplayRng(44)
+    real, hid = api.CRS.generate_crs(r1, eng), api.CRS.generate_hiding_crs(r2, eng)
+    assert r1.log == r2.log and len(r2.log) == 6
+    p1, p2, a1, a2, t1, t2 = r2.log
+    assert (hid.u[0], hid.v[0], hid.g1_gen, hid.g2_gen, hid.gt_gen) == (real.u[0], real.v[0], real.g1_gen, real.g2_gen, real.gt_gen)
+    q1, q2 = g1_mul(p1, a1), g2_mul(p2, a2)
+    assert com1_i(hid.u[1]) == (g1_mul(p1, t1), G1.add(g1_mul(q1, t1), G1.neg(p1)))
+    assert com2_i(hid.v[1]) == (g2_mul(p2, t2), G2.add(g2_mul(q2, t2), G2.neg(p2)))
+    assert hid.u[1] != real.u[1] and hid.v[1] != real.v[1]
+    # W1 under the hiding key is t1 * u[0]: iota_1'(x) = x*W1 lies in the span of u[0]
+    w1 = api.Com1.scalar_linear_map(fr_b(1), hid)
+    assert com1_i(w1) == (g1_mul(p1, t1), g1_mul(q1, t1))
+    # proofs made under the hiding key still verify under it (completeness does not depend on the key kind)
+    crs_o = ogs.generate_crs(p1, p2, a1, a2, t1, t2)
+    for ty in (0, 3):
+        _, equ, xvars, yvars, _, _ = _equation(api, crs_o, ty, 60 + ty)
+        cp = equ.commit_and_prove(xvars, yvars, hid, ReplayRng(5))
+        assert equ.verify(cp, hid) is True
+
+
 def test_batch_commit_equals_sequence_of_singles(env):
     """commit.rs:439-548: batch_commit_* == the singles appended, under the same RNG stream (row-major (r1, r2))."""
     eng, api, crs, _ = env

@@ -165,6 +165,56 @@ def test_struct_serialisation_round_trip(eng):
         api.deserialize_equ_proof(wp[:-3], eng)
 
 
+@pytest.mark.parametrize("ty", [0, 1, 2, 3])
+def test_equation_serialisation(eng, ty):
+    """PPE / MSMEG1 / MSMEG2 / QuadEqu in ark-serialize's compressed layout (statement.rs:117-185: a_consts, b_consts,
+    gamma, target): bytes equal the oracle's element encodings, round trip (PartialEq), rejection, and the
+    deserialised equation verifies the proof made for the original."""
+    from groth_sahai_rs_b200 import api
+    crs, _ = make_crs(1)
+    key = api.CRS.from_bytes(crs_bytes(crs), eng)
+    rng = SeededRng(300 + ty)
+    m, n = 3, 2
+    equ, xv, yv = random_instance(ty, m, n, crs, rng, zero_frac=0.3)
+    asz, bsz = (96 if ty in (0, 1) else 32), (192 if ty in (0, 2) else 32)
+    ab, bb = enc_A(ty, equ.a_consts), enc_B(ty, equ.b_consts)
+    cls = [api.PPE, api.MSMEG1, api.MSMEG2, api.QuadEqu][ty]
+    e = cls([ab[i:i + asz] for i in range(0, len(ab), asz)], [bb[i:i + bsz] for i in range(0, len(bb), bsz)],
+            [[fr_b(g) for g in row] for row in equ.gamma], enc_T(ty, equ.target))
+    w = api.serialize_equation(e, eng)
+    enc_a = ser.g1_compress if ty in (0, 1) else ser.fr_to_bytes
+    enc_b = ser.g2_compress if ty in (0, 2) else ser.fr_to_bytes
+    enc_t = [ser.fp12_to_bytes, ser.g1_compress, ser.g2_compress, ser.fr_to_bytes][ty]
+    u64 = lambda k: k.to_bytes(8, "little")
+    want = (u64(n) + b"".join(enc_a(a) for a in equ.a_consts) + u64(m) + b"".join(enc_b(b) for b in equ.b_consts) +
+            u64(m) + b"".join(u64(n) + b"".join(ser.fr_to_bytes(g) for g in row) for row in equ.gamma) +
+            enc_t(equ.target))
+    assert w == want
+    back = api.deserialize_equation(w, ty, eng)
+    assert type(back) is cls and back == e
+    with pytest.raises(api.SerializationError):
+        api.deserialize_equation(w[:-1], ty, eng)
+    bad = bytearray(w)
+    if ty == 0:
+        bad[-48:] = P.to_bytes(48, "little")                                    # an Fp12 coefficient >= p
+    elif ty == 3:
+        bad[-1] = 0xFF                                                          # Fr >= r
+    else:
+        bad[-1] ^= 0x5A                                                         # x moved off the curve / out of the subgroup
+    with pytest.raises(api.SerializationError):
+        api.deserialize_equation(bytes(bad), ty, eng)
+    xr, yr, T = draw_rands(ty, m, n, rng)
+    pr = ogs.commit_and_prove(equ, xv, yv, crs, xr, yr, T)
+    ep = pr.equ_proofs[0]
+    cp = api.CProof(api.Commit1([com1_b(c) for c in pr.xcoms.coms], []), api.Commit2([com2_b(c) for c in pr.ycoms.coms], []),
+                    [api.EquProof([com2_b(c) for c in ep.pi], [com1_b(c) for c in ep.theta], ty, [])])
+    assert back.verify(cp, key) is True
+    # an empty equation (no variables) keeps the u64 zero lengths
+    e0 = cls([], [], [], enc_T(ty, equ.target))
+    w0 = api.serialize_equation(e0, eng)
+    assert w0[:24] == bytes(24) and api.deserialize_equation(w0, ty, eng) == e0
+
+
 def test_uncompressed_encodings(eng):
     """serialize_uncompressed / deserialize_uncompressed (the reference round-trips both modes,
     data_structures.rs:1269-1309): bytes equal the oracle's, round trip, and the rejections of Validate::Yes."""
