@@ -136,8 +136,11 @@ struct FpOps {
   GS_HD static GS_INL void sub(fp& r, const fp& a, const fp& b) { fp::sub(r, a, b); }
   GS_HD static GS_INL void dbl(fp& r, const fp& a) { fp::add(r, a, a); }
   GS_HD static GS_INL void neg(fp& r, const fp& a) { fp::neg(r, a); }
-  GS_HD static GS_INL void mul(fp& r, const fp& a, const fp& b) { fp::mul(r, a, b); }
-  GS_HD static GS_INL void sqr(fp& r, const fp& a) { fp::mul(r, a, a); }
+  // ONE out-of-line copy of the Montgomery product for all G1 curve formulas: doubling + mixed addition are ~13 KB of
+  // code instead of ~130 KB, so the loop body of the thread-per-point kernels fits the 32 KB L1.5 instruction cache
+  // instead of streaming from L2 (k_vmsm_partial: 13 % "no instruction" stalls, 94.6 -> 80.4 ms once compact).
+  GS_HD static GS_NOINL void mul(fp& r, const fp& a, const fp& b) { fp::mul(r, a, b); }
+  GS_HD static GS_INL void sqr(fp& r, const fp& a) { mul(r, a, a); }
   GS_HD static GS_INL void inv(fp& r, const fp& a) { fp_inv(r, a); }
   GS_HD static GS_INL void set_one(fp& r) { fp_one(r); }
 };

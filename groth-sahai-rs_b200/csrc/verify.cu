@@ -169,8 +169,11 @@ __device__ GS_INL bool vmsm_scalar(fr& sv, const verify_shape& s, const verify_a
   return true;
 }
 
+#ifndef VP_BLOCKS
+#define VP_BLOCKS 4
+#endif
 // thread -> (p, jj, a, chunk)
-__global__ void __launch_bounds__(128) k_vmsm_partial(verify_shape s, verify_args v, const g1_aff* __restrict__ tab,
+__global__ void __launch_bounds__(128, VP_BLOCKS) k_vmsm_partial(verify_shape s, verify_args v, const g1_aff* __restrict__ tab,
                                                       const fp* __restrict__ tabx, g1_jac* __restrict__ part, size_t nprob) {
   size_t id = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int n_own = s.n_out_owned();  // sharded statement: the other outputs' Miller pairs run on other ranks
