@@ -263,6 +263,17 @@ def verify_batch(equations, proofs, crs: CRS) -> List[bool]:
     return [b == 1 for b in ok]
 
 
+# ---------------------------------------------------------------- vector <-> matrix helpers (data_structures.rs:143-160)
+def col_vec_to_vec(mat):
+    """Collapse a 1 x n row or an n x 1 column into a list (:145-151)."""
+    return list(mat[0]) if len(mat) == 1 else [row[0] for row in mat]
+
+
+def vec_to_col_vec(vec):
+    """Expand a list into an n x 1 column matrix (:154-160)."""
+    return [[e] for e in vec]
+
+
 # ---------------------------------------------------------------- Com1 / Com2 / ComT  (data_structures.rs)
 class _ComGroup:
     """Add / Sub / Neg / Sum / Zero of a commitment group (impl_base_commit_groups! :162-255, ComT :391-479).
@@ -292,6 +303,14 @@ class Com1(_ComGroup):
     @staticmethod
     def zero(): return bytes(192)                                           # :257-266
     @staticmethod
+    def as_col_vec(c): return [[c[:G1]], [c[G1:]]]                          # :301-303
+    @staticmethod
+    def as_vec(c): return [c[:G1], c[G1:]]                                  # :305-307
+    @staticmethod
+    def from_matrix(mat):                                                   # From<Matrix<G1Affine>> :283-290
+        assert len(mat) == 2 and len(mat[0]) == 1 and len(mat[1]) == 1
+        return mat[0][0] + mat[1][0]
+    @staticmethod
     def linear_map(x): return G1_ZERO + x                                   # :310-312
     @staticmethod
     def batch_linear_map(xs): return [G1_ZERO + x for x in xs]
@@ -309,6 +328,14 @@ class Com2(_ComGroup):
     kind, size = "com2", 384
     @staticmethod
     def zero(): return bytes(384)                                           # :268-277
+    @staticmethod
+    def as_col_vec(c): return [[c[:G2]], [c[G2:]]]                          # :346-348
+    @staticmethod
+    def as_vec(c): return [c[:G2], c[G2:]]                                  # :350-352
+    @staticmethod
+    def from_matrix(mat):                                                   # From<Matrix<G2Affine>> :291-298
+        assert len(mat) == 2 and len(mat[0]) == 1 and len(mat[1]) == 1
+        return mat[0][0] + mat[1][0]
     @staticmethod
     def linear_map(y): return G2_ZERO + y                                   # :355-357
     @staticmethod
@@ -341,6 +368,10 @@ class ComT(_ComGroup):
     def zero(engine=None): return (engine or default_engine()).group_sum("comt", b"")   # four GT identities :412-421
     @staticmethod
     def as_matrix(c): return [[c[0:576], c[576:1152]], [c[1152:1728], c[1728:2304]]]     # :1361-1377 row-major
+    @staticmethod
+    def from_matrix(mat):                                                   # From<Matrix<PairingOutput>> :467-474
+        assert len(mat) == 2 and len(mat[0]) == 2 and len(mat[1]) == 2
+        return mat[0][0] + mat[0][1] + mat[1][0] + mat[1][1]
     @staticmethod
     def pairing(x, y, engine=None):                                         # :484-491
         return (engine or default_engine()).comt_pairing(x, y)

@@ -54,3 +54,26 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".inc", ".h")):
                 txt = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in txt and "from oracle" not in txt and "oracle/" not in txt.replace("(the oracle", ""), f
+
+
+def test_vector_matrix_helpers_are_pure_host_reshapes():
+    """col_vec_to_vec / vec_to_col_vec (data_structures.rs:143-160), as_col_vec / as_vec (:301-307, :346-352) and the
+    From<Matrix> impls (:283-298, :467-474) with their dimension asserts: no device work, so they are checked here."""
+    import pytest
+    from groth_sahai_rs_b200 import api
+    a, b = bytes([1]) * 96, bytes([2]) * 96
+    c = api.Com1.from_matrix([[a], [b]])
+    assert c == a + b and api.Com1.as_vec(c) == [a, b] and api.Com1.as_col_vec(c) == [[a], [b]]
+    q, r = bytes([3]) * 192, bytes([4]) * 192
+    d = api.Com2.from_matrix(api.Com2.as_col_vec(q + r))
+    assert d == q + r and api.Com2.as_vec(d) == [q, r]
+    g = [bytes([i]) * 576 for i in range(4)]
+    t = api.ComT.from_matrix([[g[0], g[1]], [g[2], g[3]]])
+    assert api.ComT.as_matrix(t) == [[g[0], g[1]], [g[2], g[3]]]                 # row-major, :1361-1377
+    assert api.col_vec_to_vec([[a], [b]]) == [a, b] and api.col_vec_to_vec([[a, b]]) == [a, b]
+    assert api.vec_to_col_vec([a, b]) == [[a], [b]] and api.col_vec_to_vec(api.vec_to_col_vec([a])) == [a]
+    for bad in ([[a]], [[a, b], [b]], [[a], [b], [a]]):
+        with pytest.raises(AssertionError):
+            api.Com1.from_matrix(bad)
+    with pytest.raises(AssertionError):
+        api.ComT.from_matrix([[g[0]], [g[1]]])
