@@ -292,14 +292,17 @@ def main():
     dom_achieved = wm[dom] * P * IMAD_PER_M / (dom_ms * 1e-3) if dom in wm else None
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")    # per-launch DRAM bytes from the committed ncu capture
+    traffic_capture = None
     if os.path.exists(tpath):
-        traffic = json.load(open(tpath)).get(dom)
+        tj = json.load(open(tpath))
+        traffic_capture = tj.get(dom)
+        if traffic_capture:     # the capture ran 16,384 proofs per launch; scale linearly to THIS run's proofs per launch
+            traffic = int(traffic_capture * (P / dom_cnt) / tj.get("proofs_per_launch", 16384))
     hbm = None
     try:                                                        # HBM view of the same kernel (north star: report GB/s for the
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))      # point-load phases): ncu DRAM bytes per launch,
-        if traffic:                                             # scaled from the capture's 16,384 proofs per launch to this run's
-            ppl = json.load(open(tpath)).get("proofs_per_launch", 16384)
-            gbs = traffic * (P / dom_cnt / ppl) / (dom_ms / dom_cnt * 1e-3) / 1e9
+        if traffic:                                             # (already scaled to this run's proofs per launch)
+            gbs = traffic / (dom_ms / dom_cnt * 1e-3) / 1e9
             hbm = {"achieved_gbs": round(gbs, 1), "peak_gbs": peaks.get("hbm_gbs"), "frac": round(gbs / peaks["hbm_gbs"], 4),
                    "peak_source": "MEASURED_PEAKS.json (driver-measured copy bandwidth)"}
     except Exception:  # noqa: BLE001
@@ -307,7 +310,8 @@ def main():
     roofline = {
         "bound": "imad", "kernel": dom, "achieved": dom_achieved and round(dom_achieved / 1e12, 3),
         "peak": round(peak_imad / 1e12, 3), "unit": "TIMAD/s", "frac": dom_achieved and round(dom_achieved / peak_imad, 4),
-        "traffic": traffic, "hbm": hbm,
+        "traffic": traffic, "traffic_source": "profiles/traffic.json (ncu --set full at 16,384 proofs per launch: %s B) scaled to this run's "
+                                              "proofs per launch" % traffic_capture, "hbm": hbm,
         "peak_source": "measured live: register-only Fp Montgomery chain (gs_diag_fpmul_rate) x 600 IMAD/M; "
                        "MEASURED_PEAKS.json has no integer-pipe figure",
         "whole_step_frac": round(sum(wm[k] for k in wm if k != "pairs") * P / (ms_per_step * 1e-3) / peak_m, 4),
