@@ -582,8 +582,8 @@ def deserialize_crs(b: bytes, engine: Engine = None) -> CRS:
     return CRS.from_bytes(b"".join(u) + b"".join(v) + g1 + g2 + gt, eng)
 
 
-def serialize_commit(c: _Commit) -> bytes:
-    eng = default_engine()
+def serialize_commit(c: _Commit, engine: Engine = None) -> bytes:
+    eng = engine or default_engine()
     return _ser_coms(eng, c.coms, 1 if isinstance(c, Commit1) else 2) + _ser_matrix(eng, c.rand)
 
 

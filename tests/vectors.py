@@ -183,7 +183,7 @@ def api_outputs(rec, api, eng):
         rng = ListRng(flat_fr(rec["rand"]))
         c = fn(de(kind, rec["vars"]), key, rng)
         assert rng.dry()
-        return {"commit": api.serialize_commit(c).hex()}
+        return {"commit": api.serialize_commit(c, eng).hex()}
     if k == "prove":
         ty = rec["equ_type"]
         key = api.deserialize_crs(H(rec["crs"]), eng)
@@ -193,7 +193,7 @@ def api_outputs(rec, api, eng):
         rng = ListRng(flat_fr(rec["xrand"], rec["yrand"], rec["T"]))      # draw order x -> y -> T (prove.rs:82-88)
         cp = equ.commit_and_prove(xv, yv, key, rng)
         assert rng.dry()
-        return {"xcoms": api.serialize_commit(cp.xcoms).hex(), "ycoms": api.serialize_commit(cp.ycoms).hex(),
+        return {"xcoms": api.serialize_commit(cp.xcoms, eng).hex(), "ycoms": api.serialize_commit(cp.ycoms, eng).hex(),
                 "proof": api.serialize_equ_proof(cp.equ_proofs[0], eng).hex(), "verify": equ.verify(cp, key)}
     if k == "pairing_sum":
         xs = [a + b for a, b in zip(*[iter(de("g1", [x[i:i + 96] for x in rec["xs"] for i in (0, 96)]))] * 2)]
