@@ -19,6 +19,17 @@ def lib():
         _lib.gsref_verify_ppe_batch.argtypes = [ctypes.c_size_t, ctypes.c_int, ctypes.c_int] + [ctypes.c_void_p] * 10 + [ctypes.c_int]
         _lib.gsref_batch_commit_g1.argtypes = [ctypes.c_size_t] + [ctypes.c_void_p] * 4
         _lib.gsref_batch_commit_g2.argtypes = [ctypes.c_size_t] + [ctypes.c_void_p] * 4
+        V, Z, I = ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int
+        _lib.gsref_batch_commit_scalar_b1.argtypes = [Z, V, V, V, V, I]
+        _lib.gsref_batch_commit_scalar_b2.argtypes = [Z, V, V, V, V, I]
+        _lib.gsref_prove.argtypes = [I, Z, Z] + [V] * 11 + [I]
+        _lib.gsref_prove_batch.argtypes = [I, Z, Z, Z] + [V] * 8 + [I, V, V, V, I]
+        _lib.gsref_verify.argtypes = [I, Z, Z] + [V] * 9 + [I]
+        _lib.gsref_verify.restype = I
+        _lib.gsref_verify_batch.argtypes = [I, Z, Z, Z] + [V] * 10 + [I]
+        _lib.gsref_g1_mul_batch.argtypes = [Z, V, V, V, I]
+        _lib.gsref_g2_mul_batch.argtypes = [Z, V, V, V, I]
+        _lib.gsref_selftest_inv.argtypes = [V]
     return _lib
 
 
@@ -71,6 +82,94 @@ def verify_ppe_batch(count, m, n, arrays, crs: bytes, nthreads=1) -> bytes:
     keep = [bytes(a) for a in arrays]
     lib().gsref_verify_ppe_batch(count, m, n, *keep, crs, ok, nthreads)
     return ok.raw[:count]
+
+
+def x_is_group(ty): return ty in (0, 1)
+def y_is_group(ty): return ty in (0, 2)
+def x_size(ty): return 96 if x_is_group(ty) else 32
+def y_size(ty): return 192 if y_is_group(ty) else 32
+def cx_of(ty): return 2 if x_is_group(ty) else 1
+def cy_of(ty): return 2 if y_is_group(ty) else 1
+def target_size(ty): return (576, 96, 192, 32)[ty]
+
+
+def batch_commit_scalar_b1(xs: bytes, rand: bytes, crs: bytes, nthreads=1) -> bytes:
+    n = len(xs) // 32
+    o = _out(max(1, n * 192))
+    lib().gsref_batch_commit_scalar_b1(n, xs, rand, crs, o, nthreads)
+    return o.raw[:n * 192]
+
+
+def batch_commit_scalar_b2(ys: bytes, rand: bytes, crs: bytes, nthreads=1) -> bytes:
+    n = len(ys) // 32
+    o = _out(max(1, n * 384))
+    lib().gsref_batch_commit_scalar_b2(n, ys, rand, crs, o, nthreads)
+    return o.raw[:n * 384]
+
+
+def commit_x(ty, xvars: bytes, rand: bytes, crs: bytes, nthreads=1) -> bytes:
+    """batch_commit_G1 or batch_commit_scalar_to_B1 by equation type (what commit_and_prove calls first)."""
+    return batch_commit_g1(xvars, rand, crs) if x_is_group(ty) else batch_commit_scalar_b1(xvars, rand, crs, nthreads)
+
+
+def commit_y(ty, yvars: bytes, rand: bytes, crs: bytes, nthreads=1) -> bytes:
+    return batch_commit_g2(yvars, rand, crs) if y_is_group(ty) else batch_commit_scalar_b2(yvars, rand, crs, nthreads)
+
+
+def prove(ty, m, n, a, b, gamma, xvars, yvars, x_rand, y_rand, pf_rand, crs: bytes, nthreads=1):
+    """Provable::prove in the reference's evaluation order (argument layout of gs_prove) -> (pi, theta) bytes."""
+    assert len(a) == n * x_size(ty) and len(b) == m * y_size(ty) and len(gamma) == m * n * 32
+    assert len(xvars) == m * x_size(ty) and len(yvars) == n * y_size(ty)
+    assert len(x_rand) == m * cx_of(ty) * 32 and len(y_rand) == n * cy_of(ty) * 32
+    assert len(pf_rand) == cx_of(ty) * cy_of(ty) * 32
+    pi, th = _out(cx_of(ty) * 384), _out(cy_of(ty) * 192)
+    lib().gsref_prove(ty, m, n, a, b, gamma, xvars, yvars, x_rand, y_rand, pf_rand, crs, pi, th, nthreads)
+    return pi.raw, th.raw
+
+
+def prove_batch(ty, count, m, n, a, b, gamma, xvars, yvars, x_rand, y_rand, pf_rand, shared_vars, crs: bytes, nthreads=1):
+    """`count` proofs, array layout of gs_prove_batch."""
+    nv = 1 if shared_vars else count
+    assert len(a) == count * n * x_size(ty) and len(b) == count * m * y_size(ty) and len(gamma) == count * m * n * 32
+    assert len(xvars) == nv * m * x_size(ty) and len(yvars) == nv * n * y_size(ty)
+    assert len(x_rand) == nv * m * cx_of(ty) * 32 and len(y_rand) == nv * n * cy_of(ty) * 32
+    assert len(pf_rand) == count * cx_of(ty) * cy_of(ty) * 32
+    pi, th = _out(count * cx_of(ty) * 384), _out(count * cy_of(ty) * 192)
+    lib().gsref_prove_batch(ty, count, m, n, a, b, gamma, xvars, yvars, x_rand, y_rand, pf_rand, int(bool(shared_vars)),
+                            crs, pi, th, nthreads)
+    return pi.raw, th.raw
+
+
+def verify(ty, m, n, arrays, crs: bytes, nthreads=1) -> bool:
+    """Verifiable::verify for one instance; arrays = the 8 byte strings of gs_verify_batch."""
+    a, b, gamma, target, xc, yc, pi, th = [bytes(x) for x in arrays]
+    assert len(a) == n * x_size(ty) and len(b) == m * y_size(ty) and len(gamma) == m * n * 32
+    assert len(target) == target_size(ty) and len(xc) == m * 192 and len(yc) == n * 384
+    assert len(pi) == cx_of(ty) * 384 and len(th) == cy_of(ty) * 192
+    return bool(lib().gsref_verify(ty, m, n, a, b, gamma, target, xc, yc, pi, th, crs, nthreads))
+
+
+def verify_batch(ty, count, m, n, arrays, crs: bytes, nthreads=1) -> bytes:
+    keep = [bytes(x) for x in arrays]
+    sizes = [n * x_size(ty), m * y_size(ty), m * n * 32, target_size(ty), m * 192, n * 384, cx_of(ty) * 384, cy_of(ty) * 192]
+    assert all(len(k) == count * s for k, s in zip(keep, sizes))
+    ok = _out(max(1, count))
+    lib().gsref_verify_batch(ty, count, m, n, *keep, crs, ok, nthreads)
+    return ok.raw[:count]
+
+
+def g1_mul_batch(base: bytes, ks: bytes, nthreads=1) -> bytes:
+    n = len(ks) // 32
+    o = _out(max(1, n * 96))
+    lib().gsref_g1_mul_batch(n, base, ks, o, nthreads)
+    return o.raw[:n * 96]
+
+
+def g2_mul_batch(base: bytes, ks: bytes, nthreads=1) -> bytes:
+    n = len(ks) // 32
+    o = _out(max(1, n * 192))
+    lib().gsref_g2_mul_batch(n, base, ks, o, nthreads)
+    return o.raw[:n * 192]
 
 
 def host_cores():

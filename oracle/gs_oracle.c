@@ -10,13 +10,22 @@
  *   src/data_structures.rs:696-742   Mat::left_mul    = term-by-term scalar_mul then Sum
  *   src/verifier.rs:23-55            PPE::verify in the reference's order: 5 pairing_sums (20 final
  *                                    exponentiations), Gamma*d as m*n Com2 scalar muls
- *   src/prover/commit.rs:78-100      batch_commit_G1 (single-threaded, as in the reference)
+ *   src/prover/commit.rs:78-100      batch_commit_G1 (single-threaded, as in the reference); :178-200 G2 mirror
+ *   src/prover/commit.rs:125-156     batch_commit_scalar_to_B1 (x W1 + r u1, W1 recomputed per element as
+ *                                    data_structures.rs:323-326 does); :225-256 B2 mirror
+ *   src/prover/prove.rs:92-171, 195-274, 298-379, 409-488   Provable::prove for PPE / MSMEG1 / MSMEG2 / Quad,
+ *                                    every left_mul term by term (one Com::scalar_mul + one affine Com add per
+ *                                    term), the Fr products R^T Gamma etc. as Matrix<Fr>::right_mul
+ *   src/verifier.rs:23-157           Verifiable::verify for the four types (gsref_verify), same order
+ *   src/data_structures.rs:509-540   the four iota_T maps
  * PARITY STATUS: parity unpinned against arkworks bits (no golden vectors exist offline); this file
  * is checked against the independent big-int oracle (tests/test_c_oracle.py).
  *
  * Threading: the reference parallelises only inside left_mul (Rayon over output rows).  For batch
  * workloads the baseline additionally spreads independent proofs over `nthreads` host threads
  * (pthread), which is MORE parallelism than the reference has -- stated wherever it is reported.
+ * gsref_prove / gsref_verify spread the scalar multiplications of a left_mul over `nthreads` (term-level,
+ * again more than Rayon's <= 2 tasks in prove); results do not depend on it (outputs are canonical affine points).
  */
 #include <pthread.h>
 #include <stdint.h>
@@ -119,7 +128,7 @@ static void fp_mul(fp* r, const fp* a, const fp* b) { /* CIOS Montgomery */
   memcpy(r->l, t, 48);
 }
 static void fp_sqr(fp* r, const fp* a) { fp_mul(r, a, a); }
-static void fp_inv(fp* r, const fp* a) { /* a^(p-2), square-and-multiply */
+static void fp_inv_fermat(fp* r, const fp* a) { /* a^(p-2), square-and-multiply (kept as a cross-check) */
   uint64_t e[6];
   memcpy(e, P, 48);
   e[0] -= 2;
@@ -129,6 +138,64 @@ static void fp_inv(fp* r, const fp* a) { /* a^(p-2), square-and-multiply */
     fp_sqr(&base, &base);
   }
   *r = acc;
+}
+/* Binary extended Euclid on the Montgomery residue (the algorithm ark-ff's Fp::inverse uses: Guajardo et al.,
+ * alg. 16, started from b = R^2 so that the result is the Montgomery form of the inverse). */
+static fp FP_R2;
+static pthread_once_t r2_once = PTHREAD_ONCE_INIT;
+static void r2_init(void) {
+  fp t = FP_ONE; /* R mod p */
+  for (int i = 0; i < 384; i++) fp_add(&t, &t, &t);
+  FP_R2 = t; /* R * 2^384 = R^2 mod p */
+}
+static int big6_is_one(const uint64_t* t) { return t[0] == 1 && (t[1] | t[2] | t[3] | t[4] | t[5]) == 0; }
+static int big6_geq(const uint64_t* a, const uint64_t* b) {
+  for (int i = 5; i >= 0; i--) {
+    if (a[i] > b[i]) return 1;
+    if (a[i] < b[i]) return 0;
+  }
+  return 1;
+}
+static void big6_sub(uint64_t* a, const uint64_t* b) {
+  u128 br = 0;
+  for (int i = 0; i < 6; i++) {
+    u128 d = (u128)a[i] - b[i] - br;
+    a[i] = (uint64_t)d;
+    br = (d >> 64) & 1;
+  }
+}
+static void big6_shr1(uint64_t* a, uint64_t top) {
+  for (int i = 0; i < 5; i++) a[i] = (a[i] >> 1) | (a[i + 1] << 63);
+  a[5] = (a[5] >> 1) | (top << 63);
+}
+static void half_mod_p(uint64_t* b) { /* b/2 mod p */
+  uint64_t carry = 0;
+  if (b[0] & 1) {
+    u128 c = 0;
+    for (int i = 0; i < 6; i++) {
+      c += (u128)b[i] + P[i];
+      b[i] = (uint64_t)c;
+      c >>= 64;
+    }
+    carry = (uint64_t)c;
+  }
+  big6_shr1(b, carry);
+}
+static void fp_inv(fp* r, const fp* a) {
+  if (fp_is_zero(a)) { memset(r, 0, sizeof *r); return; }
+  pthread_once(&r2_once, r2_init);
+  uint64_t u[6], v[6];
+  fp b = FP_R2, c;
+  memset(&c, 0, sizeof c);
+  memcpy(u, a->l, 48);
+  memcpy(v, P, 48);
+  while (!big6_is_one(u) && !big6_is_one(v)) {
+    while (!(u[0] & 1)) { big6_shr1(u, 0); half_mod_p(b.l); }
+    while (!(v[0] & 1)) { big6_shr1(v, 0); half_mod_p(c.l); }
+    if (big6_geq(u, v)) { big6_sub(u, v); fp_sub(&b, &b, &c); }
+    else { big6_sub(v, u); fp_sub(&c, &c, &b); }
+  }
+  *r = big6_is_one(u) ? b : c;
 }
 
 /* ------------------------------------------------------------------ Fp2 */
@@ -712,4 +779,404 @@ void gsref_verify_ppe_batch(size_t count, int m, int n, const void* A, const voi
   for (int t = 0; t < nthreads; t++) pthread_join(th[t], 0);
   free(th);
   free(jobs);
+}
+
+/* ================================================================== round 2: the whole prove / verify path
+ * Everything below restates the reference with its own evaluation structure; `nthreads` only spreads the
+ * independent Com::scalar_mul calls of one left_mul over host threads. */
+
+/* ------------------------------------------------------------------ Fr (Montgomery, 4 x 64, R = 2^256) */
+static void fr_mulm(fr* r, const fr* a, const fr* b) { /* CIOS */
+  uint64_t t[6] = {0};
+  for (int i = 0; i < 4; i++) {
+    u128 c = 0;
+    for (int j = 0; j < 4; j++) {
+      c += (u128)a->l[j] * b->l[i] + t[j];
+      t[j] = (uint64_t)c;
+      c >>= 64;
+    }
+    c += t[4];
+    t[4] = (uint64_t)c;
+    t[5] = (uint64_t)(c >> 64);
+    uint64_t m = t[0] * RINV;
+    c = (u128)m * RMOD[0] + t[0];
+    c >>= 64;
+    for (int j = 1; j < 4; j++) {
+      c += (u128)m * RMOD[j] + t[j];
+      t[j - 1] = (uint64_t)c;
+      c >>= 64;
+    }
+    c += t[4];
+    t[3] = (uint64_t)c;
+    t[4] = t[5] + (uint64_t)(c >> 64);
+  }
+  int ge = t[4] != 0;
+  if (!ge) {
+    ge = 1;
+    for (int i = 3; i >= 0; i--) {
+      if (t[i] > RMOD[i]) break;
+      if (t[i] < RMOD[i]) { ge = 0; break; }
+    }
+  }
+  if (ge) {
+    u128 b2 = 0;
+    for (int i = 0; i < 4; i++) {
+      u128 d = (u128)t[i] - RMOD[i] - b2;
+      t[i] = (uint64_t)d;
+      b2 = (d >> 64) & 1;
+    }
+  }
+  memcpy(r->l, t, 32);
+}
+static void fr_addm(fr* r, const fr* a, const fr* b) {
+  u128 c = 0;
+  uint64_t t[4];
+  for (int i = 0; i < 4; i++) {
+    c += (u128)a->l[i] + b->l[i];
+    t[i] = (uint64_t)c;
+    c >>= 64;
+  }
+  int ge = 1; /* r < 2^255, no carry out */
+  for (int i = 3; i >= 0; i--) {
+    if (t[i] > RMOD[i]) break;
+    if (t[i] < RMOD[i]) { ge = 0; break; }
+  }
+  if (ge) {
+    u128 b2 = 0;
+    for (int i = 0; i < 4; i++) {
+      u128 d = (u128)t[i] - RMOD[i] - b2;
+      t[i] = (uint64_t)d;
+      b2 = (d >> 64) & 1;
+    }
+  }
+  memcpy(r->l, t, 32);
+}
+static void fr_negm(fr* r, const fr* a) {
+  if ((a->l[0] | a->l[1] | a->l[2] | a->l[3]) == 0) { *r = *a; return; }
+  u128 b2 = 0;
+  for (int i = 0; i < 4; i++) {
+    u128 d = (u128)RMOD[i] - a->l[i] - b2;
+    r->l[i] = (uint64_t)d;
+    b2 = (d >> 64) & 1;
+  }
+}
+/* Matrix<Fr>::right_mul (data_structures.rs:824-868): out (r x c) = a (r x k) * b (k x c), row-major */
+static void frmat_mul(fr* out, const fr* a, const fr* b, size_t r, size_t k, size_t c) {
+  for (size_t i = 0; i < r; i++)
+    for (size_t j = 0; j < c; j++) {
+      fr acc, t;
+      memset(&acc, 0, sizeof acc);
+      for (size_t l = 0; l < k; l++) {
+        fr_mulm(&t, &a[i * k + l], &b[l * c + j]);
+        fr_addm(&acc, &acc, &t);
+      }
+      out[i * c + j] = acc;
+    }
+}
+static void frmat_transpose(fr* out, const fr* a, size_t r, size_t c) {
+  for (size_t i = 0; i < r; i++)
+    for (size_t j = 0; j < c; j++) out[j * r + i] = a[i * c + j];
+}
+
+/* ------------------------------------------------------------------ host-thread helper */
+typedef void (*pf_fn)(size_t i, void* arg);
+typedef struct { size_t n; size_t next; pf_fn fn; void* arg; pthread_mutex_t mu; } pf_state;
+static void* pf_worker(void* p) {
+  pf_state* s = (pf_state*)p;
+  for (;;) {
+    pthread_mutex_lock(&s->mu);
+    size_t i = s->next++;
+    pthread_mutex_unlock(&s->mu);
+    if (i >= s->n) return 0;
+    s->fn(i, s->arg);
+  }
+}
+static void parallel_for(size_t n, int nthreads, pf_fn fn, void* arg) {
+  pthread_once(&frob_once, frob_init);
+  pthread_once(&r2_once, r2_init);
+  if (nthreads <= 1 || n <= 1) {
+    for (size_t i = 0; i < n; i++) fn(i, arg);
+    return;
+  }
+  pf_state s = {n, 0, fn, arg, PTHREAD_MUTEX_INITIALIZER};
+  if ((size_t)nthreads > n) nthreads = (int)n;
+  pthread_t* th = (pthread_t*)malloc(sizeof(pthread_t) * nthreads);
+  for (int t = 0; t < nthreads; t++) pthread_create(&th[t], 0, pf_worker, &s);
+  for (int t = 0; t < nthreads; t++) pthread_join(th[t], 0);
+  free(th);
+}
+
+/* ------------------------------------------------------------------ Mat::left_mul on Matrix<Com> (:696-742)
+ * mat is a column vector of k Com, lhs is rows x k (row-major): out[i] = sum_k mat[k].scalar_mul(lhs[i][k]),
+ * the sum folded from Com::zero() with one affine add (+ normalisation) per term (:244-250, :185-190). */
+#define LEFT_MUL_IMPL(C)                                                                                       \
+  typedef struct { const C* mat; const fr* lhs; C* terms; size_t k; } C##_lm_job;                              \
+  static void C##_lm_term(size_t idx, void* arg) {                                                             \
+    C##_lm_job* j = (C##_lm_job*)arg;                                                                          \
+    uint64_t s[4];                                                                                             \
+    fr_canon(s, &j->lhs[idx]);                                                                                 \
+    C##_smul(&j->terms[idx], &j->mat[idx % j->k], s);                                                          \
+  }                                                                                                            \
+  static void C##_left_mul(C* out, const C* mat, const fr* lhs, size_t rows, size_t k, int nthreads) {         \
+    C* terms = (C*)malloc(sizeof(C) * (rows * k + 1));                                              \
+    C##_lm_job job = {mat, lhs, terms, k};                                                                     \
+    parallel_for(rows * k, nthreads, C##_lm_term, &job);                                                       \
+    for (size_t i = 0; i < rows; i++) {                                                                        \
+      C acc;                                                                                                   \
+      memset(&acc, 0, sizeof acc);                                                                             \
+      for (size_t l = 0; l < k; l++) C##_add(&acc, &acc, &terms[i * k + l]);                                   \
+      out[i] = acc;                                                                                            \
+    }                                                                                                          \
+    free(terms);                                                                                               \
+  }
+LEFT_MUL_IMPL(com1)
+LEFT_MUL_IMPL(com2)
+
+/* W1 = u2 + iota_1(g1), W2 = v2 + iota_2(g2) (data_structures.rs:325, :370) */
+static void crs_w1(com1* w, const crs_t* crs) { com1 lin; memset(&lin, 0, sizeof lin); lin.p[1] = crs->g1; com1_add(w, &crs->u[1], &lin); }
+static void crs_w2(com2* w, const crs_t* crs) { com2 lin; memset(&lin, 0, sizeof lin); lin.p[1] = crs->g2; com2_add(w, &crs->v[1], &lin); }
+
+/* batch_linear_map (:315-320, :360-365) or batch_scalar_linear_map (:328-334, :373-379), by side kind */
+typedef struct { const fr* s; const com1* w1; const com2* w2; com1* o1; com2* o2; } slm_job;
+static void slm1_term(size_t i, void* arg) { slm_job* j = (slm_job*)arg; uint64_t k[4]; fr_canon(k, &j->s[i]); com1_smul(&j->o1[i], j->w1, k); }
+static void slm2_term(size_t i, void* arg) { slm_job* j = (slm_job*)arg; uint64_t k[4]; fr_canon(k, &j->s[i]); com2_smul(&j->o2[i], j->w2, k); }
+static com1* map_side1(int is_group, size_t cnt, const void* elems, const crs_t* crs, int nthreads) {
+  com1* out = (com1*)calloc(cnt ? cnt : 1, sizeof(com1));
+  if (is_group) { for (size_t i = 0; i < cnt; i++) out[i].p[1] = ((const g1a*)elems)[i]; return out; }
+  com1 w; crs_w1(&w, crs);
+  slm_job j = {(const fr*)elems, &w, 0, out, 0};
+  parallel_for(cnt, nthreads, slm1_term, &j);
+  return out;
+}
+static com2* map_side2(int is_group, size_t cnt, const void* elems, const crs_t* crs, int nthreads) {
+  com2* out = (com2*)calloc(cnt ? cnt : 1, sizeof(com2));
+  if (is_group) { for (size_t i = 0; i < cnt; i++) out[i].p[1] = ((const g2a*)elems)[i]; return out; }
+  com2 w; crs_w2(&w, crs);
+  slm_job j = {(const fr*)elems, 0, &w, 0, out};
+  parallel_for(cnt, nthreads, slm2_term, &j);
+  return out;
+}
+
+/* batch_commit_scalar_to_B1 / B2 (commit.rs:125-156, 225-256): c_i = iota'(x_i) + r_i u1 */
+void gsref_batch_commit_scalar_b1(size_t n, const void* xs, const void* rand, const void* crs_, void* out, int nthreads) {
+  const crs_t* crs = (const crs_t*)crs_;
+  com1* lin = map_side1(0, n, xs, crs, nthreads);
+  com1* ru = (com1*)malloc(sizeof(com1) * (n ? n : 1));
+  for (size_t i = 0; i < n; i++) com1_left_mul(&ru[i], &crs->u[0], (const fr*)rand + i, 1, 1, 1);
+  for (size_t i = 0; i < n; i++) com1_add(&((com1*)out)[i], &lin[i], &ru[i]);
+  free(lin);
+  free(ru);
+}
+void gsref_batch_commit_scalar_b2(size_t n, const void* ys, const void* rand, const void* crs_, void* out, int nthreads) {
+  const crs_t* crs = (const crs_t*)crs_;
+  com2* lin = map_side2(0, n, ys, crs, nthreads);
+  com2* rv = (com2*)malloc(sizeof(com2) * (n ? n : 1));
+  for (size_t i = 0; i < n; i++) com2_left_mul(&rv[i], &crs->v[0], (const fr*)rand + i, 1, 1, 1);
+  for (size_t i = 0; i < n; i++) com2_add(&((com2*)out)[i], &lin[i], &rv[i]);
+  free(lin);
+  free(rv);
+}
+
+/* Provable::prove (prove.rs:92-171 PPE, 195-274 MSMEG1, 298-379 MSMEG2, 409-488 Quad).
+ * type = EquType byte; x side is G1 points for types 0,1 and Fr for 2,3; y side is G2 points for 0,2, Fr for 1,3.
+ * x_rand m x cx, y_rand n x cy, pf_rand = T (cy x cx row-major, the draw order).  out_pi: cx Com2, out_theta: cy Com1. */
+void gsref_prove(int type, size_t m, size_t n, const void* a_consts, const void* b_consts, const void* gamma_,
+                 const void* xvars, const void* yvars, const void* x_rand, const void* y_rand, const void* pf_rand,
+                 const void* crs_, void* out_pi, void* out_theta, int nthreads) {
+  const crs_t* crs = (const crs_t*)crs_;
+  const fr* gamma = (const fr*)gamma_;
+  const fr* T = (const fr*)pf_rand;
+  int xg = (type == 0 || type == 1), yg = (type == 0 || type == 2);
+  size_t cx = xg ? 2 : 1, cy = yg ? 2 : 1;
+  fr* Rt = (fr*)malloc(sizeof(fr) * cx * m);
+  fr* St = (fr*)malloc(sizeof(fr) * cy * n);
+  frmat_transpose(Rt, (const fr*)x_rand, m, cx); /* x_rand_trans: cx x m */
+  frmat_transpose(St, (const fr*)y_rand, n, cy); /* y_rand_trans: cy x n */
+
+  /* ---- pi */
+  com2 lin_b_part[2], stmt_y_part[2], key_part[2];
+  com2* linB = map_side2(yg, m, b_consts, crs, nthreads);
+  com2_left_mul(lin_b_part, linB, Rt, cx, m, nthreads);              /* x_rand_lin_b */
+  fr* RtG = (fr*)malloc(sizeof(fr) * cx * n);
+  frmat_mul(RtG, Rt, gamma, cx, m, n);                               /* x_rand_stmt = R^T Gamma */
+  com2* linY = map_side2(yg, n, yvars, crs, nthreads);
+  com2_left_mul(stmt_y_part, linY, RtG, cx, n, nthreads);            /* x_rand_stmt_lin_y */
+  fr RtGS[4], Tt[4];
+  frmat_mul(RtGS, RtG, (const fr*)y_rand, cx, n, cy);                /* (R^T Gamma) S : cx x cy */
+  frmat_transpose(Tt, T, cy, cx);                                    /* T^T : cx x cy */
+  for (size_t i = 0; i < cx * cy; i++) { fr t; fr_negm(&t, &Tt[i]); fr_addm(&RtGS[i], &RtGS[i], &t); }
+  com2_left_mul(key_part, crs->v, RtGS, cx, cy, nthreads);           /* v (or [v1]) . pf_rand_stmt */
+  for (size_t i = 0; i < cx; i++) {
+    com2 t;
+    com2_add(&t, &lin_b_part[i], &stmt_y_part[i]);
+    com2_add(&((com2*)out_pi)[i], &t, &key_part[i]);
+  }
+
+  /* ---- theta */
+  com1 lin_a_part[2], stmt_x_part[2], ukey_part[2];
+  com1* linA = map_side1(xg, n, a_consts, crs, nthreads);
+  com1_left_mul(lin_a_part, linA, St, cy, n, nthreads);              /* y_rand_lin_a */
+  fr* Gt = (fr*)malloc(sizeof(fr) * (m * n + 1));
+  frmat_transpose(Gt, gamma, m, n);
+  fr* StGt = (fr*)malloc(sizeof(fr) * cy * m);
+  frmat_mul(StGt, St, Gt, cy, n, m);                                 /* y_rand_stmt = S^T Gamma^T */
+  com1* linX = map_side1(xg, m, xvars, crs, nthreads);
+  com1_left_mul(stmt_x_part, linX, StGt, cy, m, nthreads);           /* y_rand_stmt_lin_x */
+  com1_left_mul(ukey_part, crs->u, T, cy, cx, nthreads);             /* u (or [u1]) . pf_rand */
+  for (size_t i = 0; i < cy; i++) {
+    com1 t;
+    com1_add(&t, &lin_a_part[i], &stmt_x_part[i]);
+    com1_add(&((com1*)out_theta)[i], &t, &ukey_part[i]);
+  }
+  free(Rt); free(St); free(linB); free(RtG); free(linY); free(linA); free(Gt); free(StGt); free(linX);
+}
+
+/* ComT::pairing (:484-491): four separate full pairings */
+static void comt_pairing(comt* out, const com1* x, const com2* y) {
+  for (int a = 0; a < 2; a++)
+    for (int b = 0; b < 2; b++) multi_pairing(&out->e[2 * a + b], 1, &x->p[a], &y->p[b]);
+}
+/* pairing_sum with its four multi_pairings on separate host threads (the reference runs them one after the other) */
+typedef struct { comt* out; int k; const com1* xs; const com2* ys; } ps_job;
+static void ps_entry(size_t e, void* arg) {
+  ps_job* j = (ps_job*)arg;
+  int a = (int)e >> 1, b = (int)e & 1;
+  g1a* ps = (g1a*)malloc((size_t)(j->k ? j->k : 1) * sizeof(g1a));
+  g2a* qs = (g2a*)malloc((size_t)(j->k ? j->k : 1) * sizeof(g2a));
+  for (int i = 0; i < j->k; i++) { ps[i] = j->xs[i].p[a]; qs[i] = j->ys[i].p[b]; }
+  multi_pairing(&j->out->e[e], j->k, ps, qs);
+  free(ps);
+  free(qs);
+}
+static void pairing_sum_mt(comt* out, int k, const com1* xs, const com2* ys, int nthreads) {
+  ps_job j = {out, k, xs, ys};
+  parallel_for(4, nthreads, ps_entry, &j);
+}
+
+/* Verifiable::verify (verifier.rs:23-55, 57-89, 91-123, 125-157) for one (equation, proof). */
+static int verify_any(int type, size_t m, size_t n, const void* a_consts, const void* b_consts, const fr* gamma,
+                      const void* target, const com1* c, const com2* d, const com2* pi, const com1* theta,
+                      const crs_t* crs, int nthreads) {
+  int xg = (type == 0 || type == 1), yg = (type == 0 || type == 2);
+  com1* linA = map_side1(xg, n, a_consts, crs, nthreads);
+  com2* linB = map_side2(yg, m, b_consts, crs, nthreads);
+  comt t1, t2, t3, t4, t5, lin_t, lhs, rhs;
+  pairing_sum_mt(&t1, (int)n, linA, d, nthreads);                    /* lin_a_com_y */
+  pairing_sum_mt(&t2, (int)m, c, linB, nthreads);                    /* com_x_lin_b */
+  com2* gd = (com2*)malloc(sizeof(com2) * (m ? m : 1));
+  com2_left_mul(gd, d, gamma, m, n, nthreads);                       /* stmt_com_y = Gamma . d (:39-40) */
+  pairing_sum_mt(&t3, (int)m, c, gd, nthreads);                      /* com_x_stmt_com_y */
+  com1 w1; com2 w2;
+  crs_w1(&w1, crs);
+  crs_w2(&w2, crs);
+  if (type == 0) {                                                   /* linear_map_PPE :509-516 */
+    for (int i = 0; i < 3; i++) fp12_one(&lin_t.e[i]);
+    lin_t.e[3] = *(const fp12*)target;
+  } else if (type == 1) {                                            /* linear_map_MSMEG1 :519-524 */
+    com1 lt; memset(&lt, 0, sizeof lt); lt.p[1] = *(const g1a*)target;
+    comt_pairing(&lin_t, &lt, &w2);
+  } else if (type == 2) {                                            /* linear_map_MSMEG2 :527-532 */
+    com2 lt; memset(&lt, 0, sizeof lt); lt.p[1] = *(const g2a*)target;
+    comt_pairing(&lin_t, &w1, &lt);
+  } else {                                                           /* linear_map_quad :535-540 */
+    uint64_t k[4]; com2 tw;
+    fr_canon(k, (const fr*)target);
+    com2_smul(&tw, &w2, k);
+    comt_pairing(&lin_t, &w1, &tw);
+  }
+  if (xg) pairing_sum_mt(&t4, 2, crs->u, pi, nthreads); else comt_pairing(&t4, &crs->u[0], &pi[0]);
+  if (yg) pairing_sum_mt(&t5, 2, theta, crs->v, nthreads); else comt_pairing(&t5, &theta[0], &crs->v[0]);
+  comt_mul(&lhs, &t1, &t2);
+  comt_mul(&lhs, &lhs, &t3);
+  comt_mul(&rhs, &lin_t, &t4);
+  comt_mul(&rhs, &rhs, &t5);
+  free(linA); free(linB); free(gd);
+  for (int i = 0; i < 4; i++)
+    if (!fp12_eq(&lhs.e[i], &rhs.e[i])) return 0;
+  return 1;
+}
+int gsref_verify(int type, size_t m, size_t n, const void* a_consts, const void* b_consts, const void* gamma,
+                 const void* target, const void* xcoms, const void* ycoms, const void* pi, const void* theta,
+                 const void* crs, int nthreads) {
+  pthread_once(&frob_once, frob_init);
+  pthread_once(&r2_once, r2_init);
+  return verify_any(type, m, n, a_consts, b_consts, (const fr*)gamma, target, (const com1*)xcoms, (const com2*)ycoms,
+                    (const com2*)pi, (const com1*)theta, (const crs_t*)crs, nthreads);
+}
+
+/* `count` independent verifications of one type and shape over `nthreads` host threads (array layout of
+ * gs_verify_batch; each verification itself single-threaded) */
+typedef struct {
+  int type; size_t m, n;
+  const uint8_t *A, *B, *gamma, *target, *c, *d, *pi, *theta;
+  size_t sa, sb, st, cx, cy;
+  const crs_t* crs; uint8_t* ok;
+} vbjob;
+static void vb_one(size_t p, void* arg) {
+  vbjob* j = (vbjob*)arg;
+  j->ok[p] = (uint8_t)verify_any(j->type, j->m, j->n, j->A + p * j->n * j->sa, j->B + p * j->m * j->sb,
+                                 (const fr*)(j->gamma + p * j->m * j->n * 32), j->target + p * j->st,
+                                 (const com1*)(j->c + p * j->m * 192), (const com2*)(j->d + p * j->n * 384),
+                                 (const com2*)(j->pi + p * j->cx * 384), (const com1*)(j->theta + p * j->cy * 192), j->crs, 1);
+}
+void gsref_verify_batch(int type, size_t count, size_t m, size_t n, const void* A, const void* B, const void* gamma,
+                        const void* target, const void* c, const void* d, const void* pi, const void* theta, const void* crs,
+                        uint8_t* ok, int nthreads) {
+  int xg = (type == 0 || type == 1), yg = (type == 0 || type == 2);
+  static const size_t tsz[4] = {576, 96, 192, 32};
+  vbjob j = {type, m, n, (const uint8_t*)A, (const uint8_t*)B, (const uint8_t*)gamma, (const uint8_t*)target,
+             (const uint8_t*)c, (const uint8_t*)d, (const uint8_t*)pi, (const uint8_t*)theta,
+             xg ? 96u : 32u, yg ? 192u : 32u, tsz[type], xg ? 2u : 1u, yg ? 2u : 1u, (const crs_t*)crs, ok};
+  parallel_for(count, nthreads, vb_one, &j);
+}
+
+/* `count` independent Provable::prove calls (array layout of gs_prove_batch; shared_vars as there), spread over
+ * host threads proof by proof */
+typedef struct {
+  int type; size_t m, n; int shared;
+  const uint8_t *A, *B, *gamma, *X, *Y, *R, *S, *T;
+  size_t sx, sy, cx, cy;
+  const crs_t* crs; uint8_t *pi, *theta;
+} pbjob;
+static void pb_one(size_t p, void* arg) {
+  pbjob* j = (pbjob*)arg;
+  size_t q = j->shared ? 0 : p;
+  gsref_prove(j->type, j->m, j->n, j->A + p * j->n * j->sx, j->B + p * j->m * j->sy, j->gamma + p * j->m * j->n * 32,
+              j->X + q * j->m * j->sx, j->Y + q * j->n * j->sy, j->R + q * j->m * j->cx * 32, j->S + q * j->n * j->cy * 32,
+              j->T + p * j->cx * j->cy * 32, j->crs, j->pi + p * j->cx * 384, j->theta + p * j->cy * 192, 1);
+}
+void gsref_prove_batch(int type, size_t count, size_t m, size_t n, const void* A, const void* B, const void* gamma,
+                       const void* X, const void* Y, const void* R, const void* S, const void* T, int shared_vars,
+                       const void* crs, void* out_pi, void* out_theta, int nthreads) {
+  int xg = (type == 0 || type == 1), yg = (type == 0 || type == 2);
+  pbjob j = {type, m, n, shared_vars, (const uint8_t*)A, (const uint8_t*)B, (const uint8_t*)gamma, (const uint8_t*)X,
+             (const uint8_t*)Y, (const uint8_t*)R, (const uint8_t*)S, (const uint8_t*)T, xg ? 96u : 32u, yg ? 192u : 32u,
+             xg ? 2u : 1u, yg ? 2u : 1u, (const crs_t*)crs, (uint8_t*)out_pi, (uint8_t*)out_theta};
+  parallel_for(count, nthreads, pb_one, &j);
+}
+
+/* n scalar multiplications of ONE base (input generation for the big parity cases: points = k . g) */
+typedef struct { const void* base; const fr* k; uint8_t* out; int g2; } mb_job;
+static void mb_one(size_t i, void* arg) {
+  mb_job* j = (mb_job*)arg;
+  uint64_t s[4];
+  fr_canon(s, &j->k[i]);
+  if (j->g2) g2a_mul((g2a*)(j->out + i * 192), (const g2a*)j->base, s);
+  else g1a_mul((g1a*)(j->out + i * 96), (const g1a*)j->base, s);
+}
+void gsref_g1_mul_batch(size_t n, const void* base, const void* ks, void* out, int nthreads) {
+  mb_job j = {base, (const fr*)ks, (uint8_t*)out, 0};
+  parallel_for(n, nthreads, mb_one, &j);
+}
+void gsref_g2_mul_batch(size_t n, const void* base, const void* ks, void* out, int nthreads) {
+  mb_job j = {base, (const fr*)ks, (uint8_t*)out, 1};
+  parallel_for(n, nthreads, mb_one, &j);
+}
+/* cross-check hook for the two inversion algorithms */
+int gsref_selftest_inv(const void* a) {
+  fp x, y;
+  pthread_once(&r2_once, r2_init);
+  fp_inv(&x, (const fp*)a);
+  fp_inv_fermat(&y, (const fp*)a);
+  return fp_eq(&x, &y);
 }
