@@ -91,3 +91,77 @@ def verify_statement_sharded(partial_local, finish, count: int, rank: int, world
     local = torch.frombuffer(bytearray(mine), dtype=torch.uint8).to(device)
     allp = local if world == 1 else gather_partials(local, group)
     return finish(bytes(allp.cpu().numpy().tobytes()))
+
+
+# ---------------------------------------------------------------- a multi-equation statement split by EQUATION (C4)
+def _gather_rows(local_rows, counts, row_bytes: int, group=None):
+    """All-gather of per-unit byte rows whose number differs by at most one between ranks: uint8 tensor
+    [mine * row_bytes] -> [sum(counts) * row_bytes] in rank order (padded to the widest shard for the collective)."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    width = max(counts) * row_bytes
+    pad = torch.zeros(width, dtype=torch.uint8, device=local_rows.device)
+    pad[:local_rows.numel()] = local_rows
+    parts = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(parts, pad, group=group)
+    return torch.cat([p[:c * row_bytes] for p, c in zip(parts, counts)])
+
+
+def _to_tensor(b, device):
+    import torch
+    return torch.frombuffer(bytearray(b), dtype=torch.uint8).to(device) if len(b) else torch.zeros(0, dtype=torch.uint8, device=device)
+
+
+def commit_sharded(commit_local, var_arrays: Sequence, unit_sizes: Sequence[int], nvars: int, out_bytes: int, rank: int,
+                   world: int, group=None, device="cpu") -> bytes:
+    """batch_commit_* (commit.rs:78-256) with the VARIABLES split across ranks: rank r commits
+    its contiguous block (`commit_local(shard_arrays, count) -> count * out_bytes bytes`; var_arrays = the variables
+    and their randomness rows) and the commitments (192 / 384 B each) are all-gathered, so every rank ends with the
+    full Commit1 / Commit2 -- what every equation's prove and verify then shares."""
+    lo, hi = shard_range(nvars, rank, world)
+    mine = commit_local(slice_units(var_arrays, unit_sizes, lo, hi), hi - lo) if hi > lo else b""
+    if len(mine) != (hi - lo) * out_bytes:
+        raise ValueError("commit_local returned the wrong number of bytes")
+    if world == 1:
+        return bytes(mine)
+    full = _gather_rows(_to_tensor(mine, device), shard_counts(nvars, world), out_bytes, group)
+    return full.cpu().numpy().tobytes()
+
+
+def prove_equations_sharded(prove_local, eq_arrays: Sequence, eq_unit_sizes: Sequence[int], num_eqs: int, pi_bytes: int,
+                            theta_bytes: int, rank: int, world: int, group=None, device="cpu") -> Tuple[bytes, bytes]:
+    """Provable::prove for the `num_eqs` equations of ONE statement (same type and shape, shared witnesses and
+    commitment randomness) with the EQUATIONS split contiguously across ranks: the reference proves equation by
+    equation (prove.rs:92-488, one EquProof per call), so the shards are independent.
+    `prove_local(shard_eq_arrays, count) -> (pi bytes, theta bytes)` is Engine.prove_batch(shared_vars=True) bound
+    to the type, shape, witnesses and randomness; eq_arrays = per-equation a_consts, b_consts, gamma, pf_rand.
+    The proofs (pi_bytes + theta_bytes per equation) are all-gathered: every rank returns all of them, in order."""
+    lo, hi = shard_range(num_eqs, rank, world)
+    pi, th = prove_local(slice_units(eq_arrays, eq_unit_sizes, lo, hi), hi - lo) if hi > lo else (b"", b"")
+    if len(pi) != (hi - lo) * pi_bytes or len(th) != (hi - lo) * theta_bytes:
+        raise ValueError("prove_local returned the wrong number of bytes")
+    if world == 1:
+        return bytes(pi), bytes(th)
+    counts = shard_counts(num_eqs, world)
+    # one collective: pi and theta of an equation travel together
+    import torch
+    row = pi_bytes + theta_bytes
+    mine = torch.empty((hi - lo) * row, dtype=torch.uint8, device=device).view(hi - lo, row) if hi > lo else None
+    if hi > lo:
+        mine[:, :pi_bytes] = _to_tensor(pi, device).view(hi - lo, pi_bytes)
+        mine[:, pi_bytes:] = _to_tensor(th, device).view(hi - lo, theta_bytes)
+        mine = mine.reshape(-1)
+    else:
+        mine = torch.zeros(0, dtype=torch.uint8, device=device)
+    full = _gather_rows(mine, counts, row, group).view(num_eqs, row).cpu()
+    return full[:, :pi_bytes].contiguous().numpy().tobytes(), full[:, pi_bytes:].contiguous().numpy().tobytes()
+
+
+def verify_equations_sharded(verify_local, eq_arrays: Sequence, eq_unit_sizes: Sequence[int], num_eqs: int, rank: int,
+                             world: int, group=None, device="cpu"):
+    """Verifiable::verify for the equations of one statement split contiguously across ranks; the shared commitments
+    are replicated (bound inside `verify_local(shard_eq_arrays, count) -> count verdict bytes`, which repeats them per
+    equation for gs_verify_batch); eq_arrays = per-equation a_consts, b_consts, gamma, target, pi, theta.  One
+    verdict byte per equation is all-gathered (verifier.rs:25-26: one EquProof per verify call)."""
+    return verify_batch_sharded(verify_local, eq_arrays, eq_unit_sizes, num_eqs, rank, world, group, device)

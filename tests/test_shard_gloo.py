@@ -133,3 +133,58 @@ def test_statement_partials_all_gather_gloo(world, count):
         assert p.exitcode == 0
     for rank, ok in res:
         assert ok == [s % 2 for s in range(count)]
+
+
+# ---------------------------------------------------------------- one statement split by EQUATION (C4: shard.*_equations_sharded)
+def _eq_worker(rank, world, port, ty, E, q):
+    """The per-rank prover / verifier is the C oracle on the CPU (the CUDA path needs a GPU): what is under test is the
+    partition by variable (commit) and by equation (prove, verify), the ragged all-gathers and the ordering."""
+    import torch.distributed as dist
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    sys.path.insert(0, ROOT)
+    from bigcase import Statement, cb, make_crs
+    sh = _load_shard()
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    try:
+        m, n = 3, 2
+        st = Statement(ty, m, n, E, make_crs(1)[0], seed=900 + ty, prove=False)
+        cx, cy, xs, ys, ts = cb.cx_of(ty), cb.cy_of(ty), cb.x_size(ty), cb.y_size(ty), cb.target_size(ty)
+        xc = sh.commit_sharded(lambda a, k: cb.commit_x(ty, a[0], a[1], st.crsb), [st.X, st.xr], [xs, cx * 32], m, 192, rank, world)
+        yc = sh.commit_sharded(lambda a, k: cb.commit_y(ty, a[0], a[1], st.crsb), [st.Y, st.yr], [ys, cy * 32], n, 384, rank, world)
+        pi, th = sh.prove_equations_sharded(
+            lambda a, k: cb.prove_batch(ty, k, m, n, a[0], a[1], a[2], st.X, st.Y, st.xr, st.yr, a[3], True, st.crsb),
+            [st.A, st.B, st.G, st.Tr], [n * xs, m * ys, m * n * 32, cx * cy * 32], E, cx * 384, cy * 192, rank, world)
+        tg = bytearray(st.T)
+        tg[ts:2 * ts], tg[2 * ts:3 * ts] = tg[2 * ts:3 * ts], tg[ts:2 * ts]        # swap the targets of equations 1 and 2
+        ok = sh.verify_equations_sharded(
+            lambda a, k: cb.verify_batch(ty, k, m, n, [a[0], a[1], a[2], a[3], xc * k, yc * k, a[4], a[5]], st.crsb),
+            [st.A, st.B, st.G, bytes(tg), pi, th], [n * xs, m * ys, m * n * 32, ts, cx * 384, cy * 192], E, rank, world)
+        q.put((rank, xc, yc, pi, th, ok.tolist()))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,ty,E", [(2, 0, 5), (3, 3, 4), (2, 1, 1)])
+def test_equations_sharded_gloo(world, ty, E):
+    import torch.multiprocessing as mp
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from bigcase import Statement, make_crs
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_eq_worker, args=(r, world, port, ty, E, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=300) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    want = Statement(ty, 3, 2, E, make_crs(1)[0], seed=900 + ty)      # unsharded: commitments and proofs in one go
+    expect_ok = [0 if e in (1, 2) and E > 2 else 1 for e in range(E)]
+    for rank, xc, yc, pi, th, ok in res:
+        assert xc == want.xc and yc == want.yc, rank
+        assert pi == want.pi and th == want.theta, rank
+        assert ok == expect_ok, (rank, ok)
