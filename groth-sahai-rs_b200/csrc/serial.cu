@@ -78,6 +78,7 @@ __global__ void __launch_bounds__(128) k_g1_from_uncompressed(const uint8_t* __r
   g1_aff p;
   p.set_inf();
   bool good = (b[0] & 0x80) == 0;
+  if (good && (b[0] & 0x40)) good = wire_inf_canonical(b, 96);
   if (good && !(b[0] & 0x40)) {
     good = (b[0] & 0x20) == 0 && (b[48] & 0xE0) == 0 && fp_from_be(p.x, b) && fp_from_be(p.y, b + 48);
     if (good) {
@@ -120,6 +121,7 @@ __global__ void __launch_bounds__(128) k_g2_from_uncompressed(const uint8_t* __r
   g2_aff p;
   p.set_inf();
   bool good = (b[0] & 0x80) == 0;
+  if (good && (b[0] & 0x40)) good = wire_inf_canonical(b, 192);
   if (good && !(b[0] & 0x40)) {
     good = (b[0] & 0x20) == 0 && ((b[48] | b[96] | b[144]) & 0xE0) == 0 && fp_from_be(p.x.c1, b) && fp_from_be(p.x.c0, b + 48) &&
            fp_from_be(p.y.c1, b + 96) && fp_from_be(p.y.c0, b + 144);
@@ -192,6 +194,32 @@ __global__ void k_fp_from_bytes(const uint32_t* __restrict__ in, fp* __restrict_
   else
     r.set_zero();
   out[i] = r;
+  ok[i] = good ? 1 : 0;
+}
+// PairingOutput's Valid::check (ark-ec 0.5, what deserialize with Validate::Yes runs on a GT value): f^r == 1, i.e. f is
+// in the order-r subgroup; zero and every other Fp12 value are rejected.  thread -> one GT value (tower code: 254
+// squarings + the products of r's set bits; a CRS or an equation carries one GT value, so this is not a hot path).
+__global__ void __launch_bounds__(64) k_gt_check_order(const fp12* __restrict__ in, const uint8_t* __restrict__ ok12,
+                                                       fp12* __restrict__ out, uint8_t* __restrict__ ok, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  bool good = true;
+  for (int j = 0; j < 12; j++) good = good && ok12[i * 12 + j];
+  if (good) {
+    const fp12 f = in[i];
+    fp12 acc = f;
+    for (int bit = 253; bit >= 0; bit--) {          // r has 255 bits: bit 254 is the leading one
+      fp12::sqr(acc, acc);
+      if ((FrParams::mod(bit >> 5) >> (bit & 31)) & 1) fp12::mul(acc, acc, f);
+    }
+    fp12 one;
+    one.set_one();
+    good = acc.equals(one);
+  }
+  if (!good) {
+    fp* o = (fp*)&out[i];
+    for (int j = 0; j < 12; j++) o[j].set_zero();
+  }
   ok[i] = good ? 1 : 0;
 }
 
@@ -295,26 +323,22 @@ int gs_gt_to_bytes(gs_ctx* ctx, size_t n, const gs_gt* in, uint8_t* out) {
 }
 int gs_gt_from_bytes(gs_ctx* ctx, size_t n, const uint8_t* in, gs_gt* out, uint8_t* out_ok) {
   if (n && !out_ok) return GS_EARG;
-  // one verdict byte per Fp coefficient on the device, folded to one per GT value on the host
+  // every coefficient canonical (< p), then PairingOutput's Valid::check: f^r == 1 (k_gt_check_order)
   if (!ctx || (n && (!in || !out))) return GS_EARG;
   if (n == 0) return GS_OK;
-  std::vector<uint8_t> ok12(n * 12);
   CUDA_TRY(cudaSetDevice(ctx->device));
   Scratch sc(ctx);
-  uint8_t *din, *dok;
+  uint8_t *din, *dok12, *dok;
   fp* dout;
   CUDA_TRY(upload(ctx, sc, &din, in, n * 576));
   CUDA_TRY(sc.alloc(&dout, n * 12));
-  CUDA_TRY(sc.alloc(&dok, n * 12));
-  LAUNCH(k_fp_from_bytes, n * 12, (const uint32_t*)din, dout, dok, n * 12);
+  CUDA_TRY(sc.alloc(&dok12, n * 12));
+  CUDA_TRY(sc.alloc(&dok, n));
+  LAUNCH(k_fp_from_bytes, n * 12, (const uint32_t*)din, dout, dok12, n * 12);
+  LAUNCH_CFG(k_gt_check_order, n, 64, 0, (const fp12*)dout, dok12, (fp12*)dout, dok, n);
   CUDA_TRY(cudaMemcpyAsync(out, dout, n * 576, cudaMemcpyDeviceToHost, ctx->stream));
-  CUDA_TRY(cudaMemcpyAsync(ok12.data(), dok, n * 12, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(cudaMemcpyAsync(out_ok, dok, n, cudaMemcpyDeviceToHost, ctx->stream));
   CUDA_TRY(cudaStreamSynchronize(ctx->stream));
-  for (size_t i = 0; i < n; i++) {
-    uint8_t g = 1;
-    for (int j = 0; j < 12; j++) g &= ok12[i * 12 + j];
-    out_ok[i] = g;
-  }
   return GS_OK;
 }
 

@@ -196,9 +196,17 @@ static GS_HD GS_INL void g1_compress_point(uint8_t b[48], const g1_aff& p) {
     b[0] |= 0x80 | (fp_is_largest(p.y) ? 0x20 : 0);
   }
 }
+// infinity must be canonical, as ark-bls12-381's EncodingFlags::get_flags / read_g*_compressed require: the sort flag
+// clear and every other bit of the encoding zero (`rest` = the bytes after the flag byte)
+static GS_HD GS_INL bool wire_inf_canonical(const uint8_t* b, int len) {
+  uint8_t acc = b[0] & 0x3F;
+  for (int j = 1; j < len; j++) acc |= b[j];
+  return acc == 0;
+}
 static GS_HD GS_INL bool g1_decompress_point(g1_aff& p, const uint8_t b[48], int check_subgroup) {
   p.set_inf();
   bool good = (b[0] & 0x80) != 0;
+  if (good && (b[0] & 0x40)) good = wire_inf_canonical(b, 48);
   if (good && !(b[0] & 0x40)) {
     good = fp_from_be(p.x, b);
     if (good) {
@@ -230,6 +238,7 @@ static GS_HD GS_INL void g2_compress_point(uint8_t b[96], const g2_aff& p) {
 static GS_HD GS_INL bool g2_decompress_point(g2_aff& p, const uint8_t b[96], int check_subgroup) {
   p.set_inf();
   bool good = (b[0] & 0x80) != 0;
+  if (good && (b[0] & 0x40)) good = wire_inf_canonical(b, 96);
   if (good && !(b[0] & 0x40)) {
     // the second coordinate has no flag bits: a set top bit means >= p
     good = fp_from_be(p.x.c1, b) && (b[48] & 0xE0) == 0 && fp_from_be(p.x.c0, b + 48);

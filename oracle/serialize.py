@@ -10,7 +10,9 @@ and the equations (statement.rs:117-185).  The arithmetic-bearing part is the po
 * top three bits of byte 0: 0x80 compressed, 0x40 infinity, 0x20 "y is the lexicographically largest of {y, -y}"
   (Fp2 ordered with c1 most significant); infinity = flag byte followed by zeros.
 * deserialisation (Validate::Yes) rejects x >= p, x with no point, points outside the order-r subgroup; a set
-  infinity flag yields the identity.
+  infinity flag yields the identity ONLY in its canonical form (sort flag clear, every other bit zero: ark-bls12-381's
+  EncodingFlags::get_flags rejects sort + infinity and read_g*_compressed / _uncompressed require zero coordinates).
+* GT (PairingOutput): besides canonical coefficients, Valid::check requires f^r == 1 (ark-ec 0.5 pairing.rs).
 * Fr: 32 B little-endian canonical integer (< r); Fp12/GT: 12 x 48 B little-endian canonical, tower order.
 
 PARITY STATUS: **unpinned against arkworks bits** (no Rust toolchain).  Pinned against the public compressed
@@ -112,8 +114,8 @@ def g1_decompress(b: bytes):
     flags = b[0]
     if not flags & 0x80:
         return False, None
-    if flags & 0x40:
-        return True, None
+    if flags & 0x40:           # infinity must be canonical: sort flag clear, x bytes zero (EncodingFlags::get_flags)
+        return (True, None) if (flags & 0x3F) == 0 and not any(b[1:]) else (False, None)
     x = int.from_bytes(bytes([b[0] & 0x1F]) + b[1:], "big")
     if x >= P:
         return False, None
@@ -137,7 +139,7 @@ def g1_deserialize_uncompressed(b: bytes):
     if b[0] & 0x80:
         return False, None
     if b[0] & 0x40:
-        return True, None
+        return (True, None) if (b[0] & 0x3F) == 0 and not any(b[1:]) else (False, None)
     if b[0] & 0x20:
         return False, None
     x, y = int.from_bytes(b[:48], "big"), int.from_bytes(b[48:], "big")
@@ -159,7 +161,7 @@ def g2_deserialize_uncompressed(b: bytes):
     if b[0] & 0x80:
         return False, None
     if b[0] & 0x40:
-        return True, None
+        return (True, None) if (b[0] & 0x3F) == 0 and not any(b[1:]) else (False, None)
     if b[0] & 0x20:
         return False, None
     v = [int.from_bytes(b[48 * i:48 * (i + 1)], "big") for i in range(4)]
@@ -186,7 +188,7 @@ def g2_decompress(b: bytes):
     if not flags & 0x80:
         return False, None
     if flags & 0x40:
-        return True, None
+        return (True, None) if (flags & 0x3F) == 0 and not any(b[1:]) else (False, None)
     c1 = int.from_bytes(bytes([b[0] & 0x1F]) + b[1:48], "big")
     c0 = int.from_bytes(b[48:96], "big")
     if c1 >= P or c0 >= P:
@@ -217,3 +219,16 @@ def fp12_to_bytes(f) -> bytes:
         for c2 in (c6.c0, c6.c1, c6.c2):
             out += (c2.c0 % P).to_bytes(48, "little") + (c2.c1 % P).to_bytes(48, "little")
     return out
+
+
+def fp12_from_bytes(b: bytes):
+    """-> (ok, Fp12).  CanonicalDeserialize of a PairingOutput with Validate::Yes: 12 canonical Fp coefficients in tower
+    order, then Valid::check: f^r == 1 (zero and elements outside the order-r subgroup are rejected)."""
+    from .bls12_381 import Fp6, Fp12, FP12_ONE
+    assert len(b) == 576
+    v = [int.from_bytes(b[48 * i:48 * (i + 1)], "little") for i in range(12)]
+    if any(t >= P for t in v):
+        return False, None
+    c = [Fp2(v[2 * i], v[2 * i + 1]) for i in range(6)]
+    f = Fp12(Fp6(c[0], c[1], c[2]), Fp6(c[3], c[4], c[5]))
+    return (True, f) if f.pow(R) == FP12_ONE else (False, None)

@@ -30,7 +30,7 @@ def test_c5_batch_verify_tamper_mask(eng):
     """C5 shape: 4x4 PPE proofs, distinct instances tiled to 8,192 proofs, 1 % tampered -> exact mask."""
     sys.path.insert(0, ROOT)
     import bench
-    arrays, expected = bench.build_workload(eng, distinct=8, proofs=8192, seed=5)
+    arrays, expected, _ = bench.build_workload(eng, distinct=8, proofs=8192, seed=5)
     ok = eng.verify_batch(0, 8192, 4, 4, *[a.tobytes() for a in arrays])
     assert bytes(ok) == expected.tobytes()
     assert expected.sum() == 8192 - len(range(37, 8192, 100))

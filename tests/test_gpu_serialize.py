@@ -49,7 +49,9 @@ def test_decompress_rejections_match_oracle(eng):
     bad[0] |= 0x80
     cases.append(bytes(bad))                                                        # x = p
     cases.append(bytes([0xC0]) + bytes(47))                                         # infinity
-    cases.append(bytes([0xE0]) + bytes([7]) * 47)                                   # infinity flag wins over the rest
+    cases.append(bytes([0xE0]) + bytes(47))                                         # sort flag + infinity: rejected
+    cases.append(bytes([0xC0]) + bytes([7]) * 47)                                   # infinity with non-zero x bytes: rejected
+    cases.append(bytes([0xC1]) + bytes(47))                                         # infinity with a low bit of byte 0 set
     for x in range(2, 40):                                                          # small x: off-curve / off-subgroup
         e = bytearray(x.to_bytes(48, "big"))
         e[0] |= 0x80 | (0x20 if x % 2 else 0)
@@ -96,6 +98,9 @@ def test_decompress_rejections_match_oracle(eng):
     e = bytearray(P.to_bytes(48, "big") + bytes(48))
     e[0] |= 0x80
     cases2.append(bytes(e))
+    cases2.append(bytes([0xC0]) + bytes(95))                                        # canonical infinity
+    cases2.append(bytes([0xE0]) + bytes(95))                                        # sort flag + infinity
+    cases2.append(bytes([0xC0]) + bytes(70) + b"\x01" + bytes(24))                  # infinity with a non-zero x.c0 byte
     cases2.append(G2_GEN_COMPRESSED)
     back, ok = eng.deserialize("g2", b"".join(cases2))
     for i, c in enumerate(cases2):
@@ -123,6 +128,17 @@ def test_fr_and_gt_bytes(eng):
     bad = bytearray(w[:576])
     bad[5 * 48:6 * 48] = P.to_bytes(48, "little")
     assert eng.deserialize("gt", bytes(bad))[1] == b"\x00"
+    # PairingOutput's Valid::check: f^r == 1.  Zero, a random Fp12 and a cyclotomic element of the wrong order are rejected
+    from oracle.bls12_381 import Fp2, Fp6, Fp12, FP12_ONE
+    rnd = Fp12(Fp6(*[Fp2(rng.r.randrange(P), rng.r.randrange(P)) for _ in range(3)]),
+               Fp6(*[Fp2(rng.r.randrange(P), rng.r.randrange(P)) for _ in range(3)]))
+    cyc = rnd.pow((P ** 6 - 1) * (P ** 2 + 1))            # in the cyclotomic subgroup, order divides p^4 - p^2 + 1, not r
+    wires = [bytes(576), ser.fp12_to_bytes(rnd), ser.fp12_to_bytes(cyc), ser.fp12_to_bytes(FP12_ONE), w[:576]]
+    want = [ser.fp12_from_bytes(x)[0] for x in wires]
+    assert want == [False, False, False, True, True]
+    back, ok = eng.deserialize("gt", b"".join(wires))
+    assert [bool(x) for x in ok] == want
+    assert back[:3 * 576] == bytes(3 * 576) and back[4 * 576:] == g[:576]
 
 
 def test_struct_serialisation_round_trip(eng):
@@ -248,3 +264,11 @@ def test_uncompressed_encodings(eng):
     bad2 = [g2w[:191] + bytes([g2w[191] ^ 1]), g2w[:96] + P.to_bytes(48, "big") + g2w[144:]]
     assert eng.deserialize("g2", b"".join(bad2), compressed=False)[1] == bytes(2)
     assert all(ser.g2_deserialize_uncompressed(b_)[0] is False for b_ in bad2)
+    # infinity must be canonical in the uncompressed form too: flag byte 0x40 followed by zeros only
+    inf_cases = [bytes([0x40]) + bytes(95), bytes([0x60]) + bytes(95), bytes([0x40]) + bytes(94) + b"\x01"]
+    back, ok = eng.deserialize("g1", b"".join(inf_cases), compressed=False)
+    assert ok == b"\x01\x00\x00" and back == bytes(96 * 3)
+    assert [ser.g1_deserialize_uncompressed(b_)[0] for b_ in inf_cases] == [True, False, False]
+    inf2 = [bytes([0x40]) + bytes(191), bytes([0x40]) + bytes(100) + b"\x09" + bytes(90)]
+    assert eng.deserialize("g2", b"".join(inf2), compressed=False)[1] == b"\x01\x00"
+    assert [ser.g2_deserialize_uncompressed(b_)[0] for b_ in inf2] == [True, False]

@@ -38,6 +38,28 @@ def test_round_trips_and_infinity():
     assert ser.g1_compress(None) == bytes([0xC0]) + bytes(47)
     assert ser.g1_decompress(bytes([0xC0]) + bytes(47)) == (True, None)
     assert ser.g2_decompress(bytes([0xC0]) + bytes(95)) == (True, None)
+    # non-canonical infinity encodings are rejected (ark-bls12-381: sort flag + infinity, or non-zero coordinate bytes)
+    assert ser.g1_decompress(bytes([0xE0]) + bytes(47)) == (False, None)
+    assert ser.g1_decompress(bytes([0xC0]) + bytes(46) + b"\x01") == (False, None)
+    assert ser.g2_decompress(bytes([0xE0]) + bytes(95)) == (False, None)
+    assert ser.g2_decompress(bytes([0xC0]) + bytes(60) + b"\x01" + bytes(34)) == (False, None)
+    assert ser.g1_deserialize_uncompressed(bytes([0x40]) + bytes(95)) == (True, None)
+    assert ser.g1_deserialize_uncompressed(bytes([0x40]) + bytes(94) + b"\x02") == (False, None)
+    assert ser.g2_deserialize_uncompressed(bytes([0x60]) + bytes(191)) == (False, None)
+
+
+def test_gt_valid_check():
+    """PairingOutput's Valid::check on deserialisation: f^r == 1."""
+    from oracle.bls12_381 import Fp6, Fp12, FP12_ONE, pairing
+    e = pairing(G1_GEN, G2_GEN_FP2)
+    assert ser.fp12_from_bytes(ser.fp12_to_bytes(e)) == (True, e)
+    assert ser.fp12_from_bytes(ser.fp12_to_bytes(FP12_ONE))[0] is True
+    assert ser.fp12_from_bytes(bytes(576))[0] is False
+    two = Fp12(Fp6(Fp2(2, 0), Fp2(0, 0), Fp2(0, 0)), Fp6(Fp2(0, 0), Fp2(0, 0), Fp2(0, 0)))
+    assert ser.fp12_from_bytes(ser.fp12_to_bytes(two))[0] is False          # 2 has order dividing p - 1, not r
+    bad = bytearray(ser.fp12_to_bytes(e))
+    bad[48:96] = P.to_bytes(48, "little")
+    assert ser.fp12_from_bytes(bytes(bad))[0] is False
 
 
 def test_rejections():
