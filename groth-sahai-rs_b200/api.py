@@ -254,6 +254,13 @@ def verify_batch(equations, proofs, crs: CRS) -> List[bool]:
     assert len(equations) == len(proofs) and equations
     ty = equations[0].equ_type
     m, n = len(proofs[0].xcoms.coms), len(proofs[0].ycoms.coms)
+    for e, p in zip(equations, proofs):     # one type and one shape per batch: a mixed batch would be mis-sliced silently
+        if e.equ_type != ty or len(p.xcoms.coms) != m or len(p.ycoms.coms) != n:
+            raise ValueError("verify_batch: every (equation, proof) must have the same type and shape")
+        if len(p.equ_proofs) != 1 or p.equ_proofs[0].equ_type != ty:      # verifier.rs:25-26
+            raise ValueError("verify_batch: exactly one EquProof of the equation's type per CProof")
+        if len(e.a_consts) != n or len(e.b_consts) != m or len(e.gamma) != m or any(len(r) != n for r in e.gamma):
+            raise ValueError("verify_batch: constants / Gamma do not match the number of variables")
     cat = lambda f: b"".join(f(e, p) for e, p in zip(equations, proofs))
     ok = crs._use().verify_batch(
         ty, len(equations), m, n, cat(lambda e, p: b"".join(e.a_consts)), cat(lambda e, p: b"".join(e.b_consts)),

@@ -164,13 +164,13 @@ static int load_crs_device(gs_ctx* ctx, const gs_crs* crs) {
   CUDA_TRY(cudaMemcpyAsync(ctx->crs, &h, sizeof(h), cudaMemcpyHostToDevice, ctx->stream));
   int rc = gsi::crs_derive(ctx);
   if (rc) return rc;
-  // small (c = 8) fixed-base tables now; bigger windows are built lazily by the first big batch
-  rc = gsi::fixed_table_rebuild<FpOps>(ctx, 8);
-  if (rc) return rc;
-  rc = gsi::fixed_table_rebuild<Fp2Ops>(ctx, 8);
-  if (rc) return rc;
-  rc = gsi::crs_lines_build(ctx);  // (lambda, mu) of the Miller walk of v1, v2, W2: they never change with the proof
-  if (rc) return rc;
+  // Everything derived from the key that only SOME calls need is built by the first call that needs it: the fixed-base
+  // window tables of u, v, W (first commit / prove: batch_commit_impl, proof_element) and the stored Miller lines of
+  // v1, v2, W2 (first verify: crs_lines_build).  generate_crs itself is 6 scalar multiplications and one pairing in the
+  // reference (generator.rs:81-118); the 17 ms of table builds that used to sit here made it ~15x slower than the CPU.
+  gsi::fixed_table_release<FpOps>(ctx);
+  gsi::fixed_table_release<Fp2Ops>(ctx);
+  ctx->crs_lines_valid = false;
   CUDA_TRY(cudaStreamSynchronize(ctx->stream));
   ctx->crs_loaded = true;
   return GS_OK;

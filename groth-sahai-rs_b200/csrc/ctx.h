@@ -30,6 +30,8 @@ struct gs_ctx {
   bool crs_loaded = false;
   gs_fixed_table<gs::FpOps> tab1;
   gs_fixed_table<gs::Fp2Ops> tab2;
+  bool crs_lines_valid = false;   // the stored lines and the fixed-base tables are built by the FIRST call that needs them
+                                  // (a verify / a commit or prove), not by gs_crs_generate / gs_crs_load
   gs::fp2* crs_lines = nullptr;   // (lambda, mu) per Miller step of the fixed G2 points v1.0 v1.1 v2.0 v2.1 W2.0 W2.1:
                                   // crs_lines[(pid*68 + step)*2 + {0,1}]  (pairing.cu crs_lines_build)
   uint32_t* fe_prog = nullptr;    // op program of the cooperative final exponentiation (finalexp.cu)
@@ -132,10 +134,22 @@ constexpr uint8_t GS_SLOT_WALK = 0;     // arbitrary Com2: walk both coordinates
 constexpr uint8_t GS_SLOT_WALK_B1 = 1;  // Y_k = (O, y): only coordinate 1 exists (iota_2)
 constexpr uint8_t GS_SLOT_FIXED = 2;    // GS_SLOT_FIXED + j: Y_k is the CRS element v_1 (j = 0), v_2 (1) or W2 (2)
 struct walk_ahead {  // G2 walks started early on the second stream (lone statements), see g2_walk_ahead
+  gs_ctx* ctx = nullptr;
   fp2* lines = nullptr;
   uint32_t* dwalk = nullptr;
   int nwalk = 0;
   cudaEvent_t done = nullptr;
+  walk_ahead() = default;
+  walk_ahead(const walk_ahead&) = delete;
+  walk_ahead& operator=(const walk_ahead&) = delete;
+  // On EVERY exit (error paths included) the main stream is ordered after the walk before the Scratch that owns the
+  // walk's buffers frees them with cudaFreeAsync on the main stream: declare the walk_ahead AFTER that Scratch.
+  ~walk_ahead() {
+    if (done) {
+      if (ctx) cudaStreamWaitEvent(ctx->stream, done, 0);
+      cudaEventDestroy(done);
+    }
+  }
 };
 int g2_walk_ahead(gs_ctx* ctx, Scratch& sc, const g2_aff* Y, size_t nprob, int K, const uint8_t* slot_kind, walk_ahead* wa);
 int run_pairing_product(gs_ctx* ctx, Scratch& sc, const g1_aff* X, const g2_aff* Y, size_t nprob, int K, fp12* out_comt,

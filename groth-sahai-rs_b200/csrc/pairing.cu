@@ -484,8 +484,10 @@ __global__ void k_linear_map_slots(int type, const void* target, const crs_dev* 
 }  // namespace gs
 
 int gsi::crs_lines_build(gs_ctx* ctx) {
+  if (ctx->crs_lines_valid || !ctx->crs_loaded) return GS_OK;
   if (!ctx->crs_lines) CUDA_TRY(cudaMalloc(&ctx->crs_lines, (size_t)6 * GS_NUM_LINES * 2 * sizeof(fp2)));
   LAUNCH_CFG(k_crs_lines, 6, 32, 0, ctx->crs, ctx->crs_lines);
+  ctx->crs_lines_valid = true;
   return GS_OK;
 }
 
@@ -500,7 +502,7 @@ static void build_walk_list(gs_ctx* ctx, int K, const uint8_t* slot_kind, std::v
   fs.n = 0;
   int nfixed = 0;
   for (int k = 0; slot_kind && k < K; k++) nfixed += slot_kind[k] >= GS_SLOT_FIXED ? 1 : 0;
-  const bool use_fixed = ctx->crs_lines && nfixed > 0 && nfixed <= 4;  // no shape has more than 4 CRS slots
+  const bool use_fixed = ctx->crs_lines_valid && nfixed > 0 && nfixed <= 4;  // no shape has more than 4 CRS slots
   for (int b = 0; b < 2; b++)
     for (int k = 0; k < K; k++) {
       const uint8_t kind = slot_kind ? slot_kind[k] : GS_SLOT_WALK;
@@ -530,11 +532,15 @@ int gsi::g2_walk_ahead(gs_ctx* ctx, Scratch& sc, const g2_aff* Y, size_t nprob, 
   CUDA_TRY(upload(ctx, sc, &wa->dwalk, hwalk.data(), hwalk.size()));
   fp2* lines;
   CUDA_TRY(sc.alloc(&lines, (size_t)nwalk * nprob * GS_NUM_LINES * 2));
-  cudaEvent_t fork;
-  CUDA_TRY(cudaEventCreateWithFlags(&fork, cudaEventDisableTiming));
-  CUDA_TRY(cudaEventCreateWithFlags(&wa->done, cudaEventDisableTiming));
-  CUDA_TRY(cudaEventRecord(fork, ctx->stream));
-  CUDA_TRY(cudaStreamWaitEvent(ctx->stream2, fork, 0));
+  struct event_guard {  // the fork event is destroyed on every path
+    cudaEvent_t e = nullptr;
+    ~event_guard() {
+      if (e) cudaEventDestroy(e);
+    }
+  } fork;
+  CUDA_TRY(cudaEventCreateWithFlags(&fork.e, cudaEventDisableTiming));
+  CUDA_TRY(cudaEventRecord(fork.e, ctx->stream));
+  CUDA_TRY(cudaStreamWaitEvent(ctx->stream2, fork.e, 0));
   cudaStream_t main_stream = ctx->stream;
   ctx->stream = ctx->stream2;
   int rc = [&]() -> int {
@@ -542,9 +548,16 @@ int gsi::g2_walk_ahead(gs_ctx* ctx, Scratch& sc, const g2_aff* Y, size_t nprob, 
     return GS_OK;
   }();
   ctx->stream = main_stream;
-  cudaEventDestroy(fork);
+  // whatever happened to the launch, the main stream must not free `lines` / `dwalk` before stream2 is past this point
+  wa->ctx = ctx;
+  if (cudaEventCreateWithFlags(&wa->done, cudaEventDisableTiming) != cudaSuccess || cudaEventRecord(wa->done, ctx->stream2) != cudaSuccess) {
+    cudaStreamSynchronize(ctx->stream2);
+    if (wa->done) cudaEventDestroy(wa->done);
+    wa->done = nullptr;
+    if (rc) return rc;
+    FAIL(GS_ECUDA, "walk-ahead: event creation failed");
+  }
   if (rc) return rc;
-  CUDA_TRY(cudaEventRecord(wa->done, ctx->stream2));
   wa->lines = lines;
   wa->nwalk = nwalk;
   return GS_OK;

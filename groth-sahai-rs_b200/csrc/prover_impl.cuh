@@ -364,8 +364,9 @@ int batch_commit_impl(gs_ctx* ctx, size_t n, int base0, int base1, const gs_fr* 
   CUDA_TRY(cudaSetDevice(ctx->device));
   // big batches amortise bigger windows: 16 windows of 16 bits instead of 32 of 8
   gs_fixed_table<F>& T = table_of<F>(ctx);
+  // (never downgraded: once the c = 16 tables exist, small batches use them too instead of rebuilding c = 8)
   int want_c = n >= 8192 ? 16 : 8;
-  if (T.c != want_c) {
+  if (!T.t || (want_c == 16 && T.c != 16)) {
     int rc = fixed_table_rebuild<F>(ctx, want_c);
     if (rc) return rc;
   }
@@ -461,8 +462,11 @@ int proof_element(gs_ctx* ctx, Scratch& sc, size_t count, int rows, bool group_t
                   size_t nconst, const void* dvars, size_t nvars, bool vars_shared, int ncoef, const fr* coef, size_t coef_rs,
                   const fr* e, Aff<F>* dout) {
   size_t nt = nconst + nvars;
-  const gs_fixed_table<F>& T = table_of<F>(ctx);  // built at CRS load (c = 8) or by a big commit batch (c = 16)
-  if (!T.t) FAIL(GS_EARG, "prove: fixed-base tables missing (no CRS loaded)");
+  const gs_fixed_table<F>& T = table_of<F>(ctx);  // built by the first commit / prove under this key (c = 8) or by a big
+  if (!T.t) {                                     // commit batch (c = 16)
+    int rct = fixed_table_rebuild<F>(ctx, 8);
+    if (rct) return rct;
+  }
   if (coef_rs != (size_t)ncoef) FAIL(GS_EARG, "prove: coefficient matrix must be dense");
   if (group_typed) {
     // few terms (a lone statement): split every scalar multiplication over PARTS threads to shorten the serial chain;

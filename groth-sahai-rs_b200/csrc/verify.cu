@@ -476,6 +476,10 @@ static int verify_impl(gs_ctx* ctx, int type, size_t count, size_t m, size_t n, 
   verify_shape s = make_verify_shape(type, (int)m, (int)n);
   s.rank = rank;
   s.world = world;
+  {  // the stored Miller lines of v1, v2, W2 (once per key, on the first verification)
+    int rcl = gsi::crs_lines_build(ctx);
+    if (rcl) return rcl;
+  }
   const int Ko = world > 1 ? (s.K - rank + world - 1) / world : s.K;  // slots this rank owns
   for (size_t off = 0; off < count; off += ctx->verify_batch_max) {
     size_t nprob = count - off < ctx->verify_batch_max ? count - off : ctx->verify_batch_max;
@@ -531,7 +535,7 @@ static int verify_impl(gs_ctx* ctx, int type, size_t count, size_t m, size_t n, 
       LAUNCH(k_gather_owned_slots, nprob * (size_t)Ko * 2, X, Y, Xo, Yo, nprob, s.K, Ko, rank, world, 0, 1);
       Yp = Yo;
     }
-    gsi::walk_ahead wa;
+    gsi::walk_ahead wa;  // declared after `sc`: destroyed first, which waits for the walk on every exit path
     if (Ko > 0) {
       int rcw = gsi::g2_walk_ahead(ctx, sc, Yp, nprob, Ko, kind.data(), &wa);
       if (rcw) return rcw;
@@ -575,18 +579,10 @@ static int verify_impl(gs_ctx* ctx, int type, size_t count, size_t m, size_t n, 
     int rc;
     if (out_partial_dev) {
       rc = gsi::run_pairing_product(ctx, sc, Xp, Yp, nprob, Ko, nullptr, nullptr, nullptr, out_partial_dev + off * 4, kind.data(), &wa);
-      if (wa.done) {  // the scratch the walk writes to is freed on the main stream: order it after the walk in any case
-        cudaStreamWaitEvent(ctx->stream, wa.done, 0);
-        cudaEventDestroy(wa.done);
-      }
-      if (rc) return rc;
+      if (rc) return rc;  // (~walk_ahead orders the main stream after the walk before `sc` frees its buffers)
     } else {
       rc = gsi::run_pairing_product(ctx, sc, Xp, Yp, nprob, Ko, nullptr, ok4, type == GS_PPE ? (const fp12*)v.target : nullptr,
                                     nullptr, kind.data(), &wa);
-      if (wa.done) {  // the scratch the walk writes to is freed on the main stream: order it after the walk in any case
-        cudaStreamWaitEvent(ctx->stream, wa.done, 0);
-        cudaEventDestroy(wa.done);
-      }
       if (rc) return rc;
       LAUNCH(k_and4, nprob, ok4, out_ok_dev + off, nprob);
     }

@@ -243,13 +243,21 @@ class Engine:
                                           ctypes.cast(pi, ctypes.c_void_p), ctypes.cast(th, ctypes.c_void_p)))
         return pi.raw[: count * cx * COM2], th.raw[: count * cy * COM1]
 
-    def verify_batch(self, ty, count, m, n, a_consts, b_consts, gamma, target, xcoms, ycoms, pi, theta) -> bytes:
+    @staticmethod
+    def _check_verify_sizes(ty, count, m, n, a_consts, b_consts, gamma, target, xcoms, ycoms, pi, theta):
+        """The C side reads count * (shape) bytes from every buffer: a short one would be read past its end."""
         cx, cy = _cx(ty), _cy(ty)
+        want = [count * n * _a_size(ty), count * m * _b_size(ty), count * m * n * FR, count * _t_size(ty),
+                count * m * COM1, count * n * COM2, count * cx * COM2, count * cy * COM1]
+        names = ["a_consts", "b_consts", "gamma", "target", "xcoms", "ycoms", "pi", "theta"]
+        for nm, buf, w in zip(names, (a_consts, b_consts, gamma, target, xcoms, ycoms, pi, theta), want):
+            have = buf.nbytes if hasattr(buf, "nbytes") else len(buf)
+            if have != w:
+                raise GsError(1, f"verify: {nm} is {have} bytes, expected {w} for type {ty}, count {count}, m {m}, n {n}")
+
+    def verify_batch(self, ty, count, m, n, a_consts, b_consts, gamma, target, xcoms, ycoms, pi, theta) -> bytes:
         if count and m and n:
-            assert len(a_consts) == count * n * _a_size(ty) and len(b_consts) == count * m * _b_size(ty)
-            assert len(gamma) == count * m * n * FR and len(target) == count * _t_size(ty)
-            assert len(xcoms) == count * m * COM1 and len(ycoms) == count * n * COM2
-            assert len(pi) == count * cx * COM2 and len(theta) == count * cy * COM1
+            self._check_verify_sizes(ty, count, m, n, a_consts, b_consts, gamma, target, xcoms, ycoms, pi, theta)
         ok = ctypes.create_string_buffer(max(1, count))
         ks = [_buf(x) for x in (a_consts, b_consts, gamma, target, xcoms, ycoms, pi, theta)]
         self._chk(self.lib.gs_verify_batch(self.h, ty, count, m, n, *[k[1] for k in ks], ctypes.cast(ok, ctypes.c_void_p)))
@@ -266,6 +274,8 @@ class Engine:
     # ---- one statement sharded by slot over several GPUs (gs_verify_partial / gs_verify_finish)
     def verify_partial(self, ty, count, m, n, a_consts, b_consts, gamma, target, xcoms, ycoms, pi, theta, rank, world) -> bytes:
         """This rank's un-exponentiated Miller products: count x 4 GT values (2304 B per statement)."""
+        if count and m and n:
+            self._check_verify_sizes(ty, count, m, n, a_consts, b_consts, gamma, target, xcoms, ycoms, pi, theta)
         out = ctypes.create_string_buffer(max(1, count * COMT))
         ks = [_buf(x) for x in (a_consts, b_consts, gamma, target, xcoms, ycoms, pi, theta)]
         self._chk(self.lib.gs_verify_partial(self.h, ty, count, m, n, *[k[1] for k in ks], int(rank), int(world),

@@ -5,7 +5,7 @@
 #include <vector>
 #include <cfenv>
 #include "../../groth-sahai-rs_b200/csrc/pairing.cuh"
-#include "../../groth-sahai-rs_b200/csrc/fpd.cuh"
+#include "../../tools/experimental/fpd.cuh"
 #include "../../groth-sahai-rs_b200/csrc/endo.cuh"
 #include "../../groth-sahai-rs_b200/csrc/wire.cuh"
 using namespace gs;
@@ -81,7 +81,7 @@ void hs_final_exp(void* r, const void* a) { LD(fp12, x, a); fp12 o; final_expone
 }
 
 // ---- v2 Miller accumulator (w-basis, strided): same inputs/outputs as hs_miller
-#include "../../groth-sahai-rs_b200/csrc/miller_v2.cuh"
+#include "../../tools/experimental/miller_v2.cuh"
 extern "C" void hs_miller_v2(void* r, int n, const void* g1s, const void* g2s, int stride) {
   const g1_aff* P = (const g1_aff*)g1s; const g2_aff* Q = (const g2_aff*)g2s;
   std::vector<std::vector<line_coeffs>> lines; std::vector<g1_aff> ps;

@@ -77,3 +77,24 @@ def test_vector_matrix_helpers_are_pure_host_reshapes():
             api.Com1.from_matrix(bad)
     with pytest.raises(AssertionError):
         api.ComT.from_matrix([[g[0]], [g[1]]])
+
+
+def test_rust_shim_binds_the_header():
+    """rust/src/ffi.rs (the host shim a maintainer builds; this image has no rustc) declares every symbol of
+    include/gs_b200.h that the reference's API needs -- everything except the measurement hooks and the `_dev` variants --
+    and nothing the header does not have."""
+    src = open(os.path.join(ROOT, "rust", "src", "ffi.rs")).read()
+    rust = set(re.findall(r"pub fn (gs_[a-z0-9_]+)\s*\(", src))
+    hdr = set(header_symbols())
+    assert rust <= hdr, sorted(rust - hdr)
+    skipped = {s for s in hdr if s.endswith("_dev")} | {"gs_stream", "gs_profile_enable", "gs_profile_read", "gs_diag_fpmul_rate"}
+    assert hdr - rust <= skipped, sorted(hdr - rust - skipped)
+    # one shim body per public function of the reference's API (SURVEY.md §8b)
+    tree = "".join(open(os.path.join(ROOT, "rust", "src", f)).read() for f in
+                   ("generator.rs", "verifier.rs", "data_structures.rs", "statement.rs", "prover/commit.rs", "prover/prove.rs"))
+    for name in ("generate_crs", "batch_commit_G1", "batch_commit_G2", "batch_commit_scalar_to_B1", "batch_commit_scalar_to_B2",
+                 "commit_G1", "commit_G2", "commit_scalar_to_B1", "commit_scalar_to_B2", "commit_and_prove", "fn prove<",
+                 "fn verify(", "fn pairing(", "fn pairing_sum(", "linear_map_PPE", "linear_map_MSMEG1", "linear_map_MSMEG2",
+                 "linear_map_quad", "scalar_linear_map", "batch_scalar_linear_map", "fn scalar_mul(", "fn left_mul(", "fn right_mul(",
+                 "col_vec_to_vec", "vec_to_col_vec", "fn append("):
+        assert name in tree, name

@@ -13,7 +13,7 @@ SO = os.path.join(HERE, "hostsim", "libhostsim.so")
 @pytest.fixture(scope="module")
 def L():
     src = os.path.join(HERE, "hostsim", "hostsim.cpp")
-    subprocess.check_call(["g++", "-O2", "-std=c++17", "-frounding-math", "-shared", "-fPIC", "-o", SO, src])
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-frounding-math", "-shared", "-fPIC", "-I", os.path.join(HERE, "..", "groth-sahai-rs_b200", "csrc"), "-o", SO, src])
     return ctypes.CDLL(SO)
 
 

@@ -7,7 +7,7 @@
 #include "../groth-sahai-rs_b200/csrc/fp.cuh"
 #include "../groth-sahai-rs_b200/csrc/tower.cuh"
 #include "../groth-sahai-rs_b200/csrc/modinv.cuh"
-#include "../groth-sahai-rs_b200/csrc/fpd.cuh"
+#include "experimental/fpd.cuh"
 using namespace gs;
 
 __global__ void k_imad_wide(unsigned long long* out, unsigned a, unsigned b, int iters) {
