@@ -382,7 +382,17 @@ def bench_c3_sharded(R_, eng, size, steps):
     bad = list(arrs)
     bad[2] = bytes(g)
 
-    def sharded_verify(a):
+    import groth_sahai_rs_b200 as gsb
+    sh = gsb.shard
+
+    # every rank HOLDS the rows of Gamma it owns (rows i = rank mod N: 1 / N of the statement) -- sliced outside the timed region
+    rows_of = {id(arrs): sh.gamma_rows_of(arrs[2], 1, m, n, R_.rank, R_.world), id(bad): sh.gamma_rows_of(bad[2], 1, m, n, R_.rank, R_.world)}
+    ag = sh.make_allgather(R_.dev)
+
+    def sharded_verify(a):          # MSM split by base, Miller pairs by slot, two all-gathers over NCCL (gs_verify_sharded)
+        return eng.verify_sharded(0, 1, m, n, a[0], a[1], rows_of[id(a)], a[3], a[4], a[5], a[6], a[7], R_.rank, R_.world, ag)
+
+    def slot_verify(a):             # the round-1 path: everything split by slot, every rank uploads the whole statement
         mine = eng.verify_partial(0, 1, m, n, *a, R_.rank, R_.world)
         if R_.world == 1:
             return eng.verify_finish(0, 1, mine, a[3])
@@ -393,20 +403,24 @@ def bench_c3_sharded(R_, eng, size, steps):
 
     assert sharded_verify(arrs) == b"\x01", "honest statement rejected"
     assert sharded_verify(bad) == b"\x00", "tampered Gamma accepted"
+    assert slot_verify(arrs) == b"\x01" and slot_verify(bad) == b"\x00"
     ms = R_.wall_ms(lambda: sharded_verify(arrs), steps)
+    ms_slot = R_.wall_ms(lambda: slot_verify(arrs), steps)
     prof = profiled(eng, lambda: sharded_verify(arrs))
-    ms_prove = R_.wall_ms(lambda: eng.prove(0, m, n, A, B, G, X, Y, xr, yr, Tr), steps) if R_.rank == 0 or True else None
+    ms_prove = R_.wall_ms(lambda: eng.prove(0, m, n, A, B, G, X, Y, xr, yr, Tr), steps)
     prof_p = profiled(eng, lambda: eng.prove(0, m, n, A, B, G, X, Y, xr, yr, Tr))
     pairs = 4 * n + 2 * m + 16
-    h2d = sum(len(a) for a in arrs)
-    return {"workload": f"C3: one PPE, m=n={m}, dense Gamma (BASELINE.json configs[2]); verify split by slot x{R_.world}: "
-                        "gs_verify_partial per rank, ONE all_gather of 2,304 B, gs_verify_finish",
+    h2d = sum(len(a) for a in arrs) - len(G) + len(G) // R_.world
+    return {"workload": f"C3: one PPE, m=n={m}, dense Gamma (BASELINE.json configs[2]); gs_verify_sharded x{R_.world}: statement MSM "
+                        "split by base (every rank uploads its rows of Gamma only), all_gather of the partial sums "
+                        f"({2 * n * 96} B per rank), Miller pairs split by slot, all_gather of 2,304 B, final exponentiation on every rank",
             "scaling": "strong", "n_gpus": R_.world, "verify_ms": round(ms, 3), "verifies_per_sec": round(1e3 / ms, 2),
+            "verify_ms_split_by_slot_only": round(ms_slot, 3),
             "miller_pairs_per_verify": pairs, "pairings_per_sec": round(pairs / (ms * 1e-3), 1),
             "prove_ms_one_gpu": round(ms_prove, 3), "h2d_bytes_per_rank": h2d, "instance_build_s": round(build_s, 1),
             "rank0_verify_kernels": prof, "rank0_prove_kernels": prof_p,
-            "limiter": f"per-rank latency floors, not NCCL (2,304 B): {top_kernels(prof)}; every rank uploads the statement "
-                       f"({h2d >> 20} MiB)",
+            "limiter": f"per-rank latency floors (one dependent chain each), not NCCL: {top_kernels(prof, 4)}; "
+                       f"H2D per rank {h2d >> 20} MiB",
             "parity": "honest -> 1, one flipped Gamma bit -> 0 (sharded path); proof bytes == reference-order CPU proof at "
                       "this size in tests/test_gpu_bigparity.py::test_1024x1024_ppe"}
 
@@ -459,14 +473,19 @@ def bench_c4_by_equation(R_, eng, E, steps):
                 [Aall, Ball, Gall, tg, pi, th], [n * xs, m * ys, m * n * 32, ts, cx * 384, cy * 192], E, rank, world,
                 device=dev)
 
+        def verify_by_base(tg=Tall):   # ONE call for the type's E equations: shared-base tables split by base over the ranks
+            return sh.verify_statement_base_sharded(eng, ty, E, m, n, [Aall, Ball, Gall, tg, xc * E, yc * E, pi, th], rank, world, dev)
+
         ok = bytes(verify().cpu().tolist())
         assert ok == b"\x01" * E, f"C4 type {ty}: {ok.count(1)} of {E} verified"
+        assert verify_by_base() == b"\x01" * E, f"C4 type {ty}: base-sharded verification disagrees"
         tb = bytearray(Tall)
         tb[3 * ts:4 * ts], tb[(E - 1) * ts:E * ts] = tb[(E - 1) * ts:E * ts], tb[3 * ts:4 * ts]   # swap two targets
         okb = bytes(verify(bytes(tb)).cpu().tolist())
         exp = bytearray(b"\x01" * E)
         exp[3] = exp[E - 1] = 0
         assert okb == bytes(exp), f"C4 type {ty}: tamper mask wrong"
+        assert verify_by_base(bytes(tb)) == bytes(exp), f"C4 type {ty}: base-sharded tamper mask wrong"
         parity = None
         if rank == 0:      # two equations' proofs against the reference-order CPU prover (outside the timed region)
             from oracle import cbaseline as cb
@@ -477,10 +496,15 @@ def bench_c4_by_equation(R_, eng, E, steps):
             parity = "equations 0 and E-1: proof bytes == oracle/gs_oracle.c gsref_prove"
         t_c = R_.wall_ms(commit, steps)
         t_p = R_.wall_ms(prove, steps)
-        t_v = R_.wall_ms(verify, steps)
+        t_v_eq = R_.wall_ms(verify, steps)
+        t_v_base = R_.wall_ms(verify_by_base, steps)
+        by_base = t_v_base < t_v_eq
+        t_v = min(t_v_eq, t_v_base)
         prof_p = profiled(eng, prove)
-        prof_v = profiled(eng, verify)
+        prof_v = profiled(eng, verify_by_base if by_base else verify)
         per_type[names[ty]] = {"commit_ms": round(t_c, 3), "prove_ms": round(t_p, 3), "verify_ms": round(t_v, 3),
+                               "verify_split": "MSM by base + pairs by slot (gs_verify_sharded)" if by_base else "by equation (gs_verify_batch per rank)",
+                               "verify_ms_by_equation": round(t_v_eq, 3), "verify_ms_by_base": round(t_v_base, 3),
                                "proved_per_sec": round(E / (t_p * 1e-3), 1), "verified_per_sec": round(E / (t_v * 1e-3), 1),
                                "rank0_prove_kernels": prof_p, "rank0_verify_kernels": prof_v, "parity": parity,
                                "limiter": f"prove: {top_kernels(prof_p, 2)}; verify: {top_kernels(prof_v, 2)}"}

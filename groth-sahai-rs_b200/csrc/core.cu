@@ -2,6 +2,8 @@
 // No CPU fallback anywhere: every entry point launches CUDA kernels or fails with GS_ECUDA.
 #include "ctx.h"
 
+#include <cstdlib>
+
 using namespace gs;
 
 static_assert(sizeof(gs_fr) == sizeof(fr), "fr layout");
@@ -38,6 +40,8 @@ int gs_ctx_create(int device, gs_ctx** out) {
     uint64_t thr = ~0ull;
     cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
   }
+  if (const char* e = getenv("GS_PIP_MIN")) ctx->pip_min = (size_t)strtoull(e, nullptr, 10);
+  if (const char* e = getenv("GS_PIP_C")) ctx->pip_c = atoi(e);
   // deep call chains (Fp12 -> Fp6 -> Fp2) with big local frames
   cudaDeviceSetLimit(cudaLimitStackSize, 32 * 1024);
   if (gsi::pairing_init(ctx) != GS_OK || gsi::final_exp_init(ctx) != GS_OK) {

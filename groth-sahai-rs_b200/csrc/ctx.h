@@ -45,6 +45,8 @@ struct gs_ctx {
   std::vector<prof_rec> prof;
   size_t verify_batch_max = 23680;  // problems per verify pass (10 waves of k_miller4)
   size_t tile_budget = (size_t)16 << 30;  // bytes of HBM for the evaluated-line tiles of one pairing pass
+  size_t pip_min = 3072;  // proof MSMs of one statement with at least this many terms use the bucket method (pippenger.cuh);
+  int pip_c = 0;          // measured crossover, DESIGN.md §4.  Overrides for experiments: GS_PIP_MIN, GS_PIP_C (window bits)
   std::string err;
 };
 

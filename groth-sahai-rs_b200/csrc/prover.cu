@@ -79,11 +79,27 @@ __global__ void k_crs_derive(crs_dev* c) {
 }
 
 // ------------------------------------------------------------------ Fr matrix algebra
+// The three dot-product kernels below run with `lanes` = 1 (one thread per output: small statements, big batches) or
+// `lanes` = 32 (one warp per output, strided partial sums + a shuffle tree: ONE big statement, where an output is a
+// dot product over 1,024 .. 65,536 terms and there are only a handful of outputs).
+__device__ GS_INL void fr_warp_sum(fr& acc) {
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    fr o;
+#pragma unroll
+    for (int i = 0; i < 8; i++) o.l[i] = __shfl_down_sync(0xffffffffu, acc.l[i], off);
+    fr::add(acc, acc, o);
+  }
+}
+static inline int fr_lanes(size_t k, size_t outputs) { return (k >= 128 && outputs * 32 <= ((size_t)1 << 24)) ? 32 : 1; }
+
 // out (r x c) = A (r x k) * B (k x c), row-major; optional transposes via strides.
 // Every prover kernel is batched over blockIdx.y = proof instance; `*_bs` = elements between instances (0: shared).
 __global__ void k_fr_matmul(fr* __restrict__ out, const fr* __restrict__ A, size_t a_rs, size_t a_cs, const fr* __restrict__ B,
-                            size_t b_rs, size_t b_cs, size_t r, size_t k, size_t c, size_t a_bs, size_t b_bs) {
-  size_t id = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+                            size_t b_rs, size_t b_cs, size_t r, size_t k, size_t c, size_t a_bs, size_t b_bs, int lanes) {
+  size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t id = gid / lanes;
+  const int lane = (int)(gid % lanes);
   if (id >= r * c) return;
   out += (size_t)blockIdx.y * r * c;
   A += (size_t)blockIdx.y * a_bs;
@@ -91,18 +107,21 @@ __global__ void k_fr_matmul(fr* __restrict__ out, const fr* __restrict__ A, size
   size_t i = id / c, j = id % c;
   fr acc;
   acc.set_zero();
-  for (size_t t = 0; t < k; t++) {
+  for (size_t t = lane; t < k; t += lanes) {
     fr p;
     fr::mul(p, A[i * a_rs + t * a_cs], B[t * b_rs + j * b_cs]);
     fr::add(acc, acc, p);
   }
-  out[id] = acc;
+  if (lanes == 32) fr_warp_sum(acc);
+  if (lane == 0) out[id] = acc;
 }
 
 // coef_pi[i][l] = (RG * S)[i][l] - T[l][i]            (prove.rs:139-142)   cx x cy
 __global__ void k_coef_pi(fr* __restrict__ out, const fr* __restrict__ RG, const fr* __restrict__ S, const fr* __restrict__ T, int cx,
-                          int cy, size_t n, size_t s_bs) {
-  int id = blockIdx.x * blockDim.x + threadIdx.x;
+                          int cy, size_t n, size_t s_bs, int lanes) {
+  int gid = blockIdx.x * blockDim.x + threadIdx.x;
+  int id = gid / lanes;
+  const int lane = gid % lanes;
   if (id >= cx * cy) return;
   out += (size_t)blockIdx.y * cx * cy;
   RG += (size_t)blockIdx.y * cx * n;
@@ -111,11 +130,13 @@ __global__ void k_coef_pi(fr* __restrict__ out, const fr* __restrict__ RG, const
   int i = id / cy, l = id % cy;
   fr acc;
   acc.set_zero();
-  for (size_t j = 0; j < n; j++) {
+  for (size_t j = lane; j < n; j += lanes) {
     fr p;
     fr::mul(p, RG[i * n + j], S[j * cy + l]);
     fr::add(acc, acc, p);
   }
+  if (lanes == 32) fr_warp_sum(acc);
+  if (lane != 0) return;
   fr::sub(acc, acc, T[l * cx + i]);
   out[id] = acc;
 }
@@ -135,8 +156,10 @@ __global__ void k_concat_scalars(fr* __restrict__ sv, const fr* __restrict__ R, 
 
 // dot[i] = sum_t sv[i][t] * w[t]    (scalar-typed constants/variables: everything collapses onto W)
 __global__ void k_fr_dot(fr* __restrict__ out, const fr* __restrict__ sv, const fr* __restrict__ w0, size_t m, const fr* __restrict__ w1,
-                         size_t n, int rows, size_t w1_bs) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
+                         size_t n, int rows, size_t w1_bs, int lanes) {
+  int gid = blockIdx.x * blockDim.x + threadIdx.x;
+  int i = gid / lanes;
+  const int lane = gid % lanes;
   if (i >= rows) return;
   out += (size_t)blockIdx.y * rows;
   sv += (size_t)blockIdx.y * rows * (m + n);
@@ -144,12 +167,13 @@ __global__ void k_fr_dot(fr* __restrict__ out, const fr* __restrict__ sv, const 
   w1 += (size_t)blockIdx.y * w1_bs;
   fr acc;
   acc.set_zero();
-  for (size_t t = 0; t < m + n; t++) {
+  for (size_t t = lane; t < m + n; t += lanes) {
     fr p;
     fr::mul(p, sv[(size_t)i * (m + n) + t], t < m ? w0[t] : w1[t - m]);
     fr::add(acc, acc, p);
   }
-  out[i] = acc;
+  if (lanes == 32) fr_warp_sum(acc);
+  if (lane == 0) out[i] = acc;
 }
 
 }  // namespace gs
@@ -272,10 +296,11 @@ static int prove_impl(gs_ctx* ctx, int type, size_t count, size_t m, size_t n, c
     CUDA_TRY(sc.alloc(&sv_pi, nb * cx * (m + n)));
     CUDA_TRY(sc.alloc(&sv_th, nb * cy * (m + n)));
     // RG = R^T Gamma (cx x n)  prove.rs:133 ;  SG = S^T Gamma^T (cy x m)  prove.rs:154
-    LAUNCH_B(k_fr_matmul, (size_t)cx * n, nb, RG, dR, (size_t)1, (size_t)cx, dG, n, (size_t)1, (size_t)cx, m, n, r_bs, m * n);
-    LAUNCH_B(k_fr_matmul, (size_t)cy * m, nb, SG, dS, (size_t)1, (size_t)cy, dG, (size_t)1, n, (size_t)cy, n, m, s_bs, m * n);
+    const int l_rg = fr_lanes(m, (size_t)cx * n * nb), l_sg = fr_lanes(n, (size_t)cy * m * nb), l_cp = fr_lanes(n, (size_t)cx * cy * nb);
+    LAUNCH_B(k_fr_matmul, (size_t)cx * n * l_rg, nb, RG, dR, (size_t)1, (size_t)cx, dG, n, (size_t)1, (size_t)cx, m, n, r_bs, m * n, l_rg);
+    LAUNCH_B(k_fr_matmul, (size_t)cy * m * l_sg, nb, SG, dS, (size_t)1, (size_t)cy, dG, (size_t)1, n, (size_t)cy, n, m, s_bs, m * n, l_sg);
     // (R^T Gamma S - T^T)  prove.rs:139-142
-    LAUNCH_B(k_coef_pi, (size_t)cx * cy, nb, coef_pi, RG, dS, dT, cx, cy, n, s_bs);
+    LAUNCH_B(k_coef_pi, (size_t)cx * cy * l_cp, nb, coef_pi, RG, dS, dT, cx, cy, n, s_bs, l_cp);
     LAUNCH_B(k_concat_scalars, (size_t)cx * (m + n), nb, sv_pi, dR, RG, cx, m, n, r_bs);
     LAUNCH_B(k_concat_scalars, (size_t)cy * (m + n), nb, sv_th, dS, SG, cy, n, m, s_bs);
     g2_aff* dpi;
@@ -286,11 +311,13 @@ static int prove_impl(gs_ctx* ctx, int type, size_t count, size_t m, size_t n, c
     fr *e_pi = nullptr, *e_th = nullptr;
     if (!s.groupB) {  // scalar-typed y side: every term collapses onto W2
       CUDA_TRY(sc.alloc(&e_pi, nb * cx));
-      LAUNCH_B(k_fr_dot, (size_t)cx, nb, e_pi, sv_pi, (const fr*)dB, m, (const fr*)dY, n, cx, shared_vars ? (size_t)0 : n);
+      const int l_d = fr_lanes(m + n, (size_t)cx * nb);
+      LAUNCH_B(k_fr_dot, (size_t)cx * l_d, nb, e_pi, sv_pi, (const fr*)dB, m, (const fr*)dY, n, cx, shared_vars ? (size_t)0 : n, l_d);
     }
     if (!s.groupA) {
       CUDA_TRY(sc.alloc(&e_th, nb * cy));
-      LAUNCH_B(k_fr_dot, (size_t)cy, nb, e_th, sv_th, (const fr*)dA, n, (const fr*)dX, m, cy, shared_vars ? (size_t)0 : m);
+      const int l_d = fr_lanes(m + n, (size_t)cy * nb);
+      LAUNCH_B(k_fr_dot, (size_t)cy * l_d, nb, e_th, sv_th, (const fr*)dA, n, (const fr*)dX, m, cy, shared_vars ? (size_t)0 : m, l_d);
     }
     int rc = proof_element<Fp2Ops>(ctx, sc, nb, cx, s.groupB, sv_pi, dB, m, dY, n, shared_vars, cy, coef_pi, (size_t)cy, e_pi, dpi);
     if (rc) return rc;
@@ -332,7 +359,8 @@ int gs_fr_matmul(gs_ctx* ctx, size_t r, size_t k, size_t c, const gs_fr* a, cons
   CUDA_TRY(upload(ctx, sc, &da, a, r * k));
   CUDA_TRY(upload(ctx, sc, &db, b, k * c));
   CUDA_TRY(sc.alloc(&dout, r * c));
-  LAUNCH(k_fr_matmul, r * c, dout, da, k, (size_t)1, db, c, (size_t)1, r, k, c, (size_t)0, (size_t)0);
+  const int l_mm = fr_lanes(k, r * c);
+  LAUNCH(k_fr_matmul, r * c * l_mm, dout, da, k, (size_t)1, db, c, (size_t)1, r, k, c, (size_t)0, (size_t)0, l_mm);
   CUDA_TRY(cudaMemcpyAsync(out, dout, r * c * sizeof(fr), cudaMemcpyDeviceToHost, ctx->stream));
   CUDA_TRY(cudaStreamSynchronize(ctx->stream));
   return GS_OK;

@@ -456,6 +456,10 @@ int reduce_rows(gs_ctx* ctx, Jac<F>* terms, size_t stride, size_t cnt, int rows,
   return GS_OK;
 }
 
+}  // namespace gsi
+#include "pippenger.cuh"
+namespace gsi {
+
 // one proof element vector per proof (pi: F = G2, theta: F = G1), see k_proof_finish; batched over `count` proofs
 template <class F>
 int proof_element(gs_ctx* ctx, Scratch& sc, size_t count, int rows, bool group_typed, const fr* sv, const void* dconst,
@@ -474,6 +478,18 @@ int proof_element(gs_ctx* ctx, Scratch& sc, size_t count, int rows, bool group_t
     // many equations over one witness set: the variable terms come from shared-base window tables (break-even ~20 uses
     // of a base; required here: 64) and every thread takes a whole scalar
     const bool var_tables = vars_shared && nvars > 0 && count * rows >= 64;
+    // ONE big statement: bucket MSM (pippenger.cuh) from ctx->pip_min terms up -- W * N additions per row instead of a
+    // windowed scalar multiplication per term
+    if (count == 1 && !var_tables && nt >= ctx->pip_min) {
+      Jac<F>* rowsum;
+      size_t stride;
+      int rcp = pippenger_rows<F>(ctx, sc, sv, rows, (const Aff<F>*)dconst, nconst, (const Aff<F>*)dvars, nvars, &rowsum, &stride,
+                                  ctx->pip_c);
+      if (rcp) return rcp;
+      LAUNCH_B((k_proof_finish<F>), (size_t)rows * 2, count, dout, rows, ncoef, coef, coef_rs, (size_t)1, T.t, T.c, T.W, T.H, rowsum,
+               stride, (const fr*)nullptr);
+      return GS_OK;
+    }
     const int PARTS = (!var_tables && count * nt * rows < 32768) ? EndoSplit<F>::PARTS : 1;
     const size_t ntp = nt * PARTS;
     Jac<F>* terms;

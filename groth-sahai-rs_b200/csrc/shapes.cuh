@@ -24,6 +24,11 @@ struct verify_shape {  // slot bookkeeping shared by host and device
   int nbases;   // m (+1 when A is scalar: W1 is an extra base)
   int chunk, nchunk;  // MSM bases per thread (<= GS_MSM_CHUNK) and the number of such chunks
   int rank, world;  // statement sharding: slot k belongs to rank k % world; 0, 1 = everything
+  // MSM sharding by BASE (gs_verify_sharded): this rank sums, for EVERY output, only the bases i = brank (mod bworld); the
+  // partial sums are exchanged.  Gamma then holds only this rank's rows: gm = #{i < m : i = brank mod bworld} (m when 1).
+  int brank, bworld, gm;
+  GS_HD int nb_own() const { return bworld <= 1 ? nbases : (nbases > brank ? (nbases - brank + bworld - 1) / bworld : 0); }
+  GS_HD int base_at(int io) const { return bworld <= 1 ? io : brank + io * bworld; }
   GS_HD bool owns(int slot) const { return world <= 1 || slot % world == rank; }
   // slot that MSM output jj is written to: jj < n -> jj; the scalar-B sum -> sB; the Quad target -> sT
   GS_HD int out_slot(int jj) const { return jj < n ? jj : ((jj == n && !groupB) ? sB : sT); }
@@ -69,12 +74,22 @@ inline verify_shape make_verify_shape(int type, int m, int n) {
   s.nchunk = (s.nbases + GS_MSM_CHUNK - 1) / GS_MSM_CHUNK;
   s.rank = 0;
   s.world = 1;
+  s.brank = 0;
+  s.bworld = 1;
+  s.gm = m;
   return s;
+}
+
+inline void set_base_shard(verify_shape& s, int brank, int bworld) {
+  s.brank = brank;
+  s.bworld = bworld;
+  s.gm = bworld <= 1 ? s.m : (s.m > brank ? (s.m - brank + bworld - 1) / bworld : 0);
 }
 
 inline void set_msm_chunk(verify_shape& s, int chunk) {
   s.chunk = chunk < 1 ? 1 : (chunk > GS_MSM_CHUNK ? GS_MSM_CHUNK : chunk);
-  s.nchunk = (s.nbases + s.chunk - 1) / s.chunk;
+  const int nb = s.nb_own() > 0 ? s.nb_own() : 1;
+  s.nchunk = (nb + s.chunk - 1) / s.chunk;
 }
 
 struct verify_args {

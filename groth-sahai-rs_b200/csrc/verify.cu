@@ -108,13 +108,13 @@ __global__ void __launch_bounds__(128) k_vmsm_tables(verify_shape s, verify_args
                                                      g1_aff* __restrict__ tab, fp* __restrict__ tabx, size_t nprob) {
   __shared__ fp sm[2 * 128];
   size_t id = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  bool active = id < nprob * (size_t)s.nbases * 2;
+  bool active = id < nprob * (size_t)s.nb_own() * 2;
   size_t p = active ? id % nprob : 0;
   size_t r = active ? id / nprob : 0;
-  int a = (int)(r & 1), i = (int)(r >> 1);
+  int a = (int)(r & 1), i = (int)(r >> 1);  // i = index among this rank's bases (table row); base_at(i) = the base
   g1_aff B;
   B.set_inf();
-  if (active) B = vmsm_base(s, v, crs, p, i, a);
+  if (active) B = vmsm_base(s, v, crs, p, s.base_at(i), a);
   // all GS_VTAB multiples in Jacobian form, then ONE batched inversion (Montgomery's trick over the thread's
   // own Z values, block_batch_inv over the per-thread products) instead of one Fermat inversion per multiple
   g1_jac mlt[GS_VTAB];
@@ -156,7 +156,7 @@ __global__ void __launch_bounds__(128) k_vmsm_tables(verify_shape s, verify_args
 // scalar that multiplies base i in MSM output jj of problem p (false: no such term)
 __device__ GS_INL bool vmsm_scalar(fr& sv, const verify_shape& s, const verify_args& v, size_t p, int i, int jj) {
   if (jj < s.n) {  // P_j: Gamma column j, plus a_j on the extra base W1 when A is scalar
-    sv = i < s.m ? v.gamma[(p * s.m + i) * s.n + jj] : ((const fr*)v.a_consts)[p * s.n + jj];
+    sv = i < s.m ? v.gamma[(p * s.gm + (s.bworld <= 1 ? i : i / s.bworld)) * s.n + jj] : ((const fr*)v.a_consts)[p * s.n + jj];
     return true;
   }
   if (jj == s.n && !s.groupB) {  // C_B = sum_i b_i c_i
@@ -190,10 +190,10 @@ __global__ void __launch_bounds__(128, VP_BLOCKS) k_vmsm_partial(verify_shape s,
   uint32_t sc[2 * GS_MSM_CHUNK][5];
   int bidx[GS_MSM_CHUNK];
   int cnt = 0;
-  int i0 = ch * s.chunk, i1 = min(s.nbases, i0 + s.chunk);
-  for (int i = i0; i < i1; i++) {
+  int i0 = ch * s.chunk, i1 = min(s.nb_own(), i0 + s.chunk);
+  for (int i = i0; i < i1; i++) {  // i = index among this rank's bases = table row
     fr sv;
-    bool have = vmsm_scalar(sv, s, v, p, i, jj);
+    bool have = vmsm_scalar(sv, s, v, p, s.base_at(i), jj);
     if (!have || sv.is_zero()) continue;
     uint32_t k[8], k1[4], k2[4];
     fr_from_mont(k, sv);
@@ -262,15 +262,20 @@ __global__ void __launch_bounds__(128, VP_BLOCKS) k_vmsm_partial(verify_shape s,
 struct wt_geom {
   int c, W, H;
 };
+// The scalars are split along the G1 endomorphism (k = k1 + k2 x^2, k1, k2 < 2^127.4; endo.cuh), so the tables only span
+// 128 bits: HALF the windows -- half the doublings, half the table entries to build and to keep -- for the same number of
+// additions per scalar (k1's digits select from the table as it is, k2's digits go to a second accumulator that is mapped
+// through -phi once per thread at the end).  c = 8: 16 windows + one for the carry of the signed recoding out of the top
+// window (its digits are 0 / 1); c = 10: 13 windows cover 130 bits and the top digit is < 2^8, no carry.
 static inline wt_geom wt_choose(size_t outputs_per_base) {
-  return outputs_per_base >= 4096 ? wt_geom{10, 26, 512} : wt_geom{8, 32, 128};
+  return outputs_per_base >= 4096 ? wt_geom{10, 13, 512} : wt_geom{8, 17, 128};
 }
 // thread -> flat base b: J[b*W + w] = 2^(8w) * base_b   (one Jacobian doubling chain)
 __global__ void __launch_bounds__(128) k_wtab_bases(verify_shape s, verify_args v, const crs_dev* __restrict__ crs,
                                                     g1_jac* __restrict__ J, int nb, wt_geom g) {
   int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= nb) return;
-  g1_aff B = vmsm_base(s, v, crs, 0, b >> 1, b & 1);
+  g1_aff B = vmsm_base(s, v, crs, 0, s.base_at(b >> 1), b & 1);
   g1_jac j;
   j.from_affine(B);
   for (int w = 0; w < g.W; w++) {
@@ -355,15 +360,26 @@ __global__ void __launch_bounds__(128) k_vmsm_wsum(verify_shape s, verify_args v
   r >>= 1;
   int jj = s.owned_out((int)(r % n_own));
   int ch = (int)(r / n_own);
-  g1_jac acc;
+  g1_jac acc, acc2;  // acc: the k1 halves; acc2: the k2 halves, mapped through -phi at the end (phi is additive)
   acc.set_inf();
-  int i0 = ch * s.chunk, i1 = min(s.nbases, i0 + s.chunk);
-  for (int i = i0; i < i1; i++) {
+  acc2.set_inf();
+  int i0 = ch * s.chunk, i1 = min(s.nb_own(), i0 + s.chunk);
+  for (int i = i0; i < i1; i++) {  // i = index among this rank's bases = table row
     fr sv;
-    if (!vmsm_scalar(sv, s, v, p, i, jj) || sv.is_zero()) continue;
-    uint32_t k[8];
+    if (!vmsm_scalar(sv, s, v, p, s.base_at(i), jj) || sv.is_zero()) continue;
+    uint32_t k[8], k1[8], k2[8];
     fr_from_mont(k, sv);
-    fixed_base_accumulate<FpOps>(acc, tab + ((size_t)(i * 2 + a) * g.W) * g.H, k, g.c, g.W, (size_t)g.H);
+    glv_split(k1, k2, k);
+#pragma unroll
+    for (int t = 4; t < 8; t++) k1[t] = k2[t] = 0;
+    const g1_aff* T = tab + ((size_t)(i * 2 + a) * g.W) * g.H;
+    fixed_base_accumulate<FpOps>(acc, T, k1, g.c, g.W, (size_t)g.H);
+    fixed_base_accumulate<FpOps>(acc2, T, k2, g.c, g.W, (size_t)g.H);
+  }
+  if (!acc2.is_inf()) {  // -phi(X : Y : Z) = (beta X : -Y : Z)
+    endo_phi_x(acc2.X, acc2.X);
+    fp::neg(acc2.Y, acc2.Y);
+    g1_jac::add(acc, acc, acc2);
   }
   part[(((size_t)ch * s.n_out + jj) * 2 + a) * nprob + p] = acc;
 }
@@ -405,6 +421,65 @@ __global__ void __launch_bounds__(128) k_vmsm_reduce(verify_shape s, verify_args
     for (int ch = 1; ch < s.nchunk; ch++) {
       g1_jac t = part[(((size_t)ch * s.n_out + jj) * 2 + a) * nprob + p];
       g1_jac::add(acc, acc, t);
+    }
+    if (jj < s.n) {
+      slot = jj;
+      if (s.groupA && a == 1) {
+        g1_aff A = ((const g1_aff*)v.a_consts)[p * s.n + jj];
+        g1_jac::add_mixed(acc, acc, A);
+      }
+    } else if (jj == s.n && !s.groupB) {
+      slot = s.sB;
+    } else {
+      slot = s.sT;
+      g1_jac::neg(acc, acc);
+    }
+  }
+  g1_aff out;
+  block_to_affine<128>(out, acc, sm);
+  if (active) X[((size_t)a * s.K + slot) * nprob + p] = out;
+}
+
+// ---- MSM sharded by base (gs_verify_sharded): the partial sums travel between the ranks as affine points
+// thread -> (p, jj, a): parts[(p*n_out + jj)*2 + a] = affine( sum over this rank's chunks )
+__global__ void __launch_bounds__(128) k_vmsm_parts_out(verify_shape s, const g1_jac* __restrict__ part, g1_aff* __restrict__ parts,
+                                                        size_t nprob) {
+  __shared__ fp sm[2 * 128];
+  size_t id = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  bool active = id < nprob * (size_t)s.n_out * 2;
+  size_t p = active ? id % nprob : 0;
+  size_t r = active ? id / nprob : 0;
+  int a = (int)(r & 1), jj = (int)(r >> 1);
+  g1_jac acc;
+  acc.set_inf();
+  if (active) {
+    acc = part[((size_t)jj * 2 + a) * nprob + p];
+    for (int ch = 1; ch < s.nchunk; ch++) {
+      g1_jac t = part[(((size_t)ch * s.n_out + jj) * 2 + a) * nprob + p];
+      g1_jac::add(acc, acc, t);
+    }
+  }
+  g1_aff out;
+  block_to_affine<128>(out, acc, sm);
+  if (active) parts[(p * s.n_out + jj) * 2 + a] = out;
+}
+// thread -> (p, owned output, a): sum of the `nparts` ranks' partial sums, then the tail of k_vmsm_reduce
+__global__ void __launch_bounds__(128) k_vmsm_reduce_parts(verify_shape s, verify_args v, const g1_aff* __restrict__ parts, int nparts,
+                                                           g1_aff* __restrict__ X, size_t nprob) {
+  __shared__ fp sm[2 * 128];
+  size_t id = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  bool active = id < nprob * (size_t)s.n_out_owned() * 2;
+  size_t p = active ? id % nprob : 0;
+  size_t r = active ? id / nprob : 0;
+  int a = (int)(r & 1);
+  int jj = active ? s.owned_out((int)(r >> 1)) : 0;
+  g1_jac acc;
+  acc.set_inf();
+  int slot = 0;
+  if (active) {
+    for (int q = 0; q < nparts; q++) {
+      g1_aff t = parts[(((size_t)q * nprob + p) * s.n_out + jj) * 2 + a];
+      g1_jac::add_mixed(acc, acc, t);
     }
     if (jj < s.n) {
       slot = jj;
@@ -541,7 +616,7 @@ static int verify_impl(gs_ctx* ctx, int type, size_t count, size_t m, size_t n, 
       if (rcw) return rcw;
     }
     if (use_wtab) {
-      const int nb = s.nbases * 2;
+      const int nb = s.nb_own() * 2;
       const wt_geom g = wt_choose(owned_out * nprob);
       const size_t nrows = (size_t)nb * g.W;
       g1_aff* wtab;
@@ -556,9 +631,9 @@ static int verify_impl(gs_ctx* ctx, int type, size_t count, size_t m, size_t n, 
     } else {
       g1_aff* vtab;
       fp* vtabx;
-      CUDA_TRY(sc.alloc(&vtab, (size_t)s.nbases * 2 * GS_VTAB * nprob));
-      CUDA_TRY(sc.alloc(&vtabx, (size_t)s.nbases * 2 * GS_VTAB * nprob));
-      LAUNCH(k_vmsm_tables, nprob * (size_t)s.nbases * 2, s, v, ctx->crs, vtab, vtabx, nprob);
+      CUDA_TRY(sc.alloc(&vtab, (size_t)s.nb_own() * 2 * GS_VTAB * nprob));
+      CUDA_TRY(sc.alloc(&vtabx, (size_t)s.nb_own() * 2 * GS_VTAB * nprob));
+      LAUNCH(k_vmsm_tables, nprob * (size_t)s.nb_own() * 2, s, v, ctx->crs, vtab, vtabx, nprob);
       LAUNCH(k_vmsm_partial, nprob * owned_out * 2 * s.nchunk, s, v, vtab, vtabx, part, nprob);
     }
     const g1_jac* partr = part;
@@ -666,6 +741,169 @@ static int verify_host(gs_ctx* ctx, int type, size_t count, size_t m, size_t n, 
     CUDA_TRY(cudaMemcpyAsync(out_ok, dok, count, cudaMemcpyDeviceToHost, ctx->stream));
   else
     CUDA_TRY(cudaMemcpyAsync(out_partial, dpart, count * 4 * sizeof(fp12), cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  return GS_OK;
+}
+
+// ------------------------------------------------------------------ one statement over several GPUs, MSM split by BASE
+// gs_verify_partial splits a statement by slot: every rank still needs all m bases for its outputs, so the statement MSM
+// (the dominant cost of a big statement, 2 m n scalar products) only shrinks with the number of outputs per rank while
+// the shared-base tables do not shrink at all.  Here the MSM is split by BASE instead: rank r builds the tables of the
+// bases i = r (mod world) only, sums them into EVERY output, and the partial sums -- n_out x 2 affine G1 points per
+// statement -- are exchanged (first all-gather, a real exchange step: every rank needs every other rank's share).  From
+// there on the split is by slot as before: rank r adds the partial sums of the outputs it owns, runs its Miller pairs and
+// the 4 x 576 B partial products are exchanged (second all-gather); every rank finishes.
+// The transport is the caller's (NCCL through torch.distributed, raw NCCL, MPI ...): `allgather(user, send_dev, recv_dev,
+// bytes)` must gather `bytes` from every rank into recv_dev (rank-major) and return 0 when recv_dev is complete; both are
+// DEVICE pointers and the context's stream is idle while it runs.
+static int verify_sharded_impl(gs_ctx* ctx, int type, size_t count, size_t m, size_t n, const void* dA, const void* dB, const fr* dGrows,
+                               const void* dT, const g1_aff* dc, const g2_aff* dd, const g2_aff* dpi, const g1_aff* dth, int rank,
+                               int world, bool shared_x, gs_allgather_fn allgather, void* user, uint8_t* dok) {
+  verify_shape s = make_verify_shape(type, (int)m, (int)n);
+  s.rank = rank;
+  s.world = world;
+  set_base_shard(s, rank, world);
+  {
+    int rcl = gsi::crs_lines_build(ctx);
+    if (rcl) return rcl;
+  }
+  const size_t nprob = count;
+  if (nprob > ctx->verify_batch_max) FAIL(GS_EDIM, "verify_sharded: too many statements for one pass");
+  const int Ko = (s.K - rank + world - 1) / world;  // slots this rank owns
+  Scratch sc(ctx);
+  verify_args v;
+  v.a_consts = dA;
+  v.b_consts = dB;
+  v.gamma = dGrows;
+  v.target = dT;
+  v.xcoms = dc;
+  v.ycoms = dd;
+  v.pi = dpi;
+  v.theta = dth;
+  // ---- slots, owned G2 side, walk-ahead on the second stream (hidden behind the MSM and the first exchange)
+  g1_aff *X, *Xo;
+  g2_aff *Y, *Yo;
+  CUDA_TRY(sc.alloc(&X, 2 * (size_t)s.K * nprob));
+  CUDA_TRY(sc.alloc(&Y, 2 * (size_t)s.K * nprob));
+  CUDA_TRY(sc.alloc(&Xo, 2 * (size_t)(Ko ? Ko : 1) * nprob));
+  CUDA_TRY(sc.alloc(&Yo, 2 * (size_t)(Ko ? Ko : 1) * nprob));
+  LAUNCH(k_verify_assemble, nprob * (size_t)s.K, s, v, ctx->crs, X, Y, nprob);
+  std::vector<uint8_t> kind_all(s.K, gsi::GS_SLOT_WALK), kind;
+  for (int k = s.sB; k < s.sPi; k++) kind_all[k] = s.groupB ? gsi::GS_SLOT_WALK_B1 : (uint8_t)(gsi::GS_SLOT_FIXED + 2);
+  for (int j = 0; j < s.cy; j++) kind_all[s.sTh + j] = (uint8_t)(gsi::GS_SLOT_FIXED + j);
+  if (type == 1 || type == 3) kind_all[s.sT] = (uint8_t)(gsi::GS_SLOT_FIXED + 2);
+  if (type == 2) kind_all[s.sT] = gsi::GS_SLOT_WALK_B1;
+  for (int k = rank; k < s.K; k += world) kind.push_back(kind_all[k]);
+  LAUNCH(k_gather_owned_slots, nprob * (size_t)Ko * 2, X, Y, Xo, Yo, nprob, s.K, Ko, rank, world, 0, 1);
+  gsi::walk_ahead wa;  // after `sc`: destroyed first
+  if (Ko > 0) {
+    int rcw = gsi::g2_walk_ahead(ctx, sc, Yo, nprob, Ko, kind.data(), &wa);
+    if (rcw) return rcw;
+  }
+  // ---- phase A: this rank's bases into EVERY output
+  verify_shape sa = s;  // the MSM kernels enumerate outputs through the slot ownership: phase A owns them all
+  sa.rank = 0;
+  sa.world = 1;
+  const size_t all_out = (size_t)sa.n_out;
+  const int nbo = sa.nb_own();
+  g1_aff *myparts, *allparts;
+  CUDA_TRY(sc.alloc(&myparts, nprob * all_out * 2));
+  CUDA_TRY(sc.alloc(&allparts, (size_t)world * nprob * all_out * 2));
+  if (nbo > 0) {
+    const bool use_wtab = (nprob == 1 || shared_x) && all_out * nprob >= 320;
+    int chunk = GS_MSM_CHUNK;
+    const bool tiny = nprob * all_out * 2 * ((nbo + 7) / 8) < 16384;
+    const int floor_chunk = use_wtab ? 4 : (tiny ? 1 : 8);
+    while (chunk > floor_chunk && nprob * all_out * 2 * ((nbo + chunk - 1) / chunk) < (size_t)128 * 2368) chunk /= 2;
+    set_msm_chunk(sa, chunk);
+    g1_jac* part;
+    CUDA_TRY(sc.alloc(&part, (size_t)sa.nchunk * sa.n_out * 2 * nprob));
+    if (use_wtab) {
+      const int nb = nbo * 2;
+      const wt_geom g = wt_choose(all_out * nprob);
+      const size_t nrows = (size_t)nb * g.W;
+      g1_aff* wtab;
+      g1_jac* J;
+      CUDA_TRY(sc.alloc(&wtab, nrows * g.H));
+      CUDA_TRY(sc.alloc(&J, nrows * g.H));
+      LAUNCH(k_wtab_bases, (size_t)nb, sa, v, ctx->crs, J, nb, g);
+      LAUNCH(k_jac_to_affine_blocks<1>, nrows, J, wtab, nrows, (size_t)g.H);
+      LAUNCH(k_wtab_fill, nrows * (g.H / GS_WT_RUN), wtab, J, nrows, g.H);
+      LAUNCH(k_jac_to_affine_blocks<8>, nrows * g.H / 8, J, wtab, nrows * g.H, (size_t)1);
+      LAUNCH(k_vmsm_wsum, nprob * all_out * 2 * sa.nchunk, sa, v, wtab, part, nprob, g);
+    } else {
+      g1_aff* vtab;
+      fp* vtabx;
+      CUDA_TRY(sc.alloc(&vtab, (size_t)nbo * 2 * GS_VTAB * nprob));
+      CUDA_TRY(sc.alloc(&vtabx, (size_t)nbo * 2 * GS_VTAB * nprob));
+      LAUNCH(k_vmsm_tables, nprob * (size_t)nbo * 2, sa, v, ctx->crs, vtab, vtabx, nprob);
+      LAUNCH(k_vmsm_partial, nprob * all_out * 2 * sa.nchunk, sa, v, vtab, vtabx, part, nprob);
+    }
+    const g1_jac* partr = part;
+    if (sa.nchunk > 32) {
+      const int F = 16, ng = (sa.nchunk + F - 1) / F;
+      g1_jac* part2;
+      CUDA_TRY(sc.alloc(&part2, (size_t)ng * sa.n_out * 2 * nprob));
+      LAUNCH(k_vmsm_fold, (size_t)sa.n_out * 2 * nprob * ng, sa, part, part2, nprob, sa.nchunk, F, ng);
+      partr = part2;
+      sa.nchunk = ng;
+    }
+    LAUNCH(k_vmsm_parts_out, nprob * all_out * 2, sa, partr, myparts, nprob);
+  } else {
+    CUDA_TRY(cudaMemsetAsync(myparts, 0, nprob * all_out * 2 * sizeof(g1_aff), ctx->stream));  // no base: identities
+  }
+  // ---- first exchange: the partial sums
+  CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  if (allgather(user, myparts, allparts, nprob * all_out * 2 * sizeof(g1_aff)) != 0) FAIL(GS_EARG, "verify_sharded: all-gather of the MSM partial sums failed");
+  // ---- phase B: owned outputs -> X slots, owned Miller pairs -> partial products
+  LAUNCH(k_vmsm_reduce_parts, nprob * (size_t)s.n_out_owned() * 2, s, v, allparts, world, X, nprob);
+  LAUNCH(k_gather_owned_slots, nprob * (size_t)Ko * 2, X, Y, Xo, Yo, nprob, s.K, Ko, rank, world, 1, 0);
+  fp12 *mine, *allp;
+  CUDA_TRY(sc.alloc(&mine, nprob * 4));
+  CUDA_TRY(sc.alloc(&allp, (size_t)world * nprob * 4));
+  int rc = gsi::run_pairing_product(ctx, sc, Xo, Yo, nprob, Ko, nullptr, nullptr, nullptr, mine, kind.data(), &wa);
+  if (rc) return rc;
+  // ---- second exchange: 4 un-exponentiated GT values per statement and rank
+  CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  if (allgather(user, mine, allp, nprob * 4 * sizeof(fp12)) != 0) FAIL(GS_EARG, "verify_sharded: all-gather of the Miller partial products failed");
+  return gs_verify_finish_dev(ctx, type, nprob, world, (const gs_gt*)allp, dT, dok);
+}
+
+int gs_verify_sharded(gs_ctx* ctx, int type, size_t count, size_t m, size_t n, const void* a_consts, const void* b_consts,
+                      const gs_fr* gamma_rows, const void* target, const gs_com1* xcoms, const gs_com2* ycoms, const gs_com2* pi,
+                      const gs_com1* theta, int rank, int world, gs_allgather_fn allgather, void* user, uint8_t* out_ok) {
+  if (!ctx) return GS_EARG;
+  if (type < 0 || type > 3) FAIL(GS_EARG, "verify: bad equation type");
+  if (world < 1 || rank < 0 || rank >= world) FAIL(GS_EARG, "verify: bad shard (rank, world)");
+  if (!ctx->crs_loaded) FAIL(GS_EARG, "verify: no CRS loaded");
+  if (count == 0) return GS_OK;
+  if (m == 0 || n == 0) FAIL(GS_EDIM, "verify: empty variable list");
+  if (m > 1 << 20 || n > 1 << 20) FAIL(GS_EDIM, "verify: too many variables");
+  if (!a_consts || !b_consts || !target || !xcoms || !ycoms || !pi || !theta || !out_ok || !allgather) return GS_EARG;
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  verify_shape s = make_verify_shape(type, (int)m, (int)n);
+  set_base_shard(s, rank, world);
+  if (s.gm > 0 && !gamma_rows) return GS_EARG;
+  Scratch sc(ctx);
+  uint8_t *dA, *dB, *dT, *dok;
+  fr* dG;
+  g1_aff *dc, *dth;
+  g2_aff *dd, *dpi;
+  CUDA_TRY(upload(ctx, sc, &dA, a_consts, count * n * elem_size_A(type)));
+  CUDA_TRY(upload(ctx, sc, &dB, b_consts, count * m * elem_size_B(type)));
+  CUDA_TRY(upload(ctx, sc, &dG, gamma_rows, count * (size_t)s.gm * n));   // ONLY this rank's rows of Gamma
+  CUDA_TRY(upload(ctx, sc, &dT, target, count * elem_size_T(type)));
+  CUDA_TRY(upload(ctx, sc, &dc, xcoms, count * m * 2));
+  CUDA_TRY(upload(ctx, sc, &dd, ycoms, count * n * 2));
+  CUDA_TRY(upload(ctx, sc, &dpi, pi, count * s.cx * 2));
+  CUDA_TRY(upload(ctx, sc, &dth, theta, count * s.cy * 2));
+  CUDA_TRY(sc.alloc(&dok, count));
+  bool shared_x = count > 1;
+  for (size_t i = 1; i < count && shared_x; i++)
+    shared_x = memcmp(xcoms, (const char*)xcoms + i * m * sizeof(gs_com1), m * sizeof(gs_com1)) == 0;
+  int rc = verify_sharded_impl(ctx, type, count, m, n, dA, dB, dG, dT, dc, dd, dpi, dth, rank, world, shared_x, allgather, user, dok);
+  if (rc) return rc;
+  CUDA_TRY(cudaMemcpyAsync(out_ok, dok, count, cudaMemcpyDeviceToHost, ctx->stream));
   CUDA_TRY(cudaStreamSynchronize(ctx->stream));
   return GS_OK;
 }

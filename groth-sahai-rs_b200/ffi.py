@@ -17,7 +17,7 @@ EXPORTED_SYMBOLS = [
     "gs_crs_generate", "gs_crs_load",
     "gs_batch_commit_g1", "gs_batch_commit_g2", "gs_batch_commit_scalar_b1", "gs_batch_commit_scalar_b2",
     "gs_prove", "gs_prove_batch", "gs_verify_batch", "gs_verify_batch_dev",
-    "gs_verify_partial", "gs_verify_partial_dev", "gs_verify_finish", "gs_verify_finish_dev",
+    "gs_verify_partial", "gs_verify_partial_dev", "gs_verify_finish", "gs_verify_finish_dev", "gs_verify_sharded",
     "gs_comt_pairing", "gs_comt_pairing_sum", "gs_comt_linear_map", "gs_pairing",
     "gs_com1_matmul", "gs_com2_matmul", "gs_fr_matmul",
     "gs_com1_add", "gs_com1_sub", "gs_com1_neg", "gs_com1_sum", "gs_com2_add", "gs_com2_sub", "gs_com2_neg", "gs_com2_sum",
@@ -26,6 +26,10 @@ EXPORTED_SYMBOLS = [
     "gs_fr_to_bytes", "gs_fr_from_bytes", "gs_gt_to_bytes", "gs_gt_from_bytes",
     "gs_g1_serialize_uncompressed", "gs_g1_deserialize_uncompressed", "gs_g2_serialize_uncompressed", "gs_g2_deserialize_uncompressed",
 ]
+
+
+# gs_allgather_fn: int (*)(void* user, const void* send_dev, void* recv_dev, size_t bytes_per_rank)
+ALLGATHER_FN = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t)
 
 
 class GsError(RuntimeError):
@@ -74,6 +78,7 @@ def load_library():
         lib.gs_verify_partial_dev.argtypes = [vp, ci, sz, sz, sz] + [vp] * 8 + [ci, ci, vp]
         lib.gs_verify_finish.argtypes = [vp, ci, sz, ci, vp, vp, vp]
         lib.gs_verify_finish_dev.argtypes = [vp, ci, sz, ci, vp, vp, vp]
+        lib.gs_verify_sharded.argtypes = [vp, ci, sz, sz, sz] + [vp] * 8 + [ci, ci, ALLGATHER_FN, vp, vp]
         lib.gs_comt_pairing.argtypes = [vp, sz, vp, vp, vp]
         lib.gs_comt_pairing_sum.argtypes = [vp, sz, vp, vp, vp]
         lib.gs_comt_linear_map.argtypes = [vp, ci, vp, vp]
@@ -289,6 +294,39 @@ class Engine:
         ok = ctypes.create_string_buffer(max(1, count))
         kp, kt = _buf(partials), _buf(target)
         self._chk(self.lib.gs_verify_finish(self.h, ty, count, nparts, kp[1], kt[1], ctypes.cast(ok, ctypes.c_void_p)))
+        return ok.raw[:count]
+
+    def verify_sharded(self, ty, count, m, n, a_consts, b_consts, gamma_rows, target, xcoms, ycoms, pi, theta, rank, world,
+                       allgather) -> bytes:
+        """gs_verify_sharded: the statement MSM split by base, the Miller pairs by slot, two all-gathers through
+        `allgather(send_ptr, recv_ptr, nbytes) -> None` (device pointers; shard.make_allgather builds one over
+        torch.distributed).  gamma_rows = this rank's rows of Gamma only (shard.gamma_rows_of)."""
+        cx, cy = _cx(ty), _cy(ty)
+        gm = len(range(rank, m, world))
+        want = [count * n * _a_size(ty), count * m * _b_size(ty), count * gm * n * FR, count * _t_size(ty), count * m * COM1,
+                count * n * COM2, count * cx * COM2, count * cy * COM1]
+        for nm, buf, w in zip(("a_consts", "b_consts", "gamma_rows", "target", "xcoms", "ycoms", "pi", "theta"),
+                              (a_consts, b_consts, gamma_rows, target, xcoms, ycoms, pi, theta), want):
+            if len(buf) != w:
+                raise GsError(1, f"verify_sharded: {nm} is {len(buf)} bytes, expected {w}")
+        err = []
+
+        def cb(_user, send, recv, nbytes):
+            try:
+                allgather(int(send), int(recv), int(nbytes))
+                return 0
+            except Exception as ex:  # noqa: BLE001 -- must not unwind through the C frames
+                err.append(ex)
+                return 1
+
+        fn = ALLGATHER_FN(cb)
+        ok = ctypes.create_string_buffer(max(1, count))
+        ks = [_buf(x) if len(x) else (None, ctypes.c_void_p(0)) for x in (a_consts, b_consts, gamma_rows, target, xcoms, ycoms, pi, theta)]
+        rc = self.lib.gs_verify_sharded(self.h, ty, count, m, n, *[k[1] for k in ks], int(rank), int(world), fn, None,
+                                        ctypes.cast(ok, ctypes.c_void_p))
+        if err:
+            raise err[0]
+        self._chk(rc)
         return ok.raw[:count]
 
     # ---- ComT

@@ -165,3 +165,61 @@ def verify_equations_sharded(verify_local, eq_arrays: Sequence, eq_unit_sizes: S
     equation for gs_verify_batch); eq_arrays = per-equation a_consts, b_consts, gamma, target, pi, theta.  One
     verdict byte per equation is all-gathered (verifier.rs:25-26: one EquProof per verify call)."""
     return verify_batch_sharded(verify_local, eq_arrays, eq_unit_sizes, num_eqs, rank, world, group, device)
+
+
+# ---------------------------------------------------------------- one statement, MSM split by BASE (gs_verify_sharded)
+def gamma_rows_of(gamma, count: int, m: int, n: int, rank: int, world: int) -> bytes:
+    """Rows i = rank (mod world) of every m x n Gamma in `gamma` ([count][m][n] Fr, 32 B each), compact and in order:
+    what gs_verify_sharded uploads on this rank (1 / world of the statement)."""
+    if world <= 0 or not 0 <= rank < world:
+        raise ValueError("bad rank / world size")
+    import numpy as np
+    g = np.frombuffer(gamma, dtype=np.uint8)
+    if g.size != count * m * n * 32:
+        raise ValueError("gamma has the wrong size")
+    return np.ascontiguousarray(g.reshape(count, m, n * 32)[:, rank::world, :]).tobytes()
+
+
+class _DevMem:
+    """A raw device pointer as an object torch.as_tensor can wrap (CUDA array interface, uint8)."""
+
+    def __init__(self, ptr, nbytes):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
+
+
+def wrap_memory(ptr: int, nbytes: int, device):
+    """uint8 tensor over `nbytes` at `ptr`: device memory (torch device 'cuda:k') or, for the CPU tests, host memory."""
+    import torch
+    if str(device).startswith("cuda"):
+        return torch.as_tensor(_DevMem(ptr, nbytes), device=device)
+    import ctypes
+    return torch.frombuffer((ctypes.c_char * nbytes).from_address(ptr), dtype=torch.uint8)
+
+
+def make_allgather(device, group=None):
+    """The all-gather callback of gs_verify_sharded over torch.distributed (NCCL on device pointers: GPU to GPU over
+    NVLink, no host staging; gloo on host pointers in the CPU tests).  World size 1 degenerates to a copy."""
+    import torch
+    import torch.distributed as dist
+
+    def allgather(send_ptr, recv_ptr, nbytes):
+        world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+        send = wrap_memory(send_ptr, nbytes, device)
+        recv = wrap_memory(recv_ptr, nbytes * world, device)
+        if world == 1:
+            recv.copy_(send)
+        else:
+            dist.all_gather_into_tensor(recv, send, group=group)
+        if str(device).startswith("cuda"):
+            torch.cuda.current_stream(device).synchronize()
+
+    return allgather
+
+
+def verify_statement_base_sharded(engine, ty, count, m, n, arrays, rank, world, device, group=None) -> bytes:
+    """Verifiable::verify of `count` statements (one big one: C3; or the equations of one statement over shared
+    commitments: C4) with the statement MSM split by base and the Miller pairs by slot over `world` ranks.
+    arrays = the 8 byte strings of gs_verify_batch with the FULL Gamma; every rank returns the verdict bytes."""
+    a, b, gamma, target, xc, yc, pi, th = arrays
+    rows = gamma_rows_of(gamma, count, m, n, rank, world)
+    return engine.verify_sharded(ty, count, m, n, a, b, rows, target, xc, yc, pi, th, rank, world, make_allgather(device, group))

@@ -173,6 +173,22 @@ int gs_verify_finish(gs_ctx* ctx, int type, size_t count, int nparts, const gs_g
 int gs_verify_finish_dev(gs_ctx* ctx, int type, size_t count, int nparts, const gs_gt* partials_dev,
                          const void* target_dev, uint8_t* out_ok_dev);
 
+/* The same statement(s) with the statement MSM split by BASE as well: rank r sums only the bases i = r (mod world) into
+ * every output and the partial sums (n_out x 2 affine G1 points per statement) are exchanged before the split by slot
+ * takes over; the 4 x 576 B Miller partial products are exchanged a second time and every rank finishes.  ONE call runs
+ * the whole sharded verification; the two all-gathers go through the caller's transport (NCCL over NVLink via
+ * torch.distributed, raw NCCL, MPI ...):
+ *     allgather(user, send_dev, recv_dev, bytes) -> 0 once recv_dev[r * bytes ..] holds rank r's send_dev for every r
+ * with DEVICE pointers; the context's stream is idle during the callback.  gamma_rows holds ONLY this rank's rows of
+ * Gamma: [count][gm][n] with gm = #{i < m : i = rank (mod world)}, row i of Gamma at index i / world -- so a rank uploads
+ * 1 / world of the statement.  With world = 1 (allgather = a device copy) this equals gs_verify_batch.  Replaces the
+ * Rayon parallelism of left_mul (src/data_structures.rs:708-728) inside verify (src/verifier.rs:39-42). */
+typedef int (*gs_allgather_fn)(void* user, const void* send_dev, void* recv_dev, size_t bytes_per_rank);
+int gs_verify_sharded(gs_ctx* ctx, int type, size_t count, size_t m, size_t n, const void* a_consts, const void* b_consts,
+                      const gs_fr* gamma_rows, const void* target, const gs_com1* xcoms, const gs_com2* ycoms,
+                      const gs_com2* pi, const gs_com1* theta, int rank, int world, gs_allgather_fn allgather, void* user,
+                      uint8_t* out_ok);
+
 /* ---- ComT (src/data_structures.rs) ------------------------------------------------------- */
 /* ComT::pairing :484-491, batched: out[i] = F(xs[i], ys[i]) (4 full pairings each) */
 int gs_comt_pairing(gs_ctx* ctx, size_t count, const gs_com1* xs, const gs_com2* ys, gs_comt* out);

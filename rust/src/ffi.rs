@@ -20,6 +20,10 @@ pub const GS_EDIM: i32 = 1;
 #[repr(C)] #[derive(Clone, Copy)]
 pub struct GsCrs { pub u: [GsCom1; 2], pub v: [GsCom2; 2], pub g1_gen: GsG1, pub g2_gen: GsG2, pub gt_gen: GsGt }
 pub enum GsCtx {}
+/// `int (*)(void* user, const void* send_dev, void* recv_dev, size_t bytes_per_rank)`: gather `bytes_per_rank` from every rank
+/// into `recv_dev` (rank-major); device pointers; return 0 when complete.
+pub type GsAllgatherFn = unsafe extern "C" fn(user: *mut std::ffi::c_void, send_dev: *const std::ffi::c_void,
+                                              recv_dev: *mut std::ffi::c_void, bytes_per_rank: usize) -> i32;
 
 impl GsG1 { pub const ZERO: GsG1 = GsG1 { x: [0; 6], y: [0; 6] }; }
 impl GsG2 { pub const ZERO: GsG2 = GsG2 { x: [0; 12], y: [0; 12] }; }
@@ -55,6 +59,12 @@ extern "C" {
                              pi: *const GsCom2, theta: *const GsCom1, rank: i32, world: i32, out_partial: *mut GsGt) -> i32;
     pub fn gs_verify_finish(ctx: *mut GsCtx, ty: i32, count: usize, nparts: i32, partials: *const GsGt,
                             target: *const u8, out_ok: *mut u8) -> i32;
+    // the whole sharded verification in one call: statement MSM split by base, Miller pairs by slot; the two all-gathers
+    // go through the caller's transport (device pointers), e.g. ncclAllGather on a communicator the host owns
+    pub fn gs_verify_sharded(ctx: *mut GsCtx, ty: i32, count: usize, m: usize, n: usize, a: *const u8, b: *const u8,
+                             gamma_rows: *const GsFr, target: *const u8, xcoms: *const GsCom1, ycoms: *const GsCom2,
+                             pi: *const GsCom2, theta: *const GsCom1, rank: i32, world: i32, allgather: GsAllgatherFn,
+                             user: *mut std::ffi::c_void, out_ok: *mut u8) -> i32;
     // data_structures.rs:484-540
     pub fn gs_comt_pairing(ctx: *mut GsCtx, count: usize, xs: *const GsCom1, ys: *const GsCom2, out: *mut GsComT) -> i32;
     pub fn gs_comt_pairing_sum(ctx: *mut GsCtx, k: usize, xs: *const GsCom1, ys: *const GsCom2, out: *mut GsComT) -> i32;

@@ -49,13 +49,20 @@ def _value(a, b, gam, xs, ys):
 class Case:
     """One satisfied equation with its witnesses, randomness and the REFERENCE-ORDER commitments and proof."""
 
-    def __init__(self, ty, m, n, crs, seed, zero_frac=0.0, prove=True):
+    def __init__(self, ty, m, n, crs, seed, zero_frac=0.0, prove=True, collide=False):
         rng = SeededRng(seed)
         self.ty, self.m, self.n, self.crs, self.crsb = ty, m, n, crs, crs_bytes(crs)
         cx, cy = cb.cx_of(ty), cb.cy_of(ty)
         xs, ys = fr_list(rng, m), fr_list(rng, n)
         a, b = fr_list(rng, n, zero_frac), fr_list(rng, m, zero_frac)
         gam = [fr_list(rng, n, zero_frac) for _ in range(m)]
+        if collide and n >= 4:
+            # y_1 = y_0 and y_2 = -y_0 with equal Gamma columns: inside an MSM the three terms carry the same scalar, so a
+            # bucket / table sees P + P and P + (-P); scalars 1 and r - 1 ride along
+            ys[1], ys[2] = ys[0], (-ys[0]) % R
+            for row in gam:
+                row[1] = row[2] = row[0]
+            gam[0][3], gam[m - 1][3] = 1, R - 1
         self.A, self.B = _enc_side1(crs, ty, a), _enc_side2(crs, ty, b)
         self.X, self.Y = _enc_side1(crs, ty, xs), _enc_side2(crs, ty, ys)
         self.G = frmat_b(gam)

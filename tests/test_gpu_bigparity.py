@@ -93,6 +93,39 @@ def test_1024x1024_ppe(eng, crs):
     check_case(eng, Case(0, 1024, 1024, crs, seed=500), oracle_verify=False)
 
 
+@pytest.mark.parametrize("ty,m,n", [(0, 2, 8190), (1, 4100, 3), (2, 3, 4100)])
+def test_pippenger_proof_msm(eng, crs, ty, m, n):
+    """One statement whose proof MSMs have >= 4,096 terms takes the bucket method (csrc/pippenger.cuh): the proof must
+    still equal the reference-order CPU proof byte for byte.  Colliding terms (P + P, P + (-P) in one bucket), identity
+    constants, zero / 1 / r-1 scalars included."""
+    c = Case(ty, m, n, crs, seed=900 + ty, zero_frac=0.05, collide=True)
+    pi, th = eng.prove(ty, m, n, *c.prove_args())
+    assert pi == c.pi, "pi differs"
+    assert th == c.theta, "theta differs"
+    assert eng.verify(ty, m, n, *c.verify_arrays()) is True
+
+
+def test_pippenger_equals_per_term_path(crs):
+    """The same big proof through both MSM paths (GS_PIP_MIN decides at context creation), and at several window widths."""
+    import os
+    import groth_sahai_rs_b200 as gsb
+    c = Case(0, 2, 5000, crs, seed=950, prove=False, collide=True)
+    outs = []
+    for env in ({"GS_PIP_MIN": "1000000000"}, {"GS_PIP_MIN": "0"}, {"GS_PIP_MIN": "0", "GS_PIP_C": "5"},
+                {"GS_PIP_MIN": "0", "GS_PIP_C": "13"}):
+        old = {k: os.environ.get(k) for k in ("GS_PIP_MIN", "GS_PIP_C")}
+        os.environ.update(env)
+        try:
+            e = gsb.Engine(0)
+        finally:
+            for k, v in old.items():
+                os.environ.pop(k, None) if v is None else os.environ.__setitem__(k, v)
+        e.crs_load(c.crsb)
+        outs.append(e.prove(0, 2, 5000, *c.prove_args()))
+        e.close()
+    assert outs[0] == outs[1] == outs[2] == outs[3]
+
+
 @pytest.mark.parametrize("ty", [0, 1, 2, 3])
 def test_c4_statement_shared_vars(eng, crs, ty):
     """64 equations over one witness set (C4 shape): gs_prove_batch(shared_vars) takes the shared-base window-table

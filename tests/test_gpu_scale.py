@@ -277,3 +277,100 @@ def test_prove_batch_shared_variable_tables(eng, ty):
         pi2, th2 = eng.prove_batch(ty, E, m, n, b"".join(A), b"".join(B), b"".join(G), X2, Y, xr, yr, b"".join(Tr), shared_vars=True)
         one = eng.prove(ty, m, n, A[5], B[5], G[5], X2, Y, xr, yr, Tr[5])
         assert pi2[5 * cx * 384:6 * cx * 384] == one[0] and th2[5 * cy * 192:6 * cy * 192] == one[1]
+
+
+# ---------------------------------------------------------------- gs_verify_sharded: MSM split by base, pairs by slot
+def _sharded_on_one_gpu(ty, count, m, n, arrays, crsb, world):
+    """`world` ranks emulated by `world` contexts on THIS GPU in `world` host threads: the all-gather callback is an
+    in-process exchange (device-to-device copies between the contexts' buffers behind a barrier), everything else is the
+    code path the multi-GPU run takes.  Returns every rank's verdict bytes."""
+    import threading
+    import torch
+    import groth_sahai_rs_b200 as gsb
+    sh = gsb.shard
+    dev = "cuda:0"
+    engines = [gsb.Engine(0) for _ in range(world)]
+    for e in engines:
+        e.crs_load(crsb)
+    bar = threading.Barrier(world)
+    posted = [None] * world
+    out, errs = [None] * world, []
+
+    def run(r):
+        def allgather(send_ptr, recv_ptr, nbytes):
+            posted[r] = send_ptr
+            bar.wait()
+            recv = sh.wrap_memory(recv_ptr, nbytes * world, dev)
+            for q in range(world):
+                recv[q * nbytes:(q + 1) * nbytes].copy_(sh.wrap_memory(posted[q], nbytes, dev))
+            torch.cuda.synchronize()
+            bar.wait()
+        try:
+            a, b, gamma, target, xc, yc, pi, th = arrays
+            rows = sh.gamma_rows_of(gamma, count, m, n, r, world)
+            out[r] = engines[r].verify_sharded(ty, count, m, n, a, b, rows, target, xc, yc, pi, th, r, world, allgather)
+        except Exception as ex:  # noqa: BLE001
+            errs.append(ex)
+            bar.abort()
+
+    ts = [threading.Thread(target=run, args=(r,)) for r in range(world)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    for e in engines:
+        e.close()
+    if errs:
+        raise errs[0]
+    return out
+
+
+@pytest.mark.parametrize("ty", [0, 1, 2, 3])
+def test_verify_sharded_by_base_small(eng, ty):
+    """Every equation type, ragged split (m = 5 bases + W1 over 1 / 2 / 3 / 4 ranks, some ranks own no Gamma row or no
+    output), honest and tampered: the verdicts equal gs_verify_batch's and the CPU oracle's."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from bigcase import Case, cb, NT
+    crs = make_crs(1)[0]
+    m, n = 5, 3
+    c = Case(ty, m, n, crs, seed=1200 + ty, zero_frac=0.2)
+    good = c.verify_arrays()
+    bad = list(good)
+    g = bytearray(bad[2])
+    g[32 * 4] ^= 1
+    bad[2] = bytes(g)
+    two = [x + y for x, y in zip(good, bad)]                     # count = 2: honest, tampered
+    assert cb.verify_batch(ty, 2, m, n, two, c.crsb, NT) == b"\x01\x00"
+    assert eng.verify_batch(ty, 2, m, n, *two) == b"\x01\x00"
+    for world in (1, 2, 3, 4):
+        for ok in _sharded_on_one_gpu(ty, 2, m, n, two, c.crsb, world):
+            assert ok == b"\x01\x00", (ty, world, ok)
+
+
+def test_verify_sharded_by_base_c3_and_c4():
+    """The shapes it is meant for: one 256 x 192 PPE (shared-base window tables per rank) over 1 / 2 / 4 ranks, and a C4-style
+    statement (48 equations over shared 64-variable commitments, tables shared by the batch) over 3 ranks, with CPU-made
+    proofs and one tampered equation."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from bigcase import Case, Statement, cb
+    crs = make_crs(1)[0]
+    c = Case(0, 256, 192, crs, seed=1300)
+    good = c.verify_arrays()
+    bad = list(good)
+    t = bytearray(bad[4])
+    t[0:192], t[192:384] = t[192:384], t[0:192]                  # swap two x-commitments
+    bad[4] = bytes(t)
+    for world in (1, 2, 4):
+        assert _sharded_on_one_gpu(0, 1, 256, 192, good, c.crsb, world) == [b"\x01"] * world
+        assert _sharded_on_one_gpu(0, 1, 256, 192, bad, c.crsb, world) == [b"\x00"] * world
+    for ty in (0, 3):
+        E, m, n = 48, 64, 64
+        st = Statement(ty, m, n, E, crs, seed=1310 + ty)
+        arrays = st.verify_arrays()
+        ts = cb.target_size(ty)
+        tg = bytearray(arrays[3])
+        tg[7 * ts:8 * ts], tg[8 * ts:9 * ts] = tg[8 * ts:9 * ts], tg[7 * ts:8 * ts]
+        arrays[3] = bytes(tg)
+        want = bytearray(b"\x01" * E)
+        want[7] = want[8] = 0
+        assert _sharded_on_one_gpu(ty, E, m, n, arrays, st.crsb, 3) == [bytes(want)] * 3

@@ -188,3 +188,62 @@ def test_equations_sharded_gloo(world, ty, E):
         assert xc == want.xc and yc == want.yc, rank
         assert pi == want.pi and th == want.theta, rank
         assert ok == expect_ok, (rank, ok)
+
+
+# ---------------------------------------------------------------- MSM split by base: host-side pieces of gs_verify_sharded
+def test_gamma_rows_of():
+    import numpy as np
+    sh = _load_shard()
+    count, m, n = 2, 5, 3
+    g = np.arange(count * m * n * 32, dtype=np.uint32).astype(np.uint8).tobytes()
+    full = np.frombuffer(g, dtype=np.uint8).reshape(count, m, n * 32)
+    for world in (1, 2, 3, 7):
+        seen = []
+        for r in range(world):
+            rows = np.frombuffer(sh.gamma_rows_of(g, count, m, n, r, world), dtype=np.uint8)
+            own = list(range(r, m, world))
+            assert rows.size == count * len(own) * n * 32
+            rows = rows.reshape(count, len(own), n * 32) if own else rows
+            for k, i in enumerate(own):          # row i of Gamma sits at index i // world on rank i % world
+                assert k == i // world and (rows[:, k] == full[:, i]).all()
+            seen += own
+        assert sorted(seen) == list(range(m))
+    with pytest.raises(ValueError):
+        sh.gamma_rows_of(g[:-1], count, m, n, 0, 1)
+
+
+def _ag_worker(rank, world, port, q):
+    """The all-gather callback on host pointers over gloo: what the C library calls twice per sharded verification."""
+    import ctypes
+    import torch.distributed as dist
+    sh = _load_shard()
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    try:
+        nbytes = 96 * 5
+        send = (ctypes.c_char * nbytes).from_buffer_copy(bytes((rank * 17 + i) & 0xff for i in range(nbytes)))
+        recv = (ctypes.c_char * (nbytes * world))()
+        sh.make_allgather("cpu")(ctypes.addressof(send), ctypes.addressof(recv), nbytes)
+        q.put((rank, bytes(recv)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_allgather_callback_gloo():
+    import torch.multiprocessing as mp
+    world = 3
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_ag_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    want = b"".join(bytes((r * 17 + i) & 0xff for i in range(96 * 5)) for r in range(world))
+    for _, got in res:
+        assert got == want
