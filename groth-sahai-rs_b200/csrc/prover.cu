@@ -319,11 +319,35 @@ static int prove_impl(gs_ctx* ctx, int type, size_t count, size_t m, size_t n, c
       const int l_d = fr_lanes(m + n, (size_t)cy * nb);
       LAUNCH_B(k_fr_dot, (size_t)cy * l_d, nb, e_th, sv_th, (const fr*)dA, n, (const fr*)dX, m, cy, shared_vars ? (size_t)0 : m, l_d);
     }
-    int rc = proof_element<Fp2Ops>(ctx, sc, nb, cx, s.groupB, sv_pi, dB, m, dY, n, shared_vars, cy, coef_pi, (size_t)cy, e_pi, dpi);
-    if (rc) return rc;
+    // pi (G2) and theta (G1) are independent: in the latency regime (few proofs) theta runs on the second stream next to pi
+    const bool two_streams = nb * (m + n) * 2 < 32768;
+    cudaStream_t main_stream = ctx->stream;
+    cudaEvent_t fork = nullptr, join = nullptr;
+    if (two_streams) {
+      if (!ctx->stream2) CUDA_TRY(cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking));
+      CUDA_TRY(cudaEventCreateWithFlags(&fork, cudaEventDisableTiming));
+      if (cudaEventCreateWithFlags(&join, cudaEventDisableTiming) != cudaSuccess) {
+        cudaEventDestroy(fork);
+        FAIL(GS_ECUDA, "prove: event creation failed");
+      }
+      cudaEventRecord(fork, main_stream);
+      cudaStreamWaitEvent(ctx->stream2, fork, 0);
+      ctx->stream = ctx->stream2;
+    }
     // theta_i = sum_j S[j][i] iota(A_j) + sum_k SG[i][k] iota(X_k) + sum_l T[i][l] u_l          (l < cx)
-    rc = proof_element<FpOps>(ctx, sc, nb, cy, s.groupA, sv_th, dA, n, dX, m, shared_vars, cx, dT, (size_t)cx, e_th, dth);
-    if (rc) return rc;
+    int rc_th = proof_element<FpOps>(ctx, sc, nb, cy, s.groupA, sv_th, dA, n, dX, m, shared_vars, cx, dT, (size_t)cx, e_th, dth);
+    if (two_streams) {
+      cudaEventRecord(join, ctx->stream2);
+      ctx->stream = main_stream;
+    }
+    int rc_pi = proof_element<Fp2Ops>(ctx, sc, nb, cx, s.groupB, sv_pi, dB, m, dY, n, shared_vars, cy, coef_pi, (size_t)cy, e_pi, dpi);
+    if (two_streams) {
+      cudaStreamWaitEvent(main_stream, join, 0);  // also orders the scratch frees (main stream) after theta's kernels
+      cudaEventDestroy(fork);
+      cudaEventDestroy(join);
+    }
+    if (rc_th) return rc_th;
+    if (rc_pi) return rc_pi;
     CUDA_TRY(cudaMemcpyAsync(out_pi + off * cx, dpi, nb * 2 * cx * sizeof(g2_aff), cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(cudaMemcpyAsync(out_theta + off * cy, dth, nb * 2 * cy * sizeof(g1_aff), cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));

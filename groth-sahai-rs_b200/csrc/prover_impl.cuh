@@ -99,6 +99,24 @@ GS_HD GS_INL void fixed_base_accumulate(Jac<F>& acc, const Aff<F>* __restrict__ 
   }
 }
 
+// the windows [w0, w1) only (the recoding carry of the lower windows is recomputed: integer work, no curve operation)
+template <class F>
+GS_HD GS_INL void fixed_base_accumulate_range(Jac<F>& acc, const Aff<F>* __restrict__ T, const uint32_t k[8], int c, int W, size_t H,
+                                              int w0, int w1) {
+  uint32_t carry = 0;
+  const uint32_t half = 1u << (c - 1);
+  for (int w = 0; w < w1 && w < W; w++) {
+    uint32_t d = get_bits(k, w * c, c) + carry;
+    const bool ng = d > half;
+    carry = ng ? 1u : 0u;
+    const uint32_t mag = ng ? (1u << c) - d : d;
+    if (w < w0 || mag == 0) continue;
+    Aff<F> e = T[(size_t)w * H + (mag - 1)];
+    if (ng) F::neg(e.y, e.y);
+    Jac<F>::add_mixed(acc, acc, e);
+  }
+}
+
 template <class F>
 __global__ void __launch_bounds__(GS_TAB_NT) k_fixed_commit(const Aff<F>* __restrict__ tab, int c, int W, size_t H, int base0,
                                                             int base1, const fr* __restrict__ s0, size_t s0_stride,
@@ -245,35 +263,51 @@ __global__ void __launch_bounds__(128) k_jac_reduce_step(Jac<F>* __restrict__ te
 // final assembly of a proof element (prove.rs:146, 162):
 //   out[i].p[0] =                  sum_l coef[i][l] key_l.0  (+ e_i W.0)
 //   out[i].p[1] = varsum[i]      + sum_l coef[i][l] key_l.1  (+ e_i W.1)
-// thread -> (i, a).  `varsum` = reduced MSM rows (group-typed) or null; `e` = collapsed scalar (scalar-typed) or null.
+// `varsum` = reduced MSM rows (group-typed) or null; `e` = collapsed scalar (scalar-typed) or null.
 // key_l (u_l / v_l) and W are the CRS points the fixed-base window tables hold (bases l and 2): one table
-// lookup + mixed addition per window instead of a 255-step double-and-add in this single thread.
+// lookup + mixed addition per window instead of a 255-step double-and-add.
+// The CRS-key terms are spread over threads (a lone proof is latency: 64 - 96 dependent additions in
+// one thread were 3.2 ms per group): thread -> (i, a, scalar s, window chunk ch) adds PF_WCH windows of ONE scalar,
+//   kt[((i*2 + a) * KT) + s*PF_NCH + ch],   KT = nscal * PF_NCH,   scalar s < ncoef: coef[i][s] on key s; s == ncoef: e_i on W
+// the partial sums are tree-reduced (reduce_rows) and k_proof_finish2 adds the variable MSM and normalises.
+constexpr int PF_NCH = 8;
 template <class F>
-__global__ void k_proof_finish(Aff<F>* __restrict__ out, int rows, int ncoef, const fr* __restrict__ coef, size_t coef_rs,
-                               size_t coef_cs, const Aff<F>* __restrict__ tab, int c, int W, size_t H,
-                               const Jac<F>* __restrict__ varsum, size_t var_stride, const fr* __restrict__ e) {
+__global__ void __launch_bounds__(128) k_proof_key_terms(Jac<F>* __restrict__ kt, int rows, int ncoef, const fr* __restrict__ coef,
+                                                         const Aff<F>* __restrict__ tab, int c, int W, size_t H, const fr* __restrict__ e,
+                                                         int nscal) {
+  const int KT = nscal * PF_NCH;
+  int id = blockIdx.x * blockDim.x + threadIdx.x;
+  if (id >= rows * 2 * KT) return;
+  const int ch = id % PF_NCH, sidx = (id / PF_NCH) % nscal, ia = id / KT;
+  const int i = ia >> 1, a = ia & 1;
+  kt += (size_t)blockIdx.y * rows * 2 * KT;
+  coef += (size_t)blockIdx.y * rows * ncoef;
+  if (e != nullptr) e += (size_t)blockIdx.y * rows;
+  const int wch = (W + PF_NCH - 1) / PF_NCH;
+  uint32_t k[8];
+  fr_from_mont(k, sidx < ncoef ? coef[i * ncoef + sidx] : e[i]);
+  const int base = sidx < ncoef ? sidx : 2;  // table bases: key_0, key_1, W
+  Jac<F> acc;
+  acc.set_inf();
+  fixed_base_accumulate_range<F>(acc, tab + ((size_t)(base * 2 + a) * W) * H, k, c, W, H, ch * wch, (ch + 1) * wch);
+  kt[id] = acc;
+}
+template <class F>
+__global__ void k_proof_finish2(Aff<F>* __restrict__ out, int rows, const Jac<F>* __restrict__ kt, int KT, const Jac<F>* __restrict__ varsum,
+                                size_t var_stride) {
   int id = blockIdx.x * blockDim.x + threadIdx.x;
   if (id >= rows * 2) return;
   int i = id >> 1, a = id & 1;
   out += (size_t)blockIdx.y * rows * 2;
-  coef += (size_t)blockIdx.y * rows * ncoef;
-  if (varsum != nullptr) varsum += (size_t)blockIdx.y * var_stride * rows;
-  if (e != nullptr) e += (size_t)blockIdx.y * rows;
-  Jac<F> acc;
-  acc.set_inf();
-  if (varsum != nullptr && a == 1) acc = varsum[(size_t)i * var_stride];
-  uint32_t k[8];
-  for (int l = 0; l < ncoef; l++) {
-    fr_from_mont(k, coef[i * coef_rs + l * coef_cs]);
-    fixed_base_accumulate<F>(acc, tab + ((size_t)(l * 2 + a) * W) * H, k, c, W, H);
-  }
-  if (e != nullptr) {
-    fr_from_mont(k, e[i]);
-    fixed_base_accumulate<F>(acc, tab + ((size_t)(2 * 2 + a) * W) * H, k, c, W, H);
+  kt += (size_t)blockIdx.y * rows * 2 * KT;
+  Jac<F> acc = kt[(size_t)id * KT];
+  if (varsum != nullptr && a == 1) {
+    Jac<F> vs = varsum[(size_t)blockIdx.y * var_stride * rows + (size_t)i * var_stride];
+    Jac<F>::add(acc, acc, vs);
   }
   Aff<F> r;
   Jac<F>::to_affine(r, acc);
-  out[i * 2 + a] = r;
+  out[id] = r;
 }
 
 // ------------------------------------------------------------------ Mat::left_mul on Com matrices
@@ -456,6 +490,21 @@ int reduce_rows(gs_ctx* ctx, Jac<F>* terms, size_t stride, size_t cnt, int rows,
   return GS_OK;
 }
 
+// final assembly of the proof elements of `count` proofs (k_proof_key_terms -> tree -> k_proof_finish2)
+template <class F>
+int proof_finish(gs_ctx* ctx, Scratch& sc, size_t count, int rows, int ncoef, const fr* coef, const gs_fixed_table<F>& T,
+                 const Jac<F>* varsum, size_t var_stride, const fr* e, Aff<F>* dout) {
+  const int nscal = ncoef + (e != nullptr ? 1 : 0);
+  const int KT = nscal * PF_NCH;
+  Jac<F>* kt;
+  CUDA_TRY(sc.alloc(&kt, count * (size_t)rows * 2 * KT));
+  LAUNCH_B((k_proof_key_terms<F>), (size_t)rows * 2 * KT, count, kt, rows, ncoef, coef, T.t, T.c, T.W, T.H, e, nscal);
+  int rc = reduce_rows<F>(ctx, kt, (size_t)KT, (size_t)KT, rows * 2, count);
+  if (rc) return rc;
+  LAUNCH_B((k_proof_finish2<F>), (size_t)rows * 2, count, dout, rows, kt, KT, varsum, var_stride);
+  return GS_OK;
+}
+
 }  // namespace gsi
 #include "pippenger.cuh"
 namespace gsi {
@@ -486,9 +535,7 @@ int proof_element(gs_ctx* ctx, Scratch& sc, size_t count, int rows, bool group_t
       int rcp = pippenger_rows<F>(ctx, sc, sv, rows, (const Aff<F>*)dconst, nconst, (const Aff<F>*)dvars, nvars, &rowsum, &stride,
                                   ctx->pip_c);
       if (rcp) return rcp;
-      LAUNCH_B((k_proof_finish<F>), (size_t)rows * 2, count, dout, rows, ncoef, coef, coef_rs, (size_t)1, T.t, T.c, T.W, T.H, rowsum,
-               stride, (const fr*)nullptr);
-      return GS_OK;
+      return proof_finish<F>(ctx, sc, count, rows, ncoef, coef, T, rowsum, stride, (const fr*)nullptr, dout);
     }
     const int PARTS = (!var_tables && count * nt * rows < 32768) ? EndoSplit<F>::PARTS : 1;
     const size_t ntp = nt * PARTS;
@@ -536,14 +583,11 @@ int proof_element(gs_ctx* ctx, Scratch& sc, size_t count, int rows, bool group_t
     }
     int rc = reduce_rows<F>(ctx, terms, ntp, ntp, rows, count);
     if (rc) return rc;
-    LAUNCH_B((k_proof_finish<F>), (size_t)rows * 2, count, dout, rows, ncoef, coef, coef_rs, (size_t)1, T.t, T.c, T.W, T.H, terms, ntp,
-             (const fr*)nullptr);
+    return proof_finish<F>(ctx, sc, count, rows, ncoef, coef, T, terms, ntp, (const fr*)nullptr, dout);
   } else {
     // scalar-typed side: the caller collapsed the terms into e_i = <sv_i, (consts | vars)> (k_fr_dot, prover.cu)
-    LAUNCH_B((k_proof_finish<F>), (size_t)rows * 2, count, dout, rows, ncoef, coef, coef_rs, (size_t)1, T.t, T.c, T.W, T.H,
-             (const Jac<F>*)nullptr, (size_t)0, e);
+    return proof_finish<F>(ctx, sc, count, rows, ncoef, coef, T, (const Jac<F>*)nullptr, (size_t)0, e, dout);
   }
-  return GS_OK;
 }
 
 template <class F>
