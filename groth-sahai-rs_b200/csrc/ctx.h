@@ -45,7 +45,9 @@ struct gs_ctx {
   std::vector<prof_rec> prof;
   size_t verify_batch_max = 23680;  // problems per verify pass (10 waves of k_miller4)
   size_t tile_budget = (size_t)16 << 30;  // bytes of HBM for the evaluated-line tiles of one pairing pass
-  size_t pip_min = 3072;  // proof MSMs of one statement with at least this many terms use the bucket method (pippenger.cuh);
+  int pass_streams = 2;   // verify passes of a big batch alternate between this many streams (GS_PASS_STREAMS = 1 | 2)
+  int prep_variant = 5;   // resident blocks per SM the line-walk kernel is compiled for (GS_PREP_VARIANT = 4 | 5, experiments)
+  size_t pip_min = 2048;  // proof MSMs of one statement with at least this many terms use the bucket method (pippenger.cuh);
   int pip_c = 0;          // measured crossover, DESIGN.md §4.  Overrides for experiments: GS_PIP_MIN, GS_PIP_C (window bits)
   std::string err;
 };
@@ -92,8 +94,10 @@ struct gs_ctx {
 // stream-ordered scratch with RAII release
 struct Scratch {
   gs_ctx* ctx;
+  cudaStream_t home;  // the stream that was current at construction: everything is released there (stream-ordered), also
+                      // when ctx->stream has been switched back by then (passes that alternate between two streams)
   std::vector<void*> ptrs;
-  explicit Scratch(gs_ctx* c) : ctx(c) {}
+  explicit Scratch(gs_ctx* c) : ctx(c), home(c->stream) {}
   template <class T>
   cudaError_t alloc(T** p, size_t count) {
     void* q = nullptr;
@@ -103,8 +107,31 @@ struct Scratch {
     return e;
   }
   ~Scratch() {
-    for (void* q : ptrs) cudaFreeAsync(q, ctx->stream);
+    for (void* q : ptrs) cudaFreeAsync(q, home);
   }
+};
+// orders `main_s` after everything queued on `other` so far, on every exit path of the scope
+struct StreamJoin {
+  cudaStream_t main_s, other;
+  bool on;
+  ~StreamJoin() {
+    if (!on) return;
+    cudaEvent_t j;
+    if (cudaEventCreateWithFlags(&j, cudaEventDisableTiming) != cudaSuccess) {
+      cudaStreamSynchronize(other);
+      return;
+    }
+    cudaEventRecord(j, other);
+    cudaStreamWaitEvent(main_s, j, 0);
+    cudaEventDestroy(j);
+  }
+};
+// restores ctx->stream on every exit path of a function that switches it
+struct StreamGuard {
+  gs_ctx* ctx;
+  cudaStream_t saved;
+  explicit StreamGuard(gs_ctx* c) : ctx(c), saved(c->stream) {}
+  ~StreamGuard() { ctx->stream = saved; }
 };
 
 template <class T>

@@ -80,8 +80,8 @@ struct g2_pts_list {  // the fixed points Q_i of one thread (read again at the 5
     Y = q[i]->y;
   }
 };
-template <int E>
-__global__ void __launch_bounds__(128, E == 1 ? 2 : 5) k_g2_prepare4(const uint32_t* __restrict__ PW, const g2_aff* __restrict__ Y,
+template <int E, int MINB>
+__global__ void __launch_bounds__(128, MINB) k_g2_prepare4(const uint32_t* __restrict__ PW, const g2_aff* __restrict__ Y,
                                                         uint32_t* __restrict__ tiles, uint32_t* __restrict__ masks,
                                                         size_t nprob, size_t p0, size_t np, int K, int S,
                                                         const uint32_t* __restrict__ walk, int nwalk) {
@@ -630,9 +630,11 @@ int gsi::run_pairing_product(gs_ctx* ctx, Scratch& sc, const g1_aff* X, const g2
       CUDA_TRY(cudaStreamWaitEvent(ctx->stream, wa->done, 0));
       LAUNCH(k_eval_tiles, (size_t)nwalk * np, PW, Y, wa->lines, tiles, masks, nprob, np, K, S, dwalk, nwalk);
     } else if ((size_t)((nwalk + 3) / 4) * np < 16384)
-      LAUNCH_CFG(k_g2_prepare4<1>, (size_t)nwalk * np, 128, 0, PW, Y, tiles, masks, nprob, p0, np, K, S, dwalk, nwalk);
+      LAUNCH_CFG((k_g2_prepare4<1, 2>), (size_t)nwalk * np, 128, 0, PW, Y, tiles, masks, nprob, p0, np, K, S, dwalk, nwalk);
+    else if (ctx->prep_variant == 4)
+      LAUNCH_CFG((k_g2_prepare4<4, 4>), (size_t)((nwalk + 3) / 4) * np, 128, 0, PW, Y, tiles, masks, nprob, p0, np, K, S, dwalk, nwalk);
     else
-      LAUNCH_CFG(k_g2_prepare4<4>, (size_t)((nwalk + 3) / 4) * np, 128, 0, PW, Y, tiles, masks, nprob, p0, np, K, S, dwalk, nwalk);
+      LAUNCH_CFG((k_g2_prepare4<4, 5>), (size_t)((nwalk + 3) / 4) * np, 128, 0, PW, Y, tiles, masks, nprob, p0, np, K, S, dwalk, nwalk);
     LAUNCH_CFG(k_miller4, ((nblk + CQ_GROUPS - 1) / CQ_GROUPS) * CQ_BLOCK_THREADS, CQ_BLOCK_THREADS, CQ_GROUPS * M4_SMEM, tiles, masks,
                F, nprob, p0, np, S, nchunk, nblk);
   }

@@ -133,7 +133,13 @@ inline GS_HD GS_NOINL void g2_add_step(g2_proj& t, const g2_aff& q, line_coeffs&
 // lets them share instruction-cache lines) and a no-op in the tests.
 // The walk is latency- and I-cache-sensitive (few warps per SM, every warp at its own place in a long loop
 // body), so the field products are single out-of-line copies: the loop body stays ~3k instructions.
-inline GS_HD GS_NOINL void fp_mul_n(fp& r, const fp& a, const fp& b) { fp::mul(r, a, b); }
+// (operands and result by value: they stay in registers across the call, see FpOps::mul_v)
+inline GS_HD GS_NOINL fp fp_mul_v(fp a, fp b) {
+  fp r;
+  fp::mul(r, a, b);
+  return r;
+}
+GS_HD GS_INL void fp_mul_n(fp& r, const fp& a, const fp& b) { r = fp_mul_v(a, b); }
 inline GS_HD GS_NOINL void fp2_mul_n(fp2& r, const fp2& a, const fp2& b) {
   fp t0, t1, t2, s0, s1;
   fp::add(s0, a.c0, a.c1);

@@ -139,7 +139,15 @@ struct FpOps {
   // ONE out-of-line copy of the Montgomery product for all G1 curve formulas: doubling + mixed addition are ~13 KB of
   // code instead of ~130 KB, so the loop body of the thread-per-point kernels fits the 32 KB L1.5 instruction cache
   // instead of streaming from L2 (k_vmsm_partial: 13 % "no instruction" stalls, 94.6 -> 80.4 ms once compact).
-  GS_HD static GS_NOINL void mul(fp& r, const fp& a, const fp& b) { fp::mul(r, a, b); }
+  // ONE out-of-line copy of the product per kernel (instruction footprint) with operands and result
+  // passed BY VALUE: the device ABI then keeps all 36 limbs in registers across the call, where references forced the
+  // caller to park the operands in local memory and the callee to load them (36 LDL + 12 STL per product)
+  GS_HD static GS_NOINL fp mul_v(fp a, fp b) {
+    fp r;
+    fp::mul(r, a, b);
+    return r;
+  }
+  GS_HD static GS_INL void mul(fp& r, const fp& a, const fp& b) { r = mul_v(a, b); }
   GS_HD static GS_INL void sqr(fp& r, const fp& a) { mul(r, a, a); }
   GS_HD static GS_INL void inv(fp& r, const fp& a) { fp_inv(r, a); }
   GS_HD static GS_INL void set_one(fp& r) { fp_one(r); }

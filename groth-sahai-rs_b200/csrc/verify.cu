@@ -348,7 +348,7 @@ __global__ void __launch_bounds__(128) k_jac_to_affine_blocks(const g1_jac* __re
   }
 }
 // thread -> (p, jj, a, chunk): same outputs as k_vmsm_partial, bases looked up in the shared tables
-__global__ void __launch_bounds__(128) k_vmsm_wsum(verify_shape s, verify_args v, const g1_aff* __restrict__ tab,
+__global__ void __launch_bounds__(128, 4) k_vmsm_wsum(verify_shape s, verify_args v, const g1_aff* __restrict__ tab,
                                                    g1_jac* __restrict__ part, size_t nprob, wt_geom g) {
   size_t id = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int n_own = s.n_out_owned();  // sharded statement: the other outputs' Miller pairs run on other ranks
@@ -556,8 +556,26 @@ static int verify_impl(gs_ctx* ctx, int type, size_t count, size_t m, size_t n, 
     if (rcl) return rcl;
   }
   const int Ko = world > 1 ? (s.K - rank + world - 1) / world : s.K;  // slots this rank owns
-  for (size_t off = 0; off < count; off += ctx->verify_batch_max) {
+  // A batch that needs several passes alternates them between the context's two streams: the passes are independent,
+  // so whenever a kernel of one pass leaves SMs idle (the partial last wave of the MSM, a line walk that fills 3/4 of a
+  // wave, kernel boundaries) blocks of the other pass take them.  Everything is joined back into gs_stream() at the end.
+  const bool pipelined = count > ctx->verify_batch_max && ctx->pass_streams == 2 && !ctx->profile;  // (per-kernel event times need one stream)
+  StreamGuard guard(ctx);
+  cudaStream_t pass_stream[2] = {ctx->stream, ctx->stream};
+  if (pipelined) {
+    if (!ctx->stream2) CUDA_TRY(cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking));
+    pass_stream[1] = ctx->stream2;
+    cudaEvent_t fork;
+    CUDA_TRY(cudaEventCreateWithFlags(&fork, cudaEventDisableTiming));
+    cudaEventRecord(fork, pass_stream[0]);
+    cudaStreamWaitEvent(pass_stream[1], fork, 0);  // the inputs (uploaded / produced on the main stream) are complete
+    cudaEventDestroy(fork);
+  }
+  StreamJoin join{pass_stream[0], pass_stream[1], pipelined};  // the main stream is ordered after the second one on every exit path
+  size_t pass = 0;
+  for (size_t off = 0; off < count; off += ctx->verify_batch_max, pass++) {
     size_t nprob = count - off < ctx->verify_batch_max ? count - off : ctx->verify_batch_max;
+    ctx->stream = pass_stream[pass & 1];
     Scratch sc(ctx);
     verify_args v;
     v.a_consts = (const char*)a_consts + off * n * elem_size_A(type);
@@ -712,35 +730,54 @@ static int verify_host(gs_ctx* ctx, int type, size_t count, size_t m, size_t n, 
   if (!a_consts || !b_consts || !gamma || !target || !xcoms || !ycoms || !pi || !theta || (!out_ok && !out_partial)) return GS_EARG;
   CUDA_TRY(cudaSetDevice(ctx->device));
   verify_shape s = make_verify_shape(type, (int)m, (int)n);
-  Scratch sc(ctx);
-  uint8_t *dA, *dB, *dT, *dok = nullptr;
-  fp12* dpart = nullptr;
-  fr* dG;
-  g1_aff *dc, *dth;
-  g2_aff *dd, *dpi;
-  CUDA_TRY(upload(ctx, sc, &dA, a_consts, count * n * elem_size_A(type)));
-  CUDA_TRY(upload(ctx, sc, &dB, b_consts, count * m * elem_size_B(type)));
-  CUDA_TRY(upload(ctx, sc, &dG, gamma, count * m * n));
-  CUDA_TRY(upload(ctx, sc, &dT, target, count * elem_size_T(type)));
-  CUDA_TRY(upload(ctx, sc, &dc, xcoms, count * m * 2));
-  CUDA_TRY(upload(ctx, sc, &dd, ycoms, count * n * 2));
-  CUDA_TRY(upload(ctx, sc, &dpi, pi, count * s.cx * 2));
-  CUDA_TRY(upload(ctx, sc, &dth, theta, count * s.cy * 2));
-  if (out_ok)
-    CUDA_TRY(sc.alloc(&dok, count));
-  else
-    CUDA_TRY(sc.alloc(&dpart, count * 4));
   // a batch of equations over ONE set of x-commitments (a multi-equation statement): detected on the host copy
   bool shared_x = count > 1;
   for (size_t i = 1; i < count && shared_x; i++)
     shared_x = memcmp(xcoms, (const char*)xcoms + i * m * sizeof(gs_com1), m * sizeof(gs_com1)) == 0;
-  int rc = verify_impl(ctx, type, count, m, n, dA, dB, (const gs_fr*)dG, dT, (const gs_com1*)dc, (const gs_com2*)dd,
-                       (const gs_com2*)dpi, (const gs_com1*)dth, rank, world, dok, dpart, shared_x);
-  if (rc) return rc;
-  if (out_ok)
-    CUDA_TRY(cudaMemcpyAsync(out_ok, dok, count, cudaMemcpyDeviceToHost, ctx->stream));
-  else
-    CUDA_TRY(cudaMemcpyAsync(out_partial, dpart, count * 4 * sizeof(fp12), cudaMemcpyDeviceToHost, ctx->stream));
+  // Passes of verify_batch_max instances; with two pass streams the H2D copies of pass i + 1 run under the kernels of
+  // pass i (pinned host buffers; pageable ones are staged by the driver and serialise on the host side).
+  const size_t B = ctx->verify_batch_max;
+  const bool pipelined = count > B && ctx->pass_streams == 2 && !ctx->profile && !shared_x;
+  const size_t step = pipelined ? B : count;
+  {
+    StreamGuard guard(ctx);
+    cudaStream_t pass_stream[2] = {ctx->stream, ctx->stream};
+    if (pipelined) {
+      if (!ctx->stream2) CUDA_TRY(cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking));
+      pass_stream[1] = ctx->stream2;
+    }
+    StreamJoin join{pass_stream[0], pass_stream[1], pipelined};
+    size_t pass = 0;
+    for (size_t off = 0; off < count; off += step, pass++) {
+      const size_t cnt = count - off < step ? count - off : step;
+      ctx->stream = pass_stream[pass & 1];
+      Scratch sc(ctx);
+      uint8_t *dA, *dB, *dT, *dok = nullptr;
+      fp12* dpart = nullptr;
+      fr* dG;
+      g1_aff *dc, *dth;
+      g2_aff *dd, *dpi;
+      CUDA_TRY(upload(ctx, sc, &dA, (const char*)a_consts + off * n * elem_size_A(type), cnt * n * elem_size_A(type)));
+      CUDA_TRY(upload(ctx, sc, &dB, (const char*)b_consts + off * m * elem_size_B(type), cnt * m * elem_size_B(type)));
+      CUDA_TRY(upload(ctx, sc, &dG, gamma + off * m * n, cnt * m * n));
+      CUDA_TRY(upload(ctx, sc, &dT, (const char*)target + off * elem_size_T(type), cnt * elem_size_T(type)));
+      CUDA_TRY(upload(ctx, sc, &dc, xcoms + off * m, cnt * m * 2));
+      CUDA_TRY(upload(ctx, sc, &dd, ycoms + off * n, cnt * n * 2));
+      CUDA_TRY(upload(ctx, sc, &dpi, pi + off * s.cx, cnt * s.cx * 2));
+      CUDA_TRY(upload(ctx, sc, &dth, theta + off * s.cy, cnt * s.cy * 2));
+      if (out_ok)
+        CUDA_TRY(sc.alloc(&dok, cnt));
+      else
+        CUDA_TRY(sc.alloc(&dpart, cnt * 4));
+      int rc = verify_impl(ctx, type, cnt, m, n, dA, dB, (const gs_fr*)dG, dT, (const gs_com1*)dc, (const gs_com2*)dd,
+                           (const gs_com2*)dpi, (const gs_com1*)dth, rank, world, dok, dpart, shared_x);
+      if (rc) return rc;
+      if (out_ok)
+        CUDA_TRY(cudaMemcpyAsync(out_ok + off, dok, cnt, cudaMemcpyDeviceToHost, ctx->stream));
+      else
+        CUDA_TRY(cudaMemcpyAsync(out_partial + off * 4, dpart, cnt * 4 * sizeof(fp12), cudaMemcpyDeviceToHost, ctx->stream));
+    }
+  }
   CUDA_TRY(cudaStreamSynchronize(ctx->stream));
   return GS_OK;
 }

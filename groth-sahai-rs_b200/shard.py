@@ -223,3 +223,43 @@ def verify_statement_base_sharded(engine, ty, count, m, n, arrays, rank, world, 
     a, b, gamma, target, xc, yc, pi, th = arrays
     rows = gamma_rows_of(gamma, count, m, n, rank, world)
     return engine.verify_sharded(ty, count, m, n, a, b, rows, target, xc, yc, pi, th, rank, world, make_allgather(device, group))
+
+
+# ---------------------------------------------------------------- one large statement: prove split by y-variable block
+def prove_statement_sharded(prove_local, com2_sum, com1_sum, ty: int, m: int, n: int, arrays: Sequence, rank: int, world: int,
+                            group=None, device="cpu") -> Tuple[bytes, bytes]:
+    """Provable::prove (prove.rs:92-488) of ONE statement with the y-variables (the columns of Gamma) split contiguously
+    across ranks.  Both proof elements are linear in the statement: rank r proves the SUB-statement
+        (A[J_r], B', Gamma[:, J_r]) over all x-variables and the y-variables J_r,  B' = B and T' = T on rank 0, zero elsewhere
+    with the ordinary single-GPU call, and  pi = sum_r pi^(r),  theta = sum_r theta^(r)  entry-wise in Com2 / Com1
+    ("gather <= 4 partial sums per GPU, add, normalise").  A rank uploads 1 / world of Gamma.
+    arrays = (a_consts, b_consts, gamma, xvars, yvars, x_rand, y_rand, pf_rand) as gs_prove takes them;
+    `prove_local(ty, m, n_r, a, b, gamma, x, y, xr, yr, T) -> (pi, theta)` is Engine.prove; `com2_sum(list_bytes) -> bytes`
+    and `com1_sum` add Com elements (Engine.group_sum).  Every rank returns the full proof."""
+    import numpy as np
+    a, b, gamma, xv, yv, xr, yr, T = arrays
+    gx, gy = ty in (0, 1), ty in (0, 2)
+    asz, bsz, cx, cy = (96 if gx else 32), (192 if gy else 32), (2 if gx else 1), (2 if gy else 1)
+    lo, hi = shard_range(n, rank, world)
+    nr = hi - lo
+    if nr > 0:
+        g = np.frombuffer(gamma, dtype=np.uint8).reshape(m, n * 32)[:, lo * 32:hi * 32]
+        zero_b = bytes(len(b)) if rank else b                # identity points / zero scalars: those terms vanish
+        zero_t = bytes(len(T)) if rank else T
+        pi, th = prove_local(ty, m, nr, a[lo * asz:hi * asz], zero_b, np.ascontiguousarray(g).tobytes(), xv, yv[lo * bsz:hi * bsz], xr,
+                             yr[lo * cy * 32:hi * cy * 32], zero_t)
+    else:
+        pi, th = bytes(cx * 384), bytes(cy * 192)            # a rank without a column contributes the identity
+    if world == 1:
+        return pi, th
+    import torch
+    import torch.distributed as dist
+    mine = _to_tensor(pi + th, device)
+    parts = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(parts, mine, group=group)
+    parts = [bytes(p.cpu().numpy().tobytes()) for p in parts]
+    pis = [p[:cx * 384] for p in parts]
+    ths = [p[cx * 384:] for p in parts]
+    out_pi = b"".join(com2_sum(b"".join(q[i * 384:(i + 1) * 384] for q in pis)) for i in range(cx))
+    out_th = b"".join(com1_sum(b"".join(q[i * 192:(i + 1) * 192] for q in ths)) for i in range(cy))
+    return out_pi, out_th

@@ -12,8 +12,14 @@ SO = os.path.join(HERE, "hostsim", "libhostsim.so")
 
 @pytest.fixture(scope="module")
 def L():
+    """g++ build of the device headers for the host (~3 min of template-heavy code): rebuilt only when a source is newer
+    than the cached library."""
     src = os.path.join(HERE, "hostsim", "hostsim.cpp")
-    subprocess.check_call(["g++", "-O2", "-std=c++17", "-frounding-math", "-shared", "-fPIC", "-I", os.path.join(HERE, "..", "groth-sahai-rs_b200", "csrc"), "-o", SO, src])
+    csrc = os.path.join(HERE, "..", "groth-sahai-rs_b200", "csrc")
+    exp = os.path.join(HERE, "..", "tools", "experimental")
+    deps = [src] + [os.path.join(d, f) for d in (csrc, exp) for f in os.listdir(d) if f.endswith((".cuh", ".h"))]
+    if not os.path.exists(SO) or os.path.getmtime(SO) < max(os.path.getmtime(d) for d in deps):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-frounding-math", "-shared", "-fPIC", "-I", csrc, "-o", SO, src])
     return ctypes.CDLL(SO)
 
 

@@ -247,3 +247,60 @@ def test_allgather_callback_gloo():
     want = b"".join(bytes((r * 17 + i) & 0xff for i in range(96 * 5)) for r in range(world))
     for _, got in res:
         assert got == want
+
+
+# ---------------------------------------------------------------- one statement: prove split by y-variable block
+def _prove_worker(rank, world, port, ty, q):
+    """Per-rank prover and the Com sums are the C oracle / big-int oracle on the CPU; under test: the sub-statement
+    construction (column block of Gamma, B and T only on rank 0) and the gather + sum."""
+    import torch.distributed as dist
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    sys.path.insert(0, ROOT)
+    from bigcase import Case, cb, make_crs
+    from conv import com1_b, com1_i, com2_b, com2_i
+    from oracle import gs as ogs
+    sh = _load_shard()
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    try:
+        m, n = 3, 4
+        c = Case(ty, m, n, make_crs(1)[0], seed=1400 + ty, prove=False)
+
+        def prove_local(t, mm, nn, a, b, g, x, y, xr, yr, T):
+            return cb.prove(t, mm, nn, a, b, g, x, y, xr, yr, T, c.crsb)
+
+        def csum(conv_i, conv_b, add, size):
+            def f(blob):
+                acc = conv_i(blob[:size])
+                for o in range(size, len(blob), size):
+                    acc = add(acc, conv_i(blob[o:o + size]))
+                return conv_b(acc)
+            return f
+
+        pi, th = sh.prove_statement_sharded(prove_local, csum(com2_i, com2_b, ogs.com2_add, 384), csum(com1_i, com1_b, ogs.com1_add, 192),
+                                            ty, m, n, c.prove_args(), rank, world)
+        q.put((rank, pi, th))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,ty", [(2, 0), (3, 1), (5, 2), (2, 3)])
+def test_prove_statement_sharded_gloo(world, ty):
+    import torch.multiprocessing as mp
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from bigcase import Case, make_crs
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_prove_worker, args=(r, world, port, ty, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=300) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    want = Case(ty, 3, 4, make_crs(1)[0], seed=1400 + ty)     # the unsharded reference-order proof
+    for rank, pi, th in res:
+        assert pi == want.pi and th == want.theta, rank
