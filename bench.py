@@ -409,6 +409,18 @@ def bench_c3_sharded(R_, eng, size, steps):
     prof = profiled(eng, lambda: sharded_verify(arrs))
     ms_prove = R_.wall_ms(lambda: eng.prove(0, m, n, A, B, G, X, Y, xr, yr, Tr), steps)
     prof_p = profiled(eng, lambda: eng.prove(0, m, n, A, B, G, X, Y, xr, yr, Tr))
+    cpu_prove = None
+    if R_.rank == 0 and R_.world == 1 and m <= 1024:     # the reference-order CPU prover on the same statement (outside any timing)
+        try:
+            from oracle import cbaseline as cb
+            t0 = time.perf_counter()
+            p_, t_ = cb.prove(0, m, n, A, B, G, X, Y, xr, yr, Tr, crs_bytes(crs), cb.host_cores())
+            cpu_prove = {"prove_ms": round((time.perf_counter() - t0) * 1e3, 1), "cores": cb.host_cores(), "kind": "port",
+                         "proof_bytes_equal_gpu": bool(p_ == pi and t_ == th),
+                         "note": "C restatement, scalar multiplications of each left_mul spread over host threads "
+                                 "(the reference itself runs <= 2 Rayon tasks in prove)"}
+        except Exception as ex:  # noqa: BLE001
+            cpu_prove = {"error": str(ex)}
     pairs = 4 * n + 2 * m + 16
     h2d = sum(len(a) for a in arrs) - len(G) + len(G) // R_.world
     return {"workload": f"C3: one PPE, m=n={m}, dense Gamma (BASELINE.json configs[2]); gs_verify_sharded x{R_.world}: statement MSM "
@@ -417,7 +429,7 @@ def bench_c3_sharded(R_, eng, size, steps):
             "scaling": "strong", "n_gpus": R_.world, "verify_ms": round(ms, 3), "verifies_per_sec": round(1e3 / ms, 2),
             "verify_ms_split_by_slot_only": round(ms_slot, 3),
             "miller_pairs_per_verify": pairs, "pairings_per_sec": round(pairs / (ms * 1e-3), 1),
-            "prove_ms_one_gpu": round(ms_prove, 3), "h2d_bytes_per_rank": h2d, "instance_build_s": round(build_s, 1),
+            "prove_ms_one_gpu": round(ms_prove, 3), "cpu_prove": cpu_prove, "h2d_bytes_per_rank": h2d, "instance_build_s": round(build_s, 1),
             "rank0_verify_kernels": prof, "rank0_prove_kernels": prof_p,
             "limiter": f"per-rank latency floors (one dependent chain each), not NCCL: {top_kernels(prof, 4)}; "
                        f"H2D per rank {h2d >> 20} MiB",
