@@ -45,6 +45,9 @@ struct gs_ctx {
   std::vector<prof_rec> prof;
   size_t verify_batch_max = 23680;  // problems per verify pass (10 waves of k_miller4)
   size_t tile_budget = (size_t)16 << 30;  // bytes of HBM for the evaluated-line tiles of one pairing pass
+  size_t split_min = 4736;  // a batch between this size (2 waves of k_miller4) and one pass is still cut in two, one half per
+                            // stream, so that partial waves of one half are filled by the other (GS_SPLIT_MIN; 0 = never)
+  bool in_pass = false;     // set by a caller that already cut the batch into passes (verify_host): no second split inside
   int pass_streams = 2;   // verify passes of a big batch alternate between this many streams (GS_PASS_STREAMS = 1 | 2)
   int prep_variant = 5;   // resident blocks per SM the line-walk kernel is compiled for (GS_PREP_VARIANT = 4 | 5, experiments)
   size_t pip_min = 2048;  // proof MSMs of one statement with at least this many terms use the bucket method (pippenger.cuh);
@@ -126,6 +129,15 @@ struct StreamJoin {
     cudaEventDestroy(j);
   }
 };
+// instances per verify pass: verify_batch_max for big batches; half of a medium batch (two streams fill each other's
+// partial waves -- the strong-scaling regime of C5: 8,192 proofs per GPU are 3.46 waves of k_miller4); else everything
+static inline size_t verify_pass_size(const gs_ctx* ctx, size_t count, bool shared_x) {
+  if (ctx->in_pass) return count;
+  if (count > ctx->verify_batch_max) return ctx->verify_batch_max;
+  if (ctx->pass_streams == 2 && !ctx->profile && !shared_x && ctx->split_min && count >= ctx->split_min)
+    return (((count + 1) / 2) + 31) / 32 * 32;
+  return count;
+}
 // restores ctx->stream on every exit path of a function that switches it
 struct StreamGuard {
   gs_ctx* ctx;

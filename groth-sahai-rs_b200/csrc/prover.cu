@@ -3,6 +3,7 @@
 // Reference: src/generator.rs:81-118, src/prover/commit.rs:78-256, src/prover/prove.rs:92-488,
 // src/data_structures.rs:645-742 / 768-913.
 #include "ctx.h"
+#include "endo.cuh"
 
 using namespace gs;
 
@@ -18,35 +19,54 @@ struct crs_gen_out {
   g1_aff p1, q1, u1, v1;
   g2_aff p2, q2, u2, v2;
 };
-// generator.rs:96-109: q1 = a1 p1, u1 = t1 p1, v1 = t1 q1 = (t1 a1) p1 ; same on G2.   6 threads.
-__global__ void k_crs_generate(const crs_gen_in* in, crs_gen_out* out) {
-  int t = threadIdx.x;
-  if (blockIdx.x != 0 || t >= 6) return;
-  fr s;
-  if (t == 0 || t == 3) s = (t == 0) ? in->a1 : in->a2;
-  if (t == 1 || t == 4) s = (t == 1) ? in->t1 : in->t2;
-  if (t == 2) fr::mul(s, in->a1, in->t1);
-  if (t == 5) fr::mul(s, in->a2, in->t2);
-  uint32_t k[8];
-  fr_from_mont(k, s);
+// generator.rs:96-109: q1 = a1 p1, u1 = t1 p1, v1 = t1 q1 = (t1 a1) p1 ; same on G2.
+// Six scalar multiplications, each split along the group's endomorphism (endo.cuh: 2 x 128-bit parts on G1, 4 x 64-bit on
+// G2) so that the serial chain is 32 / 16 windows instead of 64: thread t < 6 -> G1 product t / 2, part t % 2;
+// thread 6 + t (t < 12) -> G2 product t / 4, part t % 4.  The parts are summed and normalised by thread 0 of each product.
+__global__ void __launch_bounds__(32) k_crs_generate(const crs_gen_in* in, crs_gen_out* out) {
+  __shared__ g1_jac p1s[6];
+  __shared__ g2_jac p2s[12];
+  const int t = threadIdx.x;
+  if (blockIdx.x != 0) return;
+  if (t < 18) {
+    const bool g1side = t < 6;
+    const int prod = g1side ? t / 2 : (t - 6) / 4, part = g1side ? t % 2 : (t - 6) % 4;
+    fr s;
+    if (prod == 0) s = g1side ? in->a1 : in->a2;
+    if (prod == 1) s = g1side ? in->t1 : in->t2;
+    if (prod == 2) {
+      if (g1side)
+        fr::mul(s, in->a1, in->t1);
+      else
+        fr::mul(s, in->a2, in->t2);
+    }
+    uint32_t k[8];
+    fr_from_mont(k, s);
+    if (g1side)
+      EndoSplit<FpOps>::part(p1s[t], in->p1, k, part);
+    else
+      EndoSplit<Fp2Ops>::part(p2s[t - 6], in->p2, k, part);
+  }
+  __syncthreads();
   if (t < 3) {
-    g1_jac j;
-    scalar_mul<FpOps>(j, in->p1, k);
+    g1_jac j = p1s[2 * t];
+    g1_jac::add(j, j, p1s[2 * t + 1]);
     g1_aff a;
     g1_jac::to_affine(a, j);
     if (t == 0) out->q1 = a;
     if (t == 1) out->u1 = a;
     if (t == 2) out->v1 = a;
     if (t == 0) out->p1 = in->p1;
-  } else {
-    g2_jac j;
-    scalar_mul<Fp2Ops>(j, in->p2, k);
+  } else if (t >= 6 && t < 9) {
+    const int q = t - 6;
+    g2_jac j = p2s[4 * q];
+    for (int i = 1; i < 4; i++) g2_jac::add(j, j, p2s[4 * q + i]);
     g2_aff a;
     g2_jac::to_affine(a, j);
-    if (t == 3) out->q2 = a;
-    if (t == 4) out->u2 = a;
-    if (t == 5) out->v2 = a;
-    if (t == 3) out->p2 = in->p2;
+    if (q == 0) out->q2 = a;
+    if (q == 1) out->u2 = a;
+    if (q == 2) out->v2 = a;
+    if (q == 0) out->p2 = in->p2;
   }
 }
 
@@ -199,7 +219,7 @@ int crs_generate_points(gs_ctx* ctx, const gs_g1* p1, const gs_g2* p2, const gs_
   crs_gen_out* dout;
   CUDA_TRY(upload(ctx, sc, &din, &hin, 1));
   CUDA_TRY(sc.alloc(&dout, 1));
-  LAUNCH(k_crs_generate, 6, din, dout);
+  LAUNCH_CFG(k_crs_generate, 32, 32, 0, din, dout);
   crs_gen_out hout;
   CUDA_TRY(cudaMemcpyAsync(&hout, dout, sizeof(hout), cudaMemcpyDeviceToHost, ctx->stream));
   CUDA_TRY(cudaStreamSynchronize(ctx->stream));

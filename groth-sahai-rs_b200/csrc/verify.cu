@@ -559,7 +559,8 @@ static int verify_impl(gs_ctx* ctx, int type, size_t count, size_t m, size_t n, 
   // A batch that needs several passes alternates them between the context's two streams: the passes are independent,
   // so whenever a kernel of one pass leaves SMs idle (the partial last wave of the MSM, a line walk that fills 3/4 of a
   // wave, kernel boundaries) blocks of the other pass take them.  Everything is joined back into gs_stream() at the end.
-  const bool pipelined = count > ctx->verify_batch_max && ctx->pass_streams == 2 && !ctx->profile;  // (per-kernel event times need one stream)
+  const size_t pass_n = verify_pass_size(ctx, count, shared_x);
+  const bool pipelined = count > pass_n && ctx->pass_streams == 2 && !ctx->profile;  // (per-kernel event times need one stream)
   StreamGuard guard(ctx);
   cudaStream_t pass_stream[2] = {ctx->stream, ctx->stream};
   if (pipelined) {
@@ -573,8 +574,8 @@ static int verify_impl(gs_ctx* ctx, int type, size_t count, size_t m, size_t n, 
   }
   StreamJoin join{pass_stream[0], pass_stream[1], pipelined};  // the main stream is ordered after the second one on every exit path
   size_t pass = 0;
-  for (size_t off = 0; off < count; off += ctx->verify_batch_max, pass++) {
-    size_t nprob = count - off < ctx->verify_batch_max ? count - off : ctx->verify_batch_max;
+  for (size_t off = 0; off < count; off += pass_n, pass++) {
+    size_t nprob = count - off < pass_n ? count - off : pass_n;
     ctx->stream = pass_stream[pass & 1];
     Scratch sc(ctx);
     verify_args v;
@@ -736,7 +737,7 @@ static int verify_host(gs_ctx* ctx, int type, size_t count, size_t m, size_t n, 
     shared_x = memcmp(xcoms, (const char*)xcoms + i * m * sizeof(gs_com1), m * sizeof(gs_com1)) == 0;
   // Passes of verify_batch_max instances; with two pass streams the H2D copies of pass i + 1 run under the kernels of
   // pass i (pinned host buffers; pageable ones are staged by the driver and serialise on the host side).
-  const size_t B = ctx->verify_batch_max;
+  const size_t B = verify_pass_size(ctx, count, shared_x);
   const bool pipelined = count > B && ctx->pass_streams == 2 && !ctx->profile && !shared_x;
   const size_t step = pipelined ? B : count;
   {
@@ -769,8 +770,10 @@ static int verify_host(gs_ctx* ctx, int type, size_t count, size_t m, size_t n, 
         CUDA_TRY(sc.alloc(&dok, cnt));
       else
         CUDA_TRY(sc.alloc(&dpart, cnt * 4));
+      ctx->in_pass = pipelined;  // this loop IS the pass loop: verify_impl must not cut a pass in two again
       int rc = verify_impl(ctx, type, cnt, m, n, dA, dB, (const gs_fr*)dG, dT, (const gs_com1*)dc, (const gs_com2*)dd,
                            (const gs_com2*)dpi, (const gs_com1*)dth, rank, world, dok, dpart, shared_x);
+      ctx->in_pass = false;
       if (rc) return rc;
       if (out_ok)
         CUDA_TRY(cudaMemcpyAsync(out_ok + off, dok, cnt, cudaMemcpyDeviceToHost, ctx->stream));
