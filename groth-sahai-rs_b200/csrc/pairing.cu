@@ -347,7 +347,11 @@ __global__ void __launch_bounds__(CQ_BLOCK_THREADS, 1) k_miller4(const uint32_t*
   uint16_t* slots = (uint16_t*)(smask + M4_MAXS);
   int* nact_s = (int*)(slots + M4_MAXS);
   const int k = tg >> 5, lane = tg & 31;
-  const size_t bid = (size_t)blockIdx.x * CQ_GROUPS + grp;
+  // The two groups of a block take ComT entries of EQUAL work: entries (a, 0) carry fewer slots than (a, 1) (the iota_2
+  // images have no first coordinate: 8 against 12 pairs per 4x4 PPE proof), and a block that paired entry 0 with entry 1
+  // ran its last third with one group = 6 warps.  Block q -> accumulator block q / 2, entries (q & 1) and (q & 1) + 2.
+  static_assert(CQ_GROUPS == 2, "entry pairing below assumes two groups per block");
+  const size_t bid = ((size_t)blockIdx.x >> 1) * 4 + (blockIdx.x & 1) + 2 * (size_t)grp;
   if (bid >= ngroups) return;
   if (tg == 0) {
     int n = 0;
