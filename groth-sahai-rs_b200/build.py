@@ -37,7 +37,14 @@ def _stale(target, deps):
 
 
 def build(force=False, verbose=False):
+    """GS_EXTRA_NVCC_FLAGS (e.g. "-DGS_FP2_INLINE") and GS_LIB_OUT (output path) build experiment variants beside the product."""
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    extra = os.environ.get("GS_EXTRA_NVCC_FLAGS", "").split()
+    global OBJ, OUT
+    if os.environ.get("GS_LIB_OUT"):
+        OUT = os.path.abspath(os.environ["GS_LIB_OUT"])
+        OBJ = OUT + ".objs"
+        force = True
     os.makedirs(OBJ, exist_ok=True)
     hdrs = _headers()
     jobs = []
@@ -46,7 +53,7 @@ def build(force=False, verbose=False):
         obj = os.path.join(OBJ, src.replace(".cu", ".o"))
         objs.append(obj)
         if force or _stale(obj, hdrs + [os.path.join(CSRC, src)]):
-            jobs.append([nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", "-o", obj, src])
+            jobs.append([nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", "-o", obj, src])
     if jobs:
         def run(cmd):
             r = subprocess.run(cmd, cwd=CSRC, capture_output=True, text=True)

@@ -47,6 +47,8 @@ struct gs_ctx {
   size_t tile_budget = (size_t)16 << 30;  // bytes of HBM for the evaluated-line tiles of one pairing pass
   size_t split_min = 4736;  // a batch between this size (2 waves of k_miller4) and one pass is still cut in two, one half per
                             // stream, so that partial waves of one half are filled by the other (GS_SPLIT_MIN; 0 = never)
+  int lone_walk_jac = 1;    // lone statements walk their G2 points in Jacobian coordinates + one batched inversion
+                            // (GS_LONE_WALK_JAC = 0: the affine walk with an inversion per step)
   bool in_pass = false;     // set by a caller that already cut the batch into passes (verify_host): no second split inside
   int pass_streams = 2;   // verify passes of a big batch alternate between this many streams (GS_PASS_STREAMS = 1 | 2)
   int prep_variant = 5;   // resident blocks per SM the line-walk kernel is compiled for (GS_PREP_VARIANT = 4 | 5, experiments)

@@ -278,6 +278,138 @@ __global__ void __launch_bounds__(128, 2) k_g2_walk(const g2_aff* __restrict__ Y
     }
   }
 }
+// ---- the same walk WITHOUT a field inversion per step (lone statements are pure latency: the affine walk above is 68
+// dependent steps of ~60 us, two thirds of it the per-step inversion).  The point runs in Jacobian coordinates; with
+// x = X / Z^2, y = Y / Z^3 both kinds of step have their slope over the NEW Z coordinate:
+//     doubling   lam = 3 x^2 / 2 y = 3 X^2 / (2 Y Z)        = N / Z',   Z' = 2 Y Z         (dbl-2009-l)
+//     addition   lam = (y_Q - y_T) / (x_Q - x_T) = r / (Z H) = N / Z',   Z' = Z H           (H = x_Q Z^2 - X, r = y_Q Z^3 - Y)
+// so the walk only records (N, X, Y) of the point before the step and Z' (k_g2_walk_jac, one thread per point, ~1 ms),
+// and ONE batched inversion of the 68 Z' per point gives every lam and mu = lam x_T - y_T afterwards, all 68 steps in
+// parallel (k_g2_lines_from_jac, one block per point).  rec[((e*np + pl)*68 + step)*4 + {0: N, 1: X, 2: Y, 3: Z'}].
+__global__ void __launch_bounds__(64) k_g2_walk_jac(const g2_aff* __restrict__ Y, fp2* __restrict__ rec, size_t nprob, size_t np, int K,
+                                                    const uint32_t* __restrict__ walk, int nwalk) {
+  size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= (size_t)nwalk * np) return;
+  const size_t pl = q % np;
+  const int e = (int)(q / np);
+  const uint32_t we = walk[e];
+  const int b = (int)(we >> 31), k = (int)(we & 0x7FFFFFFFu);
+  const g2_aff Q = Y[((size_t)b * K + k) * nprob + pl];
+  if (Q.is_inf()) return;  // k_eval_tiles drops the pair
+  fp2* out = rec + ((size_t)e * np + pl) * GS_NUM_LINES * 4;
+  fp2 X = Q.x, Yc = Q.y, Z;
+  Z.set_one();
+  int idx = 0;
+#pragma unroll 1
+  for (int bit = 62; bit >= 0; bit--) {
+    {  // doubling (a = 0): A = X^2, B = Y^2, C = B^2, D = 2((X+B)^2 - A - C), E = 3A, X3 = E^2 - 2D, Y3 = E(D - X3) - 8C, Z3 = 2YZ
+      fp2 A, B, C, D, E, F, t, Z3;
+      fp2::sqr(A, X);
+      fp2::sqr(B, Yc);
+      fp2::sqr(C, B);
+      fp2::add(t, X, B);
+      fp2::sqr(t, t);
+      fp2::sub(t, t, A);
+      fp2::sub(t, t, C);
+      fp2::dbl(D, t);
+      fp2::dbl(E, A);
+      fp2::add(E, E, A);
+      fp2::mul(t, Yc, Z);
+      fp2::dbl(Z3, t);
+      out[idx * 4 + 0] = E;
+      out[idx * 4 + 1] = X;
+      out[idx * 4 + 2] = Yc;
+      out[idx * 4 + 3] = Z3;
+      fp2::sqr(F, E);
+      fp2::sub(t, F, D);
+      fp2::sub(X, t, D);
+      fp2::sub(t, D, X);
+      fp2::mul(t, E, t);
+      fp2::dbl(C, C);
+      fp2::dbl(C, C);
+      fp2::dbl(C, C);
+      fp2::sub(Yc, t, C);
+      Z = Z3;
+      idx++;
+    }
+    if ((GS_X_ABS >> bit) & 1) {  // T + Q, Q affine
+      fp2 Z1Z1, U2, S2, H, r, HH, HHH, V, t, Z3;
+      fp2::sqr(Z1Z1, Z);
+      fp2::mul(U2, Q.x, Z1Z1);
+      fp2::mul(S2, Q.y, Z);
+      fp2::mul(S2, S2, Z1Z1);
+      fp2::sub(H, U2, X);
+      fp2::sub(r, S2, Yc);
+      fp2::mul(Z3, Z, H);
+      out[idx * 4 + 0] = r;
+      out[idx * 4 + 1] = X;
+      out[idx * 4 + 2] = Yc;
+      out[idx * 4 + 3] = Z3;
+      fp2::sqr(HH, H);
+      fp2::mul(HHH, H, HH);
+      fp2::mul(V, X, HH);
+      fp2::sqr(t, r);
+      fp2::sub(t, t, HHH);
+      fp2::sub(t, t, V);
+      fp2 X3;
+      fp2::sub(X3, t, V);
+      fp2::sub(t, V, X3);
+      fp2::mul(t, r, t);
+      fp2::mul(HHH, Yc, HHH);
+      fp2::sub(Yc, t, HHH);
+      X = X3;
+      Z = Z3;
+      idx++;
+    }
+  }
+}
+// block -> walked point (e, pl), thread s < 68 -> Miller step s: lines[((e*np + pl)*68 + s)*2 + {0: lam, 1: mu}]
+__global__ void __launch_bounds__(128) k_g2_lines_from_jac(const g2_aff* __restrict__ Y, const fp2* __restrict__ rec, fp2* __restrict__ lines,
+                                                           size_t nprob, size_t np, int K, const uint32_t* __restrict__ walk) {
+  __shared__ fp sm[2 * 128];
+  __shared__ fp2 zinv[GS_NUM_LINES + 1];
+  const size_t pt = blockIdx.x;  // e * np + pl
+  const size_t pl = pt % np;
+  const int e = (int)(pt / np);
+  const uint32_t we = walk[e];
+  const g2_aff* Q = &Y[((size_t)(we >> 31) * K + (we & 0x7FFFFFFFu)) * nprob + pl];
+  if (Q->x.is_zero() && Q->y.is_zero()) return;  // block-uniform
+  const int s = threadIdx.x;
+  const fp2* r = rec + (pt * GS_NUM_LINES + (s < GS_NUM_LINES ? s : 0)) * 4;
+  fp2 Zn;
+  fp nrm;
+  nrm.set_zero();
+  if (s < GS_NUM_LINES) {
+    Zn = r[3];
+    fp t;
+    fp::sqr(nrm, Zn.c0);
+    fp::sqr(t, Zn.c1);
+    fp::add(nrm, nrm, t);
+  }
+  block_batch_inv<128>(nrm, sm);  // 0 (idle threads) passes through
+  if (s < GS_NUM_LINES) {         // 1 / Z' = conj(Z') / |Z'|^2
+    fp2 zi;
+    fp::mul(zi.c0, Zn.c0, nrm);
+    fp::mul(zi.c1, Zn.c1, nrm);
+    fp::neg(zi.c1, zi.c1);
+    zinv[s + 1] = zi;
+  }
+  if (s == 0) zinv[0].set_one();
+  __syncthreads();
+  if (s >= GS_NUM_LINES) return;
+  fp2 lam, zi = zinv[s], zi2, x, y, mu;
+  fp2::mul(lam, r[0], zinv[s + 1]);
+  fp2::sqr(zi2, zi);
+  fp2::mul(x, r[1], zi2);
+  fp2::mul(zi2, zi2, zi);
+  fp2::mul(y, r[2], zi2);
+  fp2::mul(mu, lam, x);
+  fp2::sub(mu, mu, y);
+  fp2* o = lines + (pt * GS_NUM_LINES + s) * 2;
+  o[0] = lam;
+  o[1] = mu;
+}
+
 // thread -> (walk entry e, problem): the tiles of slot k, coordinate b from the lines walked ahead
 __global__ void __launch_bounds__(128) k_eval_tiles(const uint32_t* __restrict__ PW, const g2_aff* __restrict__ Y,
                                                     const fp2* __restrict__ lines, uint32_t* __restrict__ tiles,
@@ -534,8 +666,9 @@ int gsi::g2_walk_ahead(gs_ctx* ctx, Scratch& sc, const g2_aff* Y, size_t nprob, 
   if (nwalk == 0 || (size_t)((nwalk + 3) / 4) * nprob >= 16384) return GS_OK;
   if (!ctx->stream2) CUDA_TRY(cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking));
   CUDA_TRY(upload(ctx, sc, &wa->dwalk, hwalk.data(), hwalk.size()));
-  fp2* lines;
+  fp2 *lines, *rec;
   CUDA_TRY(sc.alloc(&lines, (size_t)nwalk * nprob * GS_NUM_LINES * 2));
+  CUDA_TRY(sc.alloc(&rec, (size_t)nwalk * nprob * GS_NUM_LINES * 4));
   struct event_guard {  // the fork event is destroyed on every path
     cudaEvent_t e = nullptr;
     ~event_guard() {
@@ -548,7 +681,12 @@ int gsi::g2_walk_ahead(gs_ctx* ctx, Scratch& sc, const g2_aff* Y, size_t nprob, 
   cudaStream_t main_stream = ctx->stream;
   ctx->stream = ctx->stream2;
   int rc = [&]() -> int {
-    LAUNCH(k_g2_walk, (size_t)nwalk * nprob, Y, lines, nprob, nprob, K, wa->dwalk, nwalk);
+    if (ctx->lone_walk_jac) {
+      LAUNCH_CFG(k_g2_walk_jac, (size_t)nwalk * nprob, 64, 0, Y, rec, nprob, nprob, K, wa->dwalk, nwalk);
+      LAUNCH_CFG(k_g2_lines_from_jac, (size_t)nwalk * nprob * 128, 128, 0, Y, rec, lines, nprob, nprob, K, wa->dwalk);
+    } else {
+      LAUNCH(k_g2_walk, (size_t)nwalk * nprob, Y, lines, nprob, nprob, K, wa->dwalk, nwalk);
+    }
     return GS_OK;
   }();
   ctx->stream = main_stream;
@@ -633,6 +771,14 @@ int gsi::run_pairing_product(gs_ctx* ctx, Scratch& sc, const g1_aff* X, const g2
     if (wa) {
       CUDA_TRY(cudaStreamWaitEvent(ctx->stream, wa->done, 0));
       LAUNCH(k_eval_tiles, (size_t)nwalk * np, PW, Y, wa->lines, tiles, masks, nprob, np, K, S, dwalk, nwalk);
+    } else if ((size_t)((nwalk + 3) / 4) * np < 16384 && ctx->lone_walk_jac && p0 == 0 && np == nprob && (size_t)nwalk * np <= 4096) {
+      // few points (a lone pairing / ComT product / CRS generation): the inversion-free walk, then the evaluation
+      fp2 *lines, *rec;
+      CUDA_TRY(sc.alloc(&lines, (size_t)nwalk * np * GS_NUM_LINES * 2));
+      CUDA_TRY(sc.alloc(&rec, (size_t)nwalk * np * GS_NUM_LINES * 4));
+      LAUNCH_CFG(k_g2_walk_jac, (size_t)nwalk * np, 64, 0, Y, rec, nprob, np, K, dwalk, nwalk);
+      LAUNCH_CFG(k_g2_lines_from_jac, (size_t)nwalk * np * 128, 128, 0, Y, rec, lines, nprob, np, K, dwalk);
+      LAUNCH(k_eval_tiles, (size_t)nwalk * np, PW, Y, lines, tiles, masks, nprob, np, K, S, dwalk, nwalk);
     } else if ((size_t)((nwalk + 3) / 4) * np < 16384)
       LAUNCH_CFG((k_g2_prepare4<1, 2>), (size_t)nwalk * np, 128, 0, PW, Y, tiles, masks, nprob, p0, np, K, S, dwalk, nwalk);
     else if (ctx->prep_variant == 4)

@@ -13,6 +13,9 @@ namespace gs {
 //     T[w][d-1] = d * 2^(c w) * B,   d = 1 .. 2^(c-1)     (signed digits => half tables)
 // layout: tab[((base*2 + a) * W + w) * H + (d-1)]
 constexpr int GS_TAB_NT = 128;
+#ifndef GS_FC_G2_BLOCKS
+#define GS_FC_G2_BLOCKS 2
+#endif
 
 template <class F>
 __global__ void k_table_window_bases(const Aff<F>* __restrict__ bases, Aff<F>* __restrict__ tab, int c, int W, size_t H) {
@@ -120,7 +123,7 @@ GS_HD GS_INL void fixed_base_accumulate_range(Jac<F>& acc, const Aff<F>* __restr
 // (3 resident blocks per SM on G1, 2 on G2: the register budgets the kernel had before the by-value product ABI let the
 // callers keep more in registers -- unbounded, G1 grew to 176 registers = 2 blocks and lost 5 %)
 template <class F>
-__global__ void __launch_bounds__(GS_TAB_NT, sizeof(typename F::T) == sizeof(fp) ? 3 : 2) k_fixed_commit(const Aff<F>* __restrict__ tab, int c, int W, size_t H, int base0,
+__global__ void __launch_bounds__(GS_TAB_NT, sizeof(typename F::T) == sizeof(fp) ? 3 : GS_FC_G2_BLOCKS) k_fixed_commit(const Aff<F>* __restrict__ tab, int c, int W, size_t H, int base0,
                                                             int base1, const fr* __restrict__ s0, size_t s0_stride,
                                                             const fr* __restrict__ s1, size_t s1_stride,
                                                             const Aff<F>* __restrict__ addend, Aff<F>* __restrict__ out, size_t n) {

@@ -53,6 +53,20 @@ inline GS_HD GS_NOINL void fp_inv_fermat(fp& r, const fp& a) {
 GS_HD GS_INL void fp_inv(fp& r, const fp& a) { fp_inv_sg(r, a); }
 
 // ------------------------------------------------------------------ Fp2
+// ONE out-of-line copy of the Fp product, operands and result by value (registers across the call): the Fp2 formulas
+// below go through it on the device unless GS_FP2_INLINE is defined (three inlined products = 22 KB per Fp2 product,
+// which the G2 thread-per-point kernels paid in instruction-cache misses: stall_no_inst 7 % in k_fixed_commit<G2>)
+inline GS_HD GS_NOINL fp fp_mul_ool(fp a, fp b) {
+  fp r;
+  fp::mul(r, a, b);
+  return r;
+}
+#if defined(__CUDA_ARCH__) && !defined(GS_FP2_INLINE)
+#define GS_FP2_MUL(r, a, b) (r) = fp_mul_ool((a), (b))
+#else
+#define GS_FP2_MUL(r, a, b) fp::mul((r), (a), (b))
+#endif
+
 struct fp2 {
   fp c0, c1;
 
@@ -88,9 +102,9 @@ struct fp2 {
     fp t0, t1, t2, s0, s1;
     fp::add(s0, a.c0, a.c1);
     fp::add(s1, b.c0, b.c1);
-    fp::mul(t0, a.c0, b.c0);
-    fp::mul(t1, a.c1, b.c1);
-    fp::mul(t2, s0, s1);
+    GS_FP2_MUL(t0, a.c0, b.c0);
+    GS_FP2_MUL(t1, a.c1, b.c1);
+    GS_FP2_MUL(t2, s0, s1);
     fp::sub(r.c0, t0, t1);
     fp::sub(t2, t2, t0);
     fp::sub(r.c1, t2, t1);
@@ -99,13 +113,13 @@ struct fp2 {
     fp s, d, m;
     fp::add(s, a.c0, a.c1);
     fp::sub(d, a.c0, a.c1);
-    fp::mul(m, a.c0, a.c1);
-    fp::mul(r.c0, s, d);
+    GS_FP2_MUL(m, a.c0, a.c1);
+    GS_FP2_MUL(r.c0, s, d);
     fp::add(r.c1, m, m);
   }
   GS_HD static GS_NOINL void mul_fp(fp2& r, const fp2& a, const fp& b) {
-    fp::mul(r.c0, a.c0, b);
-    fp::mul(r.c1, a.c1, b);
+    GS_FP2_MUL(r.c0, a.c0, b);
+    GS_FP2_MUL(r.c1, a.c1, b);
   }
   GS_HD static GS_NOINL void inv(fp2& r, const fp2& a) {
     fp n, t;

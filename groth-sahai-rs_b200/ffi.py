@@ -39,7 +39,8 @@ class GsError(RuntimeError):
 
 
 def lib_path():
-    return os.path.join(os.path.dirname(os.path.abspath(__file__)), "libgs_b200.so")
+    """The in-tree library; GS_B200_LIB points at an experiment build of the same sources (tools, never the tests)."""
+    return os.environ.get("GS_B200_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "libgs_b200.so")
 
 
 _lib = None
