@@ -355,6 +355,37 @@ def bench_c5(R_, eng, P, distinct, steps, warmup, full):
     out["e2e_ms"] = R_.wall_ms(step_e2e, steps, warmup=0)
     out["h2d_bytes"] = int(sum(a.nbytes for a in arrays))
     out["d2h_bytes"] = P
+    # ---- opt-in randomised batch verification (gs_verify_batch_rand): ONE verdict per call.  Timed on the
+    # honest proofs of this shard (a batch with a bad proof is rejected and then goes through the exact path above).
+    try:
+        import secrets
+        honest = torch.from_numpy(np.flatnonzero(expected == 1)).to(R_.dev)
+        Ph = int(honest.numel())
+        devh = [t.index_select(0, honest).contiguous() for t in dev]
+        ok1 = torch.zeros(4, dtype=torch.uint8, device=R_.dev)
+        rho = secrets.token_bytes(8 * (2 * P + 1))
+
+        def step_rand():
+            eng.verify_batch_rand_dev(0, Ph, m, n, [t.data_ptr() for t in devh], ok1.data_ptr(), rho=rho[:8 * (2 * Ph + 1)])
+
+        eng.verify_batch_rand_dev(0, P, m, n, [t.data_ptr() for t in dev], ok1.data_ptr(), rho=rho)   # 1 % tampered
+        R_.barrier(stream)
+        rejects = int(ok1[0].item()) == 0
+        step_rand()
+        R_.barrier(stream)
+        accepts = int(ok1[0].item()) == 1
+        l0 = eng.launch_count
+        ms_rand = timed(step_rand, steps) / steps
+        launches = (eng.launch_count - l0) // steps
+        eng.profile_enable(True)
+        step_rand()
+        prof_r = {k.split("<")[0]: v for k, v in eng.profile_read().items()}
+        eng.profile_enable(False)
+        out["rand"] = {"proofs": Ph, "ms_per_step": ms_rand, "accepts_honest_batch": accepts, "rejects_batch_with_tampered": rejects,
+                       "launches_per_step": int(launches), "prof": prof_r}
+        del devh
+    except Exception as ex:  # noqa: BLE001 -- the opt-in leg must not take the headline down
+        out["rand"] = {"error": f"{type(ex).__name__}: {ex}"}
     return out
 
 
@@ -704,6 +735,22 @@ def main():
             "gpu_launches": int(c5["launches"]), "roofline": roofline, "clocks": c5["clocks"], "limiter": limiter,
             "parity_sample": c5["parity_sample"],
         }
+        rnd = c5.get("rand")
+        if rnd and "error" not in rnd:
+            line["c5_randomised"] = {
+                "workload": "the honest proofs of the same C5 batch through gs_verify_batch_rand (opt-in, SURVEY.md 8f.4): the four "
+                            "ComT entries of all proofs folded into one pairing product with 64-bit random weights, ONE final "
+                            "exponentiation and ONE verdict per call; not bit-comparable with the reference's per-proof booleans "
+                            "(a rejected batch goes through the exact path)",
+                "value": round(world * rnd["proofs"] / (rnd["ms_per_step"] * 1e-3), 1), "unit": "verifies/s",
+                "proofs_per_gpu": rnd["proofs"], "ms_per_step": round(rnd["ms_per_step"], 3),
+                "speedup_vs_exact": round((rnd["proofs"] / rnd["ms_per_step"]) / (P / ms_per_step), 3),
+                "accepts_honest_batch": rnd["accepts_honest_batch"], "rejects_batch_with_tampered": rnd["rejects_batch_with_tampered"],
+                "launches_per_step": rnd["launches_per_step"],
+                "kernels_ms": {k: round(v[1], 3) for k, v in sorted(rnd["prof"].items(), key=lambda kv: -kv[1][1])[:10]},
+            }
+        elif rnd:
+            line["c5_randomised"] = rnd
         line.update(extras)
         if cpu is not None:
             line["cpu_baseline"] = cpu

@@ -249,8 +249,14 @@ def prove_batch(equations, xvars, yvars, xcoms, ycoms, crs: CRS, rng) -> List[Eq
     return [EquProof(_split(p, 384), _split(t, 192), ty, r) for p, t, r in zip(ps, ts, rands)]
 
 
-def verify_batch(equations, proofs, crs: CRS) -> List[bool]:
-    """Many independent (equation, CProof) pairs of one type and shape in one GPU pass."""
+def verify_batch(equations, proofs, crs: CRS, randomized: bool = False, rho: bytes = None) -> List[bool]:
+    """Many independent (equation, CProof) pairs of one type and shape in one GPU pass.
+
+    randomized=True (opt-in; not in the reference): first ONE randomised check of the whole batch
+    (gs_verify_batch_rand: a single folded pairing product, one final exponentiation); if it accepts, every proof is
+    reported valid (error <= 2^-63 over `rho`, drawn from the OS CSPRNG when not given); if it rejects, the exact
+    per-proof verification below runs and says which proofs failed.  Inputs must be group members (deserialised values
+    are), PPE targets members of GT."""
     assert len(equations) == len(proofs) and equations
     ty = equations[0].equ_type
     m, n = len(proofs[0].xcoms.coms), len(proofs[0].ycoms.coms)
@@ -262,11 +268,13 @@ def verify_batch(equations, proofs, crs: CRS) -> List[bool]:
         if len(e.a_consts) != n or len(e.b_consts) != m or len(e.gamma) != m or any(len(r) != n for r in e.gamma):
             raise ValueError("verify_batch: constants / Gamma do not match the number of variables")
     cat = lambda f: b"".join(f(e, p) for e, p in zip(equations, proofs))
-    ok = crs._use().verify_batch(
-        ty, len(equations), m, n, cat(lambda e, p: b"".join(e.a_consts)), cat(lambda e, p: b"".join(e.b_consts)),
-        cat(lambda e, p: _flat(e.gamma)), cat(lambda e, p: e.target), cat(lambda e, p: b"".join(p.xcoms.coms)),
-        cat(lambda e, p: b"".join(p.ycoms.coms)), cat(lambda e, p: b"".join(p.equ_proofs[0].pi)),
-        cat(lambda e, p: b"".join(p.equ_proofs[0].theta)))
+    arrays = (cat(lambda e, p: b"".join(e.a_consts)), cat(lambda e, p: b"".join(e.b_consts)),
+              cat(lambda e, p: _flat(e.gamma)), cat(lambda e, p: e.target), cat(lambda e, p: b"".join(p.xcoms.coms)),
+              cat(lambda e, p: b"".join(p.ycoms.coms)), cat(lambda e, p: b"".join(p.equ_proofs[0].pi)),
+              cat(lambda e, p: b"".join(p.equ_proofs[0].theta)))
+    if randomized and crs._use().verify_batch_rand(ty, len(equations), m, n, *arrays, rho=rho):
+        return [True] * len(equations)
+    ok = crs._use().verify_batch(ty, len(equations), m, n, *arrays)
     return [b == 1 for b in ok]
 
 

@@ -46,6 +46,10 @@ int gs_ctx_create(int device, gs_ctx** out) {
   if (const char* e = getenv("GS_PASS_STREAMS")) ctx->pass_streams = atoi(e);
   if (const char* e = getenv("GS_LONE_WALK_JAC")) ctx->lone_walk_jac = atoi(e);
   if (const char* e = getenv("GS_SPLIT_MIN")) ctx->split_min = (size_t)strtoull(e, nullptr, 10);
+  if (const char* e = getenv("GS_VERIFY_BATCH_MAX")) {  // problems per verify pass (tests: several passes on a small batch)
+    const size_t v = (size_t)strtoull(e, nullptr, 10);
+    if (v >= 1) ctx->verify_batch_max = v;
+  }
   // deep call chains (Fp12 -> Fp6 -> Fp2) with big local frames
   cudaDeviceSetLimit(cudaLimitStackSize, 32 * 1024);
   if (gsi::pairing_init(ctx) != GS_OK || gsi::final_exp_init(ctx) != GS_OK) {

@@ -197,13 +197,16 @@ struct walk_ahead {  // G2 walks started early on the second stream (lone statem
 int g2_walk_ahead(gs_ctx* ctx, Scratch& sc, const g2_aff* Y, size_t nprob, int K, const uint8_t* slot_kind, walk_ahead* wa);
 int run_pairing_product(gs_ctx* ctx, Scratch& sc, const g1_aff* X, const g2_aff* Y, size_t nprob, int K, fp12* out_comt,
                         uint8_t* ok4, const fp12* target, fp12* out_partial, const uint8_t* slot_kind = nullptr,
-                        const walk_ahead* wa = nullptr);
+                        const walk_ahead* wa = nullptr, int ne = 4, int S_force = 0);
 int crs_lines_build(gs_ctx* ctx);
 
-// finalexp.cu: f = prod_chunks F[(ch*4 + e)*nprob + p]; g = FE(f); writes out_comt[p*4+e] and/or ok4[e*nprob + p]
-int launch_final_exp(gs_ctx* ctx, const fp12* F, size_t nprob, int nchunk, fp12* out_comt, uint8_t* ok4, const fp12* target);
+// finalexp.cu: f = prod_chunks F[(ch*ne + e)*nprob + p]; g = FE(f); writes out_comt[p*ne+e] and/or ok4[e*nprob + p]
+// (ne = 4 entries per problem; ne = 1: single values, `target` then applies to every problem)
+int launch_final_exp(gs_ctx* ctx, const fp12* F, size_t nprob, int nchunk, fp12* out_comt, uint8_t* ok4, const fp12* target, int ne = 4);
 // finalexp.cu: multiplies groups of chunks together (cooperative kernel) until nchunk <= max_out
-int reduce_chunks(gs_ctx* ctx, Scratch& sc, const fp12** F, size_t nprob, int* nchunk, int max_out);
+int reduce_chunks(gs_ctx* ctx, Scratch& sc, const fp12** F, size_t nprob, int* nchunk, int max_out, int ne = 4);
+// finalexp.cu: out[i] = t[i]^(e[i * estride]) for 64-bit exponents, t in the cyclotomic subgroup (GT members are)
+int gt_pow64(gs_ctx* ctx, const fp12* t, const uint64_t* e, size_t estride, size_t count, fp12* out);
 
 // prover.cu
 int crs_generate_points(gs_ctx* ctx, const gs_g1* p1, const gs_g2* p2, const gs_fr* a1, const gs_fr* a2, const gs_fr* t1,

@@ -16,7 +16,7 @@ constexpr int FE3_SMEM = CQ_FE_NBUF * CQ_ACC * 4 + CQ_LANES * 4;  // per 6-warp 
 __global__ void __launch_bounds__(CQ_BLOCK_THREADS, 1) k_final_exp3(const fp12* __restrict__ F, size_t nprob, int nchunk,
                                                                    fp12* __restrict__ out_comt, uint8_t* __restrict__ ok,
                                                                    const fp12* __restrict__ target,
-                                                                   const uint32_t* __restrict__ prog, int nops, size_t ngroups) {
+                                                                   const uint32_t* __restrict__ prog, int nops, size_t ngroups, int ne) {
   extern __shared__ __align__(16) uint32_t sm_all[];
   const int grp = threadIdx.x / CQ_GROUP_THREADS, tg = threadIdx.x % CQ_GROUP_THREADS;
   uint32_t* bufs = sm_all + (size_t)grp * (FE3_SMEM / 4);
@@ -25,7 +25,7 @@ __global__ void __launch_bounds__(CQ_BLOCK_THREADS, 1) k_final_exp3(const fp12* 
   const size_t gid = (size_t)blockIdx.x * CQ_GROUPS + grp;
   if (gid >= ngroups) return;
   const size_t id = gid * CQ_LANES + lane;
-  const bool valid = id < nprob * 4;
+  const bool valid = id < nprob * ne;
   const size_t p = valid ? id % nprob : 0;
   const int e = valid ? (int)(id / nprob) : 0;
   const int pos = cq_tower_pos(k);
@@ -34,7 +34,7 @@ __global__ void __launch_bounds__(CQ_BLOCK_THREADS, 1) k_final_exp3(const fp12* 
   for (int ch = 0; ch < nchunk; ch++) {
     fp2 c;
     if (valid) {
-      c = ((const fp2*)&F[((size_t)ch * 4 + e) * nprob + p])[pos];
+      c = ((const fp2*)&F[((size_t)ch * ne + e) * nprob + p])[pos];
     } else {
       c.set_zero();
       if (k == 0) fp_one(c.c0);
@@ -56,10 +56,10 @@ __global__ void __launch_bounds__(CQ_BLOCK_THREADS, 1) k_final_exp3(const fp12* 
   fp2 g;
   cq_ld_coef(g.c0, g.c1, bufs + CQ_FE_OUT * CQ_ACC, k, lane, false, false);
   if (valid) {
-    if (out_comt) ((fp2*)&out_comt[p * 4 + e])[pos] = g;
+    if (out_comt) ((fp2*)&out_comt[p * ne + e])[pos] = g;
     if (ok) {
       fp2 want;
-      if (target != nullptr && e == 3) {
+      if (target != nullptr && e == ne - 1) {
         want = ((const fp2*)&target[p])[pos];
       } else {
         want.set_zero();
@@ -78,7 +78,7 @@ __global__ void __launch_bounds__(CQ_BLOCK_THREADS, 1) k_final_exp3(const fp12* 
 // Here 32 lanes x 6 warps multiply L chunks each:  F2[(part*4 + e)*nprob + p] = prod_{ch in part} F[(ch*4 + e)*nprob + p]
 constexpr int CR_SMEM = 3 * CQ_ACC * 4;  // per 6-warp group
 __global__ void __launch_bounds__(CQ_BLOCK_THREADS, 1) k_chunk_reduce(const fp12* __restrict__ F, fp12* __restrict__ F2, size_t nprob,
-                                                                     int nchunk, int L, int nparts, size_t ngroups) {
+                                                                     int nchunk, int L, int nparts, size_t ngroups, int ne) {
   extern __shared__ __align__(16) uint32_t sm_all[];
   const int grp = threadIdx.x / CQ_GROUP_THREADS, tg = threadIdx.x % CQ_GROUP_THREADS;
   uint32_t* bufs = sm_all + (size_t)grp * (CR_SMEM / 4);
@@ -86,17 +86,17 @@ __global__ void __launch_bounds__(CQ_BLOCK_THREADS, 1) k_chunk_reduce(const fp12
   const size_t gid = (size_t)blockIdx.x * CQ_GROUPS + grp;
   if (gid >= ngroups) return;
   const size_t id = gid * CQ_LANES + lane;
-  const bool valid = id < nprob * 4 * (size_t)nparts;
+  const bool valid = id < nprob * ne * (size_t)nparts;
   const size_t p = valid ? id % nprob : 0;
-  const int e = valid ? (int)((id / nprob) & 3) : 0;
-  const int part = valid ? (int)(id / (nprob * 4)) : 0;
+  const int e = valid ? (int)((id / nprob) % ne) : 0;
+  const int part = valid ? (int)(id / (nprob * ne)) : 0;
   const int pos = cq_tower_pos(k);
   int cur = 0;
   for (int i = 0; i < L; i++) {
     const int ch = part * L + i;
     fp2 c;
     if (valid && ch < nchunk) {
-      c = ((const fp2*)&F[((size_t)ch * 4 + e) * nprob + p])[pos];
+      c = ((const fp2*)&F[((size_t)ch * ne + e) * nprob + p])[pos];
     } else {
       c.set_zero();
       if (k == 0) fp_one(c.c0);
@@ -114,14 +114,68 @@ __global__ void __launch_bounds__(CQ_BLOCK_THREADS, 1) k_chunk_reduce(const fp12
   }
   fp2 g;
   cq_ld_coef(g.c0, g.c1, bufs + cur * CQ_ACC, k, lane, false, false);
-  if (valid) ((fp2*)&F2[((size_t)part * 4 + e) * nprob + p])[pos] = g;
+  if (valid) ((fp2*)&F2[((size_t)part * ne + e) * nprob + p])[pos] = g;
+}
+
+// ------------------------------------------------------------------ GT powers with 64-bit exponents (gs_verify_batch_rand)
+// lane = one element; out = t^e.  The multiplication of a window picks ITS lane's table entry (the X operand of cq_mul is
+// streamed from shared memory, so a per-lane buffer is only a per-lane base address); lanes whose digit is 0 copy through.
+__global__ void __launch_bounds__(CQ_BLOCK_THREADS, 1) k_gt_pow64(const fp12* __restrict__ T, const uint64_t* __restrict__ E, size_t estride,
+                                                                 size_t count, fp12* __restrict__ out, size_t ngroups) {
+  extern __shared__ __align__(16) uint32_t sm_all[];
+  const int grp = threadIdx.x / CQ_GROUP_THREADS, tg = threadIdx.x % CQ_GROUP_THREADS;
+  uint32_t* bufs = sm_all + (size_t)grp * (FE3_SMEM / 4);
+  const int k = tg >> 5, lane = tg & 31;
+  const size_t gid = (size_t)blockIdx.x * CQ_GROUPS + grp;
+  if (gid >= ngroups) return;
+  const size_t id = gid * CQ_LANES + lane;
+  const bool valid = id < count;
+  const int pos = cq_tower_pos(k);
+  const uint64_t ex = valid ? E[id * estride] : 0;
+  fp2 c;
+  if (valid) {
+    c = ((const fp2*)&T[id])[pos];
+  } else {
+    c.set_zero();
+    if (k == 0) fp_one(c.c0);
+  }
+  cq_st_coef(bufs + 2 * CQ_ACC, k, lane, c);  // t
+  cq_group_sync(grp);
+  cq_cyc_sqr(k, lane, bufs + 2 * CQ_ACC, bufs + 3 * CQ_ACC);  // t^2
+  cq_group_sync(grp);
+  cq_mul(k, lane, bufs + 2 * CQ_ACC, bufs + 3 * CQ_ACC, bufs + 4 * CQ_ACC);  // t^3
+  cq_group_sync(grp);
+  {  // top window
+    const int d = (int)(ex >> 62);
+    if (d == 0)
+      cq_set_one(k, lane, bufs);
+    else
+      cq_copy(k, lane, bufs + (1 + d) * CQ_ACC, bufs);
+  }
+  cq_group_sync(grp);
+  int cur = 0;
+#pragma unroll 1
+  for (int w = 30; w >= 0; w--) {
+    cq_cyc_sqr(k, lane, bufs + cur * CQ_ACC, bufs + (cur ^ 1) * CQ_ACC);
+    cq_group_sync(grp);
+    cq_cyc_sqr(k, lane, bufs + (cur ^ 1) * CQ_ACC, bufs + cur * CQ_ACC);
+    cq_group_sync(grp);
+    const int d = (int)((ex >> (2 * w)) & 3);
+    cq_mul(k, lane, bufs + cur * CQ_ACC, bufs + (1 + (d ? d : 1)) * CQ_ACC, bufs + (cur ^ 1) * CQ_ACC);
+    if (d == 0) cq_copy(k, lane, bufs + cur * CQ_ACC, bufs + (cur ^ 1) * CQ_ACC);
+    cq_group_sync(grp);
+    cur ^= 1;
+  }
+  fp2 g;
+  cq_ld_coef(g.c0, g.c1, bufs + cur * CQ_ACC, k, lane, false, false);
+  if (valid) ((fp2*)&out[id])[pos] = g;
 }
 
 }  // namespace gs
 
 // Reduces the chunk dimension of F ([nchunk][4][nprob]) until at most `max_out` chunks are left; *F then points
 // at scratch owned by `sc`.
-int gsi::reduce_chunks(gs_ctx* ctx, Scratch& sc, const fp12** F, size_t nprob, int* nchunk, int max_out) {
+int gsi::reduce_chunks(gs_ctx* ctx, Scratch& sc, const fp12** F, size_t nprob, int* nchunk, int max_out, int ne) {
   if (max_out < 1) max_out = 1;
   while (*nchunk > max_out) {
     int L = 2;
@@ -129,10 +183,10 @@ int gsi::reduce_chunks(gs_ctx* ctx, Scratch& sc, const fp12** F, size_t nprob, i
     if (L > 64) L = 64;
     const int nparts = (*nchunk + L - 1) / L;
     fp12* F2;
-    CUDA_TRY(sc.alloc(&F2, (size_t)nparts * 4 * nprob));
-    size_t ngroups = (nprob * 4 * (size_t)nparts + CQ_LANES - 1) / CQ_LANES;
+    CUDA_TRY(sc.alloc(&F2, (size_t)nparts * ne * nprob));
+    size_t ngroups = (nprob * ne * (size_t)nparts + CQ_LANES - 1) / CQ_LANES;
     LAUNCH_CFG(k_chunk_reduce, ((ngroups + CQ_GROUPS - 1) / CQ_GROUPS) * CQ_BLOCK_THREADS, CQ_BLOCK_THREADS, CQ_GROUPS * CR_SMEM, *F,
-               F2, nprob, *nchunk, L, nparts, ngroups);
+               F2, nprob, *nchunk, L, nparts, ngroups, ne);
     *F = F2;
     *nchunk = nparts;
   }
@@ -147,12 +201,22 @@ int gsi::final_exp_init(gs_ctx* ctx) {
   CUDA_TRY(cudaMemcpy(ctx->fe_prog, prog, n * sizeof(uint32_t), cudaMemcpyHostToDevice));
   CUDA_TRY(cudaFuncSetAttribute(k_final_exp3, cudaFuncAttributeMaxDynamicSharedMemorySize, CQ_GROUPS * FE3_SMEM));
   CUDA_TRY(cudaFuncSetAttribute(k_chunk_reduce, cudaFuncAttributeMaxDynamicSharedMemorySize, CQ_GROUPS * CR_SMEM));
+  CUDA_TRY(cudaFuncSetAttribute(k_gt_pow64, cudaFuncAttributeMaxDynamicSharedMemorySize, CQ_GROUPS * FE3_SMEM));
   return GS_OK;
 }
 
-int gsi::launch_final_exp(gs_ctx* ctx, const fp12* F, size_t nprob, int nchunk, fp12* out_comt, uint8_t* ok4, const fp12* target) {
-  size_t ngroups = (nprob * 4 + CQ_LANES - 1) / CQ_LANES;
+int gsi::launch_final_exp(gs_ctx* ctx, const fp12* F, size_t nprob, int nchunk, fp12* out_comt, uint8_t* ok4, const fp12* target, int ne) {
+  size_t ngroups = (nprob * ne + CQ_LANES - 1) / CQ_LANES;
   LAUNCH_CFG(k_final_exp3, ((ngroups + CQ_GROUPS - 1) / CQ_GROUPS) * CQ_BLOCK_THREADS, CQ_BLOCK_THREADS, CQ_GROUPS * FE3_SMEM, F, nprob,
-             nchunk, out_comt, ok4, target, ctx->fe_prog, ctx->fe_nops, ngroups);
+             nchunk, out_comt, ok4, target, ctx->fe_prog, ctx->fe_nops, ngroups, ne);
+  return GS_OK;
+}
+
+// t^e for 64-bit exponents, 32 proofs per 6-warp group: 2-bit windows over the table t, t^2, t^3 (buffers 2, 3, 4), the
+// running power ping-pongs between buffers 0 and 1; squarings are Granger-Scott (t must be in the cyclotomic subgroup).
+int gsi::gt_pow64(gs_ctx* ctx, const fp12* t, const uint64_t* e, size_t estride, size_t count, fp12* out) {
+  size_t ngroups = (count + CQ_LANES - 1) / CQ_LANES;
+  LAUNCH_CFG(k_gt_pow64, ((ngroups + CQ_GROUPS - 1) / CQ_GROUPS) * CQ_BLOCK_THREADS, CQ_BLOCK_THREADS, CQ_GROUPS * FE3_SMEM, t, e, estride,
+             count, out, ngroups);
   return GS_OK;
 }

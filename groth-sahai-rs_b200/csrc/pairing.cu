@@ -33,10 +33,10 @@ constexpr int M4_SMEM = (2 * CQ_ACC + 2 * M4_TILE) * 4 + M4_MAXS * 6 + 16;  // p
 
 // per G1 slot point: PW[((a*K + k)*2 + which)*12 + limb][pl] with which = 0: -xP/yP, 1: 1/yP (zero for identity)
 __global__ void __launch_bounds__(128) k_g1_prep(const g1_aff* __restrict__ X, uint32_t* __restrict__ PW, size_t nprob,
-                                                 size_t p0, size_t np, int K) {
+                                                 size_t p0, size_t np, int K, int na) {
   __shared__ fp sm[2 * 128];
   size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  bool in = q < 2 * (size_t)K * np;
+  bool in = q < (size_t)na * K * np;
   size_t pl = in ? q % np : 0, ak = in ? q / np : 0;
   fp x, w;
   x.set_zero();
@@ -84,8 +84,9 @@ template <int E, int MINB>
 __global__ void __launch_bounds__(128, MINB) k_g2_prepare4(const uint32_t* __restrict__ PW, const g2_aff* __restrict__ Y,
                                                         uint32_t* __restrict__ tiles, uint32_t* __restrict__ masks,
                                                         size_t nprob, size_t p0, size_t np, int K, int S,
-                                                        const uint32_t* __restrict__ walk, int nwalk) {
+                                                        const uint32_t* __restrict__ walk, int nwalk, int ne) {
   const int G = (nwalk + E - 1) / E;
+  const int na = ne == 4 ? 2 : 1;  // ne = 1: single-entry products (one G1 and one G2 coordinate per slot)
   size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const bool inrange = q < (size_t)G * np;
   if (!inrange) q = 0;
@@ -120,12 +121,13 @@ __global__ void __launch_bounds__(128, MINB) k_g2_prepare4(const uint32_t* __res
     lanes[i] = (int)(A & 31);
 #pragma unroll
     for (int a = 0; a < 2; a++) {
+      if (a >= na) continue;
       // 1/yP is zero exactly for an identity G1 point
       const uint32_t* w = PW + ((((size_t)a * K + k) * 2 + 1) * 12) * np + pl;
       uint32_t nz = 0;
       for (int j = 0; j < 12; j++) nz |= w[(size_t)j * np];
       acta[i][a] = nz != 0;
-      size_t bid = (A >> 5) * 4 + (size_t)(2 * a + b);
+      size_t bid = ne == 4 ? (A >> 5) * 4 + (size_t)(2 * a + b) : (A >> 5);
       tb[i][a] = ((bid * S + kk) * GS_NUM_LINES) * (size_t)M4_TILE;
       if (acta[i][a]) atomicOr(&masks[bid * S + kk], 1u << lanes[i]);
     }
@@ -414,7 +416,7 @@ __global__ void __launch_bounds__(128) k_g2_lines_from_jac(const g2_aff* __restr
 __global__ void __launch_bounds__(128) k_eval_tiles(const uint32_t* __restrict__ PW, const g2_aff* __restrict__ Y,
                                                     const fp2* __restrict__ lines, uint32_t* __restrict__ tiles,
                                                     uint32_t* __restrict__ masks, size_t nprob, size_t np, int K, int S,
-                                                    const uint32_t* __restrict__ walk, int nwalk) {
+                                                    const uint32_t* __restrict__ walk, int nwalk, int ne) {
   size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (q >= (size_t)nwalk * np) return;
   const size_t pl = q % np;
@@ -427,8 +429,9 @@ __global__ void __launch_bounds__(128) k_eval_tiles(const uint32_t* __restrict__
   const size_t A = (size_t)ch * np + pl;
   const int lane = (int)(A & 31);
   const fp2* L = lines + ((size_t)e * np + pl) * GS_NUM_LINES * 2;
+  const int na = ne == 4 ? 2 : 1;
 #pragma unroll 1
-  for (int a = 0; a < 2; a++) {
+  for (int a = 0; a < na; a++) {
     const uint32_t* pw = PW + ((((size_t)a * K + k) * 2) * 12) * np + pl;
     fp s, wv;
     uint32_t nz = 0;
@@ -439,7 +442,7 @@ __global__ void __launch_bounds__(128) k_eval_tiles(const uint32_t* __restrict__
       nz |= wv.l[j];
     }
     if (!nz) continue;  // identity G1 point: pair dropped
-    const size_t bid = (A >> 5) * 4 + (size_t)(2 * a + b);
+    const size_t bid = ne == 4 ? (A >> 5) * 4 + (size_t)(2 * a + b) : (A >> 5);
     atomicOr(&masks[bid * S + kk], 1u << lane);
     uint32_t* o = tiles + ((bid * S + kk) * GS_NUM_LINES) * (size_t)M4_TILE;
 #pragma unroll 1
@@ -469,7 +472,7 @@ __device__ GS_INL void cp_async_wait_all() { asm volatile("cp.async.wait_all;" :
 __global__ void __launch_bounds__(CQ_BLOCK_THREADS, 1) k_miller4(const uint32_t* __restrict__ tiles,
                                                                 const uint32_t* __restrict__ masks, fp12* __restrict__ F,
                                                                 size_t nprob, size_t p0, size_t np, int S, int nchunk,
-                                                                size_t ngroups) {
+                                                                size_t ngroups, int ne) {
   extern __shared__ __align__(16) uint32_t sm_all[];
   const int grp = threadIdx.x / CQ_GROUP_THREADS, tg = threadIdx.x % CQ_GROUP_THREADS;
   uint32_t* sm = sm_all + (size_t)grp * (M4_SMEM / 4);
@@ -483,7 +486,8 @@ __global__ void __launch_bounds__(CQ_BLOCK_THREADS, 1) k_miller4(const uint32_t*
   // images have no first coordinate: 8 against 12 pairs per 4x4 PPE proof), and a block that paired entry 0 with entry 1
   // ran its last third with one group = 6 warps.  Block q -> accumulator block q / 2, entries (q & 1) and (q & 1) + 2.
   static_assert(CQ_GROUPS == 2, "entry pairing below assumes two groups per block");
-  const size_t bid = ((size_t)blockIdx.x >> 1) * 4 + (blockIdx.x & 1) + 2 * (size_t)grp;
+  // (ne = 1, single-entry products: every accumulator block carries the same kind of work, block q -> groups 2q, 2q + 1)
+  const size_t bid = ne == 4 ? ((size_t)blockIdx.x >> 1) * 4 + (blockIdx.x & 1) + 2 * (size_t)grp : (size_t)blockIdx.x * 2 + grp;
   if (bid >= ngroups) return;
   if (tg == 0) {
     int n = 0;
@@ -536,15 +540,15 @@ __global__ void __launch_bounds__(CQ_BLOCK_THREADS, 1) k_miller4(const uint32_t*
     }
   }
   // conjugate (x < 0) and write out in tower order
-  size_t A = (bid >> 2) * 32 + lane;
-  int e = (int)(bid & 3);
+  size_t A = (ne == 4 ? (bid >> 2) : bid) * 32 + lane;
+  int e = ne == 4 ? (int)(bid & 3) : 0;
   if (A < np * (size_t)nchunk) {
     size_t pl = A % np;
     int ch = (int)(A / np);
     fp2 r;
     cq_ld_coef(r.c0, r.c1, acc + cur * CQ_ACC, k, lane, false, false);
     if (k & 1) fp2::neg(r, r);
-    fp2* dst = (fp2*)&F[((size_t)ch * 4 + e) * nprob + p0 + pl];
+    fp2* dst = (fp2*)&F[((size_t)ch * ne + e) * nprob + p0 + pl];
     dst[cq_tower_pos(k)] = r;
   }
 }
@@ -569,14 +573,14 @@ __global__ void k_fp12_set_one(fp12* out, size_t n) {
   if (i < n) out[i].set_one();
 }
 // out[p*4 + e] = prod_ch F[(ch*4 + e)*nprob + p]   (tower code: a handful of products per problem)
-__global__ void k_chunk_product(const fp12* __restrict__ F, fp12* __restrict__ out, size_t nprob, int nchunk) {
+__global__ void k_chunk_product(const fp12* __restrict__ F, fp12* __restrict__ out, size_t nprob, int nchunk, int ne) {
   size_t id = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (id >= nprob * 4) return;
-  size_t p = id >> 2;
-  int e = (int)(id & 3);
+  if (id >= nprob * ne) return;
+  size_t p = id / ne;
+  int e = (int)(id % ne);
   fp12 acc = F[(size_t)e * nprob + p];
   for (int ch = 1; ch < nchunk; ch++) {
-    fp12 t = F[((size_t)ch * 4 + e) * nprob + p];
+    fp12 t = F[((size_t)ch * ne + e) * nprob + p];
     fp12::mul(acc, acc, t);
   }
   out[id] = acc;
@@ -711,13 +715,18 @@ int gsi::g2_walk_ahead(gs_ctx* ctx, Scratch& sc, const g2_aff* Y, size_t nprob, 
 // Problems are processed in passes of `pc` so that the evaluated-line tiles stay within ctx->tile_budget
 // bytes of HBM; a pass is sized to a whole number of k_miller4 waves (2 groups x 148 SMs x 32 accumulators
 // / 4 entries = 2,368 problems per wave) when the batch is large enough.
+// ne = 1 (gs_verify_batch_rand): SINGLE-entry products prod_k e(X_k, Y_k) over arrays X[K][nprob], Y[K][nprob]; every
+// accumulator takes exactly S = S_force slots (K a multiple of it, S a multiple of 4), un-exponentiated result in out_partial.
 int gsi::run_pairing_product(gs_ctx* ctx, Scratch& sc, const g1_aff* X, const g2_aff* Y, size_t nprob, int K,
                                fp12* out_comt, uint8_t* ok4, const fp12* target, fp12* out_partial, const uint8_t* slot_kind,
-                               const walk_ahead* wa) {
+                               const walk_ahead* wa, int ne, int S_force) {
+  if (ne != 4 && (ne != 1 || nprob != 1 || !out_partial || slot_kind || wa || S_force < 4 || S_force % 4 || K % S_force))
+    FAIL(GS_EARG, "pairing product: bad single-entry configuration");
+  const int na = ne == 4 ? 2 : 1;
   const size_t wave = 2368;
   if (K == 0) {  // a shard that owns no slot: empty product
     if (!out_partial) FAIL(GS_EARG, "pairing product over zero slots");
-    LAUNCH(k_fp12_set_one, nprob * 4, out_partial, nprob * 4);
+    LAUNCH(k_fp12_set_one, nprob * ne, out_partial, nprob * ne);
     return GS_OK;
   }
   // split the slots of a big statement over several accumulators when there are few problems
@@ -732,8 +741,10 @@ int gsi::run_pairing_product(gs_ctx* ctx, Scratch& sc, const g1_aff* X, const g2
     S = (int)((K + c - 1) / c);
   }
   if (S > M4_MAXS) S = M4_MAXS;
+  if (ne == 1) S = S_force;
   nchunk = (K + S - 1) / S;
-  const size_t per_prob = (size_t)4 * nchunk * S * GS_NUM_LINES * M4_TILE * 4 / 32;  // tile bytes per problem
+  const size_t per_prob = (size_t)ne * nchunk * S * GS_NUM_LINES * M4_TILE * 4 / 32;  // tile bytes per problem
+  if (ne == 1 && per_prob > ctx->tile_budget) FAIL(GS_EDIM, "pairing product: single-entry pass exceeds the tile budget");
   size_t pc = ctx->tile_budget / per_prob;
   if (pc >= nprob) {
     pc = nprob;
@@ -742,11 +753,21 @@ int gsi::run_pairing_product(gs_ctx* ctx, Scratch& sc, const g1_aff* X, const g2
     if (pc < 32) pc = 32;
     pc -= pc % 32;
   }
-  const size_t nblk_max = ((pc * nchunk + 31) / 32) * 4;
+  const size_t nblk_max = ((pc * nchunk + 31) / 32) * ne;
   // which (coordinate, slot) pairs have a point to walk; which slots are CRS points with stored lines
   std::vector<uint32_t> hwalk;
   fixed_slots fs;
-  build_walk_list(ctx, K, slot_kind, hwalk, fs);
+  if (ne == 4) {
+    build_walk_list(ctx, K, slot_kind, hwalk, fs);
+  } else {
+    // thread g of the walk kernel takes the entries 4g .. 4g+3: slot quad r of accumulator ch, with g = r * nchunk + ch, so
+    // that the 32 threads of a warp write the 32 lanes of ONE tile (consecutive accumulators, same slot) in 512-B rows
+    fs.n = 0;
+    hwalk.resize((size_t)K);
+    for (int r = 0; r < S / 4; r++)
+      for (int ch = 0; ch < nchunk; ch++)
+        for (int i = 0; i < 4; i++) hwalk[4 * ((size_t)r * nchunk + ch) + i] = (uint32_t)(ch * S + 4 * r + i);
+  }
   const int nwalk = (int)hwalk.size();
   if (wa && (!wa->lines || wa->nwalk != nwalk || pc < nprob)) wa = nullptr;  // lines walked ahead only for a single pass
   uint32_t* dwalk;
@@ -756,21 +777,21 @@ int gsi::run_pairing_product(gs_ctx* ctx, Scratch& sc, const g1_aff* X, const g2
     CUDA_TRY(upload(ctx, sc, &dwalk, hwalk.data(), hwalk.size()));
   uint32_t *tiles, *masks, *PW;
   fp12* F;
-  CUDA_TRY(sc.alloc(&PW, 2 * (size_t)K * 24 * pc));
+  CUDA_TRY(sc.alloc(&PW, (size_t)na * K * 24 * pc));
   CUDA_TRY(sc.alloc(&tiles, nblk_max * S * GS_NUM_LINES * (size_t)M4_TILE));
   CUDA_TRY(sc.alloc(&masks, nblk_max * S));
-  CUDA_TRY(sc.alloc(&F, (size_t)nchunk * 4 * nprob));
+  CUDA_TRY(sc.alloc(&F, (size_t)nchunk * ne * nprob));
   for (size_t p0 = 0; p0 < nprob; p0 += pc) {
     size_t np = nprob - p0 < pc ? nprob - p0 : pc;
-    size_t nblk = ((np * nchunk + 31) / 32) * 4;
+    size_t nblk = ((np * nchunk + 31) / 32) * ne;
     CUDA_TRY(cudaMemsetAsync(masks, 0, nblk * S * sizeof(uint32_t), ctx->stream));
-    LAUNCH(k_g1_prep, 2 * (size_t)K * np, X, PW, nprob, p0, np, K);
+    LAUNCH(k_g1_prep, (size_t)na * K * np, X, PW, nprob, p0, np, K, na);
     // (6 points per thread was measured too: 162.6 ms vs 151.0 ms per 65,536 proofs -- the extra local memory costs
     // more than the shared inversion saves)
     if (fs.n) LAUNCH(k_fixed_tiles, (size_t)fs.n * 2 * np, PW, ctx->crs_lines, ctx->crs, tiles, masks, p0, np, K, S, fs);
     if (wa) {
       CUDA_TRY(cudaStreamWaitEvent(ctx->stream, wa->done, 0));
-      LAUNCH(k_eval_tiles, (size_t)nwalk * np, PW, Y, wa->lines, tiles, masks, nprob, np, K, S, dwalk, nwalk);
+      LAUNCH(k_eval_tiles, (size_t)nwalk * np, PW, Y, wa->lines, tiles, masks, nprob, np, K, S, dwalk, nwalk, ne);
     } else if ((size_t)((nwalk + 3) / 4) * np < 16384 && ctx->lone_walk_jac && p0 == 0 && np == nprob && (size_t)nwalk * np <= 4096) {
       // few points (a lone pairing / ComT product / CRS generation): the inversion-free walk, then the evaluation
       fp2 *lines, *rec;
@@ -778,21 +799,21 @@ int gsi::run_pairing_product(gs_ctx* ctx, Scratch& sc, const g1_aff* X, const g2
       CUDA_TRY(sc.alloc(&rec, (size_t)nwalk * np * GS_NUM_LINES * 4));
       LAUNCH_CFG(k_g2_walk_jac, (size_t)nwalk * np, 64, 0, Y, rec, nprob, np, K, dwalk, nwalk);
       LAUNCH_CFG(k_g2_lines_from_jac, (size_t)nwalk * np * 128, 128, 0, Y, rec, lines, nprob, np, K, dwalk);
-      LAUNCH(k_eval_tiles, (size_t)nwalk * np, PW, Y, lines, tiles, masks, nprob, np, K, S, dwalk, nwalk);
-    } else if ((size_t)((nwalk + 3) / 4) * np < 16384)
-      LAUNCH_CFG((k_g2_prepare4<1, 2>), (size_t)nwalk * np, 128, 0, PW, Y, tiles, masks, nprob, p0, np, K, S, dwalk, nwalk);
+      LAUNCH(k_eval_tiles, (size_t)nwalk * np, PW, Y, lines, tiles, masks, nprob, np, K, S, dwalk, nwalk, ne);
+    } else if ((size_t)((nwalk + 3) / 4) * np < 16384 && ne == 4)
+      LAUNCH_CFG((k_g2_prepare4<1, 2>), (size_t)nwalk * np, 128, 0, PW, Y, tiles, masks, nprob, p0, np, K, S, dwalk, nwalk, ne);
     else if (ctx->prep_variant == 4)
-      LAUNCH_CFG((k_g2_prepare4<4, 4>), (size_t)((nwalk + 3) / 4) * np, 128, 0, PW, Y, tiles, masks, nprob, p0, np, K, S, dwalk, nwalk);
+      LAUNCH_CFG((k_g2_prepare4<4, 4>), (size_t)((nwalk + 3) / 4) * np, 128, 0, PW, Y, tiles, masks, nprob, p0, np, K, S, dwalk, nwalk, ne);
     else
-      LAUNCH_CFG((k_g2_prepare4<4, 5>), (size_t)((nwalk + 3) / 4) * np, 128, 0, PW, Y, tiles, masks, nprob, p0, np, K, S, dwalk, nwalk);
+      LAUNCH_CFG((k_g2_prepare4<4, 5>), (size_t)((nwalk + 3) / 4) * np, 128, 0, PW, Y, tiles, masks, nprob, p0, np, K, S, dwalk, nwalk, ne);
     LAUNCH_CFG(k_miller4, ((nblk + CQ_GROUPS - 1) / CQ_GROUPS) * CQ_BLOCK_THREADS, CQ_BLOCK_THREADS, CQ_GROUPS * M4_SMEM, tiles, masks,
-               F, nprob, p0, np, S, nchunk, nblk);
+               F, nprob, p0, np, S, nchunk, nblk, ne);
   }
   const fp12* Fr = F;
   if (out_partial) {  // sharded statement: hand back the un-exponentiated Miller products, one per ComT entry
-    int rc = gsi::reduce_chunks(ctx, sc, &Fr, nprob, &nchunk, 1);
+    int rc = gsi::reduce_chunks(ctx, sc, &Fr, nprob, &nchunk, 1, ne);
     if (rc) return rc;
-    LAUNCH(k_chunk_product, nprob * 4, Fr, out_partial, nprob, nchunk);
+    LAUNCH(k_chunk_product, nprob * ne, Fr, out_partial, nprob, nchunk, ne);
     return GS_OK;
   }
   if (nchunk > 12) {

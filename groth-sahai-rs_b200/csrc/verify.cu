@@ -528,7 +528,242 @@ __global__ void k_and4(const uint8_t* __restrict__ ok4, uint8_t* __restrict__ ou
   out[p] = ok4[p] & ok4[nprob + p] & ok4[2 * nprob + p] & ok4[3 * nprob + p];
 }
 
+// ------------------------------------------------------------------ randomised batch verification
+// The four ComT entries of every proof p and all proofs of a batch are folded into ONE pairing-product check with random
+// weights: entry (a, b) of proof p gets the exponent w_{p,a} * beta_b with (w_{p,0}, w_{p,1}) = (sigma_p, tau_p) drawn per
+// proof and (beta_0, beta_1) = (beta, 1) drawn per call, all 64-bit.  By bilinearity the weighted product of the entries is
+//     prod_p prod_k e( sigma_p X_k.0 + tau_p X_k.1 ,  beta Y_k.0 + Y_k.1 )      ( = prod_p t_p^tau_p for a PPE )
+// over the SAME slots (X_k, Y_k) the exact verifier builds: one Miller pair per slot instead of four (two), and one final
+// exponentiation per call instead of four per proof.  Slots whose G2 side is a CRS element share one folded G2 point, so
+// their G1 sides are summed over the proofs first.  If any entry of any proof is wrong the check fails except with
+// probability <= 2^-63 over the weights (a non-zero polynomial of degree 2 in beta, then a non-zero linear form in the
+// independent sigma_p, tau_p) -- provided all inputs are in the prime-order groups, as deserialised values are.
+struct naf65 {
+  int8_t d[66];  // non-adjacent form of a 64-bit integer, d[i] in {-1, 0, 1}, least significant first
+};
+static naf65 make_naf(uint64_t k) {
+  naf65 r;
+  memset(r.d, 0, sizeof r.d);
+  unsigned __int128 v = k;
+  for (int i = 0; v != 0; i++) {
+    if (v & 1) {
+      int d = 2 - (int)(v & 3);  // +1 or -1
+      r.d[i] = (int8_t)d;
+      v = d > 0 ? v - 1 : v + 1;
+    }
+    v >>= 1;
+  }
+  return r;
+}
+// slot_map[k] >= 0: per-proof pair number jw of slot k (G2 side walked); < 0: -(f + 1), CRS slot number f
+// thread -> (p, k):  X' = sigma_p X[0][k][p] + tau_p X[1][k][p]   ->  X1[p*Kw + jw]  |  Xfix[f*nprob + p]
+__global__ void __launch_bounds__(128) k_rand_fold_g1(const g1_aff* __restrict__ X, size_t nprob, int K, const uint64_t* __restrict__ rho,
+                                                      const int* __restrict__ slot_map, int Kw, g1_aff* __restrict__ X1,
+                                                      g1_aff* __restrict__ Xfix) {
+  __shared__ fp sm[2 * 128];
+  size_t id = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool active = id < nprob * (size_t)K;
+  const size_t p = active ? id % nprob : 0;
+  const int k = active ? (int)(id / nprob) : 0;
+  g1_aff tab[4];  // 0, X0, X1, X0 + X1: one table addition per bit, the same instruction stream for every lane
+  tab[0].set_inf();
+  tab[1].set_inf();
+  tab[2].set_inf();
+  uint64_t sg = 0, tu = 0;
+  if (active) {
+    tab[1] = X[((size_t)0 * K + k) * nprob + p];
+    tab[2] = X[((size_t)1 * K + k) * nprob + p];
+    sg = rho[2 * p];
+    tu = rho[2 * p + 1];
+  }
+  g1_jac j;
+  j.from_affine(tab[1]);
+  g1_jac::add_mixed(j, j, tab[2]);
+  block_to_affine<128>(tab[3], j, sm);
+  __syncthreads();  // (sm is reused below)
+  g1_jac acc;
+  acc.set_inf();
+#pragma unroll 1
+  for (int bit = 63; bit >= 0; bit--) {
+    g1_jac::dbl(acc, acc);
+    const int d = (int)((sg >> bit) & 1) | ((int)((tu >> bit) & 1) << 1);
+    g1_jac::add_mixed(acc, acc, tab[d]);
+  }
+  g1_aff out;
+  block_to_affine<128>(out, acc, sm);
+  if (!active) return;
+  const int sm_k = slot_map[k];
+  if (sm_k >= 0)
+    X1[p * Kw + sm_k] = out;
+  else
+    Xfix[(size_t)(-sm_k - 1) * nprob + p] = out;
+}
+// thread -> (p, jw): Y' = beta Y[0][k][p] + Y[1][k][p] of the per-proof pair jw = slot walk_slot[jw]  ->  Y1[p*Kw + jw]
+__global__ void __launch_bounds__(128) k_rand_fold_g2(const g2_aff* __restrict__ Y, size_t nprob, int K, naf65 beta,
+                                                      const int* __restrict__ walk_slot, int Kw, g2_aff* __restrict__ Y1) {
+  __shared__ fp sm[2 * 128];
+  size_t id = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool active = id < nprob * (size_t)Kw;
+  const size_t p = active ? id % nprob : 0;
+  const int jw = active ? (int)(id / nprob) : 0;
+  g2_aff y0, y1;
+  y0.set_inf();
+  y1.set_inf();
+  if (active) {
+    const int k = walk_slot[jw];
+    y0 = Y[((size_t)0 * K + k) * nprob + p];
+    y1 = Y[((size_t)1 * K + k) * nprob + p];
+  }
+  g2_jac acc;
+  acc.set_inf();
+  const bool any = __syncthreads_or(!y0.is_inf());  // iota_2 images (B_i, a G2 target) have no first coordinate: nothing to fold
+  if (any) {
+    g2_aff ny0 = y0;
+    fp2::neg(ny0.y, y0.y);
+#pragma unroll 1
+    for (int i = 65; i >= 0; i--) {
+      g2_jac::dbl(acc, acc);
+      if (beta.d[i] > 0)
+        g2_jac::add_mixed(acc, acc, y0);
+      else if (beta.d[i] < 0)
+        g2_jac::add_mixed(acc, acc, ny0);
+    }
+  }
+  g2_jac::add_mixed(acc, acc, y1);
+  g2_aff out;
+  block_to_affine<128>(out, acc, sm);
+  if (active) Y1[p * Kw + jw] = out;
+}
+// thread pid < 3: Yfix[pid] = beta P.0 + P.1 for the CRS elements P = v_1, v_2, W2
+__global__ void k_rand_fold_crs(const crs_dev* __restrict__ crs, naf65 beta, g2_aff* __restrict__ Yfix) {
+  const int pid = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pid >= 3) return;
+  const g2_aff y0 = pid < 2 ? crs->v[pid][0] : crs->w2[0], y1 = pid < 2 ? crs->v[pid][1] : crs->w2[1];
+  g2_aff ny0 = y0;
+  fp2::neg(ny0.y, y0.y);
+  g2_jac acc;
+  acc.set_inf();
+  for (int i = 65; i >= 0; i--) {
+    g2_jac::dbl(acc, acc);
+    if (beta.d[i] > 0)
+      g2_jac::add_mixed(acc, acc, y0);
+    else if (beta.d[i] < 0)
+      g2_jac::add_mixed(acc, acc, ny0);
+  }
+  g2_jac::add_mixed(acc, acc, y1);
+  g2_jac::to_affine(Yfix[pid], acc);
+}
+// thread -> (f, strip): part[f*nstrips + strip] = sum of L consecutive points of Xfix[f][.]
+__global__ void __launch_bounds__(128) k_g1_sum_strips(const g1_aff* __restrict__ Xfix, size_t nprob, int nfix, int L, size_t nstrips,
+                                                       g1_jac* __restrict__ part) {
+  size_t id = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (id >= (size_t)nfix * nstrips) return;
+  const size_t strip = id % nstrips;
+  const int f = (int)(id / nstrips);
+  g1_jac acc;
+  acc.set_inf();
+  const size_t p1 = min(nprob, (strip + 1) * L);
+  for (size_t p = strip * L; p < p1; p++) g1_jac::add_mixed(acc, acc, Xfix[(size_t)f * nprob + p]);
+  part[id] = acc;
+}
+// block f: X1[at + f] = affine(sum of part[f][.]),  Y1[at + f] = Yfix[fpid[f]]
+struct fix_pids {
+  int pid[8];
+};
+__global__ void __launch_bounds__(128) k_g1_sum_final(const g1_jac* __restrict__ part, size_t nstrips, const g2_aff* __restrict__ Yfix,
+                                                      fix_pids fp_, size_t at, g1_aff* __restrict__ X1, g2_aff* __restrict__ Y1) {
+  __shared__ g1_jac red[128];
+  const int f = blockIdx.x, t = threadIdx.x;
+  g1_jac acc;
+  acc.set_inf();
+  for (size_t i = t; i < nstrips; i += 128) {
+    g1_jac q = part[(size_t)f * nstrips + i];
+    g1_jac::add(acc, acc, q);
+  }
+  red[t] = acc;
+  __syncthreads();
+  for (int half = 64; half >= 1; half >>= 1) {
+    if (t < half) {
+      g1_jac a = red[t], b = red[t + half];
+      g1_jac::add(a, a, b);
+      red[t] = a;
+    }
+    __syncthreads();
+  }
+  if (t == 0) {
+    g1_aff o;
+    g1_jac::to_affine(o, red[0]);
+    X1[at + f] = o;
+    Y1[at + f] = Yfix[fp_.pid[f]];
+  }
+}
+__global__ void k_ok1(const uint8_t* __restrict__ ok1, uint8_t* __restrict__ out) { out[0] = ok1[0]; }
+
 }  // namespace gs
+
+// what the shape alone says about the G2 side of every slot (k_verify_assemble): CRS points have stored lines, iota_2
+// images have no first coordinate
+static std::vector<uint8_t> slot_kinds(const verify_shape& s) {
+  std::vector<uint8_t> kind_all(s.K, gsi::GS_SLOT_WALK);
+  for (int k = s.sB; k < s.sPi; k++) kind_all[k] = s.groupB ? gsi::GS_SLOT_WALK_B1 : (uint8_t)(gsi::GS_SLOT_FIXED + 2);
+  for (int j = 0; j < s.cy; j++) kind_all[s.sTh + j] = (uint8_t)(gsi::GS_SLOT_FIXED + j);
+  if (s.type == 1 || s.type == 3) kind_all[s.sT] = (uint8_t)(gsi::GS_SLOT_FIXED + 2);
+  if (s.type == 2) kind_all[s.sT] = gsi::GS_SLOT_WALK_B1;
+  return kind_all;
+}
+
+// The G1-side statement MSM of `nprob` problems into the X slots (k_verify_assemble has filled the others).
+static int statement_msm(gs_ctx* ctx, Scratch& sc, verify_shape s, const verify_args& v, size_t nprob, bool shared_x, g1_aff* X) {
+  // outputs that share one base coordinate: this rank's MSM outputs x the problems that use the same commitments
+  const size_t owned_out = (size_t)s.n_out_owned();
+  const bool use_wtab = (nprob == 1 || shared_x) && owned_out * nprob >= 320;  // table build ~ 14.6 ms at m = 1024
+  {
+    // bases per thread: few threads (one statement, or one rank's share of it) -> smaller chunks, so that the
+    // grid is ~8 waves of the ~296 resident blocks instead of 1.7 (measured: 20.8 ms for half of C3's sums against
+    // 30.8 ms for all of them; C4's shared-table batches 91 -> 67 ms); the table kernel has no doublings to
+    // amortise, Straus keeps >= 8.  Many chunks are folded 16 at a time (k_vmsm_fold) before k_vmsm_reduce.
+    int chunk = GS_MSM_CHUNK;
+    // (a lone small statement is pure latency: one base per thread there)
+    const bool tiny = nprob * owned_out * 2 * ((s.nbases + 7) / 8) < 16384;
+    const int floor_chunk = use_wtab ? 4 : (tiny ? 1 : 8);
+    while (chunk > floor_chunk && nprob * owned_out * 2 * ((s.nbases + chunk - 1) / chunk) < (size_t)128 * 2368) chunk /= 2;
+    set_msm_chunk(s, chunk);
+  }
+  g1_jac* part;
+  CUDA_TRY(sc.alloc(&part, (size_t)s.nchunk * s.n_out * 2 * nprob));
+  if (use_wtab) {
+    const int nb = s.nb_own() * 2;
+    const wt_geom g = wt_choose(owned_out * nprob);
+    const size_t nrows = (size_t)nb * g.W;
+    g1_aff* wtab;
+    g1_jac* J;
+    CUDA_TRY(sc.alloc(&wtab, nrows * g.H));
+    CUDA_TRY(sc.alloc(&J, nrows * g.H));
+    LAUNCH(k_wtab_bases, (size_t)nb, s, v, ctx->crs, J, nb, g);
+    LAUNCH(k_jac_to_affine_blocks<1>, nrows, J, wtab, nrows, (size_t)g.H);
+    LAUNCH(k_wtab_fill, nrows * (g.H / GS_WT_RUN), wtab, J, nrows, g.H);
+    LAUNCH(k_jac_to_affine_blocks<8>, nrows * g.H / 8, J, wtab, nrows * g.H, (size_t)1);
+    LAUNCH(k_vmsm_wsum, nprob * owned_out * 2 * s.nchunk, s, v, wtab, part, nprob, g);
+  } else {
+    g1_aff* vtab;
+    fp* vtabx;
+    CUDA_TRY(sc.alloc(&vtab, (size_t)s.nb_own() * 2 * GS_VTAB * nprob));
+    CUDA_TRY(sc.alloc(&vtabx, (size_t)s.nb_own() * 2 * GS_VTAB * nprob));
+    LAUNCH(k_vmsm_tables, nprob * (size_t)s.nb_own() * 2, s, v, ctx->crs, vtab, vtabx, nprob);
+    LAUNCH(k_vmsm_partial, nprob * owned_out * 2 * s.nchunk, s, v, vtab, vtabx, part, nprob);
+  }
+  const g1_jac* partr = part;
+  if (s.nchunk > 32) {  // fold 16 chunks at a time in parallel; k_vmsm_reduce then walks the few that are left
+    const int F = 16, ng = (s.nchunk + F - 1) / F;
+    g1_jac* part2;
+    CUDA_TRY(sc.alloc(&part2, (size_t)ng * s.n_out * 2 * nprob));
+    LAUNCH(k_vmsm_fold, (size_t)s.n_out * 2 * nprob * ng, s, part, part2, nprob, s.nchunk, F, ng);
+    partr = part2;
+    s.nchunk = ng;
+  }
+  LAUNCH(k_vmsm_reduce, nprob * owned_out * 2, s, v, partr, X, nprob);
+  return GS_OK;
+}
 
 extern "C" {
 
@@ -587,37 +822,16 @@ static int verify_impl(gs_ctx* ctx, int type, size_t count, size_t m, size_t n, 
     v.ycoms = (const g2_aff*)ycoms + off * n * 2;
     v.pi = (const g2_aff*)pi + off * s.cx * 2;
     v.theta = (const g1_aff*)theta + off * s.cy * 2;
-    // outputs that share one base coordinate: this rank's MSM outputs x the problems that use the same commitments
-    const size_t owned_out = (size_t)s.n_out_owned();
-    const bool use_wtab = (nprob == 1 || shared_x) && owned_out * nprob >= 320;  // table build ~ 14.6 ms at m = 1024
-    {
-      // bases per thread: few threads (one statement, or one rank's share of it) -> smaller chunks, so that the
-      // grid is ~8 waves of the ~296 resident blocks instead of 1.7 (measured: 20.8 ms for half of C3's sums against
-      // 30.8 ms for all of them; C4's shared-table batches 91 -> 67 ms); the table kernel has no doublings to
-      // amortise, Straus keeps >= 8.  Many chunks are folded 16 at a time (k_vmsm_fold) before k_vmsm_reduce.
-      int chunk = GS_MSM_CHUNK;
-      // (a lone small statement is pure latency: one base per thread there)
-      const bool tiny = nprob * owned_out * 2 * ((s.nbases + 7) / 8) < 16384;
-      const int floor_chunk = use_wtab ? 4 : (tiny ? 1 : 8);
-      while (chunk > floor_chunk && nprob * owned_out * 2 * ((s.nbases + chunk - 1) / chunk) < (size_t)128 * 2368) chunk /= 2;
-      set_msm_chunk(s, chunk);
-    }
     g1_aff* X;
     g2_aff* Y;
-    g1_jac* part;
     uint8_t* ok4;
     CUDA_TRY(sc.alloc(&X, 2 * (size_t)s.K * nprob));
     CUDA_TRY(sc.alloc(&Y, 2 * (size_t)s.K * nprob));
-    CUDA_TRY(sc.alloc(&part, (size_t)s.nchunk * s.n_out * 2 * nprob));
     CUDA_TRY(sc.alloc(&ok4, 4 * nprob));
     LAUNCH(k_verify_assemble, nprob * (size_t)s.K, s, v, ctx->crs, X, Y, nprob);
     // what the shape alone says about the G2 side of every slot (k_verify_assemble): CRS points have stored lines,
     // iota_2 images have no first coordinate
-    std::vector<uint8_t> kind_all(s.K, gsi::GS_SLOT_WALK), kind;
-    for (int k = s.sB; k < s.sPi; k++) kind_all[k] = s.groupB ? gsi::GS_SLOT_WALK_B1 : (uint8_t)(gsi::GS_SLOT_FIXED + 2);
-    for (int j = 0; j < s.cy; j++) kind_all[s.sTh + j] = (uint8_t)(gsi::GS_SLOT_FIXED + j);
-    if (type == 1 || type == 3) kind_all[s.sT] = (uint8_t)(gsi::GS_SLOT_FIXED + 2);
-    if (type == 2) kind_all[s.sT] = gsi::GS_SLOT_WALK_B1;
+    std::vector<uint8_t> kind_all = slot_kinds(s), kind;
     for (int k = world > 1 ? rank : 0; k < s.K; k += world > 1 ? world : 1) kind.push_back(kind_all[k]);
     // the G2 side is final now: a lone statement starts its line walks on the second stream, next to the MSM below
     g1_aff* Xo = nullptr;
@@ -634,37 +848,10 @@ static int verify_impl(gs_ctx* ctx, int type, size_t count, size_t m, size_t n, 
       int rcw = gsi::g2_walk_ahead(ctx, sc, Yp, nprob, Ko, kind.data(), &wa);
       if (rcw) return rcw;
     }
-    if (use_wtab) {
-      const int nb = s.nb_own() * 2;
-      const wt_geom g = wt_choose(owned_out * nprob);
-      const size_t nrows = (size_t)nb * g.W;
-      g1_aff* wtab;
-      g1_jac* J;
-      CUDA_TRY(sc.alloc(&wtab, nrows * g.H));
-      CUDA_TRY(sc.alloc(&J, nrows * g.H));
-      LAUNCH(k_wtab_bases, (size_t)nb, s, v, ctx->crs, J, nb, g);
-      LAUNCH(k_jac_to_affine_blocks<1>, nrows, J, wtab, nrows, (size_t)g.H);
-      LAUNCH(k_wtab_fill, nrows * (g.H / GS_WT_RUN), wtab, J, nrows, g.H);
-      LAUNCH(k_jac_to_affine_blocks<8>, nrows * g.H / 8, J, wtab, nrows * g.H, (size_t)1);
-      LAUNCH(k_vmsm_wsum, nprob * owned_out * 2 * s.nchunk, s, v, wtab, part, nprob, g);
-    } else {
-      g1_aff* vtab;
-      fp* vtabx;
-      CUDA_TRY(sc.alloc(&vtab, (size_t)s.nb_own() * 2 * GS_VTAB * nprob));
-      CUDA_TRY(sc.alloc(&vtabx, (size_t)s.nb_own() * 2 * GS_VTAB * nprob));
-      LAUNCH(k_vmsm_tables, nprob * (size_t)s.nb_own() * 2, s, v, ctx->crs, vtab, vtabx, nprob);
-      LAUNCH(k_vmsm_partial, nprob * owned_out * 2 * s.nchunk, s, v, vtab, vtabx, part, nprob);
+    {
+      int rcm = statement_msm(ctx, sc, s, v, nprob, shared_x, X);
+      if (rcm) return rcm;
     }
-    const g1_jac* partr = part;
-    if (s.nchunk > 32) {  // fold 16 chunks at a time in parallel; k_vmsm_reduce then walks the few that are left
-      const int F = 16, ng = (s.nchunk + F - 1) / F;
-      g1_jac* part2;
-      CUDA_TRY(sc.alloc(&part2, (size_t)ng * s.n_out * 2 * nprob));
-      LAUNCH(k_vmsm_fold, (size_t)s.n_out * 2 * nprob * ng, s, part, part2, nprob, s.nchunk, F, ng);
-      partr = part2;
-      s.nchunk = ng;
-    }
-    LAUNCH(k_vmsm_reduce, nprob * owned_out * 2, s, v, partr, X, nprob);
     const g1_aff* Xp = X;
     if (world > 1) {
       LAUNCH(k_gather_owned_slots, nprob * (size_t)Ko * 2, X, Y, Xo, Yo, nprob, s.K, Ko, rank, world, 1, 0);
@@ -984,6 +1171,189 @@ int gs_verify_finish(gs_ctx* ctx, int type, size_t count, int nparts, const gs_g
   CUDA_TRY(cudaMemcpyAsync(out_ok, dok, count, cudaMemcpyDeviceToHost, ctx->stream));
   CUDA_TRY(cudaStreamSynchronize(ctx->stream));
   return GS_OK;
+}
+
+// ------------------------------------------------------------------ randomised batch verification: driver
+// slots per Miller accumulator: every accumulator pays 62 squarings (~53 M each as executed) next to ~29 M x 68 steps per slot,
+// and the accumulators fill waves of 2 x 148 x 32 lanes; pick the multiple of 4 that minimises waves x (time per accumulator)
+static int rand_slots_per_acc(size_t npairs) {
+  int best = 8;
+  double best_t = 1e300;
+  for (int S = 8; S <= 128; S += 4) {
+    const size_t nacc = (npairs + S - 1) / S;
+    const size_t waves = (nacc + 9471) / 9472;
+    const double t = (double)waves * (62.0 * 53.0 + (double)S * 68.0 * 29.0);
+    if (t < best_t) {
+      best_t = t;
+      best = S;
+    }
+  }
+  return best;
+}
+
+static int verify_rand_dev(gs_ctx* ctx, int type, size_t count, size_t m, size_t n, const void* a_consts, const void* b_consts,
+                           const gs_fr* gamma, const void* target, const gs_com1* xcoms, const gs_com2* ycoms, const gs_com2* pi,
+                           const gs_com1* theta, const uint64_t* rho_host, bool shared_x, uint8_t* out_ok_dev) {
+  verify_shape s = make_verify_shape(type, (int)m, (int)n);
+  const std::vector<uint8_t> kind_all = slot_kinds(s);
+  // per-proof pairs (G2 side walked) and CRS slots (G1 sides summed over the proofs)
+  std::vector<int> slot_map(s.K), walk_slot;
+  fix_pids fpids;
+  int nfix = 0;
+  for (int k = 0; k < s.K; k++) {
+    if (kind_all[k] >= gsi::GS_SLOT_FIXED) {
+      if (nfix >= 8) FAIL(GS_EDIM, "verify_rand: too many CRS slots");
+      fpids.pid[nfix] = kind_all[k] - gsi::GS_SLOT_FIXED;
+      slot_map[k] = -(nfix + 1);
+      nfix++;
+    } else {
+      slot_map[k] = (int)walk_slot.size();
+      walk_slot.push_back(k);
+    }
+  }
+  const int Kw = (int)walk_slot.size();
+  const naf65 beta = make_naf(rho_host[2 * count]);
+  const size_t pass_n = count < ctx->verify_batch_max ? count : ctx->verify_batch_max;
+  const size_t npass = (count + pass_n - 1) / pass_n;
+  if ((size_t)pass_n * Kw + nfix > ((size_t)1 << 30)) FAIL(GS_EDIM, "verify_rand: statement too large for one pass");
+  Scratch top(ctx);
+  fp12 *Mall, *Tall;
+  g2_aff* Yfix;
+  int *dmap, *dwalk_slot;
+  uint8_t* ok1;
+  CUDA_TRY(top.alloc(&Mall, npass));
+  CUDA_TRY(top.alloc(&Tall, npass + 1));
+  CUDA_TRY(top.alloc(&Yfix, 3));
+  CUDA_TRY(top.alloc(&ok1, 4));
+  CUDA_TRY(upload(ctx, top, &dmap, slot_map.data(), slot_map.size()));
+  CUDA_TRY(upload(ctx, top, &dwalk_slot, walk_slot.data(), walk_slot.size()));
+  LAUNCH_CFG(k_rand_fold_crs, 3, 32, 0, ctx->crs, beta, Yfix);
+  size_t pass = 0;
+  for (size_t off = 0; off < count; off += pass_n, pass++) {
+    const size_t nprob = count - off < pass_n ? count - off : pass_n;
+    Scratch sc(ctx);
+    verify_args v;
+    v.a_consts = (const char*)a_consts + off * n * elem_size_A(type);
+    v.b_consts = (const char*)b_consts + off * m * elem_size_B(type);
+    v.gamma = (const fr*)gamma + off * m * n;
+    v.target = (const char*)target + off * elem_size_T(type);
+    v.xcoms = (const g1_aff*)xcoms + off * m * 2;
+    v.ycoms = (const g2_aff*)ycoms + off * n * 2;
+    v.pi = (const g2_aff*)pi + off * s.cx * 2;
+    v.theta = (const g1_aff*)theta + off * s.cy * 2;
+    g1_aff *X, *X1, *Xfix;
+    g2_aff *Y, *Y1;
+    uint64_t* drho;
+    CUDA_TRY(sc.alloc(&X, 2 * (size_t)s.K * nprob));
+    CUDA_TRY(sc.alloc(&Y, 2 * (size_t)s.K * nprob));
+    LAUNCH(k_verify_assemble, nprob * (size_t)s.K, s, v, ctx->crs, X, Y, nprob);
+    {
+      int rcm = statement_msm(ctx, sc, s, v, nprob, shared_x, X);
+      if (rcm) return rcm;
+    }
+    // the folded single-entry problem: nprob * Kw per-proof pairs, then the nfix summed CRS pairs, padded with identities
+    const size_t npairs = nprob * Kw + nfix;
+    const int S = rand_slots_per_acc(npairs);
+    const size_t Ktot = (npairs + S - 1) / S * S;
+    CUDA_TRY(upload(ctx, sc, &drho, rho_host + 2 * off, 2 * nprob));
+    CUDA_TRY(sc.alloc(&X1, Ktot));
+    CUDA_TRY(sc.alloc(&Y1, Ktot));
+    CUDA_TRY(sc.alloc(&Xfix, (size_t)(nfix ? nfix : 1) * nprob));
+    CUDA_TRY(cudaMemsetAsync(X1 + npairs, 0, (Ktot - npairs) * sizeof(g1_aff), ctx->stream));
+    CUDA_TRY(cudaMemsetAsync(Y1 + npairs, 0, (Ktot - npairs) * sizeof(g2_aff), ctx->stream));
+    LAUNCH(k_rand_fold_g1, nprob * (size_t)s.K, X, nprob, s.K, drho, dmap, Kw, X1, Xfix);
+    LAUNCH(k_rand_fold_g2, nprob * (size_t)Kw, Y, nprob, s.K, beta, dwalk_slot, Kw, Y1);
+    if (nfix) {
+      const int L = 32;
+      const size_t nstrips = (nprob + L - 1) / L;
+      g1_jac* part;
+      CUDA_TRY(sc.alloc(&part, (size_t)nfix * nstrips));
+      LAUNCH(k_g1_sum_strips, (size_t)nfix * nstrips, Xfix, nprob, nfix, L, nstrips, part);
+      LAUNCH_CFG(k_g1_sum_final, (size_t)nfix * 128, 128, 0, part, nstrips, Yfix, fpids, nprob * Kw, X1, Y1);
+    }
+    int rc = gsi::run_pairing_product(ctx, sc, X1, Y1, 1, (int)Ktot, nullptr, nullptr, nullptr, Mall + pass, nullptr, nullptr, 1, S);
+    if (rc) return rc;
+    if (type == GS_PPE) {  // prod_p t_p^tau_p
+      fp12* P;
+      CUDA_TRY(sc.alloc(&P, nprob));
+      rc = gsi::gt_pow64(ctx, (const fp12*)v.target, drho + 1, 2, nprob, P);
+      if (rc) return rc;
+      const fp12* Pr = P;
+      int nch = (int)nprob;
+      rc = gsi::reduce_chunks(ctx, sc, &Pr, 1, &nch, 1, 1);
+      if (rc) return rc;
+      CUDA_TRY(cudaMemcpyAsync(Tall + pass, Pr, sizeof(fp12), cudaMemcpyDeviceToDevice, ctx->stream));
+    }
+  }
+  const fp12* want = nullptr;
+  if (type == GS_PPE) {
+    const fp12* Tr = Tall;
+    int nch = (int)npass;
+    Scratch sc(ctx);
+    int rc = gsi::reduce_chunks(ctx, sc, &Tr, 1, &nch, 1, 1);
+    if (rc) return rc;
+    CUDA_TRY(cudaMemcpyAsync(Tall + npass, Tr, sizeof(fp12), cudaMemcpyDeviceToDevice, ctx->stream));
+    want = Tall + npass;
+  }
+  int rc = gsi::launch_final_exp(ctx, Mall, 1, (int)npass, nullptr, ok1, want, 1);
+  if (rc) return rc;
+  LAUNCH_CFG(k_ok1, 1, 32, 0, ok1, out_ok_dev);
+  return GS_OK;
+}
+
+int gs_verify_batch_rand(gs_ctx* ctx, int type, size_t count, size_t m, size_t n, const void* a_consts, const void* b_consts,
+                         const gs_fr* gamma, const void* target, const gs_com1* xcoms, const gs_com2* ycoms, const gs_com2* pi,
+                         const gs_com1* theta, const uint64_t* rho, uint8_t* out_all_ok) {
+  if (!ctx) return GS_EARG;
+  if (type < 0 || type > 3) FAIL(GS_EARG, "verify: bad equation type");
+  if (!ctx->crs_loaded) FAIL(GS_EARG, "verify: no CRS loaded");
+  if (!out_all_ok) return GS_EARG;
+  if (count == 0) {
+    *out_all_ok = 1;
+    return GS_OK;
+  }
+  if (m == 0 || n == 0) FAIL(GS_EDIM, "verify: empty variable list");
+  if (m > 1 << 20 || n > 1 << 20) FAIL(GS_EDIM, "verify: too many variables");
+  if (!a_consts || !b_consts || !gamma || !target || !xcoms || !ycoms || !pi || !theta || !rho) return GS_EARG;
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  verify_shape s = make_verify_shape(type, (int)m, (int)n);
+  bool shared_x = count > 1;
+  for (size_t i = 1; i < count && shared_x; i++)
+    shared_x = memcmp(xcoms, (const char*)xcoms + i * m * sizeof(gs_com1), m * sizeof(gs_com1)) == 0;
+  Scratch sc(ctx);
+  uint8_t *dA, *dB, *dT, *dok;
+  fr* dG;
+  g1_aff *dc, *dth;
+  g2_aff *dd, *dpi;
+  CUDA_TRY(upload(ctx, sc, &dA, a_consts, count * n * elem_size_A(type)));
+  CUDA_TRY(upload(ctx, sc, &dB, b_consts, count * m * elem_size_B(type)));
+  CUDA_TRY(upload(ctx, sc, &dG, gamma, count * m * n));
+  CUDA_TRY(upload(ctx, sc, &dT, target, count * elem_size_T(type)));
+  CUDA_TRY(upload(ctx, sc, &dc, xcoms, count * m * 2));
+  CUDA_TRY(upload(ctx, sc, &dd, ycoms, count * n * 2));
+  CUDA_TRY(upload(ctx, sc, &dpi, pi, count * s.cx * 2));
+  CUDA_TRY(upload(ctx, sc, &dth, theta, count * s.cy * 2));
+  CUDA_TRY(sc.alloc(&dok, 4));
+  int rc = verify_rand_dev(ctx, type, count, m, n, dA, dB, (const gs_fr*)dG, dT, (const gs_com1*)dc, (const gs_com2*)dd,
+                           (const gs_com2*)dpi, (const gs_com1*)dth, rho, shared_x, dok);
+  if (rc) return rc;
+  CUDA_TRY(cudaMemcpyAsync(out_all_ok, dok, 1, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  return GS_OK;
+}
+
+int gs_verify_batch_rand_dev(gs_ctx* ctx, int type, size_t count, size_t m, size_t n, const void* a_consts, const void* b_consts,
+                             const gs_fr* gamma, const void* target, const gs_com1* xcoms, const gs_com2* ycoms, const gs_com2* pi,
+                             const gs_com1* theta, const uint64_t* rho, uint8_t* out_all_ok_dev) {
+  if (!ctx) return GS_EARG;
+  if (type < 0 || type > 3) FAIL(GS_EARG, "verify: bad equation type");
+  if (!ctx->crs_loaded) FAIL(GS_EARG, "verify: no CRS loaded");
+  if (count == 0 || !out_all_ok_dev) return GS_EARG;
+  if (m == 0 || n == 0) FAIL(GS_EDIM, "verify: empty variable list");
+  if (m > 1 << 20 || n > 1 << 20) FAIL(GS_EDIM, "verify: too many variables");
+  if (!a_consts || !b_consts || !gamma || !target || !xcoms || !ycoms || !pi || !theta || !rho) return GS_EARG;
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  return verify_rand_dev(ctx, type, count, m, n, a_consts, b_consts, gamma, target, xcoms, ycoms, pi, theta, rho, false, out_all_ok_dev);
 }
 
 }  // extern "C"

@@ -16,7 +16,7 @@ EXPORTED_SYMBOLS = [
     "gs_profile_enable", "gs_profile_read", "gs_diag_fpmul_rate",
     "gs_crs_generate", "gs_crs_load",
     "gs_batch_commit_g1", "gs_batch_commit_g2", "gs_batch_commit_scalar_b1", "gs_batch_commit_scalar_b2",
-    "gs_prove", "gs_prove_batch", "gs_verify_batch", "gs_verify_batch_dev",
+    "gs_prove", "gs_prove_batch", "gs_verify_batch", "gs_verify_batch_dev", "gs_verify_batch_rand", "gs_verify_batch_rand_dev",
     "gs_verify_partial", "gs_verify_partial_dev", "gs_verify_finish", "gs_verify_finish_dev", "gs_verify_sharded",
     "gs_comt_pairing", "gs_comt_pairing_sum", "gs_comt_linear_map", "gs_pairing",
     "gs_com1_matmul", "gs_com2_matmul", "gs_fr_matmul",
@@ -75,6 +75,8 @@ def load_library():
         lib.gs_prove_batch.argtypes = [vp, ci, sz, sz, sz] + [vp] * 8 + [ci, vp, vp]
         lib.gs_verify_batch.argtypes = [vp, ci, sz, sz, sz] + [vp] * 9
         lib.gs_verify_batch_dev.argtypes = [vp, ci, sz, sz, sz] + [vp] * 9
+        lib.gs_verify_batch_rand.argtypes = [vp, ci, sz, sz, sz] + [vp] * 10
+        lib.gs_verify_batch_rand_dev.argtypes = [vp, ci, sz, sz, sz] + [vp] * 10
         lib.gs_verify_partial.argtypes = [vp, ci, sz, sz, sz] + [vp] * 8 + [ci, ci, vp]
         lib.gs_verify_partial_dev.argtypes = [vp, ci, sz, sz, sz] + [vp] * 8 + [ci, ci, vp]
         lib.gs_verify_finish.argtypes = [vp, ci, sz, ci, vp, vp, vp]
@@ -276,6 +278,35 @@ class Engine:
 
     def verify(self, ty, m, n, a_consts, b_consts, gamma, target, xcoms, ycoms, pi, theta) -> bool:
         return self.verify_batch(ty, 1, m, n, a_consts, b_consts, gamma, target, xcoms, ycoms, pi, theta) == b"\x01"
+
+    # ---- randomised batch verification (gs_verify_batch_rand): ONE verdict for the batch
+    @staticmethod
+    def _rho(count, rho):
+        """2*count + 1 random 64-bit words; drawn from the OS CSPRNG unless the caller brings them (tests: a fixed seed)."""
+        need = 8 * (2 * count + 1)
+        if rho is None:
+            import secrets
+            rho = secrets.token_bytes(need)
+        if len(rho) != need:
+            raise GsError(1, f"verify_batch_rand: rho is {len(rho)} bytes, expected {need}")
+        return rho
+
+    def verify_batch_rand(self, ty, count, m, n, a_consts, b_consts, gamma, target, xcoms, ycoms, pi, theta, rho=None) -> bool:
+        """True iff every proof of the batch verifies (error <= 2^-63 over rho).  Not the reference's per-proof answer: on
+        False, verify_batch says which ones failed."""
+        if count and m and n:
+            self._check_verify_sizes(ty, count, m, n, a_consts, b_consts, gamma, target, xcoms, ycoms, pi, theta)
+        kr = _buf(self._rho(count, rho))
+        ok = ctypes.create_string_buffer(1)
+        ks = [_buf(x) for x in (a_consts, b_consts, gamma, target, xcoms, ycoms, pi, theta)]
+        self._chk(self.lib.gs_verify_batch_rand(self.h, ty, count, m, n, *[k[1] for k in ks], kr[1], ctypes.cast(ok, ctypes.c_void_p)))
+        return ok.raw == b"\x01"
+
+    def verify_batch_rand_dev(self, ty, count, m, n, ptrs, out_ok_ptr, rho=None):
+        """All-device variant (rho stays on the host); asynchronous on self.stream, one verdict byte at out_ok_ptr."""
+        kr = _buf(self._rho(count, rho))
+        self._chk(self.lib.gs_verify_batch_rand_dev(self.h, ty, count, m, n, *[ctypes.c_void_p(int(p)) for p in ptrs], kr[1],
+                                                    ctypes.c_void_p(int(out_ok_ptr))))
 
     # ---- one statement sharded by slot over several GPUs (gs_verify_partial / gs_verify_finish)
     def verify_partial(self, ty, count, m, n, a_consts, b_consts, gamma, target, xcoms, ycoms, pi, theta, rank, world) -> bytes:

@@ -189,6 +189,26 @@ int gs_verify_sharded(gs_ctx* ctx, int type, size_t count, size_t m, size_t n, c
                       const gs_com2* pi, const gs_com1* theta, int rank, int world, gs_allgather_fn allgather, void* user,
                       uint8_t* out_ok);
 
+/* Randomised batch verification -- SURVEY.md §8f.4, an OPT-IN that the reference does not have (its `verify` is
+ * src/verifier.rs:23-157, one proof at a time, four final exponentiations each).  ONE verdict for the whole batch:
+ * *out_all_ok = 1 iff every proof verifies, except with probability <= 2^-63 over `rho`.  Not bit-comparable with the
+ * reference's per-proof booleans: when the answer is 0 the caller learns which proofs failed from gs_verify_batch.
+ * rho[2*count + 1]: 64-bit words from the CALLER's cryptographic RNG, unknown to whoever made the proofs
+ * (rho[2p], rho[2p+1] weight the two Com1 coordinates of proof p, rho[2*count] the Com2 coordinates of all of them).
+ * The four ComT entries of all proofs are folded into a single pairing product: one Miller pair per slot and one final
+ * exponentiation per call (csrc/verify.cu, "randomised batch verification").  Soundness needs what the exact
+ * verifier assumes too: every point in its prime-order group (gs_g1/g2_decompress check it) and, for PPE, every target
+ * in GT (gs_gt_from_bytes checks it).  Arrays as for gs_verify_batch; the _dev variant takes device arrays (rho and
+ * nothing else on the host) and writes one byte of device memory. */
+int gs_verify_batch_rand(gs_ctx* ctx, int type, size_t count, size_t m, size_t n, const void* a_consts,
+                         const void* b_consts, const gs_fr* gamma, const void* target, const gs_com1* xcoms,
+                         const gs_com2* ycoms, const gs_com2* pi, const gs_com1* theta, const uint64_t* rho,
+                         uint8_t* out_all_ok);
+int gs_verify_batch_rand_dev(gs_ctx* ctx, int type, size_t count, size_t m, size_t n, const void* a_consts,
+                             const void* b_consts, const gs_fr* gamma, const void* target, const gs_com1* xcoms,
+                             const gs_com2* ycoms, const gs_com2* pi, const gs_com1* theta, const uint64_t* rho,
+                             uint8_t* out_all_ok_dev);
+
 /* ---- ComT (src/data_structures.rs) ------------------------------------------------------- */
 /* ComT::pairing :484-491, batched: out[i] = F(xs[i], ys[i]) (4 full pairings each) */
 int gs_comt_pairing(gs_ctx* ctx, size_t count, const gs_com1* xs, const gs_com2* ys, gs_comt* out);

@@ -52,7 +52,9 @@ impl<E: Gpu> Verifiable<E> for QuadEqu<E> {
 }
 
 /// Not in the reference: `count` independent PPE (equation, proof) pairs of one shape in ONE GPU pass (C5).
-pub fn verify_batch_ppe<E: Gpu>(equations: &[PPE<E>], proofs: &[CProof<E>], crs: &CRS<E>) -> Vec<bool> {
+/// `randomized = Some(rng)` (a cryptographic RNG the prover cannot predict) turns on the randomised pre-check.
+pub fn verify_batch_ppe<E: Gpu>(equations: &[PPE<E>], proofs: &[CProof<E>], crs: &CRS<E>,
+                                randomized: Option<&mut dyn ark_std::rand::RngCore>) -> Vec<bool> {
     assert_eq!(equations.len(), proofs.len());
     if equations.is_empty() { return vec![]; }
     let (m, n) = (proofs[0].xcoms.coms.len(), proofs[0].ycoms.coms.len());
@@ -63,6 +65,17 @@ pub fn verify_batch_ppe<E: Gpu>(equations: &[PPE<E>], proofs: &[CProof<E>], crs:
         a.extend(g1s::<E>(&e.a_consts)); b.extend(g2s::<E>(&e.b_consts)); g.extend(fr_matrix::<E>(&e.gamma)); t.push(E::gt(&e.target));
         xc.extend(com1s(&p.xcoms.coms)); yc.extend(com2s(&p.ycoms.coms));
         pi.extend(com2s(&p.equ_proofs[0].pi)); th.extend(com1s(&p.equ_proofs[0].theta));
+    }
+    // opt-in: one randomised check of the whole batch first (a single folded pairing product, one final exponentiation);
+    // only a batch that fails it pays for the exact per-proof pass below, which says WHICH proofs are bad
+    if let Some(rng) = randomized {
+        let rho: Vec<u64> = (0..2 * equations.len() + 1).map(|_| rng.next_u64()).collect();
+        let mut all_ok = 0u8;
+        with_crs(&crs.abi(), |c| check(c, unsafe {
+            gs_verify_batch_rand(c.raw(), 0, equations.len(), m, n, bytes_of(&a).as_ptr(), bytes_of(&b).as_ptr(), g.as_ptr(),
+                                 bytes_of(&t).as_ptr(), xc.as_ptr(), yc.as_ptr(), pi.as_ptr(), th.as_ptr(), rho.as_ptr(), &mut all_ok)
+        }));
+        if all_ok == 1 { return vec![true; equations.len()]; }
     }
     let mut ok = vec![0u8; equations.len()];
     with_crs(&crs.abi(), |c| check(c, unsafe {

@@ -156,6 +156,23 @@ def test_verify_panics_like_the_reference(env):
     assert equ.verify(bad, crs) is False
 
 
+def test_verify_batch_randomized_flag(env):
+    """api.verify_batch(randomized=True) -- the opt-in of SURVEY.md 8f.4: one randomised check of the batch, the exact
+    per-proof verification only when it rejects; the answers equal the exact call's, honest or not."""
+    eng, api, crs, rng = env
+    crs_o = ogs.generate_crs(*rng.log[:6])
+    eqs, proofs = [], []
+    for i in range(4):
+        _, equ, xvars, yvars, _, _ = _equation(api, crs_o, 0, 60 + i)
+        eqs.append(equ)
+        proofs.append(equ.commit_and_prove(xvars, yvars, crs, ReplayRng(90 + i)))
+    assert api.verify_batch(eqs, proofs, crs, randomized=True) == [True] * 4
+    ep = proofs[2].equ_proofs[0]
+    bad = list(proofs)
+    bad[2] = api.CProof(proofs[2].xcoms, proofs[2].ycoms, [api.EquProof(ep.pi[::-1], ep.theta, 0, ep.rand)])
+    assert api.verify_batch(eqs, bad, crs, randomized=True) == [True, True, False, True] == api.verify_batch(eqs, bad, crs)
+
+
 def test_iota_t_commutes_with_the_maps(env):
     """tests/commit.rs:22-85: iota_T(f(x, y)) == F(iota_1(x), iota_2(y)) for the four equation types."""
     eng, api, crs, rng = env
