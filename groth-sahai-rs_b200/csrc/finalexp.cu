@@ -181,6 +181,10 @@ int gsi::reduce_chunks(gs_ctx* ctx, Scratch& sc, const fp12** F, size_t nprob, i
     int L = 2;
     while (L * L < *nchunk) L++;  // ~sqrt: serial depth of this pass ~ serial depth left for the consumer
     if (L > 64) L = 64;
+    if (ne == 1 && (size_t)*nchunk * nprob > 8192) {  // a long product (tens of thousands of factors): keep ~4,096 lanes busy per level
+      L = (int)((size_t)*nchunk * nprob / 4096);
+      if (L > 64) L = 64;
+    }
     const int nparts = (*nchunk + L - 1) / L;
     fp12* F2;
     CUDA_TRY(sc.alloc(&F2, (size_t)nparts * ne * nprob));

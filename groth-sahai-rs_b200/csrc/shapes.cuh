@@ -27,6 +27,9 @@ struct verify_shape {  // slot bookkeeping shared by host and device
   // MSM sharding by BASE (gs_verify_sharded): this rank sums, for EVERY output, only the bases i = brank (mod bworld); the
   // partial sums are exchanged.  Gamma then holds only this rank's rows: gm = #{i < m : i = brank mod bworld} (m when 1).
   int brank, bworld, gm;
+  // coordinates per base / per MSM output: 2 (Com1 = two G1 points, summed independently); 1 in gs_verify_batch_rand, where
+  // the bases are the FOLDED commitments sigma c.0 + tau c.1 (verify_args::xfold) and every output is a single point
+  int na;
   GS_HD int nb_own() const { return bworld <= 1 ? nbases : (nbases > brank ? (nbases - brank + bworld - 1) / bworld : 0); }
   GS_HD int base_at(int io) const { return bworld <= 1 ? io : brank + io * bworld; }
   GS_HD bool owns(int slot) const { return world <= 1 || slot % world == rank; }
@@ -77,6 +80,7 @@ inline verify_shape make_verify_shape(int type, int m, int n) {
   s.brank = 0;
   s.bworld = 1;
   s.gm = m;
+  s.na = 2;
   return s;
 }
 
@@ -101,6 +105,15 @@ struct verify_args {
   const g2_aff* ycoms;   // [p][n][2]
   const g2_aff* pi;      // [p][cx][2]
   const g1_aff* theta;   // [p][cy][2]
+  // folded mode (verify_shape::na == 1): bases xfold[p][nbases], addends afold[p][n] = tau_p A_j (group-valued A); the MSM
+  // outputs go to pair fold_map[slot] of the folded problem (fold_X1[p*fold_Kw + .]) or, for CRS slots (fold_map < 0), to
+  // fold_Xfix[(-fold_map - 1)*nprob + p]
+  const g1_aff* xfold = nullptr;
+  const g1_aff* afold = nullptr;
+  const int* fold_map = nullptr;
+  int fold_Kw = 0;
+  g1_aff* fold_X1 = nullptr;
+  g1_aff* fold_Xfix = nullptr;
 };
 
 constexpr int GS_VTAB = 8;  // multiples 1B..8B per base in the verify-side Straus tables

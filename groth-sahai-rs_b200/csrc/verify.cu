@@ -85,6 +85,7 @@ __global__ void k_verify_assemble(verify_shape s, verify_args v, const crs_dev* 
 // all n outputs; v1's binary double-and-add left half the lanes of every addition idle.
 // base index i of problem p, coordinate a:  i < m -> xcoms[p][i].a ;  i == m (scalar A) -> W1.a
 __device__ GS_INL g1_aff vmsm_base(const verify_shape& s, const verify_args& v, const crs_dev* crs, size_t p, int i, int a) {
+  if (s.na == 1) return v.xfold[p * s.nbases + i];
   if (i < s.m) return v.xcoms[(p * s.m + i) * 2 + a];
   return crs->w1[a];
 }
@@ -108,10 +109,11 @@ __global__ void __launch_bounds__(128) k_vmsm_tables(verify_shape s, verify_args
                                                      g1_aff* __restrict__ tab, fp* __restrict__ tabx, size_t nprob) {
   __shared__ fp sm[2 * 128];
   size_t id = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  bool active = id < nprob * (size_t)s.nb_own() * 2;
+  const int na = s.na;
+  bool active = id < nprob * (size_t)s.nb_own() * na;
   size_t p = active ? id % nprob : 0;
   size_t r = active ? id / nprob : 0;
-  int a = (int)(r & 1), i = (int)(r >> 1);  // i = index among this rank's bases (table row); base_at(i) = the base
+  int a = (int)(r % na), i = (int)(r / na);  // i = index among this rank's bases (table row); base_at(i) = the base
   g1_aff B;
   B.set_inf();
   if (active) B = vmsm_base(s, v, crs, p, s.base_at(i), a);
@@ -132,7 +134,7 @@ __global__ void __launch_bounds__(128) k_vmsm_tables(verify_shape s, verify_args
   }
   fp inv = pre[GS_VTAB - 1];
   block_batch_inv<128>(inv, sm);
-  g1_aff* out = tab + ((size_t)(i * 2 + a) * GS_VTAB) * nprob + p;
+  g1_aff* out = tab + ((size_t)(i * na + a) * GS_VTAB) * nprob + p;
   for (int d = GS_VTAB - 1; d >= 0; d--) {
     fp zi;
     if (d > 0)
@@ -148,7 +150,7 @@ __global__ void __launch_bounds__(128) k_vmsm_tables(verify_shape s, verify_args
     endo_phi_x(bx, e.x);
     if (active) {
       out[(size_t)d * nprob] = e;
-      tabx[((size_t)(i * 2 + a) * GS_VTAB + d) * nprob + p] = bx;
+      tabx[((size_t)(i * na + a) * GS_VTAB + d) * nprob + p] = bx;
     }
   }
 }
@@ -177,12 +179,13 @@ __global__ void __launch_bounds__(128, VP_BLOCKS) k_vmsm_partial(verify_shape s,
                                                       const fp* __restrict__ tabx, g1_jac* __restrict__ part, size_t nprob) {
   size_t id = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int n_own = s.n_out_owned();  // sharded statement: the other outputs' Miller pairs run on other ranks
-  size_t total = nprob * (size_t)n_own * 2 * s.nchunk;
+  const int na = s.na;
+  size_t total = nprob * (size_t)n_own * na * s.nchunk;
   if (id >= total) return;
   size_t p = id % nprob;
   size_t r = id / nprob;
-  int a = (int)(r & 1);
-  r >>= 1;
+  int a = (int)(r % na);
+  r /= na;
   int jj = s.owned_out((int)(r % n_own));
   int ch = (int)(r / n_own);
 
@@ -216,7 +219,7 @@ __global__ void __launch_bounds__(128, VP_BLOCKS) k_vmsm_partial(verify_shape s,
       if (!nz) return;
       const int mag = d < 0 ? -d : d;
       const bool phi = i & 1;
-      const size_t at = ((size_t)(bidx[i >> 1] * 2 + a) * GS_VTAB + (mag - 1)) * nprob + p;
+      const size_t at = ((size_t)(bidx[i >> 1] * na + a) * GS_VTAB + (mag - 1)) * nprob + p;
       e.y = tab[at].y;
       e.x = phi ? tabx[at] : tab[at].x;
       ng = (d < 0) != phi;  // the phi half adds multiples of -phi(B) = (beta x, -y)
@@ -247,7 +250,7 @@ __global__ void __launch_bounds__(128, VP_BLOCKS) k_vmsm_partial(verify_shape s,
       }
     }
   }
-  part[(((size_t)ch * s.n_out + jj) * 2 + a) * nprob + p] = acc;
+  part[(((size_t)ch * s.n_out + jj) * na + a) * nprob + p] = acc;
 }
 
 // ------------------------------------------------------------------ verify: shared-base window tables
@@ -275,7 +278,7 @@ __global__ void __launch_bounds__(128) k_wtab_bases(verify_shape s, verify_args 
                                                     g1_jac* __restrict__ J, int nb, wt_geom g) {
   int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= nb) return;
-  g1_aff B = vmsm_base(s, v, crs, 0, s.base_at(b >> 1), b & 1);
+  g1_aff B = vmsm_base(s, v, crs, 0, s.base_at(b / s.na), b % s.na);
   g1_jac j;
   j.from_affine(B);
   for (int w = 0; w < g.W; w++) {
@@ -352,12 +355,13 @@ __global__ void __launch_bounds__(128, 4) k_vmsm_wsum(verify_shape s, verify_arg
                                                    g1_jac* __restrict__ part, size_t nprob, wt_geom g) {
   size_t id = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int n_own = s.n_out_owned();  // sharded statement: the other outputs' Miller pairs run on other ranks
-  size_t total = nprob * (size_t)n_own * 2 * s.nchunk;
+  const int na = s.na;
+  size_t total = nprob * (size_t)n_own * na * s.nchunk;
   if (id >= total) return;
   size_t p = id % nprob;
   size_t r = id / nprob;
-  int a = (int)(r & 1);
-  r >>= 1;
+  int a = (int)(r % na);
+  r /= na;
   int jj = s.owned_out((int)(r % n_own));
   int ch = (int)(r / n_own);
   g1_jac acc, acc2;  // acc: the k1 halves; acc2: the k2 halves, mapped through -phi at the end (phi is additive)
@@ -372,7 +376,7 @@ __global__ void __launch_bounds__(128, 4) k_vmsm_wsum(verify_shape s, verify_arg
     glv_split(k1, k2, k);
 #pragma unroll
     for (int t = 4; t < 8; t++) k1[t] = k2[t] = 0;
-    const g1_aff* T = tab + ((size_t)(i * 2 + a) * g.W) * g.H;
+    const g1_aff* T = tab + ((size_t)(i * na + a) * g.W) * g.H;
     fixed_base_accumulate<FpOps>(acc, T, k1, g.c, g.W, (size_t)g.H);
     fixed_base_accumulate<FpOps>(acc2, T, k2, g.c, g.W, (size_t)g.H);
   }
@@ -381,18 +385,18 @@ __global__ void __launch_bounds__(128, 4) k_vmsm_wsum(verify_shape s, verify_arg
     fp::neg(acc2.Y, acc2.Y);
     g1_jac::add(acc, acc, acc2);
   }
-  part[(((size_t)ch * s.n_out + jj) * 2 + a) * nprob + p] = acc;
+  part[(((size_t)ch * s.n_out + jj) * na + a) * nprob + p] = acc;
 }
 
 // thread -> (group g of F chunks, entry e = (jj*2 + a)*nprob + p): out[g][e] = sum_{c < F} part[g*F + c][e]
 __global__ void __launch_bounds__(128) k_vmsm_fold(verify_shape s, const g1_jac* __restrict__ part, g1_jac* __restrict__ out,
                                                    size_t nprob, int nchunk, int F, int ngroups) {
-  const size_t E = (size_t)s.n_out * 2 * nprob;
+  const size_t E = (size_t)s.n_out * s.na * nprob;
   size_t id = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (id >= E * ngroups) return;
   size_t e = id % E;
   int g = (int)(id / E);
-  int jj = (int)(e / (2 * nprob));
+  int jj = (int)(e / (s.na * nprob));
   if (!s.owns(s.out_slot(jj))) return;
   int c0 = g * F, c1 = min(nchunk, c0 + F);
   g1_jac acc = part[(size_t)c0 * E + e];
@@ -408,24 +412,25 @@ __global__ void __launch_bounds__(128) k_vmsm_reduce(verify_shape s, verify_args
                                                      g1_aff* __restrict__ X, size_t nprob) {
   __shared__ fp sm[2 * 128];
   size_t id = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  bool active = id < nprob * (size_t)s.n_out_owned() * 2;
+  const int na = s.na;
+  bool active = id < nprob * (size_t)s.n_out_owned() * na;
   size_t p = active ? id % nprob : 0;
   size_t r = active ? id / nprob : 0;
-  int a = (int)(r & 1);
-  int jj = active ? s.owned_out((int)(r >> 1)) : 0;
+  int a = (int)(r % na);
+  int jj = active ? s.owned_out((int)(r / na)) : 0;
   g1_jac acc;
   acc.set_inf();
   int slot = 0;
   if (active) {
-    acc = part[((size_t)jj * 2 + a) * nprob + p];
+    acc = part[((size_t)jj * na + a) * nprob + p];
     for (int ch = 1; ch < s.nchunk; ch++) {
-      g1_jac t = part[(((size_t)ch * s.n_out + jj) * 2 + a) * nprob + p];
+      g1_jac t = part[(((size_t)ch * s.n_out + jj) * na + a) * nprob + p];
       g1_jac::add(acc, acc, t);
     }
     if (jj < s.n) {
       slot = jj;
-      if (s.groupA && a == 1) {
-        g1_aff A = ((const g1_aff*)v.a_consts)[p * s.n + jj];
+      if (s.groupA && (a == 1 || na == 1)) {  // iota_1(A_j) = (O, A_j); folded: tau_p A_j
+        g1_aff A = na == 1 ? v.afold[p * s.n + jj] : ((const g1_aff*)v.a_consts)[p * s.n + jj];
         g1_jac::add_mixed(acc, acc, A);
       }
     } else if (jj == s.n && !s.groupB) {
@@ -437,7 +442,16 @@ __global__ void __launch_bounds__(128) k_vmsm_reduce(verify_shape s, verify_args
   }
   g1_aff out;
   block_to_affine<128>(out, acc, sm);
-  if (active) X[((size_t)a * s.K + slot) * nprob + p] = out;
+  if (!active) return;
+  if (na == 1) {
+    const int fm = v.fold_map[slot];
+    if (fm >= 0)
+      v.fold_X1[p * v.fold_Kw + fm] = out;
+    else
+      v.fold_Xfix[(size_t)(-fm - 1) * nprob + p] = out;
+  } else {
+    X[((size_t)a * s.K + slot) * nprob + p] = out;
+  }
 }
 
 // ---- MSM sharded by base (gs_verify_sharded): the partial sums travel between the ranks as affine points
@@ -538,47 +552,65 @@ __global__ void k_and4(const uint8_t* __restrict__ ok4, uint8_t* __restrict__ ou
 // their G1 sides are summed over the proofs first.  If any entry of any proof is wrong the check fails except with
 // probability <= 2^-63 over the weights (a non-zero polynomial of degree 2 in beta, then a non-zero linear form in the
 // independent sigma_p, tau_p) -- provided all inputs are in the prime-order groups, as deserialised values are.
-struct naf65 {
-  int8_t d[66];  // non-adjacent form of a 64-bit integer, d[i] in {-1, 0, 1}, least significant first
+// The G2 weight is beta = b0 + b1 |x| with b0, b1 the two 32-bit halves of the caller's word (2^64 distinct values mod r,
+// which is all the soundness argument needs): |x| Y = -psi(Y) is two Fp2 products (endo.cuh), so beta Y.0 is a JOINT
+// 33-step double-and-add over (Y.0, -psi(Y.0)) -- half the doublings of a 64-bit scalar -- and in joint sparse form
+// (Solinas) only every second step adds.  beta is the same for all threads: the digits are kernel parameters and the
+// instruction stream is uniform.
+struct jsf33 {
+  int8_t u0[34], u1[34];  // digits in {-1, 0, 1}, least significant first
+  int len;
 };
-static naf65 make_naf(uint64_t k) {
-  naf65 r;
-  memset(r.d, 0, sizeof r.d);
-  unsigned __int128 v = k;
-  for (int i = 0; v != 0; i++) {
-    if (v & 1) {
-      int d = 2 - (int)(v & 3);  // +1 or -1
-      r.d[i] = (int8_t)d;
-      v = d > 0 ? v - 1 : v + 1;
-    }
-    v >>= 1;
+static jsf33 make_jsf(uint32_t a, uint32_t b) {
+  jsf33 r;
+  memset(&r, 0, sizeof r);
+  uint64_t k0 = a, k1 = b;
+  int d0 = 0, d1 = 0, n = 0;
+  auto digit = [](uint64_t l, uint64_t lo) {
+    if ((l & 1) == 0) return 0;
+    int u = 2 - (int)(l & 3);
+    if (((l & 7) == 3 || (l & 7) == 5) && (lo & 3) == 2) u = -u;
+    return u;
+  };
+  while (k0 + d0 > 0 || k1 + d1 > 0) {
+    const uint64_t l0 = k0 + d0, l1 = k1 + d1;
+    const int u0 = digit(l0, l1), u1 = digit(l1, l0);
+    if (2 * d0 == 1 + u0) d0 = 1 - d0;
+    if (2 * d1 == 1 + u1) d1 = 1 - d1;
+    k0 >>= 1;
+    k1 >>= 1;
+    r.u0[n] = (int8_t)u0;
+    r.u1[n] = (int8_t)u1;
+    n++;
   }
+  r.len = n;
   return r;
 }
-// slot_map[k] >= 0: per-proof pair number jw of slot k (G2 side walked); < 0: -(f + 1), CRS slot number f
-// thread -> (p, k):  X' = sigma_p X[0][k][p] + tau_p X[1][k][p]   ->  X1[p*Kw + jw]  |  Xfix[f*nprob + p]
-__global__ void __launch_bounds__(128) k_rand_fold_g1(const g1_aff* __restrict__ X, size_t nprob, int K, const uint64_t* __restrict__ rho,
-                                                      const int* __restrict__ slot_map, int Kw, g1_aff* __restrict__ X1,
-                                                      g1_aff* __restrict__ Xfix) {
-  __shared__ fp sm[2 * 128];
-  size_t id = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const bool active = id < nprob * (size_t)K;
-  const size_t p = active ? id % nprob : 0;
-  const int k = active ? (int)(id / nprob) : 0;
-  g1_aff tab[4];  // 0, X0, X1, X0 + X1: one table addition per bit, the same instruction stream for every lane
-  tab[0].set_inf();
-  tab[1].set_inf();
-  tab[2].set_inf();
-  uint64_t sg = 0, tu = 0;
-  if (active) {
-    tab[1] = X[((size_t)0 * K + k) * nprob + p];
-    tab[2] = X[((size_t)1 * K + k) * nprob + p];
-    sg = rho[2 * p];
-    tu = rho[2 * p + 1];
+// acc += beta * y0 given p1 = -psi(y0) and the affine sums as = y0 + p1, ad = y0 - p1 (acc must be the identity on entry)
+__device__ GS_INL void rand_fold_g2_walk(g2_jac& acc, const g2_aff& y0, const g2_aff& p1, const g2_aff& as, const g2_aff& ad,
+                                         const jsf33& b) {
+#pragma unroll 1
+  for (int i = b.len - 1; i >= 0; i--) {
+    g2_jac::dbl(acc, acc);
+    const int u0 = b.u0[i], u1 = b.u1[i];
+    if (u0 == 0 && u1 == 0) continue;
+    g2_aff t = u1 == 0 ? y0 : (u0 == 0 ? p1 : (u0 == u1 ? as : ad));
+    const bool neg = u0 != 0 ? u0 < 0 : u1 < 0;  // the table holds the combinations whose first non-zero digit is +1
+    if (neg) fp2::neg(t.y, t.y);
+    g2_jac::add_mixed(acc, acc, t);
   }
+}
+// slot_map[k] >= 0: per-proof pair number jw of slot k (G2 side walked); < 0: -(f + 1), CRS slot number f
+// sigma x0 + tau x1 by a joint 64-step double-and-add over the table 0, x0, x1, x0 + x1 (one table addition per bit, the
+// same instruction stream for every lane; the sum is made affine with one block-wide inversion).  All 128 threads call.
+__device__ GS_INL void rand_fold_g1_point(g1_aff& out, const g1_aff& x0, const g1_aff& x1, uint64_t sg, uint64_t tu, fp* sm) {
+  g1_aff tab[4];
+  tab[0].set_inf();
+  tab[1] = x0;
+  tab[2] = x1;
   g1_jac j;
-  j.from_affine(tab[1]);
-  g1_jac::add_mixed(j, j, tab[2]);
+  j.from_affine(x0);
+  g1_jac::add_mixed(j, j, x1);
   block_to_affine<128>(tab[3], j, sm);
   __syncthreads();  // (sm is reused below)
   g1_jac acc;
@@ -589,8 +621,29 @@ __global__ void __launch_bounds__(128) k_rand_fold_g1(const g1_aff* __restrict__
     const int d = (int)((sg >> bit) & 1) | ((int)((tu >> bit) & 1) << 1);
     g1_jac::add_mixed(acc, acc, tab[d]);
   }
-  g1_aff out;
   block_to_affine<128>(out, acc, sm);
+  __syncthreads();
+}
+// thread -> (p, t), slot k = slot_list[t]:  X' = sigma_p X[0][k][p] + tau_p X[1][k][p]   ->  X1[p*Kw + jw]  |  Xfix[f*nprob + p]
+__global__ void __launch_bounds__(128) k_rand_fold_g1(const g1_aff* __restrict__ X, size_t nprob, int K, const uint64_t* __restrict__ rho,
+                                                      const int* __restrict__ slot_list, int nlist, const int* __restrict__ slot_map,
+                                                      int Kw, g1_aff* __restrict__ X1, g1_aff* __restrict__ Xfix) {
+  __shared__ fp sm[2 * 128];
+  size_t id = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool active = id < nprob * (size_t)nlist;
+  const size_t p = active ? id % nprob : 0;
+  const int k = active ? slot_list[id / nprob] : 0;
+  g1_aff x0, x1, out;
+  x0.set_inf();
+  x1.set_inf();
+  uint64_t sg = 0, tu = 0;
+  if (active) {
+    x0 = X[((size_t)0 * K + k) * nprob + p];
+    x1 = X[((size_t)1 * K + k) * nprob + p];
+    sg = rho[2 * p];
+    tu = rho[2 * p + 1];
+  }
+  rand_fold_g1_point(out, x0, x1, sg, tu, sm);
   if (!active) return;
   const int sm_k = slot_map[k];
   if (sm_k >= 0)
@@ -598,8 +651,47 @@ __global__ void __launch_bounds__(128) k_rand_fold_g1(const g1_aff* __restrict__
   else
     Xfix[(size_t)(-sm_k - 1) * nprob + p] = out;
 }
+// Folded MSM bases (the statement MSM then runs over ONE coordinate, verify_shape::na = 1):
+// thread -> (p, q):  q < nbases: xfold[p][q] = sigma_p B_q.0 + tau_p B_q.1 (B_q = c_q, or W1 when A is scalar-valued);
+//                    q >= nbases (group-valued A): afold[p][j] = tau_p A_j, j = q - nbases.
+// With group-valued B the slot (c_i, iota_2(B_i)) has exactly xfold[p][i] on its G1 side: copied to pair bmap0 + i.
+__global__ void __launch_bounds__(128) k_rand_fold_bases(verify_shape s, verify_args v, const crs_dev* __restrict__ crs, size_t nprob,
+                                                         const uint64_t* __restrict__ rho, g1_aff* __restrict__ xfold,
+                                                         g1_aff* __restrict__ afold, int bmap0, int Kw, g1_aff* __restrict__ X1) {
+  __shared__ fp sm[2 * 128];
+  const int nq = s.nbases + (s.groupA ? s.n : 0);
+  size_t id = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool active = id < nprob * (size_t)nq;
+  const size_t p = active ? id % nprob : 0;
+  const int q = active ? (int)(id / nprob) : 0;
+  g1_aff x0, x1, out;
+  x0.set_inf();
+  x1.set_inf();
+  uint64_t sg = 0, tu = 0;
+  if (active) {
+    if (q < s.m) {
+      x0 = v.xcoms[(p * s.m + q) * 2 + 0];
+      x1 = v.xcoms[(p * s.m + q) * 2 + 1];
+    } else if (q < s.nbases) {
+      x0 = crs->w1[0];
+      x1 = crs->w1[1];
+    } else {
+      x1 = ((const g1_aff*)v.a_consts)[p * s.n + (q - s.nbases)];
+    }
+    sg = rho[2 * p];
+    tu = rho[2 * p + 1];
+  }
+  rand_fold_g1_point(out, x0, x1, sg, tu, sm);
+  if (!active) return;
+  if (q < s.nbases) {
+    xfold[p * s.nbases + q] = out;
+    if (s.groupB && q < s.m) X1[p * Kw + bmap0 + q] = out;
+  } else {
+    afold[p * s.n + (q - s.nbases)] = out;
+  }
+}
 // thread -> (p, jw): Y' = beta Y[0][k][p] + Y[1][k][p] of the per-proof pair jw = slot walk_slot[jw]  ->  Y1[p*Kw + jw]
-__global__ void __launch_bounds__(128) k_rand_fold_g2(const g2_aff* __restrict__ Y, size_t nprob, int K, naf65 beta,
+__global__ void __launch_bounds__(128) k_rand_fold_g2(const g2_aff* __restrict__ Y, size_t nprob, int K, jsf33 beta,
                                                       const int* __restrict__ walk_slot, int Kw, g2_aff* __restrict__ Y1) {
   __shared__ fp sm[2 * 128];
   size_t id = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -618,16 +710,21 @@ __global__ void __launch_bounds__(128) k_rand_fold_g2(const g2_aff* __restrict__
   acc.set_inf();
   const bool any = __syncthreads_or(!y0.is_inf());  // iota_2 images (B_i, a G2 target) have no first coordinate: nothing to fold
   if (any) {
-    g2_aff ny0 = y0;
-    fp2::neg(ny0.y, y0.y);
-#pragma unroll 1
-    for (int i = 65; i >= 0; i--) {
-      g2_jac::dbl(acc, acc);
-      if (beta.d[i] > 0)
-        g2_jac::add_mixed(acc, acc, y0);
-      else if (beta.d[i] < 0)
-        g2_jac::add_mixed(acc, acc, ny0);
-    }
+    g2_aff p1, np1, as, ad;
+    endo_psi(p1, y0);
+    fp2::neg(p1.y, p1.y);  // -psi(Y.0) = |x| Y.0
+    np1 = p1;
+    fp2::neg(np1.y, p1.y);
+    g2_jac js, jd;
+    js.from_affine(y0);
+    jd = js;
+    g2_jac::add_mixed(js, js, p1);
+    g2_jac::add_mixed(jd, jd, np1);
+    block_to_affine<128>(as, js, sm);
+    __syncthreads();
+    block_to_affine<128>(ad, jd, sm);
+    __syncthreads();
+    rand_fold_g2_walk(acc, y0, p1, as, ad, beta);
   }
   g2_jac::add_mixed(acc, acc, y1);
   g2_aff out;
@@ -635,21 +732,25 @@ __global__ void __launch_bounds__(128) k_rand_fold_g2(const g2_aff* __restrict__
   if (active) Y1[p * Kw + jw] = out;
 }
 // thread pid < 3: Yfix[pid] = beta P.0 + P.1 for the CRS elements P = v_1, v_2, W2
-__global__ void k_rand_fold_crs(const crs_dev* __restrict__ crs, naf65 beta, g2_aff* __restrict__ Yfix) {
+__global__ void k_rand_fold_crs(const crs_dev* __restrict__ crs, jsf33 beta, g2_aff* __restrict__ Yfix) {
   const int pid = blockIdx.x * blockDim.x + threadIdx.x;
   if (pid >= 3) return;
   const g2_aff y0 = pid < 2 ? crs->v[pid][0] : crs->w2[0], y1 = pid < 2 ? crs->v[pid][1] : crs->w2[1];
-  g2_aff ny0 = y0;
-  fp2::neg(ny0.y, y0.y);
+  g2_aff p1, np1, as, ad;
+  endo_psi(p1, y0);
+  fp2::neg(p1.y, p1.y);
+  np1 = p1;
+  fp2::neg(np1.y, p1.y);
+  g2_jac js, jd;
+  js.from_affine(y0);
+  jd = js;
+  g2_jac::add_mixed(js, js, p1);
+  g2_jac::add_mixed(jd, jd, np1);
+  g2_jac::to_affine(as, js);
+  g2_jac::to_affine(ad, jd);
   g2_jac acc;
   acc.set_inf();
-  for (int i = 65; i >= 0; i--) {
-    g2_jac::dbl(acc, acc);
-    if (beta.d[i] > 0)
-      g2_jac::add_mixed(acc, acc, y0);
-    else if (beta.d[i] < 0)
-      g2_jac::add_mixed(acc, acc, ny0);
-  }
+  rand_fold_g2_walk(acc, y0, p1, as, ad, beta);
   g2_jac::add_mixed(acc, acc, y1);
   g2_jac::to_affine(Yfix[pid], acc);
 }
@@ -716,6 +817,7 @@ static std::vector<uint8_t> slot_kinds(const verify_shape& s) {
 static int statement_msm(gs_ctx* ctx, Scratch& sc, verify_shape s, const verify_args& v, size_t nprob, bool shared_x, g1_aff* X) {
   // outputs that share one base coordinate: this rank's MSM outputs x the problems that use the same commitments
   const size_t owned_out = (size_t)s.n_out_owned();
+  const size_t na = (size_t)s.na;
   const bool use_wtab = (nprob == 1 || shared_x) && owned_out * nprob >= 320;  // table build ~ 14.6 ms at m = 1024
   {
     // bases per thread: few threads (one statement, or one rank's share of it) -> smaller chunks, so that the
@@ -724,15 +826,15 @@ static int statement_msm(gs_ctx* ctx, Scratch& sc, verify_shape s, const verify_
     // amortise, Straus keeps >= 8.  Many chunks are folded 16 at a time (k_vmsm_fold) before k_vmsm_reduce.
     int chunk = GS_MSM_CHUNK;
     // (a lone small statement is pure latency: one base per thread there)
-    const bool tiny = nprob * owned_out * 2 * ((s.nbases + 7) / 8) < 16384;
+    const bool tiny = nprob * owned_out * na * ((s.nbases + 7) / 8) < 16384;
     const int floor_chunk = use_wtab ? 4 : (tiny ? 1 : 8);
-    while (chunk > floor_chunk && nprob * owned_out * 2 * ((s.nbases + chunk - 1) / chunk) < (size_t)128 * 2368) chunk /= 2;
+    while (chunk > floor_chunk && nprob * owned_out * na * ((s.nbases + chunk - 1) / chunk) < (size_t)128 * 2368) chunk /= 2;
     set_msm_chunk(s, chunk);
   }
   g1_jac* part;
-  CUDA_TRY(sc.alloc(&part, (size_t)s.nchunk * s.n_out * 2 * nprob));
+  CUDA_TRY(sc.alloc(&part, (size_t)s.nchunk * s.n_out * na * nprob));
   if (use_wtab) {
-    const int nb = s.nb_own() * 2;
+    const int nb = s.nb_own() * na;
     const wt_geom g = wt_choose(owned_out * nprob);
     const size_t nrows = (size_t)nb * g.W;
     g1_aff* wtab;
@@ -743,25 +845,25 @@ static int statement_msm(gs_ctx* ctx, Scratch& sc, verify_shape s, const verify_
     LAUNCH(k_jac_to_affine_blocks<1>, nrows, J, wtab, nrows, (size_t)g.H);
     LAUNCH(k_wtab_fill, nrows * (g.H / GS_WT_RUN), wtab, J, nrows, g.H);
     LAUNCH(k_jac_to_affine_blocks<8>, nrows * g.H / 8, J, wtab, nrows * g.H, (size_t)1);
-    LAUNCH(k_vmsm_wsum, nprob * owned_out * 2 * s.nchunk, s, v, wtab, part, nprob, g);
+    LAUNCH(k_vmsm_wsum, nprob * owned_out * na * s.nchunk, s, v, wtab, part, nprob, g);
   } else {
     g1_aff* vtab;
     fp* vtabx;
-    CUDA_TRY(sc.alloc(&vtab, (size_t)s.nb_own() * 2 * GS_VTAB * nprob));
-    CUDA_TRY(sc.alloc(&vtabx, (size_t)s.nb_own() * 2 * GS_VTAB * nprob));
-    LAUNCH(k_vmsm_tables, nprob * (size_t)s.nb_own() * 2, s, v, ctx->crs, vtab, vtabx, nprob);
-    LAUNCH(k_vmsm_partial, nprob * owned_out * 2 * s.nchunk, s, v, vtab, vtabx, part, nprob);
+    CUDA_TRY(sc.alloc(&vtab, (size_t)s.nb_own() * na * GS_VTAB * nprob));
+    CUDA_TRY(sc.alloc(&vtabx, (size_t)s.nb_own() * na * GS_VTAB * nprob));
+    LAUNCH(k_vmsm_tables, nprob * (size_t)s.nb_own() * na, s, v, ctx->crs, vtab, vtabx, nprob);
+    LAUNCH(k_vmsm_partial, nprob * owned_out * na * s.nchunk, s, v, vtab, vtabx, part, nprob);
   }
   const g1_jac* partr = part;
   if (s.nchunk > 32) {  // fold 16 chunks at a time in parallel; k_vmsm_reduce then walks the few that are left
     const int F = 16, ng = (s.nchunk + F - 1) / F;
     g1_jac* part2;
-    CUDA_TRY(sc.alloc(&part2, (size_t)ng * s.n_out * 2 * nprob));
-    LAUNCH(k_vmsm_fold, (size_t)s.n_out * 2 * nprob * ng, s, part, part2, nprob, s.nchunk, F, ng);
+    CUDA_TRY(sc.alloc(&part2, (size_t)ng * s.n_out * na * nprob));
+    LAUNCH(k_vmsm_fold, (size_t)s.n_out * na * nprob * ng, s, part, part2, nprob, s.nchunk, F, ng);
     partr = part2;
     s.nchunk = ng;
   }
-  LAUNCH(k_vmsm_reduce, nprob * owned_out * 2, s, v, partr, X, nprob);
+  LAUNCH(k_vmsm_reduce, nprob * owned_out * na, s, v, partr, X, nprob);
   return GS_OK;
 }
 
@@ -1212,9 +1314,15 @@ static int verify_rand_dev(gs_ctx* ctx, int type, size_t count, size_t m, size_t
     }
   }
   const int Kw = (int)walk_slot.size();
-  const naf65 beta = make_naf(rho_host[2 * count]);
-  const size_t pass_n = count < ctx->verify_batch_max ? count : ctx->verify_batch_max;
-  const size_t npass = (count + pass_n - 1) / pass_n;
+  const jsf33 beta = make_jsf((uint32_t)rho_host[2 * count], (uint32_t)(rho_host[2 * count] >> 32));
+  // Passes as large as the line tiles allow (13 KB per pair; half the budget, the slot arrays and tables need room too) and
+  // equal in size: the line walk is latency-bound, a pass that fills 0.6 of its last wave pays for a whole one.
+  size_t pass_cap = ctx->tile_budget / 2 / 13056 / (size_t)(Kw ? Kw : 1);
+  if (pass_cap > 4 * ctx->verify_batch_max) pass_cap = 4 * ctx->verify_batch_max;
+  if (ctx->verify_batch_max < 23680) pass_cap = ctx->verify_batch_max;  // (lowered by a test: several passes on a small batch)
+  if (pass_cap < 1) pass_cap = 1;
+  const size_t npass = (count + pass_cap - 1) / pass_cap;
+  const size_t pass_n = (count + npass - 1) / npass;
   if ((size_t)pass_n * Kw + nfix > ((size_t)1 << 30)) FAIL(GS_EDIM, "verify_rand: statement too large for one pass");
   Scratch top(ctx);
   fp12 *Mall, *Tall;
@@ -1227,7 +1335,54 @@ static int verify_rand_dev(gs_ctx* ctx, int type, size_t count, size_t m, size_t
   CUDA_TRY(top.alloc(&ok1, 4));
   CUDA_TRY(upload(ctx, top, &dmap, slot_map.data(), slot_map.size()));
   CUDA_TRY(upload(ctx, top, &dwalk_slot, walk_slot.data(), walk_slot.size()));
+  // slots whose G1 side k_verify_assemble writes (everything but the MSM outputs); with the commitments folded first the
+  // (c_i, iota_2(B_i)) slots need no fold either
+  const bool fold_first = !shared_x || count == 1;
+  std::vector<int> all_slots, rest_slots;
+  for (int k = 0; k < s.K; k++) {
+    all_slots.push_back(k);
+    const bool msm_out = k < s.n || (k == s.sB && !s.groupB) || (type == 3 && k == s.sT);
+    const bool b_slot = s.groupB && k >= s.sB && k < s.sPi;
+    if (!msm_out && !b_slot) rest_slots.push_back(k);
+  }
+  int *dall, *drest;
+  CUDA_TRY(upload(ctx, top, &dall, all_slots.data(), all_slots.size()));
+  CUDA_TRY(upload(ctx, top, &drest, rest_slots.data(), rest_slots.size()));
+  // The folded CRS points and the target powers prod_p t_p^tau_p depend on nothing the main stream computes: they run on
+  // the second stream (latency-bound kernels: a 66-step scalar multiplication in 3 threads, a product tree), next to the
+  // statement MSM and the line walk.  `side` is waited for before their results are used and before their buffers die.
+  if (!ctx->stream2) CUDA_TRY(cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking));
+  struct side_stream {
+    gs_ctx* ctx;
+    cudaStream_t main_s;
+    cudaEvent_t ev = nullptr;
+    bool pending = false;
+    int fork() {  // second stream ordered after everything queued on the main stream so far; ctx->stream := second stream
+      if (!ev && cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) return 1;
+      cudaEventRecord(ev, main_s);
+      cudaStreamWaitEvent(ctx->stream2, ev, 0);
+      ctx->stream = ctx->stream2;
+      return 0;
+    }
+    void back() {  // ctx->stream := main stream; the side work is pending until join()
+      cudaEventRecord(ev, ctx->stream2);
+      ctx->stream = main_s;
+      pending = true;
+    }
+    void join() {
+      if (pending) cudaStreamWaitEvent(main_s, ev, 0);
+      pending = false;
+    }
+    ~side_stream() {
+      ctx->stream = main_s;
+      join();
+      if (ev) cudaEventDestroy(ev);
+    }
+  } side{ctx, ctx->stream};
+  const bool two = !ctx->profile;  // (per-kernel event times need one stream)
+  if (two && side.fork()) FAIL(GS_ECUDA, "verify_rand: event creation failed");
   LAUNCH_CFG(k_rand_fold_crs, 3, 32, 0, ctx->crs, beta, Yfix);
+  if (two) side.back();
   size_t pass = 0;
   for (size_t off = 0; off < count; off += pass_n, pass++) {
     const size_t nprob = count - off < pass_n ? count - off : pass_n;
@@ -1244,25 +1399,65 @@ static int verify_rand_dev(gs_ctx* ctx, int type, size_t count, size_t m, size_t
     g1_aff *X, *X1, *Xfix;
     g2_aff *Y, *Y1;
     uint64_t* drho;
+    CUDA_TRY(upload(ctx, sc, &drho, rho_host + 2 * off, 2 * nprob));
+    if (type == GS_PPE) {  // prod_p t_p^tau_p, on the side stream
+      if (two && side.fork()) FAIL(GS_ECUDA, "verify_rand: event creation failed");
+      int rcg = [&]() -> int {
+        fp12* P;
+        CUDA_TRY(sc.alloc(&P, nprob));
+        int rc = gsi::gt_pow64(ctx, (const fp12*)v.target, drho + 1, 2, nprob, P);
+        if (rc) return rc;
+        const fp12* Pr = P;
+        int nch = (int)nprob;
+        rc = gsi::reduce_chunks(ctx, sc, &Pr, 1, &nch, 1, 1);
+        if (rc) return rc;
+        CUDA_TRY(cudaMemcpyAsync(Tall + pass, Pr, sizeof(fp12), cudaMemcpyDeviceToDevice, ctx->stream));
+        return GS_OK;
+      }();
+      if (two) side.back();
+      if (rcg) return rcg;
+    }
     CUDA_TRY(sc.alloc(&X, 2 * (size_t)s.K * nprob));
     CUDA_TRY(sc.alloc(&Y, 2 * (size_t)s.K * nprob));
     LAUNCH(k_verify_assemble, nprob * (size_t)s.K, s, v, ctx->crs, X, Y, nprob);
-    {
-      int rcm = statement_msm(ctx, sc, s, v, nprob, shared_x, X);
-      if (rcm) return rcm;
-    }
     // the folded single-entry problem: nprob * Kw per-proof pairs, then the nfix summed CRS pairs, padded with identities
     const size_t npairs = nprob * Kw + nfix;
     const int S = rand_slots_per_acc(npairs);
     const size_t Ktot = (npairs + S - 1) / S * S;
-    CUDA_TRY(upload(ctx, sc, &drho, rho_host + 2 * off, 2 * nprob));
     CUDA_TRY(sc.alloc(&X1, Ktot));
     CUDA_TRY(sc.alloc(&Y1, Ktot));
     CUDA_TRY(sc.alloc(&Xfix, (size_t)(nfix ? nfix : 1) * nprob));
     CUDA_TRY(cudaMemsetAsync(X1 + npairs, 0, (Ktot - npairs) * sizeof(g1_aff), ctx->stream));
     CUDA_TRY(cudaMemsetAsync(Y1 + npairs, 0, (Ktot - npairs) * sizeof(g2_aff), ctx->stream));
-    LAUNCH(k_rand_fold_g1, nprob * (size_t)s.K, X, nprob, s.K, drho, dmap, Kw, X1, Xfix);
+    if (fold_first) {
+      // the commitments are folded BEFORE the statement MSM, which then sums single points: half the scalar products;
+      // its outputs are folded slots already, the (c_i, iota_2(B_i)) slots are the folded bases themselves
+      g1_aff *xfold, *afold;
+      CUDA_TRY(sc.alloc(&xfold, nprob * (size_t)s.nbases));
+      CUDA_TRY(sc.alloc(&afold, nprob * (size_t)(s.groupA ? s.n : 1)));
+      LAUNCH(k_rand_fold_bases, nprob * (size_t)(s.nbases + (s.groupA ? s.n : 0)), s, v, ctx->crs, nprob, drho, xfold, afold,
+             s.groupB ? slot_map[s.sB] : 0, Kw, X1);
+      verify_shape sf = s;
+      sf.na = 1;
+      verify_args vf = v;
+      vf.xfold = xfold;
+      vf.afold = afold;
+      vf.fold_map = dmap;
+      vf.fold_Kw = Kw;
+      vf.fold_X1 = X1;
+      vf.fold_Xfix = Xfix;
+      int rcm = statement_msm(ctx, sc, sf, vf, nprob, false, nullptr);
+      if (rcm) return rcm;
+      LAUNCH(k_rand_fold_g1, nprob * rest_slots.size(), X, nprob, s.K, drho, drest, (int)rest_slots.size(), dmap, Kw, X1, Xfix);
+    } else {
+      // one set of commitments under many equations: the statement MSM keeps its shared-base tables (both coordinates),
+      // every slot is folded afterwards
+      int rcm = statement_msm(ctx, sc, s, v, nprob, shared_x, X);
+      if (rcm) return rcm;
+      LAUNCH(k_rand_fold_g1, nprob * all_slots.size(), X, nprob, s.K, drho, dall, (int)all_slots.size(), dmap, Kw, X1, Xfix);
+    }
     LAUNCH(k_rand_fold_g2, nprob * (size_t)Kw, Y, nprob, s.K, beta, dwalk_slot, Kw, Y1);
+    side.join();  // the folded CRS points (and, long finished, this pass's target powers)
     if (nfix) {
       const int L = 32;
       const size_t nstrips = (nprob + L - 1) / L;
@@ -1273,17 +1468,7 @@ static int verify_rand_dev(gs_ctx* ctx, int type, size_t count, size_t m, size_t
     }
     int rc = gsi::run_pairing_product(ctx, sc, X1, Y1, 1, (int)Ktot, nullptr, nullptr, nullptr, Mall + pass, nullptr, nullptr, 1, S);
     if (rc) return rc;
-    if (type == GS_PPE) {  // prod_p t_p^tau_p
-      fp12* P;
-      CUDA_TRY(sc.alloc(&P, nprob));
-      rc = gsi::gt_pow64(ctx, (const fp12*)v.target, drho + 1, 2, nprob, P);
-      if (rc) return rc;
-      const fp12* Pr = P;
-      int nch = (int)nprob;
-      rc = gsi::reduce_chunks(ctx, sc, &Pr, 1, &nch, 1, 1);
-      if (rc) return rc;
-      CUDA_TRY(cudaMemcpyAsync(Tall + pass, Pr, sizeof(fp12), cudaMemcpyDeviceToDevice, ctx->stream));
-    }
+    side.join();  // before `sc` releases the buffers of this pass's target powers
   }
   const fp12* want = nullptr;
   if (type == GS_PPE) {

@@ -134,3 +134,17 @@ def test_rand_big_statement(eng, crs):
     arrays = c.verify_arrays()
     assert eng.verify_batch_rand(0, 1, 128, 128, *arrays, rho=rho_of(1, 50)) is True
     assert eng.verify_batch_rand(0, 1, 128, 128, *tampered(0, 128, 128, arrays, 2, 0, 0), rho=rho_of(1, 51)) is False
+
+
+@pytest.mark.parametrize("ty", [0, 1, 2, 3])
+def test_rand_shared_commitments(eng, crs, ty):
+    """Equations over ONE witness set (the C4 shape): the statement MSM keeps its shared-base tables and both
+    coordinates, the slots are folded afterwards (the other order of operations than for independent proofs)."""
+    E, m, n = 40, 8, 8
+    st = Statement(ty, m, n, E, crs, seed=2600 + ty)
+    arrays = st.verify_arrays()
+    assert eng.verify_batch(ty, E, m, n, *arrays) == b"\x01" * E
+    assert eng.verify_batch_rand(ty, E, m, n, *arrays, rho=rho_of(E, 60)) is True
+    for which in (0, 2, 3, 6):
+        bad = tampered(ty, m, n, arrays, which, 17, 30)
+        assert eng.verify_batch_rand(ty, E, m, n, *bad, rho=rho_of(E, 61 + which)) is False, f"array {which} accepted"
