@@ -254,7 +254,7 @@ def verify_batch(equations, proofs, crs: CRS, randomized: bool = False, rho: byt
 
     randomized=True (opt-in; not in the reference): first ONE randomised check of the whole batch
     (gs_verify_batch_rand: a single folded pairing product, one final exponentiation); if it accepts, every proof is
-    reported valid (error <= 2^-63 over `rho`, drawn from the OS CSPRNG when not given); if it rejects, the exact
+    reported valid (error <= 2^-62 over `rho`, drawn from the OS CSPRNG when not given); if it rejects, the exact
     per-proof verification below runs and says which proofs failed.  Inputs must be group members (deserialised values
     are), PPE targets members of GT."""
     assert len(equations) == len(proofs) and equations

@@ -237,15 +237,18 @@ namespace gsi {
 // one thread's serial chain.  W windows must also cover bits + 1 so that the signed recoding never carries out of the top
 // window (a carry window would put half of all points into ONE bucket).  c is chosen to minimise
 //     max(longest chain, additions / lanes)   with chain = Np / min(H, top_vals), additions = W * Np.
+// short_bits > 0: every scalar is known to be < 2^short_bits <= 2^63 (the weights of gs_verify_batch_rand), below the bound
+// of the first sub-scalar on either group: the split leaves it where it is and the other sub-scalars are zero, so the
+// windows only span short_bits.
 template <class F>
-inline pip_geom pip_choose(size_t N, int c_override) {
+inline pip_geom pip_choose(size_t N, int c_override, int short_bits = 0) {
   pip_geom g;
   g.parts = PipSplit<F>::PARTS;
-  g.bits = PipSplit<F>::BITS;
+  g.bits = short_bits > 0 ? short_bits : PipSplit<F>::BITS;
   g.N = N;
   g.Np = N * g.parts;
   // top 64 bits of the bound, for top_vals: G1 x^2 = 0xac45a4010001a402_0000000100000000, G2 |x| = 0xd201000000010000
-  const unsigned long long bound_hi = g.bits == 128 ? 0xac45a4010001a402ull : 0xd201000000010000ull;
+  const unsigned long long bound_hi = short_bits > 0 ? ~0ull : (g.bits == 128 ? 0xac45a4010001a402ull : 0xd201000000010000ull);
   int best_c = 0;
   double best_t = 0;
   for (int c = 3; c <= 13; c++) {
@@ -275,8 +278,8 @@ inline pip_geom pip_choose(size_t N, int c_override) {
 // out_rows[row * W] (Jacobian, row stride W) = sum_t sv[row][t] * (b0 | b1)[t]; returns the stride through *stride
 template <class F>
 int pippenger_rows(gs_ctx* ctx, Scratch& sc, const fr* sv, int rows, const Aff<F>* b0, size_t n0, const Aff<F>* b1, size_t n1,
-                   Jac<F>** out_rows, size_t* stride, int c_override) {
-  const pip_geom g = pip_choose<F>(n0 + n1, c_override);
+                   Jac<F>** out_rows, size_t* stride, int c_override, int short_bits = 0) {
+  const pip_geom g = pip_choose<F>(n0 + n1, c_override, short_bits);
   const size_t nrw = (size_t)rows * g.W;
   Aff<F>* pts;
   int16_t* digits;

@@ -550,7 +550,7 @@ __global__ void k_and4(const uint8_t* __restrict__ ok4, uint8_t* __restrict__ ou
 // over the SAME slots (X_k, Y_k) the exact verifier builds: one Miller pair per slot instead of four (two), and one final
 // exponentiation per call instead of four per proof.  Slots whose G2 side is a CRS element share one folded G2 point, so
 // their G1 sides are summed over the proofs first.  If any entry of any proof is wrong the check fails except with
-// probability <= 2^-63 over the weights (a non-zero polynomial of degree 2 in beta, then a non-zero linear form in the
+// probability <= 2^-62 over the weights (their low 63 bits are used) (a non-zero polynomial of degree 2 in beta, then a non-zero linear form in the
 // independent sigma_p, tau_p) -- provided all inputs are in the prime-order groups, as deserialised values are.
 // The G2 weight is beta = b0 + b1 |x| with b0, b1 the two 32-bit halves of the caller's word (2^64 distinct values mod r,
 // which is all the soundness argument needs): |x| Y = -psi(Y) is two Fp2 products (endo.cuh), so beta Y.0 is a JOINT
@@ -690,9 +690,11 @@ __global__ void __launch_bounds__(128) k_rand_fold_bases(verify_shape s, verify_
     afold[p * s.n + (q - s.nbases)] = out;
   }
 }
-// thread -> (p, jw): Y' = beta Y[0][k][p] + Y[1][k][p] of the per-proof pair jw = slot walk_slot[jw]  ->  Y1[p*Kw + jw]
+// thread -> (p, jw): Y' = beta Y[0][k][p] + Y[1][k][p] of slot k = walk_slot[jw]  ->  Y1[p*ostride_p + jw*ostride_j]
+// (per-proof pairs: strides (Kw, 1); the pi slots of a big batch, summed over the proofs afterwards: (1, nprob))
 __global__ void __launch_bounds__(128) k_rand_fold_g2(const g2_aff* __restrict__ Y, size_t nprob, int K, jsf33 beta,
-                                                      const int* __restrict__ walk_slot, int Kw, g2_aff* __restrict__ Y1) {
+                                                      const int* __restrict__ walk_slot, int Kw, g2_aff* __restrict__ Y1,
+                                                      size_t ostride_p, size_t ostride_j) {
   __shared__ fp sm[2 * 128];
   size_t id = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const bool active = id < nprob * (size_t)Kw;
@@ -729,7 +731,7 @@ __global__ void __launch_bounds__(128) k_rand_fold_g2(const g2_aff* __restrict__
   g2_jac::add_mixed(acc, acc, y1);
   g2_aff out;
   block_to_affine<128>(out, acc, sm);
-  if (active) Y1[p * Kw + jw] = out;
+  if (active) Y1[p * ostride_p + jw * ostride_j] = out;
 }
 // thread pid < 3: Yfix[pid] = beta P.0 + P.1 for the CRS elements P = v_1, v_2, W2
 __global__ void k_rand_fold_crs(const crs_dev* __restrict__ crs, jsf33 beta, g2_aff* __restrict__ Yfix) {
@@ -799,6 +801,44 @@ __global__ void __launch_bounds__(128) k_g1_sum_final(const g1_jac* __restrict__
   }
 }
 __global__ void k_ok1(const uint8_t* __restrict__ ok1, uint8_t* __restrict__ out) { out[0] = ok1[0]; }
+// ---- big batches: the slots whose OTHER side is a CRS element are summed over the proofs with the bucket method
+// (pippenger.cuh) instead of being folded and paired proof by proof:
+//     prod_p e(sigma_p (-u_k.0) + tau_p (-u_k.1), pi'_pk) = e(-u_k.0, sum_p sigma_p pi'_pk) e(-u_k.1, sum_p tau_p pi'_pk)
+//     prod_p e(sigma_p th_pk.0 + tau_p th_pk.1, v'_k)     = e(sum_p (sigma_p th_pk.0 + tau_p th_pk.1), v'_k)
+// sv[0 .. nprob) = sigma_p, sv[nprob .. 2 nprob) = tau_p as Montgomery Fr values (the scalar format of the MSM kernels)
+__global__ void k_rho_to_fr(const uint64_t* __restrict__ rho, size_t nprob, fr* __restrict__ sv) {
+  size_t id = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (id >= 2 * nprob) return;
+  const size_t p = id % nprob;
+  const uint64_t w = rho[2 * p + (id >= nprob ? 1 : 0)];
+  fr x, r2;
+  x.set_zero();
+  x.l[0] = (uint32_t)w;
+  x.l[1] = (uint32_t)(w >> 32);
+#pragma unroll
+  for (int j = 0; j < 8; j++) r2.l[j] = FR_R2(j);
+  fr::mul(x, x, r2);
+  sv[id] = x;
+}
+// pair `at`: ( affine(*sum) , Yfix[pid] )
+__global__ void k_rand_place_theta(const g1_jac* __restrict__ sum, const g2_aff* __restrict__ Yfix, int pid, size_t at,
+                                   g1_aff* __restrict__ X1, g2_aff* __restrict__ Y1) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  g1_aff o;
+  g1_jac::to_affine(o, *sum);
+  X1[at] = o;
+  Y1[at] = Yfix[pid];
+}
+// pairs at, at + 1: ( -u_j.row , affine(sums[row * stride]) ), row = 0, 1
+__global__ void k_rand_place_pi(const g2_jac* __restrict__ sums, size_t stride, const crs_dev* __restrict__ crs, int j, size_t at,
+                                g1_aff* __restrict__ X1, g2_aff* __restrict__ Y1) {
+  const int row = threadIdx.x;
+  if (row >= 2 || blockIdx.x != 0) return;
+  g2_aff o;
+  g2_jac::to_affine(o, sums[(size_t)row * stride]);
+  X1[at + row] = crs->neg_u[j][row];
+  Y1[at + row] = o;
+}
 
 }  // namespace gs
 
@@ -1299,10 +1339,18 @@ static int verify_rand_dev(gs_ctx* ctx, int type, size_t count, size_t m, size_t
   verify_shape s = make_verify_shape(type, (int)m, (int)n);
   const std::vector<uint8_t> kind_all = slot_kinds(s);
   // per-proof pairs (G2 side walked) and CRS slots (G1 sides summed over the proofs)
-  std::vector<int> slot_map(s.K), walk_slot;
+  std::vector<int> slot_map(s.K), walk_slot, pi_slots, theta_slots;
   fix_pids fpids;
   int nfix = 0;
+  // a big batch sums its pi and theta slots over the proofs with the bucket method (one pass of >= 4,096 proofs; below
+  // that the bucket chains do not pay)
+  const bool use_pip = count >= 4096 && ctx->verify_batch_max >= 23680;
   for (int k = 0; k < s.K; k++) {
+    if (use_pip && k >= s.sPi && k < s.sT) {
+      (k < s.sTh ? pi_slots : theta_slots).push_back(k);
+      slot_map[k] = 0;  // (never looked up: neither an MSM output nor in a fold list)
+      continue;
+    }
     if (kind_all[k] >= gsi::GS_SLOT_FIXED) {
       if (nfix >= 8) FAIL(GS_EDIM, "verify_rand: too many CRS slots");
       fpids.pid[nfix] = kind_all[k] - gsi::GS_SLOT_FIXED;
@@ -1340,12 +1388,14 @@ static int verify_rand_dev(gs_ctx* ctx, int type, size_t count, size_t m, size_t
   const bool fold_first = !shared_x || count == 1;
   std::vector<int> all_slots, rest_slots;
   for (int k = 0; k < s.K; k++) {
-    all_slots.push_back(k);
     const bool msm_out = k < s.n || (k == s.sB && !s.groupB) || (type == 3 && k == s.sT);
     const bool b_slot = s.groupB && k >= s.sB && k < s.sPi;
-    if (!msm_out && !b_slot) rest_slots.push_back(k);
+    const bool summed = use_pip && k >= s.sPi && k < s.sT;
+    if (!summed) all_slots.push_back(k);
+    if (!msm_out && !b_slot && !summed) rest_slots.push_back(k);
   }
-  int *dall, *drest;
+  int *dall, *drest, *dpi_slots;
+  CUDA_TRY(upload(ctx, top, &dpi_slots, pi_slots.data(), pi_slots.size()));
   CUDA_TRY(upload(ctx, top, &dall, all_slots.data(), all_slots.size()));
   CUDA_TRY(upload(ctx, top, &drest, rest_slots.data(), rest_slots.size()));
   // The folded CRS points and the target powers prod_p t_p^tau_p depend on nothing the main stream computes: they run on
@@ -1399,7 +1449,11 @@ static int verify_rand_dev(gs_ctx* ctx, int type, size_t count, size_t m, size_t
     g1_aff *X, *X1, *Xfix;
     g2_aff *Y, *Y1;
     uint64_t* drho;
-    CUDA_TRY(upload(ctx, sc, &drho, rho_host + 2 * off, 2 * nprob));
+    {  // the low 63 bits of every weight: below |x|, so a weight is its own first sub-scalar on both groups (bucket sums)
+      std::vector<uint64_t> w(rho_host + 2 * off, rho_host + 2 * (off + nprob));
+      for (uint64_t& x : w) x &= 0x7fffffffffffffffull;
+      CUDA_TRY(upload(ctx, sc, &drho, w.data(), w.size()));
+    }
     if (type == GS_PPE) {  // prod_p t_p^tau_p, on the side stream
       if (two && side.fork()) FAIL(GS_ECUDA, "verify_rand: event creation failed");
       int rcg = [&]() -> int {
@@ -1421,7 +1475,8 @@ static int verify_rand_dev(gs_ctx* ctx, int type, size_t count, size_t m, size_t
     CUDA_TRY(sc.alloc(&Y, 2 * (size_t)s.K * nprob));
     LAUNCH(k_verify_assemble, nprob * (size_t)s.K, s, v, ctx->crs, X, Y, nprob);
     // the folded single-entry problem: nprob * Kw per-proof pairs, then the nfix summed CRS pairs, padded with identities
-    const size_t npairs = nprob * Kw + nfix;
+    const size_t nextra = theta_slots.size() + 2 * pi_slots.size();  // the summed slots: one pair per theta, two per pi
+    const size_t npairs = nprob * Kw + nfix + nextra;
     const int S = rand_slots_per_acc(npairs);
     const size_t Ktot = (npairs + S - 1) / S * S;
     CUDA_TRY(sc.alloc(&X1, Ktot));
@@ -1429,6 +1484,41 @@ static int verify_rand_dev(gs_ctx* ctx, int type, size_t count, size_t m, size_t
     CUDA_TRY(sc.alloc(&Xfix, (size_t)(nfix ? nfix : 1) * nprob));
     CUDA_TRY(cudaMemsetAsync(X1 + npairs, 0, (Ktot - npairs) * sizeof(g1_aff), ctx->stream));
     CUDA_TRY(cudaMemsetAsync(Y1 + npairs, 0, (Ktot - npairs) * sizeof(g2_aff), ctx->stream));
+    if (nextra) {
+      // bucket sums of the pi / theta slots: they need the assembled slots only, and their kernels are short dependent
+      // chains -- on the second stream, next to the statement MSM and the folds
+      if (two && side.fork()) FAIL(GS_ECUDA, "verify_rand: event creation failed");
+      int rcx = [&]() -> int {
+        fr* sv;
+        CUDA_TRY(sc.alloc(&sv, 2 * nprob));
+        LAUNCH(k_rho_to_fr, 2 * nprob, drho, nprob, sv);
+        size_t at = nprob * Kw + nfix;
+        for (size_t t = 0; t < theta_slots.size(); t++, at++) {
+          const int k = theta_slots[t];
+          g1_jac* sum;
+          size_t stride;
+          int rcp = gsi::pippenger_rows<FpOps>(ctx, sc, sv, 1, X + ((size_t)0 * s.K + k) * nprob, nprob, X + ((size_t)1 * s.K + k) * nprob,
+                                                nprob, &sum, &stride, 0, 63);
+          if (rcp) return rcp;
+          LAUNCH_CFG(k_rand_place_theta, 1, 32, 0, sum, Yfix, (int)(kind_all[k] - gsi::GS_SLOT_FIXED), at, X1, Y1);
+        }
+        if (!pi_slots.empty()) {
+          g2_aff* Ypi;
+          CUDA_TRY(sc.alloc(&Ypi, pi_slots.size() * nprob));
+          LAUNCH(k_rand_fold_g2, nprob * pi_slots.size(), Y, nprob, s.K, beta, dpi_slots, (int)pi_slots.size(), Ypi, (size_t)1, nprob);
+          for (size_t t = 0; t < pi_slots.size(); t++, at += 2) {
+            g2_jac* sums;
+            size_t stride;
+            int rcp = gsi::pippenger_rows<Fp2Ops>(ctx, sc, sv, 2, Ypi + t * nprob, nprob, (const g2_aff*)nullptr, 0, &sums, &stride, 0, 63);
+            if (rcp) return rcp;
+            LAUNCH_CFG(k_rand_place_pi, 32, 32, 0, sums, stride, ctx->crs, pi_slots[t] - s.sPi, at, X1, Y1);
+          }
+        }
+        return GS_OK;
+      }();
+      if (two) side.back();
+      if (rcx) return rcx;
+    }
     if (fold_first) {
       // the commitments are folded BEFORE the statement MSM, which then sums single points: half the scalar products;
       // its outputs are folded slots already, the (c_i, iota_2(B_i)) slots are the folded bases themselves
@@ -1456,7 +1546,7 @@ static int verify_rand_dev(gs_ctx* ctx, int type, size_t count, size_t m, size_t
       if (rcm) return rcm;
       LAUNCH(k_rand_fold_g1, nprob * all_slots.size(), X, nprob, s.K, drho, dall, (int)all_slots.size(), dmap, Kw, X1, Xfix);
     }
-    LAUNCH(k_rand_fold_g2, nprob * (size_t)Kw, Y, nprob, s.K, beta, dwalk_slot, Kw, Y1);
+    LAUNCH(k_rand_fold_g2, nprob * (size_t)Kw, Y, nprob, s.K, beta, dwalk_slot, Kw, Y1, (size_t)Kw, (size_t)1);
     side.join();  // the folded CRS points (and, long finished, this pass's target powers)
     if (nfix) {
       const int L = 32;

@@ -292,7 +292,7 @@ class Engine:
         return rho
 
     def verify_batch_rand(self, ty, count, m, n, a_consts, b_consts, gamma, target, xcoms, ycoms, pi, theta, rho=None) -> bool:
-        """True iff every proof of the batch verifies (error <= 2^-63 over rho).  Not the reference's per-proof answer: on
+        """True iff every proof of the batch verifies (error <= 2^-62 over rho).  Not the reference's per-proof answer: on
         False, verify_batch says which ones failed."""
         if count and m and n:
             self._check_verify_sizes(ty, count, m, n, a_consts, b_consts, gamma, target, xcoms, ycoms, pi, theta)

@@ -191,7 +191,7 @@ int gs_verify_sharded(gs_ctx* ctx, int type, size_t count, size_t m, size_t n, c
 
 /* Randomised batch verification -- SURVEY.md §8f.4, an OPT-IN that the reference does not have (its `verify` is
  * src/verifier.rs:23-157, one proof at a time, four final exponentiations each).  ONE verdict for the whole batch:
- * *out_all_ok = 1 iff every proof verifies, except with probability <= 2^-63 over `rho`.  Not bit-comparable with the
+ * *out_all_ok = 1 iff every proof verifies, except with probability <= 2^-62 over `rho`.  Not bit-comparable with the
  * reference's per-proof booleans: when the answer is 0 the caller learns which proofs failed from gs_verify_batch.
  * rho[2*count + 1]: 64-bit words from the CALLER's cryptographic RNG, unknown to whoever made the proofs
  * (rho[2p], rho[2p+1] weight the two Com1 coordinates of proof p, rho[2*count] the Com2 coordinates of all of them).

@@ -148,3 +148,17 @@ def test_rand_shared_commitments(eng, crs, ty):
     for which in (0, 2, 3, 6):
         bad = tampered(ty, m, n, arrays, which, 17, 30)
         assert eng.verify_batch_rand(ty, E, m, n, *bad, rho=rho_of(E, 61 + which)) is False, f"array {which} accepted"
+
+
+@pytest.mark.parametrize("ty", [0, 1, 2, 3])
+def test_rand_big_batch_bucket_sums(eng, crs, ty):
+    """>= 4,096 proofs: the pi and theta slots are summed over the proofs with the bucket method (one G2 / G1 MSM with the
+    64-bit weights per slot) instead of being paired proof by proof.  A bad pi or theta of ONE proof must still be caught."""
+    m, n, reps = 3, 2, 342
+    cases = [Case(ty, m, n, crs, seed=2700 + 20 * ty + i) for i in range(12)]
+    count = 12 * reps                                                   # 4,104
+    arrays = [b"".join(c.verify_arrays()[k] for c in cases) * reps for k in range(8)]
+    assert eng.verify_batch_rand(ty, count, m, n, *arrays, rho=rho_of(count, 70)) is True
+    for which, p in ((6, 4000), (7, 17), (3, 2222), (4, 4103)):
+        bad = tampered(ty, m, n, arrays, which, p, 5)
+        assert eng.verify_batch_rand(ty, count, m, n, *bad, rho=rho_of(count, 71 + which)) is False, f"array {which} accepted"
