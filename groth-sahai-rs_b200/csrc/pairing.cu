@@ -685,7 +685,10 @@ int gsi::g2_walk_ahead(gs_ctx* ctx, Scratch& sc, const g2_aff* Y, size_t nprob, 
   cudaStream_t main_stream = ctx->stream;
   ctx->stream = ctx->stream2;
   int rc = [&]() -> int {
-    if (ctx->lone_walk_jac) {
+    // (the inversion-free walk does MORE work per point -- a block per point to turn its 68 records into lines -- and only
+    // wins where a point's own dependent chain is the whole cost: a lone statement; 256 statements of a C4 batch walk
+    // 50 k points, and there it took 16 ms of the second stream against 8 for the affine walk)
+    if (ctx->lone_walk_jac && (size_t)nwalk * nprob <= 4096) {
       LAUNCH_CFG(k_g2_walk_jac, (size_t)nwalk * nprob, 64, 0, Y, rec, nprob, nprob, K, wa->dwalk, nwalk);
       LAUNCH_CFG(k_g2_lines_from_jac, (size_t)nwalk * nprob * 128, 128, 0, Y, rec, lines, nprob, nprob, K, wa->dwalk);
     } else {
