@@ -762,7 +762,7 @@ def main():
                 "speedup_vs_exact": round((rnd["proofs"] / rnd["ms_per_step"]) / (P / ms_per_step), 3),
                 "accepts_honest_batch": rnd["accepts_honest_batch"], "rejects_batch_with_tampered": rnd["rejects_batch_with_tampered"],
                 "launches_per_step": rnd["launches_per_step"],
-                "kernels_ms": {k: round(v[1], 3) for k, v in sorted(rnd["prof"].items(), key=lambda kv: -kv[1][1])[:10]},
+                "kernels_ms": {k: round(v[1], 3) for k, v in sorted(rnd["prof"].items(), key=lambda kv: -kv[1][1])},
             }
         elif rnd:
             line["c5_randomised"] = rnd

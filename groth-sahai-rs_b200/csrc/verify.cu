@@ -4,6 +4,7 @@
 #include "ctx.h"
 #include "endo.cuh"
 #include "prover_impl.cuh"  // fixed_base_accumulate
+#include "randfold.cuh"
 
 using namespace gs;
 
@@ -552,55 +553,14 @@ __global__ void k_and4(const uint8_t* __restrict__ ok4, uint8_t* __restrict__ ou
 // their G1 sides are summed over the proofs first.  If any entry of any proof is wrong the check fails except with
 // probability <= 2^-62 over the weights (their low 63 bits are used) (a non-zero polynomial of degree 2 in beta, then a non-zero linear form in the
 // independent sigma_p, tau_p) -- provided all inputs are in the prime-order groups, as deserialised values are.
-// The G2 weight is beta = b0 + b1 |x| with b0, b1 the two 32-bit halves of the caller's word (2^64 distinct values mod r,
-// which is all the soundness argument needs): |x| Y = -psi(Y) is two Fp2 products (endo.cuh), so beta Y.0 is a JOINT
-// 33-step double-and-add over (Y.0, -psi(Y.0)) -- half the doublings of a 64-bit scalar -- and in joint sparse form
-// (Solinas) only every second step adds.  beta is the same for all threads: the digits are kernel parameters and the
-// instruction stream is uniform.
-struct jsf33 {
-  int8_t u0[34], u1[34];  // digits in {-1, 0, 1}, least significant first
-  int len;
-};
-static jsf33 make_jsf(uint32_t a, uint32_t b) {
-  jsf33 r;
-  memset(&r, 0, sizeof r);
-  uint64_t k0 = a, k1 = b;
-  int d0 = 0, d1 = 0, n = 0;
-  auto digit = [](uint64_t l, uint64_t lo) {
-    if ((l & 1) == 0) return 0;
-    int u = 2 - (int)(l & 3);
-    if (((l & 7) == 3 || (l & 7) == 5) && (lo & 3) == 2) u = -u;
-    return u;
-  };
-  while (k0 + d0 > 0 || k1 + d1 > 0) {
-    const uint64_t l0 = k0 + d0, l1 = k1 + d1;
-    const int u0 = digit(l0, l1), u1 = digit(l1, l0);
-    if (2 * d0 == 1 + u0) d0 = 1 - d0;
-    if (2 * d1 == 1 + u1) d1 = 1 - d1;
-    k0 >>= 1;
-    k1 >>= 1;
-    r.u0[n] = (int8_t)u0;
-    r.u1[n] = (int8_t)u1;
-    n++;
-  }
-  r.len = n;
-  return r;
-}
-// acc += beta * y0 given p1 = -psi(y0) and the affine sums as = y0 + p1, ad = y0 - p1 (acc must be the identity on entry)
-__device__ GS_INL void rand_fold_g2_walk(g2_jac& acc, const g2_aff& y0, const g2_aff& p1, const g2_aff& as, const g2_aff& ad,
-                                         const jsf33& b) {
-#pragma unroll 1
-  for (int i = b.len - 1; i >= 0; i--) {
-    g2_jac::dbl(acc, acc);
-    const int u0 = b.u0[i], u1 = b.u1[i];
-    if (u0 == 0 && u1 == 0) continue;
-    g2_aff t = u1 == 0 ? y0 : (u0 == 0 ? p1 : (u0 == u1 ? as : ad));
-    const bool neg = u0 != 0 ? u0 < 0 : u1 < 0;  // the table holds the combinations whose first non-zero digit is +1
-    if (neg) fp2::neg(t.y, t.y);
-    g2_jac::add_mixed(acc, acc, t);
-  }
-}
 // slot_map[k] >= 0: per-proof pair number jw of slot k (G2 side walked); < 0: -(f + 1), CRS slot number f
+// resident blocks per SM the fold kernels are compiled for (experiments: -DRFG2_BLOCKS=.. -DRFB_BLOCKS=..)
+#ifndef RFG2_BLOCKS
+#define RFG2_BLOCKS 2
+#endif
+#ifndef RFB_BLOCKS
+#define RFB_BLOCKS 3
+#endif
 // sigma x0 + tau x1 by a joint 64-step double-and-add over the table 0, x0, x1, x0 + x1 (one table addition per bit, the
 // same instruction stream for every lane; the sum is made affine with one block-wide inversion).  All 128 threads call.
 __device__ GS_INL void rand_fold_g1_point(g1_aff& out, const g1_aff& x0, const g1_aff& x1, uint64_t sg, uint64_t tu, fp* sm) {
@@ -614,13 +574,7 @@ __device__ GS_INL void rand_fold_g1_point(g1_aff& out, const g1_aff& x0, const g
   block_to_affine<128>(tab[3], j, sm);
   __syncthreads();  // (sm is reused below)
   g1_jac acc;
-  acc.set_inf();
-#pragma unroll 1
-  for (int bit = 63; bit >= 0; bit--) {
-    g1_jac::dbl(acc, acc);
-    const int d = (int)((sg >> bit) & 1) | ((int)((tu >> bit) & 1) << 1);
-    g1_jac::add_mixed(acc, acc, tab[d]);
-  }
+  rand_fold_g1_walk(acc, tab, sg, tu);
   block_to_affine<128>(out, acc, sm);
   __syncthreads();
 }
@@ -655,7 +609,7 @@ __global__ void __launch_bounds__(128) k_rand_fold_g1(const g1_aff* __restrict__
 // thread -> (p, q):  q < nbases: xfold[p][q] = sigma_p B_q.0 + tau_p B_q.1 (B_q = c_q, or W1 when A is scalar-valued);
 //                    q >= nbases (group-valued A): afold[p][j] = tau_p A_j, j = q - nbases.
 // With group-valued B the slot (c_i, iota_2(B_i)) has exactly xfold[p][i] on its G1 side: copied to pair bmap0 + i.
-__global__ void __launch_bounds__(128) k_rand_fold_bases(verify_shape s, verify_args v, const crs_dev* __restrict__ crs, size_t nprob,
+__global__ void __launch_bounds__(128, RFB_BLOCKS) k_rand_fold_bases(verify_shape s, verify_args v, const crs_dev* __restrict__ crs, size_t nprob,
                                                          const uint64_t* __restrict__ rho, g1_aff* __restrict__ xfold,
                                                          g1_aff* __restrict__ afold, int bmap0, int Kw, g1_aff* __restrict__ X1) {
   __shared__ fp sm[2 * 128];
@@ -692,7 +646,7 @@ __global__ void __launch_bounds__(128) k_rand_fold_bases(verify_shape s, verify_
 }
 // thread -> (p, jw): Y' = beta Y[0][k][p] + Y[1][k][p] of slot k = walk_slot[jw]  ->  Y1[p*ostride_p + jw*ostride_j]
 // (per-proof pairs: strides (Kw, 1); the pi slots of a big batch, summed over the proofs afterwards: (1, nprob))
-__global__ void __launch_bounds__(128) k_rand_fold_g2(const g2_aff* __restrict__ Y, size_t nprob, int K, jsf33 beta,
+__global__ void __launch_bounds__(128, RFG2_BLOCKS) k_rand_fold_g2(const g2_aff* __restrict__ Y, size_t nprob, int K, jsf33 beta,
                                                       const int* __restrict__ walk_slot, int Kw, g2_aff* __restrict__ Y1,
                                                       size_t ostride_p, size_t ostride_j) {
   __shared__ fp sm[2 * 128];
@@ -738,23 +692,7 @@ __global__ void k_rand_fold_crs(const crs_dev* __restrict__ crs, jsf33 beta, g2_
   const int pid = blockIdx.x * blockDim.x + threadIdx.x;
   if (pid >= 3) return;
   const g2_aff y0 = pid < 2 ? crs->v[pid][0] : crs->w2[0], y1 = pid < 2 ? crs->v[pid][1] : crs->w2[1];
-  g2_aff p1, np1, as, ad;
-  endo_psi(p1, y0);
-  fp2::neg(p1.y, p1.y);
-  np1 = p1;
-  fp2::neg(np1.y, p1.y);
-  g2_jac js, jd;
-  js.from_affine(y0);
-  jd = js;
-  g2_jac::add_mixed(js, js, p1);
-  g2_jac::add_mixed(jd, jd, np1);
-  g2_jac::to_affine(as, js);
-  g2_jac::to_affine(ad, jd);
-  g2_jac acc;
-  acc.set_inf();
-  rand_fold_g2_walk(acc, y0, p1, as, ad, beta);
-  g2_jac::add_mixed(acc, acc, y1);
-  g2_jac::to_affine(Yfix[pid], acc);
+  rand_fold_g2_single(Yfix[pid], y0, y1, beta);
 }
 // thread -> (f, strip): part[f*nstrips + strip] = sum of L consecutive points of Xfix[f][.]
 __global__ void __launch_bounds__(128) k_g1_sum_strips(const g1_aff* __restrict__ Xfix, size_t nprob, int nfix, int L, size_t nstrips,

@@ -288,3 +288,24 @@ extern "C" int hs_g1_decompress(void* out, const void* in48, int check) { g1_aff
 extern "C" void hs_g2_compress(void* out96, const void* a) { LD(g2_aff, p, a); g2_compress_point((uint8_t*)out96, p); }
 extern "C" int hs_g2_decompress(void* out, const void* in96, int check) { g2_aff p; bool ok = g2_decompress_point(p, (const uint8_t*)in96, check); ST(out, p); return ok; }
 extern "C" int hs_fp2_sqrt(void* r, const void* a) { LD(fp2, x, a); fp2 y; bool ok = fp2_sqrt(y, x); ST(r, y); return ok; }
+
+// ---- randfold.cuh: the folding primitives of gs_verify_batch_rand
+#include "randfold.cuh"
+extern "C" void hs_rand_jsf(void* out /* 34 + 34 digits, then len as one byte */, uint32_t a, uint32_t b) {
+  jsf33 j = make_jsf(a, b);
+  memcpy(out, j.u0, 34);
+  memcpy((char*)out + 34, j.u1, 34);
+  ((uint8_t*)out)[68] = (uint8_t)j.len;
+}
+extern "C" void hs_rand_fold_g2(void* r, const void* y0, const void* y1, uint64_t w) {
+  LD(g2_aff, a, y0); LD(g2_aff, b, y1);
+  g2_aff o;
+  rand_fold_g2_single(o, a, b, make_jsf((uint32_t)w, (uint32_t)(w >> 32)));
+  ST(r, o);
+}
+extern "C" void hs_rand_fold_g1(void* r, const void* x0, const void* x1, uint64_t sg, uint64_t tu) {
+  LD(g1_aff, a, x0); LD(g1_aff, b, x1);
+  g1_aff o;
+  rand_fold_g1_single(o, a, b, sg, tu);
+  ST(r, o);
+}

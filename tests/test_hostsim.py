@@ -326,3 +326,58 @@ def test_wire_format_device_code(L):
         if ser.fp2_sqrt(a) is None:
             nonres = a
     assert L.hs_fp2_sqrt(out, fp2_b(nonres)) == 0
+
+
+def test_rand_fold_primitives(L):
+    """randfold.cuh on the host (gs_verify_batch_rand): the joint sparse form reconstructs its two 32-bit inputs with
+    digits in {-1, 0, 1} and no two adjacent non-zero columns pattern longer than 33; beta Y0 + Y1 with
+    beta = b0 + b1 |x| through the psi walk, and sigma X0 + tau X1 through the joint table walk, equal the oracle's
+    scalar multiplications -- identities and equal / opposite points included."""
+    import ctypes
+    XA = 0xD201000000010000
+    L.hs_rand_jsf.argtypes = [ctypes.c_void_p, ctypes.c_uint32, ctypes.c_uint32]
+    L.hs_rand_fold_g2.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint64]
+    L.hs_rand_fold_g1.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint64, ctypes.c_uint64]
+    pairs = [(0, 0), (1, 0), (0, 1), (0xFFFFFFFF, 0xFFFFFFFF), (0xFFFFFFFF, 0), (3, 5), (0x80000000, 0x7FFFFFFF)]
+    pairs += [(rng.getrandbits(32), rng.getrandbits(32)) for _ in range(300)]
+    nz = 0
+    for a, b in pairs:
+        buf = ctypes.create_string_buffer(72)
+        L.hs_rand_jsf(buf, a, b)
+        n = buf.raw[68]
+        u0 = [int.from_bytes(buf.raw[i:i + 1], "little", signed=True) for i in range(34)]
+        u1 = [int.from_bytes(buf.raw[34 + i:35 + i], "little", signed=True) for i in range(34)]
+        assert n <= 33 and all(d in (-1, 0, 1) for d in u0 + u1) and not any(u0[n:]) and not any(u1[n:])
+        assert sum(d << i for i, d in enumerate(u0)) == a and sum(d << i for i, d in enumerate(u1)) == b
+        nz += sum(1 for x, y in zip(u0, u1) if x or y)
+    assert nz / len(pairs) < 18.5                                  # joint density 1/2 (a plain binary pair has 3/4)
+
+    def fold_g2(y0, y1, w):
+        out = ctypes.create_string_buffer(192)
+        k0, k1 = ctypes.create_string_buffer(g2_b(y0), 192), ctypes.create_string_buffer(g2_b(y1), 192)
+        L.hs_rand_fold_g2(out, k0, k1, w)
+        return g2_i(out.raw)
+
+    def fold_g1(x0, x1, sg, tu):
+        out = ctypes.create_string_buffer(96)
+        k0, k1 = ctypes.create_string_buffer(g1_b(x0), 96), ctypes.create_string_buffer(g1_b(x1), 96)
+        L.hs_rand_fold_g1(out, k0, k1, sg, tu)
+        return g1_i(out.raw)
+
+    q0, q1 = g2_mul(G2_GEN_FP2, rng.randrange(R)), g2_mul(G2_GEN_FP2, rng.randrange(R))
+    for w in (0, 1, 1 << 32, (1 << 64) - 1, rng.getrandbits(64), rng.getrandbits(64)):
+        beta = ((w & 0xFFFFFFFF) + (w >> 32) * XA) % R
+        assert fold_g2(q0, q1, w) == G2.add(g2_mul(q0, beta), q1), hex(w)
+    w = rng.getrandbits(64)
+    beta = ((w & 0xFFFFFFFF) + (w >> 32) * XA) % R
+    assert fold_g2(None, q1, w) == q1                               # iota_2 image: no first coordinate
+    assert fold_g2(q0, None, w) == g2_mul(q0, beta)
+    assert fold_g2(q0, g2_mul(q0, (R - beta) % R), w) is None         # the sum is the identity
+    p0, p1 = g1_mul(G1_GEN, rng.randrange(R)), g1_mul(G1_GEN, rng.randrange(R))
+    M63 = (1 << 63) - 1
+    for sg, tu in ((0, 0), (1, 0), (0, 1), (M63, M63), (rng.getrandbits(63), rng.getrandbits(63)), (5, rng.getrandbits(63))):
+        assert fold_g1(p0, p1, sg, tu) == G1.add(g1_mul(p0, sg), g1_mul(p1, tu)), (sg, tu)
+    sg, tu = rng.getrandbits(63), rng.getrandbits(63)
+    assert fold_g1(None, p1, sg, tu) == g1_mul(p1, tu) and fold_g1(p0, None, sg, tu) == g1_mul(p0, sg)
+    assert fold_g1(p0, p0, sg, tu) == g1_mul(p0, sg + tu)           # x0 + x1 is a doubling
+    assert fold_g1(p0, g1_mul(p0, R - 1), sg, tu) == g1_mul(p0, (sg - tu) % R)   # x0 + x1 is the identity
