@@ -42,6 +42,7 @@ int gs_ctx_create(int device, gs_ctx** out) {
   }
   if (const char* e = getenv("GS_PIP_MIN")) ctx->pip_min = (size_t)strtoull(e, nullptr, 10);
   if (const char* e = getenv("GS_PIP_C")) ctx->pip_c = atoi(e);
+  if (const char* e = getenv("GS_RAND_PIP_MIN")) ctx->rand_pip_min = (size_t)strtoull(e, nullptr, 10);
   if (const char* e = getenv("GS_PREP_VARIANT")) ctx->prep_variant = atoi(e);
   if (const char* e = getenv("GS_PASS_STREAMS")) ctx->pass_streams = atoi(e);
   if (const char* e = getenv("GS_LONE_WALK_JAC")) ctx->lone_walk_jac = atoi(e);

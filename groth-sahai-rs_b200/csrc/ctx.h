@@ -52,6 +52,8 @@ struct gs_ctx {
   bool in_pass = false;     // set by a caller that already cut the batch into passes (verify_host): no second split inside
   int pass_streams = 2;   // verify passes of a big batch alternate between this many streams (GS_PASS_STREAMS = 1 | 2)
   int prep_variant = 5;   // resident blocks per SM the line-walk kernel is compiled for (GS_PREP_VARIANT = 4 | 5, experiments)
+  size_t rand_pip_min = 4096;   // gs_verify_batch_rand: batches of at least this many proofs sum their pi / theta slots over the
+                                // proofs with the bucket method (GS_RAND_PIP_MIN; measured better from 8,192 proofs up: 50.6 vs 51.7 ms)
   size_t pip_min = 2048;  // proof MSMs of one statement with at least this many terms use the bucket method (pippenger.cuh);
   int pip_c = 0;          // measured crossover, DESIGN.md §4.  Overrides for experiments: GS_PIP_MIN, GS_PIP_C (window bits)
   std::string err;

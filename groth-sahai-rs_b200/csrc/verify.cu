@@ -1280,9 +1280,9 @@ static int verify_rand_dev(gs_ctx* ctx, int type, size_t count, size_t m, size_t
   std::vector<int> slot_map(s.K), walk_slot, pi_slots, theta_slots;
   fix_pids fpids;
   int nfix = 0;
-  // a big batch sums its pi and theta slots over the proofs with the bucket method (one pass of >= 4,096 proofs; below
-  // that the bucket chains do not pay)
-  const bool use_pip = count >= 4096 && ctx->verify_batch_max >= 23680;
+  // a big batch sums its pi and theta slots over the proofs with the bucket method (small ones pair them proof by proof:
+  // the bucket kernels are dependent chains that do not shrink with the batch)
+  const bool use_pip = count >= ctx->rand_pip_min && ctx->verify_batch_max >= 23680;
   for (int k = 0; k < s.K; k++) {
     if (use_pip && k >= s.sPi && k < s.sT) {
       (k < s.sTh ? pi_slots : theta_slots).push_back(k);
@@ -1375,6 +1375,10 @@ static int verify_rand_dev(gs_ctx* ctx, int type, size_t count, size_t m, size_t
   for (size_t off = 0; off < count; off += pass_n, pass++) {
     const size_t nprob = count - off < pass_n ? count - off : pass_n;
     Scratch sc(ctx);
+    struct join_on_exit {  // declared after `sc`, destroyed first: on EVERY exit of the pass (error returns included) the
+      side_stream& s;      // main stream is ordered after the side work before `sc` releases buffers that work still uses
+      ~join_on_exit() { s.join(); }
+    } joined{side};
     verify_args v;
     v.a_consts = (const char*)a_consts + off * n * elem_size_A(type);
     v.b_consts = (const char*)b_consts + off * m * elem_size_B(type);
@@ -1496,7 +1500,6 @@ static int verify_rand_dev(gs_ctx* ctx, int type, size_t count, size_t m, size_t
     }
     int rc = gsi::run_pairing_product(ctx, sc, X1, Y1, 1, (int)Ktot, nullptr, nullptr, nullptr, Mall + pass, nullptr, nullptr, 1, S);
     if (rc) return rc;
-    side.join();  // before `sc` releases the buffers of this pass's target powers
   }
   const fp12* want = nullptr;
   if (type == GS_PPE) {

@@ -194,7 +194,8 @@ int gs_verify_sharded(gs_ctx* ctx, int type, size_t count, size_t m, size_t n, c
  * *out_all_ok = 1 iff every proof verifies, except with probability <= 2^-62 over `rho`.  Not bit-comparable with the
  * reference's per-proof booleans: when the answer is 0 the caller learns which proofs failed from gs_verify_batch.
  * rho[2*count + 1]: 64-bit words from the CALLER's cryptographic RNG, unknown to whoever made the proofs
- * (rho[2p], rho[2p+1] weight the two Com1 coordinates of proof p, rho[2*count] the Com2 coordinates of all of them).
+ * (the low 63 bits of rho[2p], rho[2p+1] weight the two Com1 coordinates of proof p, rho[2*count] the Com2 coordinates of
+ * all of them).
  * The four ComT entries of all proofs are folded into a single pairing product: one Miller pair per slot and one final
  * exponentiation per call (csrc/verify.cu, "randomised batch verification").  Soundness needs what the exact
  * verifier assumes too: every point in its prime-order group (gs_g1/g2_decompress check it) and, for PPE, every target

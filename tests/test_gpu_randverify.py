@@ -151,9 +151,17 @@ def test_rand_shared_commitments(eng, crs, ty):
 
 
 @pytest.mark.parametrize("ty", [0, 1, 2, 3])
-def test_rand_big_batch_bucket_sums(eng, crs, ty):
+def test_rand_big_batch_bucket_sums(crs, ty):
     """>= 4,096 proofs: the pi and theta slots are summed over the proofs with the bucket method (one G2 / G1 MSM with the
     64-bit weights per slot) instead of being paired proof by proof.  A bad pi or theta of ONE proof must still be caught."""
+    import groth_sahai_rs_b200 as gsb
+    old = os.environ.get("GS_RAND_PIP_MIN")
+    os.environ["GS_RAND_PIP_MIN"] = "4096"                              # (the default, pinned here)
+    try:
+        eng = gsb.Engine(0)
+    finally:
+        os.environ.pop("GS_RAND_PIP_MIN", None) if old is None else os.environ.__setitem__("GS_RAND_PIP_MIN", old)
+    eng.crs_load(crs_bytes(crs))
     m, n, reps = 3, 2, 342
     cases = [Case(ty, m, n, crs, seed=2700 + 20 * ty + i) for i in range(12)]
     count = 12 * reps                                                   # 4,104
@@ -162,3 +170,4 @@ def test_rand_big_batch_bucket_sums(eng, crs, ty):
     for which, p in ((6, 4000), (7, 17), (3, 2222), (4, 4103)):
         bad = tampered(ty, m, n, arrays, which, p, 5)
         assert eng.verify_batch_rand(ty, count, m, n, *bad, rho=rho_of(count, 71 + which)) is False, f"array {which} accepted"
+    eng.close()
