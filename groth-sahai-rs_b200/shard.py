@@ -57,6 +57,23 @@ def verify_batch_sharded(verify_local, arrays: Sequence, unit_sizes: Sequence[in
     return gather_verdicts(local, count, group)
 
 
+def verify_batch_rand_sharded(verify_rand_local, arrays: Sequence, unit_sizes: Sequence[int], count: int, rank: int, world: int,
+                              group=None, device="cpu") -> bool:
+    """The opt-in randomised batch check (gs_verify_batch_rand) over `world` ranks: every rank checks its
+    contiguous block of proofs with ITS OWN random weights (`verify_rand_local(shard_arrays, n) -> bool`, i.e.
+    Engine.verify_batch_rand bound to a type and shape) and the one-byte verdicts are AND-ed (all-reduce MIN).  True iff
+    every proof of the batch verifies, up to the per-rank error of 2^-62; no data-path collective."""
+    import torch
+    import torch.distributed as dist
+    lo, hi = shard_range(count, rank, world)
+    ok = bool(verify_rand_local(slice_units(arrays, unit_sizes, lo, hi), hi - lo)) if hi > lo else True
+    if world == 1:
+        return ok
+    t = torch.tensor([1 if ok else 0], dtype=torch.int32, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MIN, group=group)
+    return bool(int(t.item()))
+
+
 # ---------------------------------------------------------------- one large statement over several GPUs
 PARTIAL_BYTES = 4 * 576   # four un-exponentiated GT values per statement (include/gs_b200.h gs_verify_partial)
 

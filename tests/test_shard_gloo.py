@@ -79,6 +79,44 @@ def test_verdict_all_gather_gloo(world, count):
         assert seen == ([hi - lo] if hi > lo else [])
 
 
+def _rand_worker(rank, world, port, count, bad_at, q):
+    import torch.distributed as dist
+    sh = _load_shard()
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    try:
+        a0 = bytes(0xff if i == bad_at else i & 0x7f for i in range(count))      # one tag byte per "proof"; 0xff = bad
+
+        def verify_rand_local(arrs, n):                                          # ONE verdict for the rank's block
+            assert len(arrs[0]) == n
+            return 0xff not in arrs[0]
+
+        q.put((rank, sh.verify_batch_rand_sharded(verify_rand_local, [a0], [1], count, rank, world)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,count,bad_at", [(2, 11, -1), (2, 11, 0), (2, 11, 10), (3, 10, 4), (2, 1, -1), (2, 1, 0)])
+def test_rand_verdict_all_reduce_gloo(world, count, bad_at):
+    """shard.verify_batch_rand_sharded: per-rank one-byte verdicts AND-ed over the ranks (a bad proof in ANY block, also on
+    a rank other than the caller's, turns every rank's answer to False; a rank with an empty block says True)."""
+    import torch.multiprocessing as mp
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_rand_worker, args=(r, world, port, count, bad_at, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert sorted(r for r, _ in res) == list(range(world))
+    assert all(ok is (bad_at < 0) for _, ok in res), res
+
+
 # ---------------------------------------------------------------- one statement split by slot (gs_verify_partial)
 def test_owned_slots_partition():
     sh = _load_shard()
