@@ -178,6 +178,8 @@ int final_exp_init(gs_ctx* ctx);
 constexpr uint8_t GS_SLOT_WALK = 0;     // arbitrary Com2: walk both coordinates
 constexpr uint8_t GS_SLOT_WALK_B1 = 1;  // Y_k = (O, y): only coordinate 1 exists (iota_2)
 constexpr uint8_t GS_SLOT_FIXED = 2;    // GS_SLOT_FIXED + j: Y_k is the CRS element v_1 (j = 0), v_2 (1) or W2 (2)
+constexpr uint8_t GS_SLOT_WALK_SHARED = 0x40;  // arbitrary Com2 that is THE SAME in every problem of the call (the y-commitments of
+                                               // a multi-equation statement): walked once when the lines are walked ahead
 struct walk_ahead {  // G2 walks started early on the second stream (lone statements), see g2_walk_ahead
   gs_ctx* ctx = nullptr;
   fp2* lines = nullptr;

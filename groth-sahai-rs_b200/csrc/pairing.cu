@@ -110,7 +110,7 @@ __global__ void __launch_bounds__(128, MINB) k_g2_prepare4(const uint32_t* __res
     Q.q[i] = Y;
     if (e >= nwalk || !inrange) continue;
     const uint32_t we = walk[e];
-    const int b = (int)(we >> 31), k = (int)(we & 0x7FFFFFFFu);
+    const int b = (int)(we >> 31), k = (int)(we & 0x3FFFFFFFu);
     kslot[i] = k;
     Q.q[i] = &Y[((size_t)b * K + k) * nprob + p0 + pl];
     fp2 qx, qy;
@@ -260,11 +260,12 @@ __global__ void __launch_bounds__(128, 2) k_g2_walk(const g2_aff* __restrict__ Y
   const size_t pl = q % np;
   const int e = (int)(q / np);
   const uint32_t we = walk[e];
-  const int b = (int)(we >> 31), k = (int)(we & 0x7FFFFFFFu);
+  const int b = (int)(we >> 31), k = (int)(we & 0x3FFFFFFFu);
+  const bool dup = ((we >> 30) & 1) && pl != 0;  // a point shared by all problems is walked for problem 0 only
   const g2_aff P = Y[((size_t)b * K + k) * nprob + pl];
   fp2 Tx[1] = {P.x}, Ty[1] = {P.y}, Qx[1] = {P.x}, Qy[1] = {P.y};
   g2_pts_arr T{Tx, Ty}, Qa{Qx, Qy};
-  bool act[1] = {inrange && !P.is_inf()};
+  bool act[1] = {inrange && !dup && !P.is_inf()};
   if (!__syncthreads_or(act[0])) return;
   fp2* out = lines + ((size_t)e * np + pl) * GS_NUM_LINES * 2;
   int idx = 0;
@@ -295,7 +296,8 @@ __global__ void __launch_bounds__(64) k_g2_walk_jac(const g2_aff* __restrict__ Y
   const size_t pl = q % np;
   const int e = (int)(q / np);
   const uint32_t we = walk[e];
-  const int b = (int)(we >> 31), k = (int)(we & 0x7FFFFFFFu);
+  const int b = (int)(we >> 31), k = (int)(we & 0x3FFFFFFFu);
+  if (((we >> 30) & 1) && pl != 0) return;  // shared by all problems: walked for problem 0 only
   const g2_aff Q = Y[((size_t)b * K + k) * nprob + pl];
   if (Q.is_inf()) return;  // k_eval_tiles drops the pair
   fp2* out = rec + ((size_t)e * np + pl) * GS_NUM_LINES * 4;
@@ -374,7 +376,8 @@ __global__ void __launch_bounds__(128) k_g2_lines_from_jac(const g2_aff* __restr
   const size_t pl = pt % np;
   const int e = (int)(pt / np);
   const uint32_t we = walk[e];
-  const g2_aff* Q = &Y[((size_t)(we >> 31) * K + (we & 0x7FFFFFFFu)) * nprob + pl];
+  if (((we >> 30) & 1) && pl != 0) return;  // shared by all problems: problem 0's lines serve everyone (block-uniform)
+  const g2_aff* Q = &Y[((size_t)(we >> 31) * K + (we & 0x3FFFFFFFu)) * nprob + pl];
   if (Q->x.is_zero() && Q->y.is_zero()) return;  // block-uniform
   const int s = threadIdx.x;
   const fp2* r = rec + (pt * GS_NUM_LINES + (s < GS_NUM_LINES ? s : 0)) * 4;
@@ -422,13 +425,13 @@ __global__ void __launch_bounds__(128) k_eval_tiles(const uint32_t* __restrict__
   const size_t pl = q % np;
   const int e = (int)(q / np);
   const uint32_t we = walk[e];
-  const int b = (int)(we >> 31), k = (int)(we & 0x7FFFFFFFu);
+  const int b = (int)(we >> 31), k = (int)(we & 0x3FFFFFFFu);
   const g2_aff* P = &Y[((size_t)b * K + k) * nprob + pl];
   if (P->x.is_zero() && P->y.is_zero()) return;
   const int ch = k / S, kk = k % S;
   const size_t A = (size_t)ch * np + pl;
   const int lane = (int)(A & 31);
-  const fp2* L = lines + ((size_t)e * np + pl) * GS_NUM_LINES * 2;
+  const fp2* L = lines + ((size_t)e * np + (((we >> 30) & 1) ? 0 : pl)) * GS_NUM_LINES * 2;  // (shared point: problem 0's lines)
   const int na = ne == 4 ? 2 : 1;
 #pragma unroll 1
   for (int a = 0; a < na; a++) {
@@ -641,12 +644,13 @@ static void build_walk_list(gs_ctx* ctx, int K, const uint8_t* slot_kind, std::v
   using namespace gsi;
   fs.n = 0;
   int nfixed = 0;
-  for (int k = 0; slot_kind && k < K; k++) nfixed += slot_kind[k] >= GS_SLOT_FIXED ? 1 : 0;
+  for (int k = 0; slot_kind && k < K; k++) nfixed += (slot_kind[k] >= GS_SLOT_FIXED && slot_kind[k] != GS_SLOT_WALK_SHARED) ? 1 : 0;
   const bool use_fixed = ctx->crs_lines_valid && nfixed > 0 && nfixed <= 4;  // no shape has more than 4 CRS slots
   for (int b = 0; b < 2; b++)
     for (int k = 0; k < K; k++) {
       const uint8_t kind = slot_kind ? slot_kind[k] : GS_SLOT_WALK;
-      if (kind >= GS_SLOT_FIXED && use_fixed) {
+      const bool shared = kind == GS_SLOT_WALK_SHARED;
+      if (!shared && kind >= GS_SLOT_FIXED && use_fixed) {
         if (b == 0) {
           fs.k[fs.n] = k;
           fs.pid[fs.n] = kind - GS_SLOT_FIXED;
@@ -655,7 +659,7 @@ static void build_walk_list(gs_ctx* ctx, int K, const uint8_t* slot_kind, std::v
         continue;
       }
       if (kind == GS_SLOT_WALK_B1 && b == 0) continue;
-      hwalk.push_back(((uint32_t)b << 31) | (uint32_t)k);
+      hwalk.push_back(((uint32_t)b << 31) | (shared ? 1u << 30 : 0u) | (uint32_t)k);
     }
 }
 
@@ -688,7 +692,9 @@ int gsi::g2_walk_ahead(gs_ctx* ctx, Scratch& sc, const g2_aff* Y, size_t nprob, 
     // (the inversion-free walk does MORE work per point -- a block per point to turn its 68 records into lines -- and only
     // wins where a point's own dependent chain is the whole cost: a lone statement; 256 statements of a C4 batch walk
     // 50 k points, and there it took 16 ms of the second stream against 8 for the affine walk)
-    if (ctx->lone_walk_jac && (size_t)nwalk * nprob <= 4096) {
+    size_t walked = 0;  // points actually walked: a point shared by all problems counts once
+    for (uint32_t we : hwalk) walked += ((we >> 30) & 1) ? 1 : nprob;
+    if (ctx->lone_walk_jac && walked <= 4096) {
       LAUNCH_CFG(k_g2_walk_jac, (size_t)nwalk * nprob, 64, 0, Y, rec, nprob, nprob, K, wa->dwalk, nwalk);
       LAUNCH_CFG(k_g2_lines_from_jac, (size_t)nwalk * nprob * 128, 128, 0, Y, rec, lines, nprob, nprob, K, wa->dwalk);
     } else {
