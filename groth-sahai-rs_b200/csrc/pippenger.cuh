@@ -228,6 +228,131 @@ __global__ void __launch_bounds__(64) k_pip_window_shift(const Jac<F>* __restric
   Wd[rw] = p;
 }
 
+
+// ------------------------------------------------------------------ many equations, ONE scalar vector (C4 proofs)
+// A multi-equation statement proves every equation under the SAME commitment randomness: the constant part of a proof
+// element is  sum_t s[row][t] * B_e[t]  with one scalar vector for all equations e and per-equation bases (B_e = the
+// equation's constants).  The bucket structure depends on the scalars only, so it is built ONCE (k_cs_digits, k_cs_sort:
+// which sub-term goes to which bucket of which window) and every equation sums its own points along those lists:
+//   k_cs_accumulate  thread (e, row, window, bucket): the bucket's points, endomorphism images taken on the fly
+//   k_cs_reduce      thread (e, row, window): sum_b (b+1) Bucket_b by running sums
+//   k_cs_combine     thread (e, row): Horner over the windows  ->  term slot 0 of (e, row)
+// ~W * Np mixed additions per (equation, row) -- 13 per 64-bit sub-scalar at c = 5 -- against a 4-bit-window scalar
+// multiplication (~64 doublings + 23 additions per sub-scalar) per term.
+struct cs_geom {
+  int c, W, H, rows;
+  size_t N, Np, nt;  // constant terms, sub-terms (N * PARTS), terms per row of `sv`
+};
+// thread -> (row, t): signed c-bit digits of the PARTS sub-scalars of sv[row][t]:  digits[(row*W + w)*Np + t*PARTS + j]
+template <class F>
+__global__ void __launch_bounds__(128) k_cs_digits(const fr* __restrict__ sv, int16_t* __restrict__ digits, cs_geom g) {
+  constexpr int PARTS = PipSplit<F>::PARTS;
+  size_t id = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (id >= g.N * g.rows) return;
+  const size_t t = id % g.N;
+  const int row = (int)(id / g.N);
+  uint32_t k[8], sub[PARTS][4];
+  fr_from_mont(k, sv[(size_t)row * g.nt + t]);
+  PipSplit<F>::split(sub, k);
+  const uint32_t half = 1u << (g.c - 1);
+  for (int j = 0; j < PARTS; j++) {
+    uint32_t carry = 0;
+    for (int w = 0; w < g.W; w++) {
+      uint32_t d = pip_bits(sub[j], w * g.c, g.c) + carry;
+      int sd;
+      if (d > half) {
+        sd = (int)d - (int)(1u << g.c);
+        carry = 1;
+      } else {
+        sd = (int)d;
+        carry = 0;
+      }
+      digits[((size_t)row * g.W + w) * g.Np + t * PARTS + j] = (int16_t)sd;
+    }
+  }
+}
+// block -> rw = (row, window): counting sort of its sub-terms by |digit| (one thread: a few hundred items, once per call)
+//   off[rw*(H+1) + b] = start of bucket b (b = |digit| - 1), off[.. + H] = number of non-zero digits
+//   list[rw*Np + pos] = (q << 1) | negative
+template <class F>
+__global__ void k_cs_sort(const int16_t* __restrict__ digits, uint32_t* __restrict__ off, uint32_t* __restrict__ cursor,
+                          uint32_t* __restrict__ list, cs_geom g) {
+  if (threadIdx.x != 0) return;
+  const size_t rw = blockIdx.x;
+  const int16_t* d = digits + rw * g.Np;
+  uint32_t* o = off + rw * (g.H + 1);
+  uint32_t* cu = cursor + rw * g.H;
+  uint32_t* l = list + rw * g.Np;
+  for (int b = 0; b < g.H; b++) cu[b] = 0;
+  for (size_t q = 0; q < g.Np; q++)
+    if (d[q] != 0) cu[(d[q] < 0 ? -d[q] : d[q]) - 1]++;
+  uint32_t run = 0;
+  for (int b = 0; b < g.H; b++) {
+    const uint32_t cnt = cu[b];
+    o[b] = run;
+    cu[b] = run;
+    run += cnt;
+  }
+  o[g.H] = run;
+  for (size_t q = 0; q < g.Np; q++)
+    if (d[q] != 0) l[cu[(d[q] < 0 ? -d[q] : d[q]) - 1]++] = ((uint32_t)q << 1) | (d[q] < 0 ? 1u : 0u);
+}
+// thread -> (e, rw, b): buckets[(e*RW + rw)*H + b] = sum of the bucket's sub-terms of equation e
+template <class F>
+__global__ void __launch_bounds__(128) k_cs_accumulate(const Aff<F>* __restrict__ bases, const uint32_t* __restrict__ off,
+                                                       const uint32_t* __restrict__ list, Jac<F>* __restrict__ buckets, size_t neq,
+                                                       cs_geom g) {
+  constexpr int PARTS = PipSplit<F>::PARTS;
+  const size_t RW = (size_t)g.rows * g.W;
+  size_t id = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (id >= neq * RW * g.H) return;
+  const size_t b = id % g.H, rw = (id / g.H) % RW, e = id / (g.H * RW);
+  const uint32_t i0 = off[rw * (g.H + 1) + b], i1 = off[rw * (g.H + 1) + b + 1];
+  Jac<F> acc;
+  acc.set_inf();
+  for (uint32_t i = i0; i < i1; i++) {
+    const uint32_t en = list[rw * g.Np + i];
+    const uint32_t q = en >> 1;
+    Aff<F> P;
+    PipSplit<F>::image(P, bases[e * g.N + q / PARTS], (int)(q % PARTS));
+    if (en & 1) F::neg(P.y, P.y);
+    Jac<F>::add_mixed(acc, acc, P);
+  }
+  buckets[id] = acc;
+}
+// thread -> (e, rw): S[e*RW + rw] = sum_b (b + 1) * Bucket_b   (running sums from the top bucket down)
+template <class F>
+__global__ void __launch_bounds__(128) k_cs_reduce(const Jac<F>* __restrict__ buckets, Jac<F>* __restrict__ S, size_t neq, cs_geom g) {
+  const size_t RW = (size_t)g.rows * g.W;
+  size_t id = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (id >= neq * RW) return;
+  const Jac<F>* bk = buckets + id * g.H;
+  Jac<F> run, acc;
+  run.set_inf();
+  acc.set_inf();
+  for (int b = g.H - 1; b >= 0; b--) {
+    Jac<F> t = bk[b];
+    Jac<F>::add(run, run, t);
+    Jac<F>::add(acc, acc, run);
+  }
+  S[id] = acc;
+}
+// thread -> (e, row): out[(e*rows + row) * ostride] = sum_w 2^(c w) S[e][row][w]
+template <class F>
+__global__ void __launch_bounds__(64) k_cs_combine(const Jac<F>* __restrict__ S, Jac<F>* __restrict__ out, size_t ostride, size_t neq,
+                                                   cs_geom g) {
+  size_t id = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (id >= neq * g.rows) return;
+  const Jac<F>* s = S + id * g.W;
+  Jac<F> acc = s[g.W - 1];
+  for (int w = g.W - 2; w >= 0; w--) {
+    for (int i = 0; i < g.c; i++) Jac<F>::dbl(acc, acc);
+    Jac<F> t = s[w];
+    Jac<F>::add(acc, acc, t);
+  }
+  out[id * ostride] = acc;
+}
+
 }  // namespace gs
 
 namespace gsi {
@@ -273,6 +398,39 @@ inline pip_geom pip_choose(size_t N, int c_override, int short_bits = 0) {
   g.G = g.H < 16 ? g.H : 16;
   g.NG = g.H / g.G;
   return g;
+}
+
+// terms[(e*rows + row) * ostride] = sum_{t < N} sv[row*nt + t] * bases[e*N + t] for e < neq: ONE scalar vector (the first
+// equation's rows of `sv`) for all equations.  `terms` slots other than the written ones are untouched.
+template <class F>
+int shared_scalar_sums(gs_ctx* ctx, Scratch& sc, const fr* sv, size_t nt, int rows, const Aff<F>* bases, size_t N, size_t neq,
+                       Jac<F>* terms, size_t ostride) {
+  cs_geom g;
+  g.rows = rows;
+  g.N = N;
+  g.Np = N * PipSplit<F>::PARTS;
+  g.nt = nt;
+  int lg = 0;
+  while (((size_t)1 << (lg + 1)) <= g.Np) lg++;
+  g.c = lg - 3 < 4 ? 4 : (lg - 3 > 10 ? 10 : lg - 3);  // ~Np / 8 points per bucket chain: W * (Np + 2 H) near its minimum
+  g.H = 1 << (g.c - 1);
+  g.W = (PipSplit<F>::BITS + 1 + g.c - 1) / g.c;
+  const size_t RW = (size_t)rows * g.W;
+  int16_t* digits;
+  uint32_t *off, *cursor, *list;
+  Jac<F>*buckets, *S;
+  CUDA_TRY(sc.alloc(&digits, RW * g.Np));
+  CUDA_TRY(sc.alloc(&off, RW * (g.H + 1)));
+  CUDA_TRY(sc.alloc(&cursor, RW * g.H));
+  CUDA_TRY(sc.alloc(&list, RW * g.Np));
+  CUDA_TRY(sc.alloc(&buckets, neq * RW * g.H));
+  CUDA_TRY(sc.alloc(&S, neq * RW));
+  LAUNCH((k_cs_digits<F>), N * rows, sv, digits, g);
+  LAUNCH_CFG((k_cs_sort<F>), RW * 32, 32, 0, digits, off, cursor, list, g);
+  LAUNCH((k_cs_accumulate<F>), neq * RW * g.H, bases, off, list, buckets, neq, g);
+  LAUNCH((k_cs_reduce<F>), neq * RW, buckets, S, neq, g);
+  LAUNCH_CFG((k_cs_combine<F>), neq * rows, 64, 0, S, terms, ostride, neq, g);
+  return GS_OK;
 }
 
 // out_rows[row * W] (Jacobian, row stride W) = sum_t sv[row][t] * (b0 | b1)[t]; returns the stride through *stride

@@ -576,6 +576,15 @@ int proof_element(gs_ctx* ctx, Scratch& sc, size_t count, int rows, bool group_t
       cudaEventRecord(join, ctx->stream2);
       ctx->stream = main_stream;
       int rcc = [&]() -> int {
+        if (nconst * PipSplit<F>::PARTS >= 64 && count >= 16) {
+          // shared witnesses = shared commitment randomness: the constants of ALL equations are multiplied by the same
+          // scalar vector, so the bucket lists are built once and every equation sums its points along them
+          // (pippenger.cuh, "ONE scalar vector").  The sum lands in term slot 0, the other constant slots are identities.
+          for (int row = 0; row < rows; row++)
+            CUDA_TRY(cudaMemset2DAsync(terms + (size_t)row * nt, nt * rows * sizeof(Jac<F>), 0, nconst * sizeof(Jac<F>), count,
+                                       ctx->stream));
+          return shared_scalar_sums<F>(ctx, sc, sv, nt, rows, (const Aff<F>*)dconst, nconst, count, terms, nt);
+        }
         LAUNCH_B((k_msm_terms<F>), nconst * rows, count, terms, sv, (const Aff<F>*)dconst, nconst, (const Aff<F>*)dvars, (size_t)0, rows,
                  (size_t)0, 1, nt);
         return GS_OK;
