@@ -1310,7 +1310,8 @@ static int verify_rand_dev(gs_ctx* ctx, int type, size_t count, size_t m, size_t
   const int Kw = (int)walk_slot.size();
   const jsf33 beta = make_jsf((uint32_t)rho_host[2 * count], (uint32_t)(rho_host[2 * count] >> 32));
   // Passes as large as the line tiles allow (13 KB per pair; half the budget, the slot arrays and tables need room too) and
-  // equal in size: the line walk is latency-bound, a pass that fills 0.6 of its last wave pays for a whole one.
+  // equal in size: the per-pass fixed costs (bucket-sum chains, product trees, partial last waves) are paid as rarely as
+  // possible -- 65,536 4x4 PPE proofs are ONE pass.
   size_t pass_cap = ctx->tile_budget / 2 / 13056 / (size_t)(Kw ? Kw : 1);
   if (pass_cap > 4 * ctx->verify_batch_max) pass_cap = 4 * ctx->verify_batch_max;
   if (ctx->verify_batch_max < 23680) pass_cap = ctx->verify_batch_max;  // (lowered by a test: several passes on a small batch)
