@@ -171,3 +171,16 @@ def test_rand_big_batch_bucket_sums(crs, ty):
         bad = tampered(ty, m, n, arrays, which, p, 5)
         assert eng.verify_batch_rand(ty, count, m, n, *bad, rho=rho_of(count, 71 + which)) is False, f"array {which} accepted"
     eng.close()
+
+
+def test_rand_two_big_passes(eng, crs):
+    """96,000 PPE proofs: more than one pass holds at full size (94,720), so two equal passes of 48,000 run, each with its
+    own bucket sums and target powers on the second stream; their products meet in the one final exponentiation.  A bad
+    theta in the SECOND pass must be caught."""
+    ty, m, n, reps = 0, 3, 2, 8000
+    cases = [Case(ty, m, n, crs, seed=2800 + i) for i in range(12)]
+    count = 12 * reps
+    arrays = [b"".join(c.verify_arrays()[k] for c in cases) * reps for k in range(8)]
+    assert eng.verify_batch_rand(ty, count, m, n, *arrays, rho=rho_of(count, 80)) is True
+    bad = tampered(ty, m, n, arrays, 7, 95000, 0)
+    assert eng.verify_batch_rand(ty, count, m, n, *bad, rho=rho_of(count, 81)) is False
