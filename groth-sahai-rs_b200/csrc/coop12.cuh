@@ -230,8 +230,13 @@ GS_HD GS_INL void cq_mul(int k, int lane, const uint32_t* f, const uint32_t* g, 
 //     a_0' = 3 S_0 - 2 a_0   a_3' = 3 P_0 + 2 a_3
 //     a_2' = 3 S_1 - 2 a_2   a_5' = 3 P_1 + 2 a_5
 //     a_4' = 3 S_2 - 2 a_4   a_1' = 3 xi P_2 + 2 a_1        (= ark-ff cyclotomic_square in the w basis)
-// Balanced over the 6 warps by Fp COMPONENT: warp (g = k % 3, c = k / 3) computes component c of S_g
-// (4 Fp products) and of P_g (2 Fp products), each with one lazy reduction.
+// Balanced over the 6 warps by Fp COMPONENT: warp (g = k % 3, c = k / 3) computes component c of S_g and of P_g, each
+// as ONE lazily reduced sum of products with BOTH operands in registers (the factors are sums / differences of the
+// loaded coefficients, which the squaring structure allows):
+//     S.c0 = (x0 + x1)(x0 - x1) + (y0 + y1)(y0 - y1) - (2 y0) y1        (xi y^2).c0 = y0^2 - y1^2 - 2 y0 y1
+//     S.c1 = (2 x0) x1          + (y0 + y1)(y0 - y1) + (2 y0) y1        (xi y^2).c1 = y0^2 - y1^2 + 2 y0 y1
+//     P.c0 = X0 y0 - X1 y1,  P.c1 = X0 y1 + X1 y0,  X = 2 x (times xi for g = 2)
+// 3 + 2 Fp products and 2 reductions per warp (the schoolbook form with one operand streamed from shared memory took 4 + 2).
 GS_HD GS_INL void cq_cyc_sqr(int k, int lane, const uint32_t* fin, uint32_t* fout) {
   const int g = k % 3, c = k / 3;
   const int ix = g, iy = g + 3;
@@ -241,31 +246,23 @@ GS_HD GS_INL void cq_cyc_sqr(int k, int lane, const uint32_t* fin, uint32_t* fou
   cq_ld_coef(y0, y1, fin, iy, lane, false, false);
   fp S, Pp;
   {
-    // Y-side for S: (x, xi y);  comp 0: x0*x0 + (-x1)*x1 + e0*y0 + (-e1)*y1 ; comp 1: x0*x1 + x1*x0 + e0*y1 + e1*y0
-    fp a[4];
-    a[0] = x0;
-    a[1] = x1;
-    fp::sub(a[2], y0, y1);
-    fp::add(a[3], y0, y1);
-    const uint32_t* b[4];
+    fp a[3], b[3];
+    fp::add(a[1], y0, y1);
+    fp::sub(b[1], y0, y1);
+    fp::add(a[2], y0, y0);
+    b[2] = y1;
     if (c == 0) {
-      fp::neg(a[1], a[1]);
-      fp::neg(a[3], a[3]);
-      b[0] = cq_ptr(fin, 2 * ix, lane);
-      b[1] = cq_ptr(fin, 2 * ix + 1, lane);
-      b[2] = cq_ptr(fin, 2 * iy, lane);
-      b[3] = cq_ptr(fin, 2 * iy + 1, lane);
+      fp::add(a[0], x0, x1);
+      fp::sub(b[0], x0, x1);
+      fp::neg(a[2], a[2]);
     } else {
-      b[0] = cq_ptr(fin, 2 * ix + 1, lane);
-      b[1] = cq_ptr(fin, 2 * ix, lane);
-      b[2] = cq_ptr(fin, 2 * iy + 1, lane);
-      b[3] = cq_ptr(fin, 2 * iy, lane);
+      fp::add(a[0], x0, x0);
+      b[0] = x1;
     }
-    mulsum_q<4>(S, a, b);
+    fp::mulsum<3>(S, a, b);
   }
   {
-    // Y-side for P: X = 2x (times xi for g = 2);  comp 0: X0*y0 + (-X1)*y1 ; comp 1: X0*y1 + X1*y0
-    fp a[2];
+    fp a[2], b[2];
     if (g == 2) {
       fp::sub(a[0], x0, x1);
       fp::add(a[1], x0, x1);
@@ -275,16 +272,15 @@ GS_HD GS_INL void cq_cyc_sqr(int k, int lane, const uint32_t* fin, uint32_t* fou
     }
     fp::add(a[0], a[0], a[0]);
     fp::add(a[1], a[1], a[1]);
-    const uint32_t* b[2];
     if (c == 0) {
       fp::neg(a[1], a[1]);
-      b[0] = cq_ptr(fin, 2 * iy, lane);
-      b[1] = cq_ptr(fin, 2 * iy + 1, lane);
+      b[0] = y0;
+      b[1] = y1;
     } else {
-      b[0] = cq_ptr(fin, 2 * iy + 1, lane);
-      b[1] = cq_ptr(fin, 2 * iy, lane);
+      b[0] = y1;
+      b[1] = y0;
     }
-    mulsum_q<2>(Pp, a, b);
+    fp::mulsum<2>(Pp, a, b);
   }
   fp t, o;
   // 3 S - 2 a_tS
