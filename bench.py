@@ -71,12 +71,21 @@ def work_model(m, n):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region.  The sampler process is started before the
+    warm-up (nvidia-smi needs ~0.5 s to come up, longer than a short timed region on 8 GPUs) and only the samples that
+    arrive between begin() and end() are kept."""
 
     def __init__(self, index):
         self.index = index
         self.rows = []
         self.proc = None
+        self.t0 = self.t1 = None
+
+    def begin(self):
+        self.t0 = time.time()
+
+    def end(self):
+        self.t1 = time.time()
 
     def start(self):
         q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
@@ -92,7 +101,7 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
 
     def stop(self):
         if self.proc is None:
@@ -102,13 +111,23 @@ class ClockSampler:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
-        sm = sorted(int(float(r[0])) for r in self.rows if r and r[0].replace(".", "").isdigit())
+        t0, t1 = self.t0 or 0.0, self.t1 or float("inf")
+        inside = [r for ts, r in self.rows if t0 <= ts <= t1 + 0.2]     # (a sample is printed up to one period after it is taken)
+        note = None
+        if not inside and self.rows:                                    # region shorter than one sampling period
+            inside = [min(self.rows, key=lambda tr: abs(tr[0] - t1))[1]]
+            note = "timed region shorter than the 200 ms sampling period: nearest sample"
+        rows = inside
+        sm = sorted(int(float(r[0])) for r in rows if r and r[0].replace(".", "").isdigit())
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(len(r) > 3 + i and r[3 + i].lower().startswith("active") for r in self.rows)]
-        mx = [int(float(r[1])) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
-        pw = [float(r[2]) for r in self.rows if len(r) > 2 and r[2].replace(".", "").isdigit()]
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": reasons}
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 3 + i and r[3 + i].lower().startswith("active") for r in rows)]
+        mx = [int(float(r[1])) for r in rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        pw = [float(r[2]) for r in rows if len(r) > 2 and r[2].replace(".", "").isdigit()]
+        out = {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+               "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": reasons}
+        if note:
+            out["note"] = note
+        return out
 
 
 # ---------------------------------------------------------------- synthetic workload (C5)
@@ -318,17 +337,20 @@ def bench_c5(R_, eng, P, distinct, steps, warmup, full):
         R_.barrier(stream)
         return R_.max_over_ranks(e0.elapsed_time(e1))
 
+    sampler = ClockSampler(R_.local)
+    sampler.start()
     for _ in range(max(1, warmup)):
         step_dev()
     R_.barrier(stream)
     got = ok_dev.cpu().numpy()
     if not (got == expected).all():
+        sampler.stop()
         raise SystemExit(f"verdict mismatch on rank {R_.rank}: {(got != expected).sum()} wrong of {P}")
     out = {"build_s": round(build_s, 1), "distinct": distinct or P}
-    sampler = ClockSampler(R_.local)
-    sampler.start()
     l0 = eng.launch_count
+    sampler.begin()
     ms_total = timed(step_dev, steps)
+    sampler.end()
     out["launches"] = eng.launch_count - l0
     out["clocks"] = sampler.stop()
     out["ms_per_step"] = ms_total / steps
