@@ -139,15 +139,54 @@ GS_HD GS_INL void cq_line_mul(int k, int lane, const uint32_t* fin, uint32_t* fo
 //     fout.a_k = alpha a_k + beta a_{k-2} + a_{k-3}
 // `tile` holds alpha.c0, alpha.c1, beta.c0, beta.c1 (4 Fp): 8 Fp products + 2 reductions per coefficient
 // instead of 12 + 2, and only two register-side operands.
+#ifndef GS_LINE_KARATSUBA
+#define GS_LINE_KARATSUBA 1
+#endif
 GS_HD GS_INL void cq_line_mul_u(int k, int lane, const uint32_t* fin, uint32_t* fout, const uint32_t* tile, bool active) {
   fp y[4];
   const int j1 = k >= 2 ? k - 2 : k + 4, j2 = k >= 3 ? k - 3 : k + 3;
   cq_ld_coef(y[0], y[1], fin, k, lane, false, false);
   cq_ld_coef(y[2], y[3], fin, j1, lane, k < 2, false);
+  fp2 r, u;
+#if GS_LINE_KARATSUBA
+  // Karatsuba over the TWO Fp2 products at once, every part one lazily reduced sum of two Fp products:
+  //     P0 = y1.c0 alpha.c0 + y2.c0 beta.c0,   P1 = y1.c1 alpha.c1 + y2.c1 beta.c1,
+  //     P2 = (y1.c0 + y1.c1)(alpha.c0 + alpha.c1) + (y2.c0 + y2.c1)(beta.c0 + beta.c1)
+  //     r.c0 = P0 - P1,  r.c1 = P2 - P0 - P1
+  // 6 Fp products + 3 reductions (1,332 multiply-adds) instead of 8 + 2 (1,464)
+  {
+    fp P0, P1, P2;
+    {
+      const fp a[2] = {y[0], y[2]};
+      const uint32_t* b[2] = {cq_ptr(tile, 0, lane), cq_ptr(tile, 2, lane)};
+      mulsum_q<2>(P0, a, b);
+    }
+    {
+      const fp a[2] = {y[1], y[3]};
+      const uint32_t* b[2] = {cq_ptr(tile, 1, lane), cq_ptr(tile, 3, lane)};
+      mulsum_q<2>(P1, a, b);
+    }
+    {
+      fp a[2], b[2], t0, t1;
+      fp::add(a[0], y[0], y[1]);
+      fp::add(a[1], y[2], y[3]);
+      cq_ld(t0, cq_ptr(tile, 0, lane));
+      cq_ld(t1, cq_ptr(tile, 1, lane));
+      fp::add(b[0], t0, t1);
+      cq_ld(t0, cq_ptr(tile, 2, lane));
+      cq_ld(t1, cq_ptr(tile, 3, lane));
+      fp::add(b[1], t0, t1);
+      fp::mulsum<2>(P2, a, b);
+    }
+    fp::sub(r.c0, P0, P1);
+    fp::sub(r.c1, P2, P0);
+    fp::sub(r.c1, r.c1, P1);
+  }
+#else
   const uint32_t* x0[2] = {cq_ptr(tile, 0, lane), cq_ptr(tile, 2, lane)};
   const uint32_t* x1[2] = {cq_ptr(tile, 1, lane), cq_ptr(tile, 3, lane)};
-  fp2 r, u;
   cq_fp2_dot<2>(r, y, x0, x1);
+#endif
   cq_ld_coef(u.c0, u.c1, fin, j2, lane, k < 3, false);
   fp2::add(r, r, u);
   if (!active) cq_ld_coef(r.c0, r.c1, fin, k, lane, false, false);
