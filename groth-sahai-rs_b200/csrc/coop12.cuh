@@ -95,6 +95,38 @@ GS_HD GS_INL void cq_fp2_dot(fp2& r, fp (&y)[2 * NT], const uint32_t* const (&x0
   mulsum_q<2 * NT>(r.c0, y, b);
 }
 
+// r = Y_0 X_0 + Y_1 X_1 in Fp2 by Karatsuba over BOTH products at once: three lazily reduced sums of two Fp products
+//     P0 = sum Y_t.c0 X_t.c0,  P1 = sum Y_t.c1 X_t.c1,  P2 = sum (Y_t.c0 + Y_t.c1)(X_t.c0 + X_t.c1);  r = (P0 - P1, P2 - P0 - P1)
+// 6 Fp products + 3 reductions (1,332 multiply-adds) instead of the 8 + 2 (1,464) of cq_fp2_dot<2>.  y[2t], y[2t+1] =
+// Y_t.c0, Y_t.c1 in registers (unchanged); the X operands are read from the Q layout, their component sums formed in
+// registers.
+GS_HD GS_INL void cq_fp2_dot2_k(fp2& r, const fp (&y)[4], const uint32_t* const (&x0)[2], const uint32_t* const (&x1)[2]) {
+  fp P0, P1, P2;
+  {
+    const fp a[2] = {y[0], y[2]};
+    mulsum_q<2>(P0, a, x0);
+  }
+  {
+    const fp a[2] = {y[1], y[3]};
+    mulsum_q<2>(P1, a, x1);
+  }
+  {
+    fp a[2], b[2], t0, t1;
+    fp::add(a[0], y[0], y[1]);
+    fp::add(a[1], y[2], y[3]);
+    cq_ld(t0, x0[0]);
+    cq_ld(t1, x1[0]);
+    fp::add(b[0], t0, t1);
+    cq_ld(t0, x0[1]);
+    cq_ld(t1, x1[1]);
+    fp::add(b[1], t0, t1);
+    fp::mulsum<2>(P2, a, b);
+  }
+  fp::sub(r.c0, P0, P1);
+  fp::sub(r.c1, P2, P0);
+  fp::sub(r.c1, r.c1, P1);
+}
+
 // load coefficient j of the accumulator set `f` into (y0, y1), optionally times xi and/or 2
 GS_HD GS_INL void cq_ld_coef(fp& y0, fp& y1, const uint32_t* f, int j, int lane, bool xi, bool dbl) {
   cq_ld(y0, cq_ptr(f, 2 * j, lane));
@@ -148,43 +180,11 @@ GS_HD GS_INL void cq_line_mul_u(int k, int lane, const uint32_t* fin, uint32_t* 
   cq_ld_coef(y[0], y[1], fin, k, lane, false, false);
   cq_ld_coef(y[2], y[3], fin, j1, lane, k < 2, false);
   fp2 r, u;
-#if GS_LINE_KARATSUBA
-  // Karatsuba over the TWO Fp2 products at once, every part one lazily reduced sum of two Fp products:
-  //     P0 = y1.c0 alpha.c0 + y2.c0 beta.c0,   P1 = y1.c1 alpha.c1 + y2.c1 beta.c1,
-  //     P2 = (y1.c0 + y1.c1)(alpha.c0 + alpha.c1) + (y2.c0 + y2.c1)(beta.c0 + beta.c1)
-  //     r.c0 = P0 - P1,  r.c1 = P2 - P0 - P1
-  // 6 Fp products + 3 reductions (1,332 multiply-adds) instead of 8 + 2 (1,464)
-  {
-    fp P0, P1, P2;
-    {
-      const fp a[2] = {y[0], y[2]};
-      const uint32_t* b[2] = {cq_ptr(tile, 0, lane), cq_ptr(tile, 2, lane)};
-      mulsum_q<2>(P0, a, b);
-    }
-    {
-      const fp a[2] = {y[1], y[3]};
-      const uint32_t* b[2] = {cq_ptr(tile, 1, lane), cq_ptr(tile, 3, lane)};
-      mulsum_q<2>(P1, a, b);
-    }
-    {
-      fp a[2], b[2], t0, t1;
-      fp::add(a[0], y[0], y[1]);
-      fp::add(a[1], y[2], y[3]);
-      cq_ld(t0, cq_ptr(tile, 0, lane));
-      cq_ld(t1, cq_ptr(tile, 1, lane));
-      fp::add(b[0], t0, t1);
-      cq_ld(t0, cq_ptr(tile, 2, lane));
-      cq_ld(t1, cq_ptr(tile, 3, lane));
-      fp::add(b[1], t0, t1);
-      fp::mulsum<2>(P2, a, b);
-    }
-    fp::sub(r.c0, P0, P1);
-    fp::sub(r.c1, P2, P0);
-    fp::sub(r.c1, r.c1, P1);
-  }
-#else
   const uint32_t* x0[2] = {cq_ptr(tile, 0, lane), cq_ptr(tile, 2, lane)};
   const uint32_t* x1[2] = {cq_ptr(tile, 1, lane), cq_ptr(tile, 3, lane)};
+#if GS_LINE_KARATSUBA
+  cq_fp2_dot2_k(r, y, x0, x1);
+#else
   cq_fp2_dot<2>(r, y, x0, x1);
 #endif
   cq_ld_coef(u.c0, u.c1, fin, j2, lane, k < 3, false);
@@ -213,7 +213,11 @@ GS_HD GS_INL void cq_sqr(int k, int lane, const uint32_t* fin, uint32_t* fout) {
     cq_ld_coef(y[2], y[3], fin, tj[1], lane, ti[1] + tj[1] >= 6, ti[1] < tj[1]);
     const uint32_t* x0[2] = {cq_ptr(fin, 2 * ti[0], lane), cq_ptr(fin, 2 * ti[1], lane)};
     const uint32_t* x1[2] = {cq_ptr(fin, 2 * ti[0] + 1, lane), cq_ptr(fin, 2 * ti[1] + 1, lane)};
+#if GS_LINE_KARATSUBA
+    cq_fp2_dot2_k(r, y, x0, x1);
+#else
     cq_fp2_dot<2>(r, y, x0, x1);
+#endif
     cq_st_coef(fout, k, lane, r);  // parked in the output slot (nobody reads fout during this op)
   }
   if (nt == 4) {
@@ -222,7 +226,11 @@ GS_HD GS_INL void cq_sqr(int k, int lane, const uint32_t* fin, uint32_t* fout) {
     cq_ld_coef(y[2], y[3], fin, tj[3], lane, ti[3] + tj[3] >= 6, ti[3] < tj[3]);
     const uint32_t* x0[2] = {cq_ptr(fin, 2 * ti[2], lane), cq_ptr(fin, 2 * ti[3], lane)};
     const uint32_t* x1[2] = {cq_ptr(fin, 2 * ti[2] + 1, lane), cq_ptr(fin, 2 * ti[3] + 1, lane)};
+#if GS_LINE_KARATSUBA
+    cq_fp2_dot2_k(r2, y, x0, x1);
+#else
     cq_fp2_dot<2>(r2, y, x0, x1);
+#endif
   } else {
     fp y[2];
     cq_ld_coef(y[0], y[1], fin, tj[2], lane, ti[2] + tj[2] >= 6, ti[2] < tj[2]);
