@@ -127,6 +127,36 @@ GS_HD GS_INL void cq_fp2_dot2_k(fp2& r, const fp (&y)[4], const uint32_t* const 
   fp::sub(r.c1, r.c1, P1);
 }
 
+// the same over three products (the two passes of cq_mul): 9 Fp products + 3 reductions (1,764 multiply-adds) instead of
+// 12 + 2 (2,040).  The component sums of Y are formed first, so that Y itself is dead by the time P2 is computed.
+GS_HD GS_INL void cq_fp2_dot3_k(fp2& r, const fp (&y)[6], const uint32_t* const (&x0)[3], const uint32_t* const (&x1)[3]) {
+  fp P0, P1, P2, sa[3];
+#pragma unroll
+  for (int t = 0; t < 3; t++) fp::add(sa[t], y[2 * t], y[2 * t + 1]);
+  {
+    const fp a[3] = {y[0], y[2], y[4]};
+    mulsum_q<3>(P0, a, x0);
+  }
+  {
+    const fp a[3] = {y[1], y[3], y[5]};
+    mulsum_q<3>(P1, a, x1);
+  }
+  {
+    fp b[3];
+#pragma unroll
+    for (int t = 0; t < 3; t++) {
+      fp t0, t1;
+      cq_ld(t0, x0[t]);
+      cq_ld(t1, x1[t]);
+      fp::add(b[t], t0, t1);
+    }
+    fp::mulsum<3>(P2, sa, b);
+  }
+  fp::sub(r.c0, P0, P1);
+  fp::sub(r.c1, P2, P0);
+  fp::sub(r.c1, r.c1, P1);
+}
+
 // load coefficient j of the accumulator set `f` into (y0, y1), optionally times xi and/or 2
 GS_HD GS_INL void cq_ld_coef(fp& y0, fp& y1, const uint32_t* f, int j, int lane, bool xi, bool dbl) {
   cq_ld(y0, cq_ptr(f, 2 * j, lane));
@@ -259,11 +289,22 @@ GS_HD GS_INL void cq_mul(int k, int lane, const uint32_t* f, const uint32_t* g, 
       x0[t] = cq_ptr(g, 2 * i, lane);
       x1[t] = cq_ptr(g, 2 * i + 1, lane);
     }
+#ifndef GS_MUL_KARATSUBA
+#define GS_MUL_KARATSUBA 1
+#endif
     if (h == 0) {
+#if GS_MUL_KARATSUBA
+      cq_fp2_dot3_k(r, y, x0, x1);
+#else
       cq_fp2_dot<3>(r, y, x0, x1);
+#endif
       cq_st_coef(fout, k, lane, r);  // parked in the output slot
     } else {
+#if GS_MUL_KARATSUBA
+      cq_fp2_dot3_k(r2, y, x0, x1);
+#else
       cq_fp2_dot<3>(r2, y, x0, x1);
+#endif
     }
   }
   cq_ld_coef(r.c0, r.c1, fout, k, lane, false, false);
